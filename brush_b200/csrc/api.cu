@@ -1,0 +1,424 @@
+// api.cu -- the extern "C" boundary declared in include/brush_b200.h: context/arena management and
+// host-side orchestration of the kernels (what <MainBackendBase as SplatOps>::render does in
+// brush-render/src/render.rs:37-315, minus its blocking readback).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "bg_common.cuh"
+#include "bg_project.cuh"
+
+namespace bg {
+// project.cu
+cudaError_t launch_project_cull(cudaStream_t, int, bool, const float *, const float *, uint32_t, const BgCamera &,
+                                uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *, uint32_t *, float *,
+                                uint32_t *, uint32_t *, unsigned long long *, uint32_t);
+cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, const uint32_t *,
+                               uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *, unsigned long long *, uint32_t);
+cudaError_t launch_project_visible_emit(cudaStream_t, int, bool, int, const float *, const float *, const float *,
+                                        const uint32_t *, const uint32_t *, const BgCamera &, uint32_t, uint32_t,
+                                        float *, uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *);
+cudaError_t launch_tile_offsets(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, uint32_t *);
+// sort.cu
+cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, const uint32_t *, uint32_t, uint32_t,
+                              uint32_t *);
+cudaError_t launch_onesweep_pass(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *,
+                                 uint32_t, const uint32_t *, uint32_t, uint32_t, const uint32_t *, uint32_t *,
+                                 unsigned long long *, uint32_t);
+uint32_t sort_tile_size();
+// raster_fwd.cu / raster_bwd.cu / project_bwd.cu
+cudaError_t launch_rasterize_fwd(cudaStream_t, bool, bool, uint32_t, const uint32_t *, uint32_t *, const float *,
+                                 const uint32_t *, void *, float *, uint32_t, uint32_t, uint32_t, const float *);
+cudaError_t launch_rasterize_bwd(cudaStream_t, bool, uint32_t, const uint32_t *, const uint32_t *, const float *,
+                                 const float *, const float *, float *, uint32_t, uint32_t, uint32_t, const float *);
+cudaError_t launch_project_bwd(cudaStream_t, bool, int, const float *, const float *, const float *,
+                               const uint32_t *, const float *, uint32_t, const BgCamera &, float *, float *, float *,
+                               float *);
+// loss.cu / optim.cu
+cudaError_t launch_image_loss_fwd(cudaStream_t, const float *, const uint32_t *, uint32_t, uint32_t, uint32_t, int64_t,
+                                  int64_t, int64_t, float, float, const float *, bool, float *);
+cudaError_t launch_image_loss_bwd(cudaStream_t, const float *, const uint32_t *, const float *, uint32_t, uint32_t,
+                                  uint32_t, int64_t, int64_t, int64_t, float, float, const float *, bool, float *);
+cudaError_t launch_adam(cudaStream_t, float *, const float *, float *, float *, uint64_t, uint32_t, const float *, float,
+                        float, float, float, float, float, bool, bool);
+cudaError_t launch_refine_stats_noise(cudaStream_t, uint32_t, const float *, const float *, const float *, float *,
+                                      float *, float *, float *, const float *, const float *, float, float);
+}  // namespace bg
+
+using namespace bg;
+
+static thread_local char g_err[512] = "";
+static void set_err(const char *what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+}
+
+#define BG_CUDA(call)                          \
+    do {                                       \
+        cudaError_t e__ = (call);              \
+        if (e__ != cudaSuccess) {              \
+            set_err(#call, e__);               \
+            return BG_ERR_CUDA;                \
+        }                                      \
+    } while (0)
+
+struct BgContext {
+    int device = 0;
+    int sm_count = 0;
+    uint32_t max_n = 0, max_w = 0, max_h = 0, max_tiles = 0;
+    uint32_t max_isect = 0;
+    uint32_t epoch = 1;
+    uint64_t arena_bytes = 0;
+    // device arena
+    uint32_t *ctl = nullptr;               // CTL_WORDS u32 (forward pipeline), then CTL_WORDS (standalone ops)
+    uint32_t *depth_key[2] = {nullptr, nullptr};
+    uint32_t *depth_val[2] = {nullptr, nullptr};
+    uint32_t *counts = nullptr, *cum = nullptr, *cgid_from_gid = nullptr;
+    float *projected = nullptr;
+    uint32_t *isect_key[2] = {nullptr, nullptr};
+    uint32_t *isect_val[2] = {nullptr, nullptr};
+    uint32_t *tile_offsets = nullptr;
+    unsigned long long *lb_scan = nullptr;  // look-back words for project/scan kernels
+    unsigned long long *lb_sort = nullptr;  // look-back words for the sort passes: [tiles][256]
+    uint64_t lb_scan_words = 0, lb_sort_words = 0;
+    uint32_t *counters_host = nullptr;      // pinned [4]
+    // last forward (for state pointers)
+    int depth_out = 0, isect_out = 0;
+};
+
+static uint32_t next_epoch(BgContext *c) {
+    c->epoch++;
+    if (c->epoch >= (1u << 30)) c->epoch = 1;  // words of 2^30 launches ago are long overwritten
+    return c->epoch;
+}
+
+extern "C" uint32_t bg_abi_version(void) { return BG_ABI_VERSION; }
+extern "C" const char *bg_last_error_string(void) { return g_err; }
+
+template <typename T>
+static cudaError_t arena_alloc(BgContext *c, T **p, uint64_t count) {
+    uint64_t bytes = std::max<uint64_t>(count, 1) * sizeof(T);
+    bytes = (bytes + 255) & ~uint64_t(255);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e == cudaSuccess) c->arena_bytes += bytes;
+    return e;
+}
+
+extern "C" int32_t bg_ctx_destroy(BgContext *c) {
+    if (!c) return BG_ERR_NULL;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->ctl, c->depth_key[0], c->depth_key[1], c->depth_val[0], c->depth_val[1], c->counts, c->cum,
+                    c->cgid_from_gid, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
+                    c->tile_offsets, c->lb_scan, c->lb_sort};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->counters_host) cudaFreeHost(c->counters_host);
+    delete c;
+    return BG_OK;
+}
+
+extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t max_w, uint32_t max_h,
+                                 uint64_t max_intersections, BgContext **out_ctx) {
+    if (!out_ctx) return BG_ERR_NULL;
+    *out_ctx = nullptr;
+    if (max_splats == 0 || max_w == 0 || max_h == 0) { set_err("bg_ctx_create: zero capacity", cudaSuccess); return BG_ERR_INVALID; }
+    if (max_intersections == 0) max_intersections = std::max<uint64_t>(16ull * max_splats, 1ull << 22);
+    if (max_intersections >= (1ull << 31)) { set_err("bg_ctx_create: max_intersections must be < 2^31", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(device));
+    BgContext *c = new (std::nothrow) BgContext();
+    if (!c) return BG_ERR_CUDA;
+    c->device = device;
+    c->max_n = max_splats; c->max_w = max_w; c->max_h = max_h;
+    c->max_isect = (uint32_t)max_intersections;
+    c->max_tiles = ((max_w + TILE_W - 1) / TILE_W) * ((max_h + TILE_W - 1) / TILE_W);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { set_err("cudaGetDeviceProperties", e); delete c; return BG_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    const uint64_t n = max_splats, I = c->max_isect;
+    const uint64_t sort_tiles = (std::max<uint64_t>(n, I) + sort_tile_size() - 1) / sort_tile_size() + 1;
+    c->lb_sort_words = sort_tiles * 256;
+    c->lb_scan_words = (n + 255) / 256 + 64;
+    bool ok = true;
+    ok = ok && arena_alloc(c, &c->ctl, 2 * CTL_WORDS) == cudaSuccess;
+    for (int i = 0; i < 2; i++) {
+        ok = ok && arena_alloc(c, &c->depth_key[i], n) == cudaSuccess;
+        ok = ok && arena_alloc(c, &c->depth_val[i], n) == cudaSuccess;
+        ok = ok && arena_alloc(c, &c->isect_key[i], I) == cudaSuccess;
+        ok = ok && arena_alloc(c, &c->isect_val[i], I) == cudaSuccess;
+    }
+    ok = ok && arena_alloc(c, &c->counts, n) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->cum, n) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->cgid_from_gid, n) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->projected, n * BG_PROJECTED_STRIDE) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->tile_offsets, (uint64_t)c->max_tiles * 2) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->lb_scan, c->lb_scan_words) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->lb_sort, c->lb_sort_words) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&c->counters_host, 16 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemset(c->lb_scan, 0, c->lb_scan_words * 8) == cudaSuccess &&
+             cudaMemset(c->lb_sort, 0, c->lb_sort_words * 8) == cudaSuccess &&
+             cudaMemset(c->ctl, 0, 2 * CTL_WORDS * 4) == cudaSuccess;
+    }
+    if (!ok) {
+        set_err("bg_ctx_create: arena allocation", cudaGetLastError());
+        bg_ctx_destroy(c);
+        return BG_ERR_CUDA;
+    }
+    memset(c->counters_host, 0, 16 * sizeof(uint32_t));
+    *out_ctx = c;
+    return BG_OK;
+}
+
+extern "C" uint64_t bg_ctx_arena_bytes(const BgContext *c) { return c ? c->arena_bytes : 0; }
+
+// One-sweep sort of the low `bits` bits.  bufs: ping-pong pairs; the input is (key_in,val_in); the
+// result lands in (keys[out_idx], vals[out_idx]) where out_idx is returned.  `hist` must be zero.
+static int32_t run_sort(BgContext *c, cudaStream_t s, const uint32_t *key_in, const uint32_t *val_in,
+                        uint32_t *keys[2], uint32_t *vals[2], uint32_t n_host, const uint32_t *n_dev, uint32_t bits,
+                        uint32_t *hist, uint32_t *tickets /* [1 + passes] zeroed */, int first_dst, int *out_idx) {
+    const uint32_t passes = (bits + 7) / 8;
+    *out_idx = first_dst;
+    if (passes == 0 || n_host == 0) return BG_OK;
+    const int grid = c->sm_count * 4;
+    BG_CUDA(launch_radix_hist(s, grid, key_in, n_host, n_dev, bits, passes, hist));
+    const uint32_t *kin = key_in, *vin = val_in;
+    int dst = first_dst;
+    for (uint32_t p = 0; p < passes; p++) {
+        const uint32_t shift = p * 8, width = std::min(8u, bits - shift);
+        BG_CUDA(launch_onesweep_pass(s, c->sm_count * 2, kin, vin, keys[dst], vals[dst], n_host, n_dev, shift, width,
+                                     hist + p * 256, tickets + 1 + p, c->lb_sort, next_epoch(c)));
+        kin = keys[dst]; vin = vals[dst];
+        *out_idx = dst;
+        dst ^= 1;
+    }
+    return BG_OK;
+}
+
+extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera *cam, uint32_t w, uint32_t h,
+                                     uint32_t n, uint32_t k, const float *transforms, const float *sh,
+                                     const float *raw_opac, int32_t mip, const float *bg, int32_t pass, void *out_img,
+                                     float *visible, float *max_radius, BgRenderState *st) {
+    if (!c || !cam || !bg || !out_img || !st) return BG_ERR_NULL;
+    if (n > 0 && !max_radius) return BG_ERR_NULL;
+    if (n > 0 && (!transforms || !sh || !raw_opac)) return BG_ERR_NULL;
+    if (w == 0 || h == 0) { set_err("Can't render images with 0 size", cudaSuccess); return BG_ERR_INVALID; }
+    const int deg = sh_degree_from_k(k);
+    if (deg < 0) { set_err("Invalid nr. of sh bases", cudaSuccess); return BG_ERR_INVALID; }
+    if (pass < 0 || pass > 2) { set_err("invalid pass", cudaSuccess); return BG_ERR_INVALID; }
+    if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
+    const bool bwd_info = pass != BG_PASS_FORWARD;
+    if (bwd_info && n > 0 && !visible) return BG_ERR_NULL;
+    const uint32_t tiles_x = (w + TILE_W - 1) / TILE_W, tiles_y = (h + TILE_W - 1) / TILE_W;
+    const uint32_t num_tiles = tiles_x * tiles_y;
+    if (n > c->max_n || num_tiles > c->max_tiles) { set_err("bg_render_forward: exceeds context capacity", cudaSuccess); return BG_ERR_CAPACITY; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+
+    BG_CUDA(cudaMemsetAsync(c->ctl, 0, CTL_WORDS * sizeof(uint32_t), s));
+    BG_CUDA(cudaMemsetAsync(c->tile_offsets, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
+    if (bwd_info && n > 0) BG_CUDA(cudaMemsetAsync(visible, 0, (size_t)n * sizeof(float), s));
+
+    const int pgrid = c->sm_count * 4;
+    uint32_t *counters = c->ctl + CTL_COUNTERS;
+    // K1: cull + compaction in index order
+    BG_CUDA(launch_project_cull(s, pgrid, mip != 0, transforms, raw_opac, n, *cam, w, h, tiles_x, tiles_y,
+                                c->depth_key[0], c->depth_val[0], c->counts, max_radius, c->cgid_from_gid, c->ctl,
+                                c->lb_scan, next_epoch(c)));
+    // depth sort: 32-bit keys, 4 passes, (0)->(1)->(0)->(1)->(0)
+    int dout = 0;
+    {
+        int32_t r = run_sort(c, s, c->depth_key[0], c->depth_val[0], c->depth_key, c->depth_val, n, counters + 0, 32,
+                             c->ctl + CTL_HIST_DEPTH, c->ctl + CTL_TICKETS + TK_DEPTH_HIST, 1, &dout);
+        if (r != BG_OK) return r;
+    }
+    c->depth_out = dout;
+    const uint32_t *gid_sorted = c->depth_val[dout];
+    // gather counts + inclusive scan -> cum, num_intersections
+    BG_CUDA(launch_gather_scan(s, c->sm_count * 2, c->counts, gid_sorted, n, counters + 0, c->cum, counters + 1,
+                               c->max_isect, counters + 2, c->ctl + CTL_TICKETS + TK_SCAN, c->lb_scan, next_epoch(c)));
+    // K2+K3
+    if (n > 0)
+        BG_CUDA(launch_project_visible_emit(s, pgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
+                                            tiles_x, tiles_y, c->projected, c->isect_key[0], c->isect_val[0],
+                                            c->max_isect, c->cgid_from_gid, c->ctl));
+    // tile sort on bits = 32 - clz(num_tiles)
+    uint32_t bits = 0;
+    while (bits < 32 && (num_tiles >> bits) != 0) bits++;
+    int iout = 0;
+    {
+        const uint32_t passes = (bits + 7) / 8;
+        const int first_dst = 1;
+        int32_t r = run_sort(c, s, c->isect_key[0], c->isect_val[0], c->isect_key, c->isect_val, c->max_isect,
+                             counters + 1, bits, c->ctl + CTL_HIST_TILE, c->ctl + CTL_TICKETS + TK_TILE_HIST, first_dst,
+                             &iout);
+        if (r != BG_OK) return r;
+        (void)passes;
+    }
+    c->isect_out = iout;
+    // K4
+    BG_CUDA(launch_tile_offsets(s, c->sm_count * 4, c->isect_key[iout], c->ctl, num_tiles, c->tile_offsets));
+    // K5
+    BG_CUDA(launch_rasterize_fwd(s, bwd_info, pass == BG_PASS_BACKWARD_SMOOTH, num_tiles, c->isect_val[iout],
+                                 c->tile_offsets, c->projected, gid_sorted, out_img, visible, tiles_x, w, h, bg));
+    BG_CUDA(cudaMemcpyAsync(c->counters_host, counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+
+    st->projected = c->projected;
+    st->compact_gid_from_isect = c->isect_val[iout];
+    st->global_from_compact_gid = gid_sorted;
+    st->compact_from_global_gid = c->cgid_from_gid;
+    st->tile_offsets = c->tile_offsets;
+    st->depths = reinterpret_cast<const float *>(c->depth_key[dout]);
+    st->tile_id_from_isect = c->isect_key[iout];
+    st->counters_dev = counters;
+    st->counters_host = c->counters_host;
+    st->n = n; st->k = k; st->w = w; st->h = h; st->tiles_x = tiles_x; st->tiles_y = tiles_y;
+    st->mip = mip != 0; st->pass = pass;
+    return BG_OK;
+}
+
+extern "C" int32_t bg_rasterize_backward(BgContext *c, void *stream, const BgRenderState *st, const float *out_img,
+                                         const float *v_output, const float *bg, int32_t smooth, float *v_combined,
+                                         uint32_t rows) {
+    if (!c || !st || !out_img || !v_output || !bg || !v_combined) return BG_ERR_NULL;
+    if (st->pass == BG_PASS_FORWARD) { set_err("bg_rasterize_backward requires a Backward pass state", cudaSuccess); return BG_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    const uint32_t zr = std::min(rows, std::max(st->n, 1u));
+    BG_CUDA(cudaMemsetAsync(v_combined, 0, (size_t)zr * BG_VCOMBINED_STRIDE * sizeof(float), s));
+    const uint32_t num_tiles = st->tiles_x * st->tiles_y;
+    BG_CUDA(launch_rasterize_bwd(s, smooth != 0, num_tiles, st->compact_gid_from_isect, st->tile_offsets, st->projected,
+                                 out_img, v_output, v_combined, st->tiles_x, st->w, st->h, bg));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_project_backward(BgContext *c, void *stream, const BgCamera *cam, const BgRenderState *st,
+                                       const float *transforms, const float *sh, const float *raw_opac,
+                                       const float *v_combined, float *v_transforms, float *v_sh, float *v_raw_opac,
+                                       float *v_refine) {
+    if (!c || !cam || !st || !v_combined || !v_transforms || !v_sh || !v_raw_opac || !v_refine) return BG_ERR_NULL;
+    if (st->n > 0 && (!transforms || !sh || !raw_opac)) return BG_ERR_NULL;
+    const int deg = sh_degree_from_k(st->k);
+    if (deg < 0) return BG_ERR_INVALID;
+    if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,
+                               st->n, *cam, v_transforms, v_sh, v_raw_opac, v_refine));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_radix_argsort_u32(BgContext *c, void *stream, const uint32_t *keys, const uint32_t *vals,
+                                        uint32_t n, const uint32_t *n_dev, uint32_t bits, uint32_t *keys_out,
+                                        uint32_t *vals_out) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!keys || !vals || !keys_out || !vals_out) return BG_ERR_NULL;
+    if (bits > 32) { set_err("Can only sort up to 32 bits", cudaSuccess); return BG_ERR_INVALID; }
+    if (n > std::max(c->max_n, c->max_isect)) { set_err("bg_radix_argsort_u32: n exceeds context capacity", cudaSuccess); return BG_ERR_CAPACITY; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    uint32_t *ctl2 = c->ctl + CTL_WORDS;
+    BG_CUDA(cudaMemsetAsync(ctl2, 0, CTL_WORDS * sizeof(uint32_t), s));
+    const uint32_t passes = (bits + 7) / 8;
+    if (passes == 0) {
+        BG_CUDA(cudaMemcpyAsync(keys_out, keys, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        BG_CUDA(cudaMemcpyAsync(vals_out, vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        return BG_OK;
+    }
+    // temp = the intersection ping-pong buffer (large enough by the capacity check for n <= max_isect,
+    // otherwise the depth buffers)
+    uint32_t *tk = (n <= c->max_isect) ? c->isect_key[1] : c->depth_key[1];
+    uint32_t *tv = (n <= c->max_isect) ? c->isect_val[1] : c->depth_val[1];
+    uint32_t *kb[2] = {keys_out, tk};
+    uint32_t *vb[2] = {vals_out, tv};
+    const int first_dst = (passes & 1u) ? 0 : 1;  // so that the last pass writes into (keys_out, vals_out)
+    int out_idx = 0;
+    int32_t r = run_sort(c, s, keys, vals, kb, vb, n, n_dev, bits, ctl2 + CTL_HIST_DEPTH, ctl2 + CTL_TICKETS, first_dst,
+                         &out_idx);
+    if (r != BG_OK) return r;
+    if (out_idx != 0) { set_err("internal: sort parity", cudaSuccess); return BG_ERR_INVALID; }
+    return BG_OK;
+}
+
+extern "C" int32_t bg_inclusive_scan_u32(BgContext *c, void *stream, const uint32_t *in, uint32_t n, uint32_t *out) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!in || !out) return BG_ERR_NULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    if ((uint64_t)(n + 2047) / 2048 > c->lb_scan_words) { set_err("bg_inclusive_scan_u32: n exceeds context capacity", cudaSuccess); return BG_ERR_CAPACITY; }
+    uint32_t *ctl2 = c->ctl + CTL_WORDS;
+    BG_CUDA(cudaMemsetAsync(ctl2 + CTL_TICKETS, 0, 48 * sizeof(uint32_t), s));
+    BG_CUDA(launch_gather_scan(s, c->sm_count * 2, in, nullptr, n, nullptr, out, nullptr, 0xFFFFFFFFu, nullptr,
+                               ctl2 + CTL_TICKETS, c->lb_scan, next_epoch(c)));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_image_loss_forward(BgContext *c, void *stream, const float *pred, const uint32_t *gt,
+                                         uint32_t channels, uint32_t h, uint32_t w, int64_t sc, int64_t sy, int64_t sx,
+                                         float l1_w, float ssim_w, const float *bg, int32_t mask, float *loss_map) {
+    if (!c || !pred || !gt || !loss_map) return BG_ERR_NULL;
+    if (channels < 3 || channels > 4 || h == 0 || w == 0) { set_err("image_loss expects 3 or 4 channels and a non-empty image", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_image_loss_fwd((cudaStream_t)stream, pred, gt, channels, h, w, sc, sy, sx, l1_w, ssim_w, bg, mask != 0,
+                                  loss_map));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_image_loss_backward(BgContext *c, void *stream, const float *pred, const uint32_t *gt,
+                                          const float *dl_dmap, uint32_t channels, uint32_t h, uint32_t w, int64_t sc,
+                                          int64_t sy, int64_t sx, float l1_w, float ssim_w, const float *bg,
+                                          int32_t mask, float *dl_dpred) {
+    if (!c || !pred || !gt || !dl_dmap || !dl_dpred) return BG_ERR_NULL;
+    if (channels < 3 || channels > 4 || h == 0 || w == 0) { set_err("image_loss expects 3 or 4 channels and a non-empty image", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_image_loss_bwd((cudaStream_t)stream, pred, gt, dl_dmap, channels, h, w, sc, sy, sx, l1_w, ssim_w, bg,
+                                  mask != 0, dl_dpred));
+    return BG_OK;
+}
+
+// compiler-rt __powisf2, what Rust's f32::powi lowers to (adam_scaled.rs:135-142)
+static float powi_f32(float a, int b) {
+    const bool recip = b < 0;
+    float r = 1.0f;
+    while (true) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0f / r : r;
+}
+
+extern "C" int32_t bg_adam_step(BgContext *c, void *stream, float *p, const float *g, float *m, float *v,
+                                uint64_t rows, uint32_t cols, const float *lr_scale, float lr, float beta1, float beta2,
+                                float eps, int32_t t, int32_t reduce_v) {
+    if (!c) return BG_ERR_NULL;
+    if (rows == 0 || cols == 0) return BG_OK;
+    if (!p || !g || !m || !v) return BG_ERR_NULL;
+    if (t < 1) { set_err("bg_adam_step: t is 1-based", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    const float bc1 = 1.0f - powi_f32(beta1, t), bc2 = 1.0f - powi_f32(beta2, t);
+    BG_CUDA(launch_adam((cudaStream_t)stream, p, g, m, v, rows, cols, lr_scale, lr, beta1, beta2, eps, bc1, bc2, t == 1,
+                        reduce_v != 0));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_refine_stats_noise(BgContext *c, void *stream, uint32_t n, const float *v_refine,
+                                         const float *visible, const float *max_radius, float *refine_weight_norm,
+                                         float *vis_weight, float *max_screen_size, float *transforms,
+                                         const float *raw_opac, const float *noise, float noise_scale,
+                                         float median_scale) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!v_refine || !visible || !max_radius || !refine_weight_norm || !vis_weight || !max_screen_size) return BG_ERR_NULL;
+    if (noise && (!transforms || !raw_opac)) return BG_ERR_NULL;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_refine_stats_noise((cudaStream_t)stream, n, v_refine, visible, max_radius, refine_weight_norm,
+                                      vis_weight, max_screen_size, transforms, raw_opac, noise, noise_scale,
+                                      median_scale));
+    return BG_OK;
+}

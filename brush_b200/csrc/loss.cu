@@ -1,0 +1,318 @@
+// loss.cu -- fused L1 + SSIM image loss, forward map and recompute-in-backward VJP.
+// Replaces image_loss_forward_kernel (brush-loss/src/lib.rs:180-359) and image_loss_backward_kernel
+// (lib.rs:370-661): 11-tap sigma=1.5 separable Gaussian window, zero padding, C1=1e-4, C2=9e-4,
+// sigma^2 = max(0, .), ssim clamped to [-1,1] with zero gradient where clamped, GT decoded from packed
+// rgba8, optional background compositing and alpha masking, channel 3 = |pred.a - gt.a|.
+//
+// Differences in mechanism only: pred is addressed through (stride_c, stride_y, stride_x) so the
+// rasterizer's [h,w,4] output is consumed in place (the reference permutes HWC->CHW around the op,
+// lib.rs:1076,1103), and the backward uses a 16x16 tile like the forward (the reference's 8x8
+// backward tile is an Apple threadgroup-memory constraint, lib.rs:75-87).  Accumulation order of the
+// window sums follows the reference (symmetric pairs d=1..5, then the centre tap).
+// HBM-bound: ~28 P bytes forward, ~40 P backward for C=3.
+#include "bg_common.cuh"
+
+namespace bg {
+
+constexpr int LB = 16;        // tile edge
+constexpr int HALO = 5;
+constexpr int SH1 = LB + 2 * HALO;   // 26
+constexpr int SH2 = LB + 4 * HALO;   // 36
+constexpr float SSIM_C1 = 0.01f * 0.01f;
+constexpr float SSIM_C2 = 0.03f * 0.03f;
+constexpr float INV_255 = 1.0f / 255.0f;
+
+struct Taps { float w[11]; };
+
+struct LossArgs {
+    const float *pred;
+    const uint32_t *gt;
+    uint32_t h, w;
+    int64_t sc, sy, sx;
+    float l1_w, ssim_w;
+    float bg[3];
+    int composite, mask;
+};
+
+__device__ __forceinline__ float ld_pred(const LossArgs &a, uint32_t c, int y, int x) {
+    if (y < 0 || x < 0 || y >= (int)a.h || x >= (int)a.w) return 0.0f;
+    return __ldg(a.pred + (int64_t)c * a.sc + (int64_t)y * a.sy + (int64_t)x * a.sx);
+}
+__device__ __forceinline__ float ld_gt_eff(const LossArgs &a, uint32_t c, int y, int x, float bg_c) {
+    float gt_c = 0.0f, gt_a = 0.0f;
+    if (!(y < 0 || x < 0 || y >= (int)a.h || x >= (int)a.w)) {
+        uint32_t v = __ldg(a.gt + (size_t)y * a.w + x);
+        gt_c = (float)((v >> (c * 8u)) & 0xffu) * INV_255;
+        gt_a = (float)((v >> 24u) & 0xffu) * INV_255;
+    }
+    return a.composite ? gt_c + (1.0f - gt_a) * bg_c : gt_c;
+}
+__device__ __forceinline__ float ld_gt_a(const LossArgs &a, int y, int x) {
+    return (float)((__ldg(a.gt + (size_t)y * a.w + x) >> 24u) & 0xffu) * INV_255;
+}
+
+// Blur of five moment images along one axis, reference accumulation order.
+#define BG_BLUR5_PAIR(o, l0, l1, r0, r1, wd)          \
+    o[0] += (l0 + r0) * wd;                           \
+    o[1] += (l0 * l0 + r0 * r0) * wd;                 \
+    o[2] += (l1 + r1) * wd;                           \
+    o[3] += (l1 * l1 + r1 * r1) * wd;                 \
+    o[4] += (l0 * l1 + r0 * r1) * wd;
+
+__global__ void __launch_bounds__(LB * LB)
+image_loss_fwd_kernel(LossArgs a, Taps taps, float *__restrict__ loss_map) {
+    const uint32_t c = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tile_x0 = blockIdx.x * LB, tile_y0 = blockIdx.y * LB;
+    const int pix_x = tile_x0 + tx, pix_y = tile_y0 + ty;
+    const int rank = ty * LB + tx;
+    if (c == 3) {  // alpha-match channel (lib.rs:215-227)
+        if (pix_x < (int)a.w && pix_y < (int)a.h) {
+            float ga = ld_gt_a(a, pix_y, pix_x);
+            float v = fabsf(ld_pred(a, 3, pix_y, pix_x) - ga);
+            if (a.mask) v = v * ga;
+            loss_map[(size_t)3 * a.h * a.w + (size_t)pix_y * a.w + pix_x] = v;
+        }
+        return;
+    }
+    __shared__ float s_tile[SH1 * SH1 * 2];
+    __shared__ float s_h[SH1 * LB * 5];
+    const float bg_c = a.composite ? a.bg[c] : 0.0f;
+    for (int i = rank; i < SH1 * SH1; i += LB * LB) {
+        int ly = i / SH1, lx = i - ly * SH1;
+        int gy = tile_y0 + ly - HALO, gx = tile_x0 + lx - HALO;
+        s_tile[i * 2] = ld_pred(a, c, gy, gx);
+        s_tile[i * 2 + 1] = ld_gt_eff(a, c, gy, gx, bg_c);
+    }
+    __syncthreads();
+    for (int i = rank; i < SH1 * LB; i += LB * LB) {  // horizontal pass: SH1 rows x LB columns
+        int ly = i / LB, ox = i - ly * LB;
+        int lx = ox + HALO;
+        float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int d = 1; d <= 5; d++) {
+            const float wd = taps.w[5 - d];
+            const float *l = &s_tile[(ly * SH1 + lx - d) * 2], *r = &s_tile[(ly * SH1 + lx + d) * 2];
+            BG_BLUR5_PAIR(o, l[0], l[1], r[0], r[1], wd)
+        }
+        const float *cc = &s_tile[(ly * SH1 + lx) * 2];
+        const float wc = taps.w[5];
+        o[0] += cc[0] * wc; o[1] += cc[0] * cc[0] * wc; o[2] += cc[1] * wc; o[3] += cc[1] * cc[1] * wc;
+        o[4] += cc[0] * cc[1] * wc;
+#pragma unroll
+        for (int k = 0; k < 5; k++) s_h[i * 5 + k] = o[k];
+    }
+    __syncthreads();
+    float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    {
+        const int ly = ty + HALO;
+#pragma unroll
+        for (int d = 1; d <= 5; d++) {
+            const float wd = taps.w[5 - d];
+            const float *t = &s_h[((ly - d) * LB + tx) * 5], *b = &s_h[((ly + d) * LB + tx) * 5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) o[k] += (t[k] + b[k]) * wd;
+        }
+        const float *m = &s_h[(ly * LB + tx) * 5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) o[k] += m[k] * taps.w[5];
+    }
+    if (pix_x < (int)a.w && pix_y < (int)a.h) {
+        float mu1 = o[0], mu2 = o[2];
+        float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
+        float s1 = fmaxf(0.0f, o[1] - mu1_sq), s2 = fmaxf(0.0f, o[3] - mu2_sq);
+        float s12 = o[4] - mu1 * mu2;
+        float A = mu1_sq + mu2_sq + SSIM_C1, B = s1 + s2 + SSIM_C2;
+        float c_top = 2.0f * mu1 * mu2 + SSIM_C1, d_top = 2.0f * s12 + SSIM_C2;
+        float raw = (c_top * d_top) / (A * B);
+        float val = fminf(fmaxf(raw, -1.0f), 1.0f);
+        const float *cc = &s_tile[((ty + HALO) * SH1 + tx + HALO) * 2];
+        float loss_v = a.l1_w * fabsf(cc[0] - cc[1]) + a.ssim_w * val;
+        if (a.mask) loss_v = loss_v * ld_gt_a(a, pix_y, pix_x);
+        loss_map[(size_t)c * a.h * a.w + (size_t)pix_y * a.w + pix_x] = loss_v;
+    }
+}
+
+__global__ void __launch_bounds__(LB * LB)
+image_loss_bwd_kernel(LossArgs a, Taps taps, const float *__restrict__ dl_dmap, float *__restrict__ dl_dpred) {
+    const uint32_t c = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tile_x0 = blockIdx.x * LB, tile_y0 = blockIdx.y * LB;
+    const int pix_x = tile_x0 + tx, pix_y = tile_y0 + ty;
+    const int rank = ty * LB + tx;
+    const bool in_img = pix_x < (int)a.w && pix_y < (int)a.h;
+    auto out_at = [&](uint32_t ch, int y, int x) -> float & {
+        return dl_dpred[(int64_t)ch * a.sc + (int64_t)y * a.sy + (int64_t)x * a.sx];
+    };
+    if (c == 3) {  // lib.rs:393-414
+        if (in_img) {
+            float ga = ld_gt_a(a, pix_y, pix_x);
+            float diff = ld_pred(a, 3, pix_y, pix_x) - ga;
+            float sign = diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f);
+            float chain = __ldg(dl_dmap + (size_t)3 * a.h * a.w + (size_t)pix_y * a.w + pix_x);
+            if (a.mask) chain = chain * ga;
+            out_at(3, pix_y, pix_x) = sign * chain;
+        }
+        return;
+    }
+    __shared__ float s_a[SH2 * SH2 * 2];   // image tile (+2 halos), later chain*partials [SH1*SH1*3]
+    __shared__ float s_b[SH2 * SH1 * 5];   // first h-blur, later second h-blur [SH1*LB*3]
+    const float bg_c = a.composite ? a.bg[c] : 0.0f;
+    for (int i = rank; i < SH2 * SH2; i += LB * LB) {
+        int ly = i / SH2, lx = i - ly * SH2;
+        int gy = tile_y0 + ly - 2 * HALO, gx = tile_x0 + lx - 2 * HALO;
+        s_a[i * 2] = ld_pred(a, c, gy, gx);
+        s_a[i * 2 + 1] = ld_gt_eff(a, c, gy, gx, bg_c);
+    }
+    __syncthreads();
+    for (int i = rank; i < SH2 * SH1; i += LB * LB) {  // h-blur: SH2 rows x SH1 cols
+        int ly = i / SH1, ox = i - ly * SH1;
+        int lx = ox + HALO;
+        float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int d = 1; d <= 5; d++) {
+            const float wd = taps.w[5 - d];
+            const float *l = &s_a[(ly * SH2 + lx - d) * 2], *r = &s_a[(ly * SH2 + lx + d) * 2];
+            BG_BLUR5_PAIR(o, l[0], l[1], r[0], r[1], wd)
+        }
+        const float *cc = &s_a[(ly * SH2 + lx) * 2];
+        const float wc = taps.w[5];
+        o[0] += cc[0] * wc; o[1] += cc[0] * cc[0] * wc; o[2] += cc[1] * wc; o[3] += cc[1] * cc[1] * wc;
+        o[4] += cc[0] * cc[1] * wc;
+#pragma unroll
+        for (int k = 0; k < 5; k++) s_b[i * 5 + k] = o[k];
+    }
+    __syncthreads();
+    // centre values needed at the end are read back from global (s_a is about to be overwritten)
+    float p1 = 0.0f, gt_eff_c = 0.0f;
+    if (in_img) { p1 = ld_pred(a, c, pix_y, pix_x); gt_eff_c = ld_gt_eff(a, c, pix_y, pix_x, bg_c); }
+    constexpr int NPART = (SH1 * SH1 + LB * LB - 1) / (LB * LB);  // 3 partial positions per thread
+    float part[NPART][3];
+#pragma unroll
+    for (int it = 0; it < NPART; it++) {  // v-blur + SSIM partials on the SH1 x SH1 region
+        const int i = rank + it * LB * LB;
+        part[it][0] = part[it][1] = part[it][2] = 0.0f;
+        if (i >= SH1 * SH1) continue;
+        int py_ = i / SH1, px_ = i - py_ * SH1;
+        int ly = py_ + HALO;
+        float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int d = 1; d <= 5; d++) {
+            const float wd = taps.w[5 - d];
+            const float *t = &s_b[((ly - d) * SH1 + px_) * 5], *b = &s_b[((ly + d) * SH1 + px_) * 5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) o[k] += (t[k] + b[k]) * wd;
+        }
+        const float *m = &s_b[(ly * SH1 + px_) * 5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) o[k] += m[k] * taps.w[5];
+        float mu1 = o[0], mu2 = o[2];
+        float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
+        float s1 = fmaxf(0.0f, o[1] - mu1_sq), s2 = fmaxf(0.0f, o[3] - mu2_sq);
+        float s12 = o[4] - mu1 * mu2;
+        float A = mu1_sq + mu2_sq + SSIM_C1, B = s1 + s2 + SSIM_C2;
+        float c_top = 2.0f * mu1 * mu2 + SSIM_C1, d_top = 2.0f * s12 + SSIM_C2;
+        float inv_ab = 1.0f / (A * B);
+        float cd = c_top * d_top * inv_ab;
+        bool clamped = cd < -1.0f || cd > 1.0f;
+        float dmu1 = clamped ? 0.0f : 2.0f * mu2 * inv_ab * (d_top - c_top) - 2.0f * mu1 * cd * (1.0f / A - 1.0f / B);
+        float ds1 = clamped ? 0.0f : -cd / B;
+        float ds12 = clamped ? 0.0f : 2.0f * c_top * inv_ab;
+        int gy = tile_y0 + py_ - HALO, gx = tile_x0 + px_ - HALO;
+        float chain = 0.0f;
+        if (gy >= 0 && gx >= 0 && gy < (int)a.h && gx < (int)a.w) {
+            chain = __ldg(dl_dmap + (size_t)c * a.h * a.w + (size_t)gy * a.w + gx);
+            if (a.mask) chain = chain * ld_gt_a(a, gy, gx);
+        }
+        part[it][0] = dmu1 * chain; part[it][1] = ds1 * chain; part[it][2] = ds12 * chain;
+    }
+    __syncthreads();  // everyone done reading s_a (h-blur) and s_b (v-blur)
+#pragma unroll
+    for (int it = 0; it < NPART; it++) {
+        const int i = rank + it * LB * LB;
+        if (i < SH1 * SH1) { s_a[i * 3] = part[it][0]; s_a[i * 3 + 1] = part[it][1]; s_a[i * 3 + 2] = part[it][2]; }
+    }
+    __syncthreads();
+    for (int i = rank; i < SH1 * LB; i += LB * LB) {  // second h-blur: SH1 rows x LB cols
+        int ly = i / LB, ox = i - ly * LB;
+        int lx = ox + HALO;
+        float o[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int d = 1; d <= 5; d++) {
+            const float wd = taps.w[5 - d];
+            const float *l = &s_a[(ly * SH1 + lx - d) * 3], *r = &s_a[(ly * SH1 + lx + d) * 3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) o[k] += (l[k] + r[k]) * wd;
+        }
+        const float *m = &s_a[(ly * SH1 + lx) * 3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) o[k] += m[k] * taps.w[5];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s_b[i * 3 + k] = o[k];
+    }
+    __syncthreads();
+    if (in_img) {
+        const int ly = ty + HALO;
+        float s[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int d = 1; d <= 5; d++) {
+            const float wd = taps.w[5 - d];
+            const float *t = &s_b[((ly - d) * LB + tx) * 3], *b = &s_b[((ly + d) * LB + tx) * 3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) s[k] += (t[k] + b[k]) * wd;
+        }
+        const float *m = &s_b[(ly * LB + tx) * 3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[k] += m[k] * taps.w[5];
+        float ssim_grad = s[0] + (2.0f * p1) * s[1] + gt_eff_c * s[2];
+        float diff = p1 - gt_eff_c;
+        float l1_sign = diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f);
+        float chain_c = __ldg(dl_dmap + (size_t)c * a.h * a.w + (size_t)pix_y * a.w + pix_x);
+        if (a.mask) chain_c = chain_c * ld_gt_a(a, pix_y, pix_x);
+        out_at(c, pix_y, pix_x) = a.ssim_w * ssim_grad + a.l1_w * l1_sign * chain_c;
+    }
+}
+
+static Taps make_taps() {
+    // brush-loss/src/lib.rs:55-68: f32 arithmetic on the host, sigma = 1.5, normalised to sum 1.
+    Taps t;
+    const float sigma = 1.5f;
+    float sum = 0.0f;
+    for (int i = 0; i < 11; i++) {
+        float x = (float)i - 5.0f;
+        t.w[i] = expf(-x * x / (2.0f * sigma * sigma));
+        sum += t.w[i];
+    }
+    for (int i = 0; i < 11; i++) t.w[i] /= sum;
+    return t;
+}
+
+static LossArgs make_args(const float *pred, const uint32_t *gt, uint32_t h, uint32_t w, int64_t sc, int64_t sy,
+                          int64_t sx, float l1_w, float ssim_w, const float *bg, bool mask) {
+    LossArgs a;
+    a.pred = pred; a.gt = gt; a.h = h; a.w = w; a.sc = sc; a.sy = sy; a.sx = sx; a.l1_w = l1_w; a.ssim_w = ssim_w;
+    a.composite = bg != nullptr;
+    for (int i = 0; i < 3; i++) a.bg[i] = bg ? bg[i] : 0.0f;
+    a.mask = mask ? 1 : 0;
+    return a;
+}
+
+cudaError_t launch_image_loss_fwd(cudaStream_t s, const float *pred, const uint32_t *gt, uint32_t c, uint32_t h,
+                                  uint32_t w, int64_t sc, int64_t sy, int64_t sx, float l1_w, float ssim_w,
+                                  const float *bg, bool mask, float *loss_map) {
+    dim3 grid((w + LB - 1) / LB, (h + LB - 1) / LB, c), block(LB, LB);
+    image_loss_fwd_kernel<<<grid, block, 0, s>>>(make_args(pred, gt, h, w, sc, sy, sx, l1_w, ssim_w, bg, mask),
+                                                 make_taps(), loss_map);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_image_loss_bwd(cudaStream_t s, const float *pred, const uint32_t *gt, const float *dl_dmap,
+                                  uint32_t c, uint32_t h, uint32_t w, int64_t sc, int64_t sy, int64_t sx, float l1_w,
+                                  float ssim_w, const float *bg, bool mask, float *dl_dpred) {
+    dim3 grid((w + LB - 1) / LB, (h + LB - 1) / LB, c), block(LB, LB);
+    image_loss_bwd_kernel<<<grid, block, 0, s>>>(make_args(pred, gt, h, w, sc, sy, sx, l1_w, ssim_w, bg, mask),
+                                                 make_taps(), dl_dmap, dl_dpred);
+    return cudaGetLastError();
+}
+
+}  // namespace bg

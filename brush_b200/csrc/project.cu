@@ -1,0 +1,395 @@
+// project.cu -- per-Gaussian forward stages (compiled with -fmad=false, see bg_math.cuh).
+//
+//   project_cull_kernel        <- project_forward_kernel  (kernels/project_forward.rs:20-125)
+//   gather_scan_kernel         <- int_gather + prefix_sum (render.rs:185-187, brush-prefix-sum)
+//   project_visible_emit_kernel<- project_visible_kernel  (kernels/project_visible.rs:22-88)
+//                                 + map_gaussians_to_intersect_kernel (kernels/map_gaussians.rs:14-80)
+//   tile_offsets_kernel        <- get_tile_offsets        (get_tile_offset.rs:10-58)
+//
+// All four are HBM-bound streaming kernels.  Design notes:
+//   * persistent CTAs pull tiles from an atomic ticket; counts that the reference reads back to
+//     the host (num_visible, num_intersections) stay on the device and downstream kernels read
+//     them from the control block;
+//   * compaction of visible Gaussians is a single-pass decoupled look-back in index order --
+//     deterministic, unlike the reference's atomic slot (project_forward.rs:122-124);
+//   * the [n,10] AoS rows are staged through shared memory with 128-bit loads, the gathered SH
+//     rows with coalesced warp-cooperative loads, so every DRAM sector that is fetched is used.
+#include "bg_project.cuh"
+
+namespace bg {
+
+constexpr int PROJ_THREADS = 256;
+
+struct CullResult {
+    bool visible;
+    float depth;
+    uint32_t tiles;
+    float radius;
+};
+
+template <bool MIP>
+__device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, const BgCamera &u, uint32_t img_w,
+                                               uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y) {
+    CullResult r;
+    r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f;
+    V3 mean_c = world_to_cam(mk3(t[0], t[1], t[2]), u);
+    if (!(is_finite(mean_c) && mean_c.z <= 1.0e10f)) return r;
+    if (mean_c.z < 0.01f) return r;
+    V3 scl = mk3(det_expf(t[7]), det_expf(t[8]), det_expf(t[9]));
+    if (!is_finite(scl)) return r;
+    Q4 qu; qu.w = t[3]; qu.x = t[4]; qu.y = t[5]; qu.z = t[6];
+    float qn = dot(qu, qu);
+    if (!(qn >= 1.0e-6f && is_finite(qn))) return r;
+    if (!is_finite(raw_opac)) return r;
+    Q4 quat = normalize(qu);
+    S2 raw_cov = calc_cov2d(scl, quat, mean_c, u);
+    float comp;
+    S2 cov = compensate_cov2d<MIP>(raw_cov, comp);
+    float opac = det_sigmoid(raw_opac) * comp;
+    if (!is_finite(cov)) return r;
+    float mx, my;
+    project_pinhole(mean_c, u, mx, my);
+    if (!(opac >= 1.0f / 255.0f)) return r;
+    float pt = det_logf(opac * 255.0f);
+    S2 conic = inverse(cov);
+    float ex, ey;
+    bbox_extent(conic, pt, ex, ey);
+    if (!(ex >= 0.0f && ey >= 0.0f)) return r;
+    float wf = (float)img_w, hf = (float)img_h;
+    bool on_screen = mx + ex > 0.0f && mx - ex < wf && my + ey > 0.0f && my - ey < hf;
+    if (!on_screen) return r;
+    TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
+    uint32_t bbw = bb.max_x - bb.min_x;
+    uint32_t num = (bb.max_y - bb.min_y) * bbw;
+    uint32_t hits = 0;
+    for (uint32_t i = 0; i < num; i++) {
+        uint32_t tx = (i % bbw) + bb.min_x;
+        uint32_t ty = (i / bbw) + bb.min_y;
+        hits += tile_hit(tx, ty, mx, my, conic, pt) ? 1u : 0u;
+    }
+    r.visible = true;
+    r.depth = mean_c.z;
+    r.tiles = hits;
+    r.radius = fmaxf(ex / wf, ey / hf);
+    return r;
+}
+
+// K1.  One thread per Gaussian, 256 Gaussians per tile, persistent CTAs.
+template <bool MIP>
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_cull_kernel(const float *__restrict__ transforms, const float *__restrict__ raw_opac, uint32_t n,
+                    BgCamera u, uint32_t img_w, uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y,
+                    uint32_t *__restrict__ depth_keys, uint32_t *__restrict__ gids,
+                    uint32_t *__restrict__ counts_by_gid, float *__restrict__ max_radius,
+                    uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl,
+                    unsigned long long *__restrict__ lb_state, uint32_t epoch) {
+    __shared__ __align__(16) float s_rows[PROJ_THREADS * 10];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint32_t num_tiles = (n + PROJ_THREADS - 1) / PROJ_THREADS;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl[CTL_TICKETS + TK_PROJECT], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t base = tile * PROJ_THREADS;
+        const uint32_t rows = min((uint32_t)PROJ_THREADS, n - base);
+        // stage rows*10 floats: 128-bit loads for the bulk, scalar tail
+        {
+            const float *src = transforms + (size_t)base * 10;
+            const uint32_t nf = rows * 10, nv = nf >> 2;
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            float4 *dst4 = reinterpret_cast<float4 *>(s_rows);
+            for (uint32_t i = threadIdx.x; i < nv; i += PROJ_THREADS) dst4[i] = __ldg(src4 + i);
+            for (uint32_t i = (nv << 2) + threadIdx.x; i < nf; i += PROJ_THREADS) s_rows[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        const uint32_t gid = base + threadIdx.x;
+        CullResult r;
+        r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f;
+        if (threadIdx.x < rows) {
+            float t[10];
+#pragma unroll
+            for (int j = 0; j < 10; j++) t[j] = s_rows[threadIdx.x * 10 + j];
+            r = cull_one<MIP>(t, __ldg(raw_opac + gid), u, img_w, img_h, tiles_x, tiles_y);
+            max_radius[gid] = r.radius;  // zero for culled splats (render_aux.rs:76-78)
+            cgid_from_gid[gid] = 0xFFFFFFFFu;  // overwritten for visible splats by project_visible_emit
+        }
+        uint32_t total;
+        uint32_t local = block_exclusive_scan(r.visible ? 1u : 0u, s_scan, &total);
+        if (threadIdx.x < 32) {
+            unsigned long long *st = lb_state + tile;
+            if (threadIdx.x == 0) lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total);
+            uint32_t prefix = (tile == 0) ? 0u : lb_lookback_warp(lb_state, tile, epoch);
+            if (threadIdx.x == 0) {
+                if (tile != 0) lb_store(st, epoch, LB_INCLUSIVE, prefix + total);
+                s_prefix = prefix;
+                if (tile == num_tiles - 1) ctl[CTL_COUNTERS + 0] = prefix + total;  // num_visible
+            }
+        }
+        __syncthreads();
+        if (r.visible) {
+            uint32_t slot = s_prefix + local;
+            depth_keys[slot] = __float_as_uint(r.depth);  // z >= 0.01: float order == uint order
+            gids[slot] = gid;
+            counts_by_gid[gid] = r.tiles;
+        }
+        __syncthreads();
+    }
+}
+
+// int_gather(counts, sorted gid) fused with the inclusive prefix sum over the visible Gaussians.
+// Single pass, decoupled look-back, 8 items per thread.  Writes cum[i] (inclusive) and
+// num_intersections = cum[V-1] (clamped against the arena capacity, overflow flag set).
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ gather_idx /* nullable */,
+                   uint32_t n_host, const uint32_t *__restrict__ n_dev, uint32_t *__restrict__ out,
+                   uint32_t *__restrict__ total_out /* nullable */, uint32_t capacity,
+                   uint32_t *__restrict__ overflow_flag /* nullable */, uint32_t *__restrict__ ticket,
+                   unsigned long long *__restrict__ lb_state, uint32_t epoch) {
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    const uint32_t num_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (num_tiles == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
+        return;
+    }
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            uint32_t idx = base + i;
+            uint32_t x = 0;
+            if (idx < n) x = gather_idx ? __ldg(in + __ldg(gather_idx + idx)) : __ldg(in + idx);
+            sum += x;
+            v[i] = sum;  // thread-local inclusive
+        }
+        uint32_t total;
+        uint32_t excl = block_exclusive_scan(sum, s_scan, &total);
+        if (threadIdx.x < 32) {
+            unsigned long long *st = lb_state + tile;
+            if (threadIdx.x == 0) lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total);
+            uint32_t prefix = (tile == 0) ? 0u : lb_lookback_warp(lb_state, tile, epoch);
+            if (threadIdx.x == 0) {
+                if (tile != 0) lb_store(st, epoch, LB_INCLUSIVE, prefix + total);
+                s_prefix = prefix;
+                if (tile == num_tiles - 1 && total_out) {
+                    uint32_t tot = prefix + total;
+                    if (tot > capacity) {
+                        if (overflow_flag) *overflow_flag = tot;
+                        tot = capacity;
+                    }
+                    *total_out = tot;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t off = s_prefix + excl;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            uint32_t idx = base + i;
+            if (idx < n) out[idx] = off + v[i];
+        }
+        __syncthreads();
+    }
+}
+
+// K2 + K3.  One thread per visible Gaussian in depth order (compact gid = position in the
+// depth-sorted list).  128 threads per CTA; each warp stages the SH rows of its 32 Gaussians in
+// shared memory with coalesced loads, then every lane evaluates its own row.
+constexpr int VIS_THREADS = 128;
+
+template <bool MIP, int DEG>
+__global__ void __launch_bounds__(VIS_THREADS)
+project_visible_emit_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
+                            const float *__restrict__ raw_opac, const uint32_t *__restrict__ gid_sorted,
+                            const uint32_t *__restrict__ cum, BgCamera u, uint32_t tiles_x, uint32_t tiles_y,
+                            float *__restrict__ projected, uint32_t *__restrict__ tile_keys,
+                            uint32_t *__restrict__ isect_vals, uint32_t isect_capacity,
+                            uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl) {
+    constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
+    constexpr int STRIDE = (KF % 2 == 0) ? KF + 1 : KF;  // odd stride: conflict-free per-lane row reads
+    __shared__ float s_sh[VIS_THREADS * STRIDE];
+    __shared__ uint32_t s_tile;
+    const uint32_t nvis = ctl[CTL_COUNTERS + 0];
+    const uint32_t num_tiles = (nvis + VIS_THREADS - 1) / VIS_THREADS;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    float *wsh = s_sh + wid * 32 * STRIDE;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl[CTL_TICKETS + TK_VISIBLE], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t cgid = tile * VIS_THREADS + threadIdx.x;
+        const bool active = cgid < nvis;
+        const uint32_t gid = active ? __ldg(gid_sorted + cgid) : 0u;
+        // ---- stage SH rows (warp cooperative, coalesced inside each row)
+        {
+            const uint32_t warp_first = tile * VIS_THREADS + wid * 32;
+            const uint32_t rows = (warp_first < nvis) ? min(32u, nvis - warp_first) : 0u;
+            const uint32_t total = rows * KF;
+            for (uint32_t j = lane; j < ((total + 31u) & ~31u); j += 32) {
+                uint32_t row = j / KF, col = j - row * KF;
+                uint32_t g = __shfl_sync(0xffffffffu, gid, row & 31u);
+                if (j < total) wsh[row * STRIDE + col] = __ldg(sh + (size_t)g * KF + col);
+            }
+            __syncwarp();
+        }
+        if (active) {
+            const float2 *t2 = reinterpret_cast<const float2 *>(transforms + (size_t)gid * 10);
+            float2 a0 = __ldg(t2), a1 = __ldg(t2 + 1), a2 = __ldg(t2 + 2), a3 = __ldg(t2 + 3), a4 = __ldg(t2 + 4);
+            V3 mean = mk3(a0.x, a0.y, a1.x);
+            Q4 qu; qu.w = a1.y; qu.x = a2.x; qu.y = a2.y; qu.z = a3.x;
+            V3 scl = mk3(det_expf(a3.y), det_expf(a4.x), det_expf(a4.y));
+            Q4 quat = normalize(qu);
+            V3 mean_c = world_to_cam(mean, u);
+            S2 raw_cov = calc_cov2d(scl, quat, mean_c, u);
+            float comp;
+            S2 cov = compensate_cov2d<MIP>(raw_cov, comp);
+            float opac = det_sigmoid(__ldg(raw_opac + gid)) * comp;
+            S2 conic = inverse(cov);
+            float mx, my;
+            project_pinhole(mean_c, u, mx, my);
+            V3 vdir = normalize(sub(mean, mk3(u.cam_pos[0], u.cam_pos[1], u.cam_pos[2])));
+            const float *row = wsh + lane * STRIDE;
+            V3 raw = sh_to_color<DEG>([&](int i) { return row[i]; }, vdir);
+            float cr = raw.x + 0.5f, cg = raw.y + 0.5f, cb = raw.z + 0.5f;
+            cr = clampf(is_finite(cr) ? cr : 0.0f, -100.0f, 100.0f);
+            cg = clampf(is_finite(cg) ? cg : 0.0f, -100.0f, 100.0f);
+            cb = clampf(is_finite(cb) ? cb : 0.0f, -100.0f, 100.0f);
+            float pt = det_logf(opac * 255.0f);
+            float4 *dst = reinterpret_cast<float4 *>(projected + (size_t)cgid * BG_PROJECTED_STRIDE);
+            dst[0] = make_float4(mx, my, conic.c00, conic.c01);
+            dst[1] = make_float4(conic.c11, opac, cr, cg);
+            dst[2] = make_float4(cb, pt, 0.0f, 0.0f);
+            cgid_from_gid[gid] = cgid;
+            // ---- emit (tile id, compact gid) pairs (map_gaussians.rs:26-79)
+            float ex, ey;
+            bbox_extent(conic, pt, ex, ey);
+            TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
+            uint32_t base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
+            uint32_t budget = __ldg(cum + cgid) - base;
+            uint32_t bbw = bb.max_x - bb.min_x;
+            uint32_t num = (bb.max_y - bb.min_y) * bbw;
+            uint32_t hits = 0;
+            for (uint32_t i = 0; i < num && hits < budget; i++) {
+                uint32_t tx = (i % bbw) + bb.min_x;
+                uint32_t ty = (i / bbw) + bb.min_y;
+                if (tile_hit(tx, ty, mx, my, conic, pt)) {
+                    uint32_t o = base + hits;
+                    if (o < isect_capacity) {
+                        tile_keys[o] = tx + ty * tiles_x;
+                        isect_vals[o] = cgid;
+                    }
+                    hits++;
+                }
+            }
+            // same tile_hit as the counting pass => hits == budget; keep the reference's padding
+            // so that no slot is ever left unwritten.
+            for (uint32_t pad = hits; pad < budget; pad++) {
+                uint32_t o = base + pad;
+                if (o < isect_capacity) {
+                    tile_keys[o] = tiles_x * tiles_y;
+                    isect_vals[o] = cgid;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// K4.  tile_offsets must be zeroed by the caller (render.rs:232-236).
+__global__ void __launch_bounds__(256)
+tile_offsets_kernel(const uint32_t *__restrict__ tile_ids, const uint32_t *__restrict__ ctl, uint32_t num_tiles,
+                    uint32_t *__restrict__ tile_offsets) {
+    const uint32_t n = ctl[CTL_COUNTERS + 1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t tid = __ldg(tile_ids + i);
+        if (tid < num_tiles) {
+            if (i == n - 1) tile_offsets[tid * 2 + 1] = i + 1;
+            if (i == 0) {
+                tile_offsets[tid * 2] = 0;
+            } else {
+                uint32_t prev = __ldg(tile_ids + i - 1);
+                if (tid != prev) {
+                    if (prev < num_tiles) tile_offsets[prev * 2 + 1] = i;
+                    tile_offsets[tid * 2] = i;
+                }
+            }
+        }
+    }
+}
+
+// ---- host launchers (called from api.cu) ----
+cudaError_t launch_project_cull(cudaStream_t s, int grid, bool mip, const float *transforms, const float *raw_opac,
+                                uint32_t n, const BgCamera &u, uint32_t w, uint32_t h, uint32_t tx, uint32_t ty,
+                                uint32_t *depth_keys, uint32_t *gids, uint32_t *counts, float *max_radius,
+                                uint32_t *cgid_from_gid, uint32_t *ctl, unsigned long long *lb, uint32_t epoch) {
+    if (n == 0) return cudaSuccess;
+    if (mip)
+        project_cull_kernel<true><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
+                                                                 gids, counts, max_radius, cgid_from_gid, ctl, lb, epoch);
+    else
+        project_cull_kernel<false><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
+                                                                  gids, counts, max_radius, cgid_from_gid, ctl, lb, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_scan(cudaStream_t s, int grid, const uint32_t *in, const uint32_t *gather_idx,
+                               uint32_t n_host, const uint32_t *n_dev, uint32_t *out, uint32_t *total_out,
+                               uint32_t capacity, uint32_t *overflow_flag, uint32_t *ticket,
+                               unsigned long long *lb, uint32_t epoch) {
+    if (n_host == 0) return cudaSuccess;
+    gather_scan_kernel<<<grid, SCAN_THREADS, 0, s>>>(in, gather_idx, n_host, n_dev, out, total_out, capacity,
+                                                     overflow_flag, ticket, lb, epoch);
+    return cudaGetLastError();
+}
+
+template <bool MIP>
+static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const float *transforms, const float *sh,
+                                      const float *raw_opac, const uint32_t *gid_sorted, const uint32_t *cum,
+                                      const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
+                                      uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
+                                      uint32_t *cgid_from_gid, uint32_t *ctl) {
+#define BG_LAUNCH_VIS(D)                                                                                          \
+    project_visible_emit_kernel<MIP, D><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, ctl)
+    switch (deg) {
+        case 0: BG_LAUNCH_VIS(0); break;
+        case 1: BG_LAUNCH_VIS(1); break;
+        case 2: BG_LAUNCH_VIS(2); break;
+        case 3: BG_LAUNCH_VIS(3); break;
+        case 4: BG_LAUNCH_VIS(4); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef BG_LAUNCH_VIS
+    return cudaGetLastError();
+}
+
+cudaError_t launch_project_visible_emit(cudaStream_t s, int grid, bool mip, int deg, const float *transforms,
+                                        const float *sh, const float *raw_opac, const uint32_t *gid_sorted,
+                                        const uint32_t *cum, const BgCamera &u, uint32_t tx, uint32_t ty,
+                                        float *projected, uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
+                                        uint32_t *cgid_from_gid, uint32_t *ctl) {
+    return mip ? launch_visible_deg<true>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty, projected,
+                                          tile_keys, isect_vals, cap, cgid_from_gid, ctl)
+               : launch_visible_deg<false>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty,
+                                           projected, tile_keys, isect_vals, cap, cgid_from_gid, ctl);
+}
+
+cudaError_t launch_tile_offsets(cudaStream_t s, int grid, const uint32_t *tile_ids, const uint32_t *ctl,
+                                uint32_t num_tiles, uint32_t *tile_offsets) {
+    tile_offsets_kernel<<<grid, 256, 0, s>>>(tile_ids, ctl, num_tiles, tile_offsets);
+    return cudaGetLastError();
+}
+
+}  // namespace bg

@@ -1,0 +1,180 @@
+// sort.cu -- one-sweep LSD radix sort of (u32 key, u32 value) pairs, 8-bit digits.
+//
+// Replaces brush_sort::radix_argsort (brush-sort/src/lib.rs:16-125; kernels.rs:28-443), which runs
+// 5 dispatches per 4-bit digit (count, reduce, scan, scan_add, scatter): 40 dispatches for the
+// 32-bit depth sort and 20 for a 13-bit tile sort.  Here: one histogram kernel for all digits,
+// then one kernel per 8-bit digit that reads every key once and writes it once (chained scan with
+// decoupled look-back): 1 + 4 launches for 32 bits, 1 + 2 for 13..16 bits.
+//
+// Result spec (the reference's tests, brush-sort/src/lib.rs:147-151): equal to a stable argsort on
+// the low `bits` bits.  Stability comes from (a) ranking keys inside a warp in lane order with
+// match_any, (b) warps and tiles being ordered by the look-back chain.
+//
+// The element count may live on the device (n_dev): CTAs are persistent and pull tiles from a
+// ticket, so no host readback is needed to size the grid.
+#include "bg_common.cuh"
+
+namespace bg {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
+constexpr int RADIX = 256;
+
+// hist[p*256 + d] += #keys whose p-th digit is d, for p < passes.
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n_host, const uint32_t *__restrict__ n_dev,
+                  uint32_t bits, uint32_t passes, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_hist[4 * RADIX];
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    for (uint32_t i = threadIdx.x; i < passes * RADIX; i += SORT_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * SORT_THREADS;
+    for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += stride) {
+        uint32_t k = __ldg(keys + i);
+        for (uint32_t p = 0; p < passes; p++) {
+            uint32_t shift = p * 8, width = min(8u, bits - shift);
+            atomicAdd(&s_hist[p * RADIX + ((k >> shift) & ((1u << width) - 1u))], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < passes * RADIX; i += SORT_THREADS) {
+        uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// One digit pass.  lb_state: [num_tiles][256] look-back words for this pass.
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
+                     const uint32_t *__restrict__ n_dev, uint32_t shift, uint32_t width,
+                     const uint32_t *__restrict__ hist /* this pass: [256] */, uint32_t *__restrict__ ticket,
+                     unsigned long long *__restrict__ lb_state, uint32_t epoch) {
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_warp_hist[(SORT_THREADS / 32) * RADIX];
+    __shared__ uint32_t s_bin_start[RADIX];    // exclusive scan of the tile's digit counts
+    __shared__ int64_t s_bin_dst[RADIX];       // global destination of tile-local position 0 of each bin
+    __shared__ uint32_t s_digit_base[RADIX];   // exclusive scan of the global histogram
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    const uint32_t num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const uint32_t mask = (1u << width) - 1u;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    if (num_tiles == 0) return;
+    {   // exclusive scan of the global digit histogram (thread d owns digit d)
+        uint32_t total;
+        uint32_t c = __ldg(hist + threadIdx.x);
+        uint32_t e = block_exclusive_scan(c, s_scan, &total);
+        s_digit_base[threadIdx.x] = e;
+    }
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t tile_base = tile * SORT_TILE;
+        const uint32_t tile_count = min((uint32_t)SORT_TILE, n - tile_base);
+        for (uint32_t i = threadIdx.x; i < (SORT_THREADS / 32) * RADIX; i += SORT_THREADS) s_warp_hist[i] = 0;
+        __syncthreads();
+        // ---- load (warp-striped: warp w owns SORT_ITEMS*32 consecutive keys) and rank
+        uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
+        uint16_t rank[SORT_ITEMS];
+        const uint32_t warp_base = tile_base + wid * (SORT_ITEMS * 32);
+        uint32_t *wh = s_warp_hist + wid * RADIX;
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            uint32_t idx = warp_base + i * 32 + lane;
+            bool valid = idx < n;
+            key[i] = valid ? __ldg(keys_in + idx) : 0xFFFFFFFFu;
+            val[i] = valid ? __ldg(vals_in + idx) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            // out-of-range keys are all-ones: they rank after every real key of the last digit
+            // in this (final, partial) tile and are dropped at scatter time.
+            uint32_t d = (key[i] >> shift) & mask;
+            uint32_t peers = __match_any_sync(0xffffffffu, d);
+            uint32_t pre = wh[d];
+            __syncwarp();
+            if ((peers & lt_mask) == 0) wh[d] = pre + __popc(peers);
+            __syncwarp();
+            rank[i] = (uint16_t)(pre + __popc(peers & lt_mask));
+        }
+        __syncthreads();
+        // ---- per digit: exclusive scan over warps, tile count
+        uint32_t my_count;
+        {
+            uint32_t d = threadIdx.x, sum = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; w++) {
+                uint32_t c = s_warp_hist[w * RADIX + d];
+                s_warp_hist[w * RADIX + d] = sum;
+                sum += c;
+            }
+            my_count = sum;
+        }
+        // ---- publish aggregate, look back (thread d serves digit d)
+        unsigned long long *st = lb_state + (size_t)tile * RADIX + threadIdx.x;
+        lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, my_count);
+        uint32_t bin_total;
+        uint32_t bin_start = block_exclusive_scan(my_count, s_scan, &bin_total);
+        uint32_t prefix = 0;
+        if (tile != 0) {
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                unsigned long long w = lb_load(lb_state + (size_t)t * RADIX + threadIdx.x);
+                uint32_t stt = lb_status(w, epoch);
+                if (stt == LB_INVALID) continue;
+                prefix += lb_value(w);
+                if (stt == LB_INCLUSIVE) break;
+                t--;
+            }
+            lb_store(st, epoch, LB_INCLUSIVE, prefix + my_count);
+        }
+        s_bin_start[threadIdx.x] = bin_start;
+        s_bin_dst[threadIdx.x] = (int64_t)s_digit_base[threadIdx.x] + (int64_t)prefix - (int64_t)bin_start;
+        __syncthreads();
+        // ---- reorder inside the tile through shared memory
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            uint32_t d = (key[i] >> shift) & mask;
+            uint32_t pos = s_bin_start[d] + s_warp_hist[wid * RADIX + d] + rank[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];
+        }
+        __syncthreads();
+        // ---- coalesced scatter: consecutive positions of one bin go to consecutive addresses
+        for (uint32_t j = threadIdx.x; j < tile_count; j += SORT_THREADS) {
+            uint32_t k = s_keys[j];
+            uint32_t d = (k >> shift) & mask;
+            int64_t dst = s_bin_dst[d] + (int64_t)j;
+            keys_out[dst] = k;
+            vals_out[dst] = s_vals[j];
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_radix_hist(cudaStream_t s, int grid, const uint32_t *keys, uint32_t n_host, const uint32_t *n_dev,
+                              uint32_t bits, uint32_t passes, uint32_t *hist) {
+    radix_hist_kernel<<<grid, SORT_THREADS, 0, s>>>(keys, n_host, n_dev, bits, passes, hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_onesweep_pass(cudaStream_t s, int grid, const uint32_t *keys_in, const uint32_t *vals_in,
+                                 uint32_t *keys_out, uint32_t *vals_out, uint32_t n_host, const uint32_t *n_dev,
+                                 uint32_t shift, uint32_t width, const uint32_t *hist, uint32_t *ticket,
+                                 unsigned long long *lb, uint32_t epoch) {
+    onesweep_pass_kernel<<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift, width,
+                                                       hist, ticket, lb, epoch);
+    return cudaGetLastError();
+}
+
+uint32_t sort_tile_size() { return SORT_TILE; }
+
+}  // namespace bg

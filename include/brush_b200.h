@@ -1,0 +1,181 @@
+/*
+ * brush_b200.h -- C ABI of libbrush_b200.so: the sm_100a CUDA hot path of the
+ * differentiable Gaussian-splat rasterizer, behind the operator boundary of
+ * ArthurBrussee/brush.  Plain pointers and sizes only; no torch / burn types.
+ *
+ * Every entry point replaces one Rust-side operator of the reference (cited
+ * per function, paths relative to the reference checkout).  INTEGRATION.md
+ * shows the `extern "C"` block + `impl SplatOps / SplatBwdOps / LossOps`
+ * shim a Brush maintainer would add on the Rust side.
+ *
+ * Conventions (modelled on apps/brush-c/src/lib.rs:14-163, the reference's
+ * only C ABI):
+ *   - every call returns int32_t status (BG_OK == 0); nothing panics/aborts;
+ *     null or inconsistent arguments give BG_ERR_NULL / BG_ERR_INVALID;
+ *   - all array pointers are DEVICE pointers on the context's device unless
+ *     the parameter comment says "host"; arrays are dense, row major, f32 or
+ *     u32, 16-byte aligned;
+ *   - every call takes the cudaStream_t (as void*) to enqueue on and returns
+ *     without synchronising: there is no device->host readback inside the
+ *     forward (the reference blocks on one, render.rs:146-168).  Counters are
+ *     mirrored into pinned host memory and are valid after the caller
+ *     synchronises the stream;
+ *   - the context owns the scratch arena (sort buffers, intersection lists,
+ *     saved forward state).  One context serves one logical task at a time
+ *     (the reference's threading contract, brush-async/src/lib.rs:1-17);
+ *     distinct contexts are independent and may be used from different
+ *     threads / streams concurrently.
+ */
+#ifndef BRUSH_B200_H
+#define BRUSH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_ABI_VERSION 1u
+
+/* f32 lanes per projected splat.  Lanes 0..8 are the reference layout
+ * (kernels/helpers.rs:49-53: xy_x, xy_y, conic_x, conic_y, conic_z, color_a,
+ * color_r, color_g, color_b); lanes 9..11 pad the row to 48 B so that a row
+ * is three aligned 128-bit loads (lane 9 caches ln(255*opacity)). */
+#define BG_PROJECTED_STRIDE 12u
+/* f32 lanes per row of v_combined (bwd/burn_glue.rs:36-43). */
+#define BG_VCOMBINED_STRIDE 10u
+
+typedef enum {
+    BG_OK = 0,
+    BG_ERR_NULL = 1,        /* a required pointer was null */
+    BG_ERR_INVALID = 2,     /* inconsistent sizes / unsupported K / zero image size */
+    BG_ERR_CUDA = 3,        /* a CUDA runtime call failed; see bg_last_error_string */
+    BG_ERR_CAPACITY = 4,    /* request exceeds what the context was created for */
+    BG_ERR_UNSUPPORTED = 5  /* camera model / feature not built */
+} BgStatus;
+
+/* gaussian_splats.rs:27-48 RasterPass */
+typedef enum { BG_PASS_FORWARD = 0, BG_PASS_BACKWARD = 1, BG_PASS_BACKWARD_SMOOTH = 2 } BgPass;
+
+/* kernels/camera_model/mod.rs:32-39 CameraModel (only pinhole is built) */
+typedef enum { BG_CAMERA_PINHOLE = 0 } BgCameraModel;
+
+/* Host struct.  Mirror of ProjectUniforms (shaders.rs:17-66, kernels/types.rs:51-80) minus the
+ * sizes that are passed as arguments.  viewmat = camera.world_to_local(), top 3 rows, column
+ * major: column i at viewmat[3*i .. 3*i+3], column 3 is the translation. */
+typedef struct {
+    float viewmat[12];
+    float fx, fy, cx, cy;                              /* PinholeParams, camera.rs:64-73 */
+    float cam_pos[3];                                  /* camera.position */
+    float lim_pos_x, lim_pos_y, lim_neg_x, lim_neg_y;  /* JacobianClampLimits, camera.rs:200-254 */
+    float half_max_render_fov;                         /* render.rs:70-71 */
+    uint32_t camera_model;                             /* BgCameraModel */
+} BgCamera;
+
+/* Saved forward state handed to the backward calls: mirror of the non-image fields of
+ * RenderOutput (render_aux.rs:16-28) + GaussianBackwardState (bwd/burn_glue.rs:95-112).
+ * Pointers refer to the context arena and stay valid until the next bg_render_forward on
+ * the same context. */
+typedef struct {
+    const float *projected;                 /* [num_visible, BG_PROJECTED_STRIDE] depth-sorted */
+    const uint32_t *compact_gid_from_isect; /* [num_intersections] tile-major, depth order inside a tile */
+    const uint32_t *global_from_compact_gid;/* [num_visible] */
+    const uint32_t *compact_from_global_gid;/* [n] inverse map; 0xFFFFFFFF for culled Gaussians */
+    const uint32_t *tile_offsets;           /* [tiles_y, tiles_x, 2] (start,end); end trimmed when pass != FORWARD */
+    const float *depths;                    /* [num_visible] sorted camera-space z (diagnostic) */
+    const uint32_t *tile_id_from_isect;     /* [num_intersections] sorted tile ids (diagnostic) */
+    const uint32_t *counters_dev;           /* device [4]: num_visible, num_intersections, overflow flag, reserved */
+    const volatile uint32_t *counters_host; /* host (pinned) mirror of counters_dev; valid after stream sync */
+    uint32_t n, k, w, h, tiles_x, tiles_y;
+    int32_t mip, pass;
+} BgRenderState;
+
+typedef struct BgContext BgContext;
+
+/* Version / capability probe.  Returns BG_ABI_VERSION. */
+uint32_t bg_abi_version(void);
+/* Thread-local description of the last BG_ERR_CUDA / BG_ERR_INVALID on this thread. */
+const char *bg_last_error_string(void);
+
+/* Creates the scratch arena on `device`.  max_intersections bounds num_intersections
+ * (the reference sizes these buffers after a blocking readback, render.rs:146-168,211-213);
+ * 0 picks max(16*max_splats, 1<<22).  Exceeding it at run time sets counters[2] != 0 and the
+ * extra intersections are dropped (never written out of bounds). */
+int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t max_w, uint32_t max_h,
+                      uint64_t max_intersections, BgContext **out_ctx);
+int32_t bg_ctx_destroy(BgContext *ctx);
+/* Bytes of device memory held by the arena (for sizing against 180 GB HBM3e). */
+uint64_t bg_ctx_arena_bytes(const BgContext *ctx);
+
+/* Replaces <MainBackendBase as SplatOps>::render, brush-render/src/render.rs:37-315
+ * (trait: brush-render/src/lib.rs:54-77).
+ *   transforms [n,10] means(3)+quat wxyz(4)+log_scales(3); sh [n,k,3], k in {1,4,9,16,25};
+ *   raw_opac [n]; bg: host float[3].
+ *   out_img: [h,w,4] f32 when pass != FORWARD, [h,w] u32 rgba8 when pass == FORWARD.
+ *   visible [n] f32 (written only when pass != FORWARD, may be null otherwise); max_radius [n].
+ * Panics of the reference (render.rs:50-64, dim_check.rs) become BG_ERR_INVALID. */
+int32_t bg_render_forward(BgContext *ctx, void *stream, const BgCamera *cam, uint32_t w, uint32_t h,
+                          uint32_t n, uint32_t k, const float *transforms, const float *sh,
+                          const float *raw_opac, int32_t mip, const float *bg, int32_t pass,
+                          void *out_img, float *visible, float *max_radius, BgRenderState *state_out);
+
+/* Replaces SplatBwdOps::rasterize_bwd, bwd/render_bwd.rs:22-99 (kernel:
+ * bwd/kernels/rasterize_backwards.rs:100-391).  v_combined: [rows, 10] with rows >= num_visible
+ * (n rows always suffice); the first min(rows, n) rows are zeroed here, as float_zeros does. */
+int32_t bg_rasterize_backward(BgContext *ctx, void *stream, const BgRenderState *state, const float *out_img,
+                              const float *v_output, const float *bg, int32_t smooth_cutoff,
+                              float *v_combined, uint32_t v_combined_rows);
+
+/* Replaces SplatBwdOps::project_bwd, bwd/render_bwd.rs:102-171 (kernel:
+ * bwd/kernels/project_backwards.rs:99-254).  Dense outputs; every row is written (zeros for
+ * Gaussians that received no gradient), so no separate zero-fill is needed. */
+int32_t bg_project_backward(BgContext *ctx, void *stream, const BgCamera *cam, const BgRenderState *state,
+                            const float *transforms, const float *sh, const float *raw_opac,
+                            const float *v_combined, float *v_transforms, float *v_sh, float *v_raw_opac,
+                            float *v_refine);
+
+/* Replaces brush_sort::radix_argsort, brush-sort/src/lib.rs:16-125: stable ascending sort of
+ * (key,value) pairs on the low `bits` bits.  n_dev (device, may be null) overrides n with a
+ * device-resident count <= n. */
+int32_t bg_radix_argsort_u32(BgContext *ctx, void *stream, const uint32_t *keys, const uint32_t *vals,
+                             uint32_t n, const uint32_t *n_dev, uint32_t bits, uint32_t *keys_out,
+                             uint32_t *vals_out);
+
+/* Replaces brush_prefix_sum::prefix_sum, brush-prefix-sum/src/lib.rs:11-89 (inclusive). */
+int32_t bg_inclusive_scan_u32(BgContext *ctx, void *stream, const uint32_t *in, uint32_t n, uint32_t *out);
+
+/* Replaces LossOps::image_loss_forward / image_loss_backward, brush-loss/src/lib.rs:718-733
+ * (kernels lib.rs:180-359, 370-661).  pred and dl_dpred are addressed as
+ * p[c*stride_c + y*stride_y + x*stride_x] so both the reference's CHW-permuted tensor (stride_c=h*w,
+ * stride_y=w, stride_x=1) and the rasterizer's [h,w,4] image (stride_c=1, stride_y=4w, stride_x=4)
+ * are accepted without a permute; loss_map and dl_dmap are dense [channels,h,w].
+ * channels in {3,4}; channel 3 is the alpha-match path.  bg: host float[3] or null (no compositing). */
+int32_t bg_image_loss_forward(BgContext *ctx, void *stream, const float *pred, const uint32_t *gt_packed,
+                              uint32_t channels, uint32_t h, uint32_t w, int64_t stride_c, int64_t stride_y,
+                              int64_t stride_x, float l1_weight, float ssim_weight, const float *bg,
+                              int32_t mask, float *loss_map);
+int32_t bg_image_loss_backward(BgContext *ctx, void *stream, const float *pred, const uint32_t *gt_packed,
+                               const float *dl_dmap, uint32_t channels, uint32_t h, uint32_t w,
+                               int64_t stride_c, int64_t stride_y, int64_t stride_x, float l1_weight,
+                               float ssim_weight, const float *bg, int32_t mask, float *dl_dpred);
+
+/* Replaces AdamScaled::step for one parameter tensor, brush-train/src/adam_scaled.rs:75-165.
+ * p,g,m: [rows,cols]; v: [rows,cols], or [rows] when reduce_v (second moment = row mean of g^2).
+ * lr_scale_per_col: device [cols] or null.  t: 1-based step count (t == 1 initialises the moments). */
+int32_t bg_adam_step(BgContext *ctx, void *stream, float *p, const float *g, float *m, float *v,
+                     uint64_t rows, uint32_t cols, const float *lr_scale_per_col, float lr, float beta1,
+                     float beta2, float eps, int32_t t, int32_t reduce_v);
+
+/* Replaces RefineRecord::gather_stats (brush-train/src/stats.rs:40-50) and the mean-noise update
+ * (brush-train/src/train.rs:389-416) in one pass over the Gaussians.  noise: device [n,3] standard
+ * normal draws (null skips the noise update). */
+int32_t bg_refine_stats_noise(BgContext *ctx, void *stream, uint32_t n, const float *v_refine,
+                              const float *visible, const float *max_radius, float *refine_weight_norm,
+                              float *vis_weight, float *max_screen_size, float *transforms,
+                              const float *raw_opac, const float *noise, float noise_scale,
+                              float median_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRUSH_B200_H */

