@@ -1,0 +1,60 @@
+"""View-sharded data parallelism (no counterpart in the single-device reference).
+
+Every rank holds the full parameter set, renders its own view(s) of the step's batch and the dense
+per-Gaussian gradients are summed with ONE all-reduce over a flat buffer ((10+3K+1) N floats), then
+scaled by 1/views because the loss is a per-view mean (train.rs:254-260).  The three refine statistics
+use MAX / SUM / MAX (stats.rs:40-50).  Parity definition: equal to the single-GPU step that
+accumulates the views' gradients sequentially, up to f32 summation order.
+
+Backend-agnostic: NCCL over NVLink on the GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class ViewShardedReducer:
+    def __init__(self, num_views_total: int, group=None):
+        self.views = num_views_total
+        self.group = group
+        self._flat = None
+
+    def _flat_buf(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        total = sum(t.numel() for t in tensors)
+        if self._flat is None or self._flat.numel() != total or self._flat.device != tensors[0].device:
+            self._flat = torch.empty(total, dtype=torch.float32, device=tensors[0].device)
+        return self._flat
+
+    def reduce_gradients(self, grads: Sequence[torch.Tensor]) -> None:
+        """In place: grads <- sum over ranks / views.  One collective for all tensors."""
+        flat = self._flat_buf(grads)
+        off = 0
+        for g in grads:
+            flat[off:off + g.numel()].copy_(g.reshape(-1))
+            off += g.numel()
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.mul_(1.0 / self.views)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def reduce_stats(self, refine_weight: torch.Tensor, visible: torch.Tensor, max_radius: torch.Tensor) -> None:
+        """stats.rs:40-50 across ranks: MAX(refine), SUM(visible), MAX(max_radius).  Two collectives."""
+        if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return
+        mx = torch.stack([refine_weight, max_radius])
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        refine_weight.copy_(mx[0])
+        max_radius.copy_(mx[1])
+        dist.all_reduce(visible, op=dist.ReduceOp.SUM, group=self.group)
+
+    def hook(self, tensors: Sequence[torch.Tensor]) -> None:
+        """SplatTrainer.grad_hook signature: (v_t, v_sh, v_o, v_refine, visible, max_radius)."""
+        v_t, v_sh, v_o, v_r, visible, max_radius = tensors
+        self.reduce_gradients((v_t, v_sh, v_o))
+        self.reduce_stats(v_r, visible, max_radius)

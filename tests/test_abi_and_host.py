@@ -1,0 +1,114 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol declared in
+include/brush_b200.h (no compute calls without a GPU), and the host-side mirrors of the reference's
+camera / bounds logic behave as the reference's unit tests require."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "brush_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from brush_b200 import _lib, build
+    lib_path = build.build()
+    h = ctypes.CDLL(lib_path)
+    declared = _declared_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in brush_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(declared)
+    lib = _lib.load()
+    assert lib.bg_abi_version() == _lib.ABI_VERSION
+
+
+def test_null_and_invalid_arguments_return_status_codes():
+    """apps/brush-c/src/lib.rs:119-121 style: null -> error code, never a crash (no GPU needed)."""
+    from brush_b200 import _lib
+    lib = _lib.load()
+    assert lib.bg_ctx_create(0, 0, 64, 64, 0, ctypes.byref(ctypes.c_void_p())) == _lib.BG_ERR_INVALID
+    assert lib.bg_ctx_create(0, 10, 64, 64, 0, None) == _lib.BG_ERR_NULL
+    assert lib.bg_ctx_destroy(None) == _lib.BG_ERR_NULL
+    assert lib.bg_render_forward(None, None, None, 1, 1, 0, 1, None, None, None, 0, None, 0, None, None, None, None) == _lib.BG_ERR_NULL
+    assert lib.bg_adam_step(None, None, None, None, None, None, 1, 1, None, 0.0, 0.9, 0.999, 1e-15, 1, 0) == _lib.BG_ERR_NULL
+    assert lib.bg_ctx_arena_bytes(None) == 0
+
+
+def test_struct_layouts_match_header():
+    from brush_b200 import _lib
+    assert ctypes.sizeof(_lib.BgCamera) == 4 * (12 + 4 + 3 + 4 + 1 + 1)
+    assert _lib.BgRenderState.n.offset == 9 * 8
+
+
+def test_no_product_module_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "brush_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle" not in txt.replace("no CPU fallback", ""), f"{f} mentions the oracle"
+
+
+def test_fov_focal_round_trip():
+    """brush-render/src/tests/mod.rs:710-789."""
+    from brush_b200.camera import focal_to_fov, fov_to_focal
+    for px in (64, 123, 1920):
+        for fov in (0.2, 0.6, math.pi / 2, 2.5):
+            f = fov_to_focal(fov, px)
+            assert abs(focal_to_fov(f, px) - fov) < 1e-12
+    assert abs(fov_to_focal(math.pi / 2, 256) - 128.0) < 1e-9
+
+
+def test_world_to_local_inverts_pose():
+    from brush_b200.camera import Camera
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        p = rng.normal(size=3) * 3
+        cam = Camera(position=tuple(p), rotation=tuple(q))
+        vm = cam.world_to_local().reshape(4, 3)  # rows = columns c0,c1,c2,t
+        R = vm[:3].T
+        t = vm[3]
+        x, y, z, w = q
+        Rl2w = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        np.testing.assert_allclose(R, Rl2w.T, atol=2e-6)
+        np.testing.assert_allclose(R @ p + t, 0, atol=1e-5)  # the camera centre maps to the origin
+
+
+def test_uniforms_match_reference_formulas():
+    from brush_b200.camera import Camera, build_uniforms
+    cam = Camera(position=(0.123, 0.456, -8.0), rotation=(0, 0, 0, 1), fov_x=math.pi / 2, fov_y=1.2, center_uv=(0.5, 0.4))
+    u = build_uniforms(cam, 123, 82)
+    assert abs(u.fx - 61.5) < 1e-4 and abs(u.cx - 61.5) < 1e-5 and abs(u.cy - 32.8) < 1e-5
+    assert abs(u.lim_pos_x - (1.15 * 123 - u.cx) / u.fx) < 1e-6 and abs(u.lim_neg_y - (-0.15 * 82 - u.cy) / u.fy) < 1e-6
+    np.testing.assert_allclose(u.viewmat, [1, 0, 0, 0, 1, 0, 0, 0, 1, -0.123, -0.456, 8.0], atol=1e-7)
+
+
+def test_bounds_and_median_size():
+    """splat_init.rs:130-160 / bounding_box.rs:23-29."""
+    from brush_b200.train import bounds_from_pos
+    pts = np.stack([np.linspace(-10, 10, 1001), np.linspace(0, 2, 1001), np.linspace(-1, 5, 1001)], 1).astype(np.float32)
+    pts[0] = np.nan
+    b = bounds_from_pos(0.8, pts)
+    assert abs(b.extent[0] - 8.0) < 0.05 and abs(b.extent[1] - 0.8) < 0.01 and abs(b.extent[2] - 2.4) < 0.02
+    assert abs(b.median_size() - 2 * 2.4) < 0.05
+
+
+def test_synthetic_scene_is_deterministic():
+    from scenes import synthetic_scene
+    a = synthetic_scene(1000, 64, 64)
+    b = synthetic_scene(1000, 64, 64)
+    for x, y in zip(a[1:], b[1:]):
+        np.testing.assert_array_equal(x, y)
