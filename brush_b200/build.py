@@ -21,6 +21,8 @@ LIB = os.path.join(HERE, "libbrush_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
           "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177"]
+if os.environ.get("BG_STATS"):  # development-only instrumentation of the blend kernels
+    COMMON.append("-DBG_STATS")
 SOURCES = {
     "api.cu": [],
     "project.cu": ["-fmad=false"],

@@ -15,12 +15,13 @@ namespace bg {
 // project.cu
 cudaError_t launch_project_cull(cudaStream_t, int, bool, const float *, const float *, uint32_t, const BgCamera &,
                                 uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *, uint32_t *, float *,
-                                uint32_t *, uint32_t *, unsigned long long *, uint32_t);
+                                uint32_t *, unsigned long long *, uint32_t *, unsigned long long *, uint32_t);
 cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, const uint32_t *,
                                uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *, unsigned long long *, uint32_t);
 cudaError_t launch_project_visible_emit(cudaStream_t, int, bool, int, const float *, const float *, const float *,
                                         const uint32_t *, const uint32_t *, const BgCamera &, uint32_t, uint32_t,
-                                        float *, uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *);
+                                        float *, uint32_t *, uint32_t *, uint32_t, uint32_t *, const unsigned long long *,
+                                        uint32_t *);
 cudaError_t launch_tile_offsets(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, uint32_t *);
 // sort.cu
 cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, const uint32_t *, uint32_t, uint32_t,
@@ -76,6 +77,7 @@ struct BgContext {
     uint32_t *depth_key[2] = {nullptr, nullptr};
     uint32_t *depth_val[2] = {nullptr, nullptr};
     uint32_t *counts = nullptr, *cum = nullptr, *cgid_from_gid = nullptr;
+    unsigned long long *hit_masks = nullptr;  // per-Gaussian tile hit bits from the counting pass
     float *projected = nullptr;
     uint32_t *isect_key[2] = {nullptr, nullptr};
     uint32_t *isect_val[2] = {nullptr, nullptr};
@@ -110,7 +112,7 @@ extern "C" int32_t bg_ctx_destroy(BgContext *c) {
     if (!c) return BG_ERR_NULL;
     cudaSetDevice(c->device);
     void *ptrs[] = {c->ctl, c->depth_key[0], c->depth_key[1], c->depth_val[0], c->depth_val[1], c->counts, c->cum,
-                    c->cgid_from_gid, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
+                    c->cgid_from_gid, c->hit_masks, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
                     c->tile_offsets, c->lb_scan, c->lb_sort};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -152,6 +154,7 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
     ok = ok && arena_alloc(c, &c->counts, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->cum, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->cgid_from_gid, n) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->hit_masks, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->projected, n * BG_PROJECTED_STRIDE) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->tile_offsets, (uint64_t)c->max_tiles * 2) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->lb_scan, c->lb_scan_words) == cudaSuccess;
@@ -188,7 +191,7 @@ static int32_t run_sort(BgContext *c, cudaStream_t s, const uint32_t *key_in, co
     int dst = first_dst;
     for (uint32_t p = 0; p < passes; p++) {
         const uint32_t shift = p * 8, width = std::min(8u, bits - shift);
-        BG_CUDA(launch_onesweep_pass(s, c->sm_count * 2, kin, vin, keys[dst], vals[dst], n_host, n_dev, shift, width,
+        BG_CUDA(launch_onesweep_pass(s, c->sm_count * 3, kin, vin, keys[dst], vals[dst], n_host, n_dev, shift, width,
                                      hist + p * 256, tickets + 1 + p, c->lb_sort, next_epoch(c)));
         kin = keys[dst]; vin = vals[dst];
         *out_idx = dst;
@@ -225,7 +228,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     uint32_t *counters = c->ctl + CTL_COUNTERS;
     // K1: cull + compaction in index order
     BG_CUDA(launch_project_cull(s, pgrid, mip != 0, transforms, raw_opac, n, *cam, w, h, tiles_x, tiles_y,
-                                c->depth_key[0], c->depth_val[0], c->counts, max_radius, c->cgid_from_gid, c->ctl,
+                                c->depth_key[0], c->depth_val[0], c->counts, max_radius, c->cgid_from_gid, c->hit_masks, c->ctl,
                                 c->lb_scan, next_epoch(c)));
     // depth sort: 32-bit keys, 4 passes, (0)->(1)->(0)->(1)->(0)
     int dout = 0;
@@ -243,7 +246,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     if (n > 0)
         BG_CUDA(launch_project_visible_emit(s, pgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
                                             tiles_x, tiles_y, c->projected, c->isect_key[0], c->isect_val[0],
-                                            c->max_isect, c->cgid_from_gid, c->ctl));
+                                            c->max_isect, c->cgid_from_gid, c->hit_masks, c->ctl));
     // tile sort on bits = 32 - clz(num_tiles)
     uint32_t bits = 0;
     while (bits < 32 && (num_tiles >> bits) != 0) bits++;
@@ -259,7 +262,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     }
     c->isect_out = iout;
     // K4
-    BG_CUDA(launch_tile_offsets(s, c->sm_count * 4, c->isect_key[iout], c->ctl, num_tiles, c->tile_offsets));
+    BG_CUDA(launch_tile_offsets(s, c->sm_count * 16, c->isect_key[iout], c->ctl, num_tiles, c->tile_offsets));
     // K5
     BG_CUDA(launch_rasterize_fwd(s, bwd_info, pass == BG_PASS_BACKWARD_SMOOTH, num_tiles, c->isect_val[iout],
                                  c->tile_offsets, c->projected, gid_sorted, out_img, visible, tiles_x, w, h, bg));

@@ -99,10 +99,17 @@ __device__ __forceinline__ bool tile_hit(uint32_t tx, uint32_t ty, float mx, flo
         float dxf = x_left ? width : -width;
         float dyf = y_above ? height : -height;
         float diff_x = mx - corner_x, diff_y = my - corner_y;
-        float tx_raw = (dxf * conic.c00 * diff_x + dxf * conic.c01 * diff_y) / (dxf * conic.c00 * dxf);
-        float ty_raw = (dyf * conic.c01 * diff_x + dyf * conic.c11 * diff_y) / (dyf * conic.c11 * dyf);
-        float tx_ = in_y ? 0.0f : clampf(tx_raw, 0.0f, 1.0f);
-        float ty_ = in_x ? 0.0f : clampf(ty_raw, 0.0f, 1.0f);
+        // helpers.rs:251-256: t = select(in_range, 0, clamp(raw)).  The quotient is only evaluated
+        // where the select keeps it; the value is identical to the reference's unconditional form.
+        float tx_ = 0.0f, ty_ = 0.0f;
+        if (!in_y) {
+            float tx_raw = (dxf * conic.c00 * diff_x + dxf * conic.c01 * diff_y) / (dxf * conic.c00 * dxf);
+            tx_ = clampf(tx_raw, 0.0f, 1.0f);
+        }
+        if (!in_x) {
+            float ty_raw = (dyf * conic.c01 * diff_x + dyf * conic.c11 * diff_y) / (dyf * conic.c11 * dyf);
+            ty_ = clampf(ty_raw, 0.0f, 1.0f);
+        }
         float qx = corner_x + tx_ * dxf;
         float qy = corner_y + ty_ * dyf;
         hit = calc_sigma(qx, qy, conic, mx, my) <= pt;

@@ -25,13 +25,14 @@ struct CullResult {
     float depth;
     uint32_t tiles;
     float radius;
+    unsigned long long mask;  // hit bits of the bbox tiles, row major, valid when the bbox has <= 64 tiles
 };
 
 template <bool MIP>
 __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, const BgCamera &u, uint32_t img_w,
                                                uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y) {
     CullResult r;
-    r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f;
+    r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
     V3 mean_c = world_to_cam(mk3(t[0], t[1], t[2]), u);
     if (!(is_finite(mean_c) && mean_c.z <= 1.0e10f)) return r;
     if (mean_c.z < 0.01f) return r;
@@ -59,14 +60,16 @@ __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, c
     bool on_screen = mx + ex > 0.0f && mx - ex < wf && my + ey > 0.0f && my - ey < hf;
     if (!on_screen) return r;
     TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
-    uint32_t bbw = bb.max_x - bb.min_x;
-    uint32_t num = (bb.max_y - bb.min_y) * bbw;
     uint32_t hits = 0;
-    for (uint32_t i = 0; i < num; i++) {
-        uint32_t tx = (i % bbw) + bb.min_x;
-        uint32_t ty = (i / bbw) + bb.min_y;
-        hits += tile_hit(tx, ty, mx, my, conic, pt) ? 1u : 0u;
-    }
+    unsigned long long mask = 0ull;
+    uint32_t bit = 0;
+    for (uint32_t ty = bb.min_y; ty < bb.max_y; ty++)
+        for (uint32_t tx = bb.min_x; tx < bb.max_x; tx++, bit++) {
+            bool h = tile_hit(tx, ty, mx, my, conic, pt);
+            hits += h ? 1u : 0u;
+            mask |= (h && bit < 64u) ? (1ull << bit) : 0ull;
+        }
+    r.mask = mask;
     r.visible = true;
     r.depth = mean_c.z;
     r.tiles = hits;
@@ -81,7 +84,8 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
                     BgCamera u, uint32_t img_w, uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y,
                     uint32_t *__restrict__ depth_keys, uint32_t *__restrict__ gids,
                     uint32_t *__restrict__ counts_by_gid, float *__restrict__ max_radius,
-                    uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl,
+                    uint32_t *__restrict__ cgid_from_gid, unsigned long long *__restrict__ hit_masks,
+                    uint32_t *__restrict__ ctl,
                     unsigned long long *__restrict__ lb_state, uint32_t epoch) {
     __shared__ __align__(16) float s_rows[PROJ_THREADS * 10];
     __shared__ uint32_t s_scan[33];
@@ -106,7 +110,7 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
         __syncthreads();
         const uint32_t gid = base + threadIdx.x;
         CullResult r;
-        r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f;
+        r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
         if (threadIdx.x < rows) {
             float t[10];
 #pragma unroll
@@ -133,6 +137,7 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             depth_keys[slot] = __float_as_uint(r.depth);  // z >= 0.01: float order == uint order
             gids[slot] = gid;
             counts_by_gid[gid] = r.tiles;
+            hit_masks[gid] = r.mask;
         }
         __syncthreads();
     }
@@ -215,10 +220,13 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                             const uint32_t *__restrict__ cum, BgCamera u, uint32_t tiles_x, uint32_t tiles_y,
                             float *__restrict__ projected, uint32_t *__restrict__ tile_keys,
                             uint32_t *__restrict__ isect_vals, uint32_t isect_capacity,
-                            uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl) {
+                            uint32_t *__restrict__ cgid_from_gid, const unsigned long long *__restrict__ hit_masks,
+                            uint32_t *__restrict__ ctl) {
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
-    constexpr int STRIDE = (KF % 2 == 0) ? KF + 1 : KF;  // odd stride: conflict-free per-lane row reads
-    __shared__ float s_sh[VIS_THREADS * STRIDE];
+    constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B: 128-bit staging
+    constexpr int S4 = (KF / 4) | 1;                     // odd float4 stride: conflict-free LDS.128 per lane
+    constexpr int STRIDE = VEC4 ? S4 * 4 : ((KF % 2 == 0) ? KF + 1 : KF);
+    __shared__ __align__(16) float s_sh[VIS_THREADS * STRIDE];
     __shared__ uint32_t s_tile;
     const uint32_t nvis = ctl[CTL_COUNTERS + 0];
     const uint32_t num_tiles = (nvis + VIS_THREADS - 1) / VIS_THREADS;
@@ -236,11 +244,22 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         {
             const uint32_t warp_first = tile * VIS_THREADS + wid * 32;
             const uint32_t rows = (warp_first < nvis) ? min(32u, nvis - warp_first) : 0u;
-            const uint32_t total = rows * KF;
-            for (uint32_t j = lane; j < ((total + 31u) & ~31u); j += 32) {
-                uint32_t row = j / KF, col = j - row * KF;
-                uint32_t g = __shfl_sync(0xffffffffu, gid, row & 31u);
-                if (j < total) wsh[row * STRIDE + col] = __ldg(sh + (size_t)g * KF + col);
+            if (VEC4) {
+                constexpr uint32_t R4 = KF / 4;
+                const uint32_t total4 = rows * R4;
+                float4 *wsh4 = reinterpret_cast<float4 *>(wsh);
+                for (uint32_t j = lane; j < ((total4 + 31u) & ~31u); j += 32) {
+                    uint32_t row = j / R4, c4 = j - row * R4;
+                    uint32_t g = __shfl_sync(0xffffffffu, gid, row & 31u);
+                    if (j < total4) wsh4[row * S4 + c4] = __ldg(reinterpret_cast<const float4 *>(sh + (size_t)g * KF) + c4);
+                }
+            } else {
+                const uint32_t total = rows * KF;
+                for (uint32_t j = lane; j < ((total + 31u) & ~31u); j += 32) {
+                    uint32_t row = j / KF, col = j - row * KF;
+                    uint32_t g = __shfl_sync(0xffffffffu, gid, row & 31u);
+                    if (j < total) wsh[row * STRIDE + col] = __ldg(sh + (size_t)g * KF + col);
+                }
             }
             __syncwarp();
         }
@@ -260,8 +279,20 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             float mx, my;
             project_pinhole(mean_c, u, mx, my);
             V3 vdir = normalize(sub(mean, mk3(u.cam_pos[0], u.cam_pos[1], u.cam_pos[2])));
-            const float *row = wsh + lane * STRIDE;
-            V3 raw = sh_to_color<DEG>([&](int i) { return row[i]; }, vdir);
+            float coef[KF];
+            if (VEC4) {
+                const float4 *row4 = reinterpret_cast<const float4 *>(wsh) + lane * S4;
+#pragma unroll
+                for (int i = 0; i < KF / 4; i++) {
+                    float4 q = row4[i];
+                    coef[4 * i] = q.x; coef[4 * i + 1] = q.y; coef[4 * i + 2] = q.z; coef[4 * i + 3] = q.w;
+                }
+            } else {
+                const float *row = wsh + lane * STRIDE;
+#pragma unroll
+                for (int i = 0; i < KF; i++) coef[i] = row[i];
+            }
+            V3 raw = sh_to_color<DEG>([&](int i) { return coef[i]; }, vdir);
             float cr = raw.x + 0.5f, cg = raw.y + 0.5f, cb = raw.z + 0.5f;
             cr = clampf(is_finite(cr) ? cr : 0.0f, -100.0f, 100.0f);
             cg = clampf(is_finite(cg) ? cg : 0.0f, -100.0f, 100.0f);
@@ -278,19 +309,34 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
             uint32_t base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
             uint32_t budget = __ldg(cum + cgid) - base;
-            uint32_t bbw = bb.max_x - bb.min_x;
-            uint32_t num = (bb.max_y - bb.min_y) * bbw;
             uint32_t hits = 0;
-            for (uint32_t i = 0; i < num && hits < budget; i++) {
-                uint32_t tx = (i % bbw) + bb.min_x;
-                uint32_t ty = (i / bbw) + bb.min_y;
-                if (tile_hit(tx, ty, mx, my, conic, pt)) {
+            const uint32_t bbw = bb.max_x - bb.min_x, bbh = bb.max_y - bb.min_y;
+            if (bbw * bbh <= 64u) {
+                // the counting pass left the hit bits of this bbox: no tile test is repeated here
+                unsigned long long m = __ldg(hit_masks + gid);
+                while (m && hits < budget) {
+                    uint32_t bit = (uint32_t)__ffsll((long long)m) - 1u;
+                    m &= m - 1ull;
+                    uint32_t ry = bit / bbw, rx = bit - ry * bbw;
                     uint32_t o = base + hits;
                     if (o < isect_capacity) {
-                        tile_keys[o] = tx + ty * tiles_x;
+                        tile_keys[o] = (bb.min_x + rx) + (bb.min_y + ry) * tiles_x;
                         isect_vals[o] = cgid;
                     }
                     hits++;
+                }
+            } else {
+                for (uint32_t ty = bb.min_y; ty < bb.max_y && hits < budget; ty++) {
+                    for (uint32_t tx = bb.min_x; tx < bb.max_x && hits < budget; tx++) {
+                        if (tile_hit(tx, ty, mx, my, conic, pt)) {
+                            uint32_t o = base + hits;
+                            if (o < isect_capacity) {
+                                tile_keys[o] = tx + ty * tiles_x;
+                                isect_vals[o] = cgid;
+                            }
+                            hits++;
+                        }
+                    }
                 }
             }
             // same tile_hit as the counting pass => hits == budget; keep the reference's padding
@@ -333,14 +379,15 @@ tile_offsets_kernel(const uint32_t *__restrict__ tile_ids, const uint32_t *__res
 cudaError_t launch_project_cull(cudaStream_t s, int grid, bool mip, const float *transforms, const float *raw_opac,
                                 uint32_t n, const BgCamera &u, uint32_t w, uint32_t h, uint32_t tx, uint32_t ty,
                                 uint32_t *depth_keys, uint32_t *gids, uint32_t *counts, float *max_radius,
-                                uint32_t *cgid_from_gid, uint32_t *ctl, unsigned long long *lb, uint32_t epoch) {
+                                uint32_t *cgid_from_gid, unsigned long long *hit_masks, uint32_t *ctl,
+                                unsigned long long *lb, uint32_t epoch) {
     if (n == 0) return cudaSuccess;
     if (mip)
         project_cull_kernel<true><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
-                                                                 gids, counts, max_radius, cgid_from_gid, ctl, lb, epoch);
+                                                                 gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch);
     else
         project_cull_kernel<false><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
-                                                                  gids, counts, max_radius, cgid_from_gid, ctl, lb, epoch);
+                                                                  gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch);
     return cudaGetLastError();
 }
 
@@ -359,10 +406,10 @@ static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const f
                                       const float *raw_opac, const uint32_t *gid_sorted, const uint32_t *cum,
                                       const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
                                       uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
-                                      uint32_t *cgid_from_gid, uint32_t *ctl) {
+                                      uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl) {
 #define BG_LAUNCH_VIS(D)                                                                                          \
     project_visible_emit_kernel<MIP, D><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
-                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, ctl)
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl)
     switch (deg) {
         case 0: BG_LAUNCH_VIS(0); break;
         case 1: BG_LAUNCH_VIS(1); break;
@@ -379,11 +426,11 @@ cudaError_t launch_project_visible_emit(cudaStream_t s, int grid, bool mip, int 
                                         const float *sh, const float *raw_opac, const uint32_t *gid_sorted,
                                         const uint32_t *cum, const BgCamera &u, uint32_t tx, uint32_t ty,
                                         float *projected, uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
-                                        uint32_t *cgid_from_gid, uint32_t *ctl) {
+                                        uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl) {
     return mip ? launch_visible_deg<true>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty, projected,
-                                          tile_keys, isect_vals, cap, cgid_from_gid, ctl)
+                                          tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl)
                : launch_visible_deg<false>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty,
-                                           projected, tile_keys, isect_vals, cap, cgid_from_gid, ctl);
+                                           projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl);
 }
 
 cudaError_t launch_tile_offsets(cudaStream_t s, int grid, const uint32_t *tile_ids, const uint32_t *ctl,

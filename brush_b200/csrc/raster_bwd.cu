@@ -4,8 +4,9 @@
 // The reference assigns one thread per splat and walks pixels through shared memory on a diagonal
 // schedule with a barrier per step (a design for 32-wide Apple SIMD groups, rasterize_backwards.rs:25-27).
 // On B200 the same forward-replay recurrence runs with one thread per pixel (state in registers, same
-// tile/batch/cull structure as the forward kernel); the per-splat sums over the 32 pixels of a warp are
-// formed with a 12-shuffle reduce-scatter (10 values -> 10 lanes), then one f32 atomic per value.
+// warp-autonomous tile walk and block culling as the forward kernel); the per-splat sums over the 32
+// pixels of a warp are formed with a 12-shuffle reduce-scatter (10 values -> 10 lanes), then one f32
+// atomic (RED) per value.
 //
 // Replay semantics (rasterize_backwards.rs:186-228, 279-383): pixel state starts at
 // (final_rgb - T_final*bg, T = 1); per splat, with the forward's skip/stop rules:
@@ -29,19 +30,18 @@ __global__ void __launch_bounds__(256)
 rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *__restrict__ tile_offsets,
                      const float *__restrict__ projected, const float4 *__restrict__ out_img,
                      const float4 *__restrict__ v_output, float *__restrict__ v_combined, RasterBwdUniforms u) {
-    __shared__ __align__(16) float s_rows[2][RB * ROW];
-    __shared__ uint32_t s_hits[2][8][8];
-    __shared__ uint32_t s_ids[2][RB];
+    __shared__ __align__(16) float s_rows[8][2][WB * ROW];  // per warp, double buffered
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t range_lo = tile_offsets[tile * 2], range_hi = tile_offsets[tile * 2 + 1];
     if (range_hi <= range_lo) return;
     const uint32_t tile_x0 = (tile % u.tiles_x) * TILE_W, tile_y0 = (tile / u.tiles_x) * TILE_W;
-    const uint32_t pix_x = tile_x0 + 8u * (wid & 1u) + (lane & 7u);
-    const uint32_t pix_y = tile_y0 + 4u * (wid >> 1) + (lane >> 3);
+    const uint32_t blk_x0 = tile_x0 + 8u * (wid & 1u), blk_y0 = tile_y0 + 4u * (wid >> 1);
+    const uint32_t pix_x = blk_x0 + (lane & 7u), pix_y = blk_y0 + (lane >> 3);
     const bool inside = pix_x < u.img_w && pix_y < u.img_h;
     const float px = (float)pix_x + 0.5f, py = (float)pix_y + 0.5f;
+    const float rx0 = (float)blk_x0 + 0.5f, rx1 = rx0 + 7.0f, ry0 = (float)blk_y0 + 0.5f, ry1 = ry0 + 3.0f;
 
     // per-pixel constants and running state (load_pixel_state, rasterize_backwards.rs:186-228)
     float rem_r = 0.0f, rem_g = 0.0f, rem_b = 0.0f, T = 0.0f;
@@ -67,154 +67,141 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
     const bool owner = !(lane & 1u) && !(b2 && b1) && !(b3 && b2);
     const uint32_t slot = (b4 ? 5u : 0u) + idx5;
 
-    const uint32_t num_batches = (range_hi - range_lo + RB - 1) / RB;
+    const uint32_t num_batches = (range_hi - range_lo + WB - 1) / WB;
+    uint32_t next_id = 0;
     auto prefetch = [&](uint32_t b) {
-        uint32_t idx = range_lo + b * RB + tid;
+        uint32_t idx = range_lo + b * WB + lane;
         if (idx < range_hi) {
             uint32_t id = __ldg(cgid_from_isect + idx);
-            s_ids[b & 1][tid] = id;
+            next_id = id;
             const float *src = projected + (size_t)id * ROW;
-            float *dst = &s_rows[b & 1][tid * ROW];
+            float *dst = &s_rows[wid][b & 1u][lane * ROW];
             cp_async16(dst, src);
             cp_async16(dst + 4, src + 4);
             cp_async16(dst + 8, src + 8);
         }
         cp_async_commit();
     };
+    if (__all_sync(0xffffffffu, !(T > 1.0e-4f))) return;  // nothing inside the image in this block
     prefetch(0);
 
     for (uint32_t b = 0; b < num_batches; b++) {
-        const uint32_t buf = b & 1u;
-        const uint32_t batch_start = range_lo + b * RB;
-        const uint32_t count = min((uint32_t)RB, range_hi - batch_start);
+        const uint32_t batch_start = range_lo + b * WB;
+        const uint32_t count = min((uint32_t)WB, range_hi - batch_start);
+        const uint32_t my_id = next_id;
         if (b + 1 < num_batches) {
             prefetch(b + 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();
-        {
-            uint32_t mask = 0;
-            if (tid < count) {
-                const float4 A = *reinterpret_cast<const float4 *>(&s_rows[buf][tid * ROW]);
-                const float4 B = *reinterpret_cast<const float4 *>(&s_rows[buf][tid * ROW + 4]);
-                const float4 Cc = *reinterpret_cast<const float4 *>(&s_rows[buf][tid * ROW + 8]);
-                float thr = Cc.y + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f);
-                mask = block_hit_mask(A.x, A.y, A.z, A.w, B.x, thr, (float)tile_x0, (float)tile_y0);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                uint32_t w = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-                if (lane == 0) s_hits[buf][k][wid] = w;
-            }
+        __syncwarp();
+        const float *rows = s_rows[wid][b & 1u];
+        bool hit = false;
+        if (lane < count) {
+            const float4 A = *reinterpret_cast<const float4 *>(rows + lane * ROW);
+            const float2 B = *reinterpret_cast<const float2 *>(rows + lane * ROW + 4);
+            const float pt = rows[lane * ROW + 9];
+            hit = block_may_hit(A.x, A.y, A.z, A.w, B.x, pt + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f), rx0, rx1, ry0, ry1);
         }
-        __syncthreads();
-        bool warp_done = __all_sync(0xffffffffu, !(T > 1.0e-4f));
-        if (!warp_done) {
-#pragma unroll 1
-            for (int j = 0; j < 8; j++) {
-                uint32_t bits = s_hits[buf][wid][j];
-                while (bits) {
-                    const uint32_t s = (uint32_t)(j * 32 + __ffs(bits) - 1);
-                    bits &= bits - 1;
-                    const float *row = &s_rows[buf][s * ROW];
-                    const float4 A = *reinterpret_cast<const float4 *>(row);      // mx my a b
-                    const float4 B = *reinterpret_cast<const float4 *>(row + 4);  // c opac r g
-                    const float col_b = row[8];
-                    const float dx = A.x - px, dy = A.y - py;
-                    const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
-                    const float gaussian = __expf(-sigma);
-                    const float oa = B.y * gaussian;
-                    const float alpha = fminf(0.999f, oa);
-                    float w_cut = 1.0f;
-                    bool contrib;
-                    if (SMOOTH) {
-                        w_cut = cutoff_weight(alpha);
-                        contrib = T > 1.0e-4f && sigma >= 0.0f && w_cut > 0.0f;
-                    } else {
-                        contrib = T > 1.0e-4f && sigma >= 0.0f && alpha >= ALPHA_CUTOFF_MID;
-                    }
-                    const float alpha_eff = alpha * w_cut;
-                    const float next_T = T * (1.0f - alpha_eff);
-                    if (contrib && next_T <= 1.0e-4f) { T = 0.0f; contrib = false; }
-                    if (!__any_sync(0xffffffffu, contrib)) {
-                        if (__all_sync(0xffffffffu, !(T > 1.0e-4f))) { bits = 0; j = 8; }
-                        continue;
-                    }
-                    float g[10];
+        uint32_t bits = __ballot_sync(0xffffffffu, hit);
+        while (bits) {
+            const uint32_t s = (uint32_t)__ffs(bits) - 1u;
+            bits &= bits - 1u;
+            const float *row = rows + s * ROW;
+            const float4 A = *reinterpret_cast<const float4 *>(row);      // mx my a b
+            const float4 B = *reinterpret_cast<const float4 *>(row + 4);  // c opac r g
+            const float col_b = row[8];
+            const float dx = A.x - px, dy = A.y - py;
+            const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
+            const float gaussian = __expf(-sigma);
+            const float oa = B.y * gaussian;
+            const float alpha = fminf(0.999f, oa);
+            float w_cut = 1.0f;
+            bool contrib;
+            if (SMOOTH) {
+                w_cut = cutoff_weight(alpha);
+                contrib = T > 1.0e-4f && sigma >= 0.0f && w_cut > 0.0f;
+            } else {
+                contrib = T > 1.0e-4f && sigma >= 0.0f && alpha >= ALPHA_CUTOFF_MID;
+            }
+            const float alpha_eff = alpha * w_cut;
+            const float next_T = T * (1.0f - alpha_eff);
+            const bool stop = contrib && next_T <= 1.0e-4f;
+            if (stop) { T = 0.0f; contrib = false; }
+            if (!__any_sync(0xffffffffu, contrib)) {
+                if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, !(T > 1.0e-4f))) bits = 0;
+                continue;
+            }
+            float g[10];
 #pragma unroll
-                    for (int i = 0; i < 10; i++) g[i] = 0.0f;
-                    if (contrib) {
-                        const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cbl = fmaxf(col_b, 0.0f);
-                        const float vis = alpha_eff * T;
-                        g[5] = (B.z >= 0.0f) ? vis * vo_r : 0.0f;
-                        g[6] = (B.w >= 0.0f) ? vis * vo_g : 0.0f;
-                        g[7] = (col_b >= 0.0f) ? vis * vo_b : 0.0f;
-                        const float ra = __fdividef(1.0f, 1.0f - alpha_eff);
-                        const float dot_rgb = ((T * cr - rem_r) * vo_r + (T * cg - rem_g) * vo_g + (T * cbl - rem_b) * vo_b) * ra;
-                        const float v_alpha_eff = dot_rgb + vo_w * ra;
-                        float v_alpha = v_alpha_eff;
-                        if (SMOOTH) v_alpha = v_alpha_eff * (w_cut + alpha * cutoff_weight_deriv(alpha));
-                        const float v_sigma = -alpha * v_alpha;
-                        const float vxy_x = v_sigma * (A.z * dx + A.w * dy);
-                        const float vxy_y = v_sigma * (A.w * dx + B.x * dy);
-                        if (oa <= 0.999f) {
-                            g[0] = vxy_x;
-                            g[1] = vxy_y;
-                            g[2] = 0.5f * v_sigma * dx * dx;
-                            g[3] = v_sigma * dx * dy;
-                            g[4] = 0.5f * v_sigma * dy * dy;
-                            g[8] = v_alpha * gaussian;
-                            const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
-                            g[9] = sqrtf(sx * sx + sy * sy) * inv_fa;
-                        }
-                        rem_r -= vis * cr;
-                        rem_g -= vis * cg;
-                        rem_b -= vis * cbl;
-                        T = next_T;
-                    }
-                    // ---- reduce-scatter 10 values over 32 lanes: 5+3+2+1+1 shuffles
-                    float a5[6];
-#pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        float send = b4 ? g[i] : g[i + 5];
-                        float keep = b4 ? g[i + 5] : g[i];
-                        a5[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-                    a5[5] = 0.0f;
-                    float b3v[4];
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        float send = b3 ? a5[i] : a5[i + 3];
-                        float keep = b3 ? a5[i + 3] : a5[i];
-                        b3v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    b3v[3] = 0.0f;
-                    float c2[2];
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        float send = b2 ? b3v[i] : b3v[i + 2];
-                        float keep = b2 ? b3v[i + 2] : b3v[i];
-                        c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    float d1;
-                    {
-                        float send = b1 ? c2[0] : c2[1];
-                        float keep = b1 ? c2[1] : c2[0];
-                        d1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-                    if (owner && d1 != 0.0f) {
-                        const uint32_t id = s_ids[buf][s];
-                        atomicAdd(v_combined + (size_t)id * BG_VCOMBINED_STRIDE + slot, d1);
-                    }
+            for (int i = 0; i < 10; i++) g[i] = 0.0f;
+            if (contrib) {
+                const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cbl = fmaxf(col_b, 0.0f);
+                const float vis = alpha_eff * T;
+                g[5] = (B.z >= 0.0f) ? vis * vo_r : 0.0f;
+                g[6] = (B.w >= 0.0f) ? vis * vo_g : 0.0f;
+                g[7] = (col_b >= 0.0f) ? vis * vo_b : 0.0f;
+                const float ra = __fdividef(1.0f, 1.0f - alpha_eff);
+                const float dot_rgb = ((T * cr - rem_r) * vo_r + (T * cg - rem_g) * vo_g + (T * cbl - rem_b) * vo_b) * ra;
+                const float v_alpha_eff = dot_rgb + vo_w * ra;
+                float v_alpha = v_alpha_eff;
+                if (SMOOTH) v_alpha = v_alpha_eff * (w_cut + alpha * cutoff_weight_deriv(alpha));
+                const float v_sigma = -alpha * v_alpha;
+                const float vxy_x = v_sigma * (A.z * dx + A.w * dy);
+                const float vxy_y = v_sigma * (A.w * dx + B.x * dy);
+                if (oa <= 0.999f) {
+                    g[0] = vxy_x;
+                    g[1] = vxy_y;
+                    g[2] = 0.5f * v_sigma * dx * dx;
+                    g[3] = v_sigma * dx * dy;
+                    g[4] = 0.5f * v_sigma * dy * dy;
+                    g[8] = v_alpha * gaussian;
+                    const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
+                    g[9] = sqrtf(sx * sx + sy * sy) * inv_fa;
                 }
+                rem_r -= vis * cr;
+                rem_g -= vis * cg;
+                rem_b -= vis * cbl;
+                T = next_T;
             }
-            warp_done = __all_sync(0xffffffffu, !(T > 1.0e-4f));
+            // ---- reduce-scatter 10 values over 32 lanes: 5+3+2+1+1 shuffles
+            float a5[6];
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                float send = b4 ? g[i] : g[i + 5];
+                float keep = b4 ? g[i + 5] : g[i];
+                a5[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            a5[5] = 0.0f;
+            float b3v[4];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                float send = b3 ? a5[i] : a5[i + 3];
+                float keep = b3 ? a5[i + 3] : a5[i];
+                b3v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            b3v[3] = 0.0f;
+            float c2[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                float send = b2 ? b3v[i] : b3v[i + 2];
+                float keep = b2 ? b3v[i + 2] : b3v[i];
+                c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            float d1;
+            {
+                float send = b1 ? c2[0] : c2[1];
+                float keep = b1 ? c2[1] : c2[0];
+                d1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+            const uint32_t id = __shfl_sync(0xffffffffu, my_id, s);
+            if (owner && d1 != 0.0f) atomicAdd(v_combined + (size_t)id * BG_VCOMBINED_STRIDE + slot, d1);
+            if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, !(T > 1.0e-4f))) bits = 0;
         }
-        const int any_active = __syncthreads_or(warp_done ? 0 : 1);
-        if (!any_active) break;
+        if (__all_sync(0xffffffffu, !(T > 1.0e-4f))) break;
+        __syncwarp();
     }
     cp_async_wait<0>();
 }

@@ -12,6 +12,12 @@
 
 namespace bg {
 
+#ifdef BG_STATS
+// development-only counters (build with BG_STATS=1): [0] splats tested, [1] warp-splat iterations,
+// [2] iterations with a contribution, [3] contributing pixel-splat pairs
+__device__ unsigned long long g_fwd_stats[4];
+#endif
+
 struct RasterUniforms {
     uint32_t tiles_x, img_w, img_h;
     float bg_r, bg_g, bg_b;
@@ -23,130 +29,126 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
                      const float *__restrict__ projected, const uint32_t *__restrict__ gid_from_cgid,
                      float4 *__restrict__ out_f32, uint32_t *__restrict__ out_packed, float *__restrict__ visible,
                      RasterUniforms u) {
-    __shared__ __align__(16) float s_rows[2][RB * ROW];
-    __shared__ uint32_t s_hits[2][8][8];  // [buffer][target warp][word of 32 splats]
-    __shared__ uint8_t s_used[RB];
+    __shared__ __align__(16) float s_rows[8][2][WB * ROW];  // per warp, double buffered: 24 KB
     __shared__ uint32_t s_max_useful;
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t tile_x0 = (tile % u.tiles_x) * TILE_W, tile_y0 = (tile / u.tiles_x) * TILE_W;
-    const uint32_t pix_x = tile_x0 + 8u * (wid & 1u) + (lane & 7u);
-    const uint32_t pix_y = tile_y0 + 4u * (wid >> 1) + (lane >> 3);
+    const uint32_t blk_x0 = tile_x0 + 8u * (wid & 1u), blk_y0 = tile_y0 + 4u * (wid >> 1);
+    const uint32_t pix_x = blk_x0 + (lane & 7u), pix_y = blk_y0 + (lane >> 3);
     const bool inside = pix_x < u.img_w && pix_y < u.img_h;
     const float px = (float)pix_x + 0.5f, py = (float)pix_y + 0.5f;
+    // rectangle of this warp's pixel centres
+    const float rx0 = (float)blk_x0 + 0.5f, rx1 = rx0 + 7.0f, ry0 = (float)blk_y0 + 0.5f, ry1 = ry0 + 3.0f;
 
     const uint32_t range_lo = tile_offsets[tile * 2], range_hi = tile_offsets[tile * 2 + 1];
     if (BWD_INFO && tid == 0) s_max_useful = range_lo;
 
+#ifdef BG_STATS
+    unsigned long long st_tested = 0, st_iters = 0, st_useful = 0, st_pairs = 0;
+#endif
     float T = 1.0f, acc_r = 0.0f, acc_g = 0.0f, acc_b = 0.0f;
     bool done = !inside;
     uint32_t last_useful = range_lo;
 
-    const uint32_t num_batches = (range_hi - range_lo + RB - 1) / RB;
-    uint32_t my_id = 0, next_id = 0;
-    auto prefetch = [&](uint32_t b, uint32_t &id_out) {
-        uint32_t idx = range_lo + b * RB + tid;
+    const uint32_t num_batches = (range_hi - range_lo + WB - 1) / WB;
+    uint32_t next_id = 0;
+    auto prefetch = [&](uint32_t b) {
+        uint32_t idx = range_lo + b * WB + lane;
         if (idx < range_hi) {
             uint32_t id = __ldg(cgid_from_isect + idx);
-            id_out = id;
+            next_id = id;
             const float *src = projected + (size_t)id * ROW;
-            float *dst = &s_rows[b & 1][tid * ROW];
+            float *dst = &s_rows[wid][b & 1u][lane * ROW];
             cp_async16(dst, src);
             cp_async16(dst + 4, src + 4);
             cp_async16(dst + 8, src + 8);
         }
         cp_async_commit();
     };
-    if (num_batches > 0) prefetch(0, next_id);
-
-    for (uint32_t b = 0; b < num_batches; b++) {
-        const uint32_t buf = b & 1u;
-        const uint32_t batch_start = range_lo + b * RB;
-        const uint32_t count = min((uint32_t)RB, range_hi - batch_start);
-        my_id = next_id;
-        if (b + 1 < num_batches) {
-            prefetch(b + 1, next_id);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        // ---- per-splat block culling
-        {
-            uint32_t mask = 0;
-            if (tid < count) {
-                const float4 A = *reinterpret_cast<const float4 *>(&s_rows[buf][tid * ROW]);
-                const float4 B = *reinterpret_cast<const float4 *>(&s_rows[buf][tid * ROW + 4]);
-                const float4 Cc = *reinterpret_cast<const float4 *>(&s_rows[buf][tid * ROW + 8]);
-                float thr = Cc.y + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f);
-                mask = block_hit_mask(A.x, A.y, A.z, A.w, B.x, thr, (float)tile_x0, (float)tile_y0);
+    // a warp whose pixels are all outside the image has nothing to blend
+    if (num_batches > 0 && !__all_sync(0xffffffffu, done)) {
+        prefetch(0);
+        for (uint32_t b = 0; b < num_batches; b++) {
+            const uint32_t batch_start = range_lo + b * WB;
+            const uint32_t count = min((uint32_t)WB, range_hi - batch_start);
+            const uint32_t my_id = next_id;
+            if (b + 1 < num_batches) {
+                prefetch(b + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                uint32_t w = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-                if (lane == 0) s_hits[buf][k][wid] = w;
+            __syncwarp();
+            const float *rows = s_rows[wid][b & 1u];
+            bool hit = false;
+            if (lane < count) {
+                const float4 A = *reinterpret_cast<const float4 *>(rows + lane * ROW);
+                const float2 B = *reinterpret_cast<const float2 *>(rows + lane * ROW + 4);
+                const float pt = rows[lane * ROW + 9];
+                hit = block_may_hit(A.x, A.y, A.z, A.w, B.x, pt + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f), rx0, rx1, ry0, ry1);
             }
-            if (BWD_INFO) s_used[tid] = 0;
-        }
-        __syncthreads();
-        // ---- blend: this warp walks its own hit bits in depth order
-        bool warp_done = __all_sync(0xffffffffu, done);
-        if (!warp_done) {
-#pragma unroll 1
-            for (int j = 0; j < 8; j++) {
-                uint32_t bits = s_hits[buf][wid][j];
-                while (bits) {
-                    const uint32_t s = (uint32_t)(j * 32 + __ffs(bits) - 1);
-                    bits &= bits - 1;
-                    const float *row = &s_rows[buf][s * ROW];
-                    const float4 A = *reinterpret_cast<const float4 *>(row);       // mx my a b
-                    const float2 B = *reinterpret_cast<const float2 *>(row + 4);   // c opac
-                    const float dx = px - A.x, dy = py - A.y;
-                    const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
-                    const float alpha = fminf(0.999f, B.y * __expf(-sigma));
-                    float alpha_eff;
-                    bool contrib;
-                    if (SMOOTH) {
-                        float wc = cutoff_weight(alpha);
-                        alpha_eff = alpha * wc;
-                        contrib = !done && sigma >= 0.0f && wc > 0.0f;
-                    } else {
-                        alpha_eff = alpha;
-                        contrib = !done && sigma >= 0.0f && alpha >= ALPHA_CUTOFF_MID;
-                    }
-                    const float next_T = T * (1.0f - alpha_eff);
-                    if (contrib && next_T <= 1.0e-4f) { done = true; contrib = false; }
-                    if (__any_sync(0xffffffffu, contrib)) {
-                        const float2 Cl = *reinterpret_cast<const float2 *>(row + 6);  // r g
-                        const float cb = row[8];
-                        if (contrib) {
-                            const float vis = alpha_eff * T;
-                            acc_r += fmaxf(Cl.x, 0.0f) * vis;
-                            acc_g += fmaxf(Cl.y, 0.0f) * vis;
-                            acc_b += fmaxf(cb, 0.0f) * vis;
-                            T = next_T;
-                        }
-                        if (BWD_INFO && lane == 0) s_used[s] = 1;
-                    } else if (__all_sync(0xffffffffu, done)) {
-                        bits = 0;
-                        j = 8;
-                    }
+            uint32_t bits = __ballot_sync(0xffffffffu, hit);
+            uint32_t used = 0;
+#ifdef BG_STATS
+            st_tested += count; st_iters += __popc(bits);
+#endif
+            while (bits) {
+                const uint32_t s = (uint32_t)__ffs(bits) - 1u;
+                bits &= bits - 1u;
+                const float *row = rows + s * ROW;
+                const float4 A = *reinterpret_cast<const float4 *>(row);       // mx my a b
+                const float2 B = *reinterpret_cast<const float2 *>(row + 4);   // c opac
+                const float dx = px - A.x, dy = py - A.y;
+                const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
+                const float alpha = fminf(0.999f, B.y * __expf(-sigma));
+                float alpha_eff;
+                bool contrib;
+                if (SMOOTH) {
+                    float wc = cutoff_weight(alpha);
+                    alpha_eff = alpha * wc;
+                    contrib = !done && sigma >= 0.0f && wc > 0.0f;
+                } else {
+                    alpha_eff = alpha;
+                    contrib = !done && sigma >= 0.0f && alpha >= ALPHA_CUTOFF_MID;
                 }
+                const float next_T = T * (1.0f - alpha_eff);
+                const bool stop = contrib && next_T <= 1.0e-4f;
+                if (stop) { done = true; contrib = false; }
+#ifdef BG_STATS
+                { uint32_t cb_ = __ballot_sync(0xffffffffu, contrib); st_pairs += __popc(cb_); st_useful += cb_ ? 1 : 0; }
+#endif
+                if (__any_sync(0xffffffffu, contrib)) {
+                    const float2 Cl = *reinterpret_cast<const float2 *>(row + 6);  // r g
+                    const float cb = row[8];
+                    if (contrib) {
+                        const float vis = alpha_eff * T;
+                        acc_r += fmaxf(Cl.x, 0.0f) * vis;
+                        acc_g += fmaxf(Cl.y, 0.0f) * vis;
+                        acc_b += fmaxf(cb, 0.0f) * vis;
+                        T = next_T;
+                    }
+                    used |= 1u << s;
+                }
+                if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, done)) bits = 0;
             }
-            warp_done = __all_sync(0xffffffffu, done);
-        }
-        const int any_active = __syncthreads_or(warp_done ? 0 : 1);
-        if (BWD_INFO) {
-            if (tid < count && s_used[tid]) {
+            if (BWD_INFO && ((used >> lane) & 1u)) {
                 visible[__ldg(gid_from_cgid + my_id)] = 1.0f;
-                last_useful = batch_start + tid + 1;
+                last_useful = batch_start + lane + 1;
             }
+            if (__all_sync(0xffffffffu, done)) break;
+            __syncwarp();  // all lanes are done with this buffer before the next prefetch overwrites its twin
         }
-        if (!any_active) break;
+        cp_async_wait<0>();
     }
-    cp_async_wait<0>();
 
+#ifdef BG_STATS
+    if (lane == 0) {
+        atomicAdd(&g_fwd_stats[0], st_tested); atomicAdd(&g_fwd_stats[1], st_iters);
+        atomicAdd(&g_fwd_stats[2], st_useful); atomicAdd(&g_fwd_stats[3], st_pairs);
+    }
+#endif
     if (inside) {
         const float fr = acc_r + T * u.bg_r, fg = acc_g + T * u.bg_g, fb = acc_b + T * u.bg_b, fa = 1.0f - T;
         const size_t pix_id = (size_t)pix_x + (size_t)pix_y * u.img_w;
@@ -161,7 +163,11 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
         }
     }
     if (BWD_INFO) {
-        if (last_useful > range_lo) atomicMax(&s_max_useful, last_useful);
+        // one block barrier, after all blending: publish the trimmed range end
+        uint32_t m = last_useful;
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        __syncthreads();
+        if (lane == 0 && m > range_lo) atomicMax(&s_max_useful, m);
         __syncthreads();
         if (tid == 0) tile_offsets[tile * 2 + 1] = s_max_useful;
     }
@@ -185,5 +191,16 @@ cudaError_t launch_rasterize_fwd(cudaStream_t s, bool bwd_info, bool smooth, uin
                                                                     gid_from_cgid, (float4 *)out_img, nullptr, visible, u);
     return cudaGetLastError();
 }
+
+#ifdef BG_STATS
+extern "C" int bg_debug_fwd_stats(unsigned long long *out4, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out4, g_fwd_stats, sizeof(g_fwd_stats));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_fwd_stats, z, sizeof(z));
+    }
+    return (int)e;
+}
+#endif
 
 }  // namespace bg

@@ -45,7 +45,7 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n_host, const uint
 }
 
 // One digit pass.  lb_state: [num_tiles][256] look-back words for this pass.
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
                      const uint32_t *__restrict__ n_dev, uint32_t shift, uint32_t width,
@@ -125,14 +125,33 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         uint32_t bin_start = block_exclusive_scan(my_count, s_scan, &bin_total);
         uint32_t prefix = 0;
         if (tile != 0) {
+            // Serial look-back costs one L2 round trip per predecessor; in the first wave every
+            // running tile has ~gridDim predecessors that only hold aggregates.  Issue LB_BATCH
+            // independent loads per round and consume them in order.
+            constexpr int LB_BATCH = 8;
             int64_t t = (int64_t)tile - 1;
-            while (true) {
-                unsigned long long w = lb_load(lb_state + (size_t)t * RADIX + threadIdx.x);
-                uint32_t stt = lb_status(w, epoch);
-                if (stt == LB_INVALID) continue;
-                prefix += lb_value(w);
-                if (stt == LB_INCLUSIVE) break;
-                t--;
+            bool done_lb = false;
+            while (!done_lb) {
+                unsigned long long w[LB_BATCH];
+#pragma unroll
+                for (int q = 0; q < LB_BATCH; q++) {
+                    int64_t tt = t - q;
+                    w[q] = (tt >= 0) ? lb_load(lb_state + (size_t)tt * RADIX + threadIdx.x) : 0ull;
+                }
+#pragma unroll
+                for (int q = 0; q < LB_BATCH; q++) {
+                    if (done_lb) break;
+                    int64_t tt = t - q;
+                    if (tt < 0) { done_lb = true; break; }
+                    uint32_t stt = lb_status(w[q], epoch);
+                    while (stt == LB_INVALID) {  // not published yet: wait on this one word
+                        w[q] = lb_load(lb_state + (size_t)tt * RADIX + threadIdx.x);
+                        stt = lb_status(w[q], epoch);
+                    }
+                    prefix += lb_value(w[q]);
+                    if (stt == LB_INCLUSIVE) done_lb = true;
+                }
+                t -= LB_BATCH;
             }
             lb_store(st, epoch, LB_INCLUSIVE, prefix + my_count);
         }
