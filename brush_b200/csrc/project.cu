@@ -26,13 +26,19 @@ struct CullResult {
     uint32_t tiles;
     float radius;
     unsigned long long mask;  // hit bits of the bbox tiles, row major, valid when the bbox has <= 64 tiles
+    // screen-space footprint, consumed by the warp-cooperative tile count
+    float mx, my, c00, c01, c11, pt;
+    uint32_t min_x, min_y, bbw, ntiles;
 };
 
+// Everything of project_forward up to the tile bbox (project_forward.rs:43-117).
 template <bool MIP>
 __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, const BgCamera &u, uint32_t img_w,
                                                uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y) {
     CullResult r;
     r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
+    r.mx = r.my = r.c00 = r.c01 = r.c11 = r.pt = 0.0f;
+    r.min_x = r.min_y = r.bbw = r.ntiles = 0;
     V3 mean_c = world_to_cam(mk3(t[0], t[1], t[2]), u);
     if (!(is_finite(mean_c) && mean_c.z <= 1.0e10f)) return r;
     if (mean_c.z < 0.01f) return r;
@@ -60,21 +66,61 @@ __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, c
     bool on_screen = mx + ex > 0.0f && mx - ex < wf && my + ey > 0.0f && my - ey < hf;
     if (!on_screen) return r;
     TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
-    uint32_t hits = 0;
-    unsigned long long mask = 0ull;
-    uint32_t bit = 0;
-    for (uint32_t ty = bb.min_y; ty < bb.max_y; ty++)
-        for (uint32_t tx = bb.min_x; tx < bb.max_x; tx++, bit++) {
-            bool h = tile_hit(tx, ty, mx, my, conic, pt);
-            hits += h ? 1u : 0u;
-            mask |= (h && bit < 64u) ? (1ull << bit) : 0ull;
-        }
-    r.mask = mask;
     r.visible = true;
     r.depth = mean_c.z;
-    r.tiles = hits;
     r.radius = fmaxf(ex / wf, ey / hf);
+    r.mx = mx; r.my = my; r.c00 = conic.c00; r.c01 = conic.c01; r.c11 = conic.c11; r.pt = pt;
+    r.min_x = bb.min_x; r.min_y = bb.min_y; r.bbw = bb.max_x - bb.min_x;
+    r.ntiles = (bb.max_y - bb.min_y) * r.bbw;
     return r;
+}
+
+// count_contributing_tiles (helpers.rs:203-222) for the 32 Gaussians of a warp at once.  A per-thread
+// walk costs the warp the LARGEST bbox among its lanes; here the warp's candidate tiles are flattened
+// into one list and tested 32 at a time, whoever they belong to (binary search of the owner over the
+// exclusive prefix of the per-lane tile counts).  Hit counts and hit bits go to the owner through
+// shared-memory atomics.  `w_hits` / `w_mask`: this warp's 32-entry scratch arrays.
+__device__ __forceinline__ void warp_count_tiles(CullResult &r, uint32_t *w_hits, unsigned long long *w_mask) {
+    const uint32_t lane = threadIdx.x & 31u;
+    w_hits[lane] = 0;
+    w_mask[lane] = 0ull;
+    uint32_t incl = r.ntiles;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t pre = incl - r.ntiles;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        uint32_t own = 0;  // largest lane whose exclusive prefix is <= j
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            uint32_t cand = own + step;
+            uint32_t pc = __shfl_sync(0xffffffffu, pre, cand & 31u);
+            if (pc <= j) own = cand;
+        }
+        const uint32_t local = j - __shfl_sync(0xffffffffu, pre, own);
+        const float mx = __shfl_sync(0xffffffffu, r.mx, own), my = __shfl_sync(0xffffffffu, r.my, own);
+        S2 conic;
+        conic.c00 = __shfl_sync(0xffffffffu, r.c00, own);
+        conic.c01 = __shfl_sync(0xffffffffu, r.c01, own);
+        conic.c11 = __shfl_sync(0xffffffffu, r.c11, own);
+        const float pt = __shfl_sync(0xffffffffu, r.pt, own);
+        const uint32_t min_x = __shfl_sync(0xffffffffu, r.min_x, own), min_y = __shfl_sync(0xffffffffu, r.min_y, own);
+        const uint32_t bbw = __shfl_sync(0xffffffffu, r.bbw, own);
+        if (j < total) {
+            const uint32_t ry = local / bbw, rx = local - ry * bbw;
+            if (tile_hit(min_x + rx, min_y + ry, mx, my, conic, pt)) {
+                atomicAdd(&w_hits[own], 1u);
+                if (local < 64u) atomicOr(&w_mask[own], 1ull << local);
+            }
+        }
+    }
+    __syncwarp();
+    r.tiles = w_hits[lane];
+    r.mask = w_mask[lane];
 }
 
 // K1.  One thread per Gaussian, 256 Gaussians per tile, persistent CTAs.
@@ -90,6 +136,8 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
     __shared__ __align__(16) float s_rows[PROJ_THREADS * 10];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_hits[PROJ_THREADS];
+    __shared__ unsigned long long s_mask[PROJ_THREADS];
     const uint32_t num_tiles = (n + PROJ_THREADS - 1) / PROJ_THREADS;
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&ctl[CTL_TICKETS + TK_PROJECT], 1u);
@@ -111,6 +159,8 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
         const uint32_t gid = base + threadIdx.x;
         CullResult r;
         r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
+        r.mx = r.my = r.c00 = r.c01 = r.c11 = r.pt = 0.0f;
+        r.min_x = r.min_y = r.bbw = r.ntiles = 0;
         if (threadIdx.x < rows) {
             float t[10];
 #pragma unroll
@@ -119,6 +169,7 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             max_radius[gid] = r.radius;  // zero for culled splats (render_aux.rs:76-78)
             cgid_from_gid[gid] = 0xFFFFFFFFu;  // overwritten for visible splats by project_visible_emit
         }
+        warp_count_tiles(r, s_hits + (threadIdx.x & ~31u), s_mask + (threadIdx.x & ~31u));
         uint32_t total;
         uint32_t local = block_exclusive_scan(r.visible ? 1u : 0u, s_scan, &total);
         if (threadIdx.x < 32) {
@@ -314,16 +365,20 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             if (bbw * bbh <= 64u) {
                 // the counting pass left the hit bits of this bbox: no tile test is repeated here
                 unsigned long long m = __ldg(hit_masks + gid);
-                while (m && hits < budget) {
-                    uint32_t bit = (uint32_t)__ffsll((long long)m) - 1u;
-                    m &= m - 1ull;
-                    uint32_t ry = bit / bbw, rx = bit - ry * bbw;
-                    uint32_t o = base + hits;
-                    if (o < isect_capacity) {
-                        tile_keys[o] = (bb.min_x + rx) + (bb.min_y + ry) * tiles_x;
-                        isect_vals[o] = cgid;
+                const unsigned long long row_mask = (bbw >= 64u) ? ~0ull : ((1ull << bbw) - 1ull);
+                uint32_t row_key = bb.min_x + bb.min_y * tiles_x;
+                for (uint32_t ry = 0; ry < bbh && hits < budget; ry++, m = (bbw >= 64u) ? 0ull : (m >> bbw), row_key += tiles_x) {
+                    unsigned long long rb = m & row_mask;
+                    while (rb && hits < budget) {
+                        uint32_t rx = (uint32_t)__ffsll((long long)rb) - 1u;
+                        rb &= rb - 1ull;
+                        uint32_t o = base + hits;
+                        if (o < isect_capacity) {
+                            tile_keys[o] = row_key + rx;
+                            isect_vals[o] = cgid;
+                        }
+                        hits++;
                     }
-                    hits++;
                 }
             } else {
                 for (uint32_t ty = bb.min_y; ty < bb.max_y && hits < budget; ty++) {

@@ -6,7 +6,8 @@
 // On B200 the same forward-replay recurrence runs with one thread per pixel (state in registers, same
 // warp-autonomous tile walk and block culling as the forward kernel); the per-splat sums over the 32
 // pixels of a warp are formed with a 12-shuffle reduce-scatter (10 values -> 10 lanes), then one f32
-// atomic (RED) per value.
+// atomic (RED) per value.  As in the forward kernel every lane owns two pixels of the warp's 8x8 block,
+// so one reduction and one set of atomics serves 64 pixel-splat pairs.
 //
 // Replay semantics (rasterize_backwards.rs:186-228, 279-383): pixel state starts at
 // (final_rgb - T_final*bg, T = 1); per splat, with the forward's skip/stop rules:
@@ -25,40 +26,109 @@ struct RasterBwdUniforms {
     float bg_r, bg_g, bg_b;
 };
 
+struct BwdPixel {
+    float rem_r, rem_g, rem_b, T;            // running state (forward replay)
+    float vo_r, vo_g, vo_b, vo_w, inv_fa;    // per-pixel constants
+};
+
+__device__ __forceinline__ BwdPixel load_bwd_pixel(bool inside, size_t pix_id, const float4 *__restrict__ out_img,
+                                                   const float4 *__restrict__ v_output, const RasterBwdUniforms &u) {
+    BwdPixel p;
+    p.rem_r = p.rem_g = p.rem_b = p.T = 0.0f;
+    p.vo_r = p.vo_g = p.vo_b = p.vo_w = p.inv_fa = 0.0f;
+    if (inside) {  // load_pixel_state, rasterize_backwards.rs:186-228
+        const float4 o = __ldg(out_img + pix_id);
+        const float4 vo = __ldg(v_output + pix_id);
+        const float t_final = 1.0f - o.w;
+        p.rem_r = o.x - t_final * u.bg_r;
+        p.rem_g = o.y - t_final * u.bg_g;
+        p.rem_b = o.z - t_final * u.bg_b;
+        p.T = 1.0f;
+        p.vo_r = vo.x; p.vo_g = vo.y; p.vo_b = vo.z;
+        p.vo_w = (vo.w - (u.bg_r * vo.x + u.bg_g * vo.y + u.bg_b * vo.z)) * t_final;
+        p.inv_fa = 1.0f / fmaxf(o.w, 1.0e-5f);
+    }
+    return p;
+}
+
+// Forward-replay test of one pixel against one splat.  Returns whether the pair contributes; on the
+// stop rule the pixel's T drops to 0 (rasterize_backwards.rs:318-320).
 template <bool SMOOTH>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ bool bwd_test(BwdPixel &p, float sigma, float opac, float &gaussian, float &oa, float &alpha,
+                                         float &w_cut, float &next_T, bool &stop) {
+    gaussian = __expf(-sigma);
+    oa = opac * gaussian;
+    alpha = fminf(0.999f, oa);
+    w_cut = 1.0f;
+    bool contrib;
+    if (SMOOTH) {
+        w_cut = cutoff_weight(alpha);
+        contrib = p.T > 1.0e-4f && sigma >= 0.0f && w_cut > 0.0f;
+    } else {
+        contrib = p.T > 1.0e-4f && sigma >= 0.0f && alpha >= ALPHA_CUTOFF_MID;
+    }
+    next_T = p.T * (1.0f - alpha * w_cut);
+    stop = contrib && next_T <= 1.0e-4f;
+    if (stop) { p.T = 0.0f; contrib = false; }
+    return contrib;
+}
+
+// Adds one contributing pair's terms to the lane's partial sums g[0..9] and advances the pixel state.
+template <bool SMOOTH>
+__device__ __forceinline__ void bwd_accumulate(BwdPixel &p, float *g, float dx, float dy, float ca, float cb, float cc,
+                                               float raw_r, float raw_g, float raw_b, float gaussian, float oa,
+                                               float alpha, float w_cut, float next_T, float img_wf, float img_hf) {
+    const float cr = fmaxf(raw_r, 0.0f), cg = fmaxf(raw_g, 0.0f), cbl = fmaxf(raw_b, 0.0f);
+    const float alpha_eff = alpha * w_cut;
+    const float vis = alpha_eff * p.T;
+    g[5] += (raw_r >= 0.0f) ? vis * p.vo_r : 0.0f;
+    g[6] += (raw_g >= 0.0f) ? vis * p.vo_g : 0.0f;
+    g[7] += (raw_b >= 0.0f) ? vis * p.vo_b : 0.0f;
+    const float ra = __fdividef(1.0f, 1.0f - alpha_eff);
+    const float dot_rgb = ((p.T * cr - p.rem_r) * p.vo_r + (p.T * cg - p.rem_g) * p.vo_g + (p.T * cbl - p.rem_b) * p.vo_b) * ra;
+    const float v_alpha_eff = dot_rgb + p.vo_w * ra;
+    float v_alpha = v_alpha_eff;
+    if (SMOOTH) v_alpha = v_alpha_eff * (w_cut + alpha * cutoff_weight_deriv(alpha));
+    const float v_sigma = -alpha * v_alpha;
+    const float vxy_x = v_sigma * (ca * dx + cb * dy);
+    const float vxy_y = v_sigma * (cb * dx + cc * dy);
+    if (oa <= 0.999f) {
+        g[0] += vxy_x;
+        g[1] += vxy_y;
+        g[2] += 0.5f * v_sigma * dx * dx;
+        g[3] += v_sigma * dx * dy;
+        g[4] += 0.5f * v_sigma * dy * dy;
+        g[8] += v_alpha * gaussian;
+        const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
+        g[9] += sqrtf(sx * sx + sy * sy) * p.inv_fa;
+    }
+    p.rem_r -= vis * cr;
+    p.rem_g -= vis * cg;
+    p.rem_b -= vis * cbl;
+    p.T = next_T;
+}
+
+template <bool SMOOTH>
+__global__ void __launch_bounds__(RASTER_THREADS)
 rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *__restrict__ tile_offsets,
                      const float *__restrict__ projected, const float4 *__restrict__ out_img,
                      const float4 *__restrict__ v_output, float *__restrict__ v_combined, RasterBwdUniforms u) {
-    __shared__ __align__(16) float s_rows[8][2][WB * ROW];  // per warp, double buffered
+    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * ROW];  // per warp, double buffered
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t range_lo = tile_offsets[tile * 2], range_hi = tile_offsets[tile * 2 + 1];
     if (range_hi <= range_lo) return;
     const uint32_t tile_x0 = (tile % u.tiles_x) * TILE_W, tile_y0 = (tile / u.tiles_x) * TILE_W;
-    const uint32_t blk_x0 = tile_x0 + 8u * (wid & 1u), blk_y0 = tile_y0 + 4u * (wid >> 1);
-    const uint32_t pix_x = blk_x0 + (lane & 7u), pix_y = blk_y0 + (lane >> 3);
-    const bool inside = pix_x < u.img_w && pix_y < u.img_h;
-    const float px = (float)pix_x + 0.5f, py = (float)pix_y + 0.5f;
-    const float rx0 = (float)blk_x0 + 0.5f, rx1 = rx0 + 7.0f, ry0 = (float)blk_y0 + 0.5f, ry1 = ry0 + 3.0f;
+    const uint32_t blk_x0 = tile_x0 + 8u * (wid & 1u), blk_y0 = tile_y0 + 8u * (wid >> 1);
+    const uint32_t pix_x = blk_x0 + (lane & 7u), pix_y0 = blk_y0 + (lane >> 3), pix_y1 = pix_y0 + 4u;
+    const bool inside0 = pix_x < u.img_w && pix_y0 < u.img_h;
+    const bool inside1 = pix_x < u.img_w && pix_y1 < u.img_h;
+    const float px = (float)pix_x + 0.5f, py0 = (float)pix_y0 + 0.5f;
+    const float rx0 = (float)blk_x0 + 0.5f, rx1 = rx0 + 7.0f, ry0 = (float)blk_y0 + 0.5f, ry1 = ry0 + 7.0f;
 
-    // per-pixel constants and running state (load_pixel_state, rasterize_backwards.rs:186-228)
-    float rem_r = 0.0f, rem_g = 0.0f, rem_b = 0.0f, T = 0.0f;
-    float vo_r = 0.0f, vo_g = 0.0f, vo_b = 0.0f, vo_w = 0.0f, inv_fa = 0.0f;
-    if (inside) {
-        const size_t pix_id = (size_t)pix_x + (size_t)pix_y * u.img_w;
-        const float4 o = __ldg(out_img + pix_id);
-        const float4 vo = __ldg(v_output + pix_id);
-        const float t_final = 1.0f - o.w;
-        rem_r = o.x - t_final * u.bg_r;
-        rem_g = o.y - t_final * u.bg_g;
-        rem_b = o.z - t_final * u.bg_b;
-        T = 1.0f;
-        vo_r = vo.x; vo_g = vo.y; vo_b = vo.z;
-        vo_w = (vo.w - (u.bg_r * vo.x + u.bg_g * vo.y + u.bg_b * vo.z)) * t_final;
-        inv_fa = 1.0f / fmaxf(o.w, 1.0e-5f);
-    }
+    BwdPixel p0 = load_bwd_pixel(inside0, (size_t)pix_x + (size_t)pix_y0 * u.img_w, out_img, v_output, u);
+    BwdPixel p1 = load_bwd_pixel(inside1, (size_t)pix_x + (size_t)pix_y1 * u.img_w, out_img, v_output, u);
     const float img_wf = (float)u.img_w, img_hf = (float)u.img_h;
 
     // reduce-scatter bookkeeping: which of the 10 sums this lane ends up owning
@@ -82,7 +152,8 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
         }
         cp_async_commit();
     };
-    if (__all_sync(0xffffffffu, !(T > 1.0e-4f))) return;  // nothing inside the image in this block
+    auto all_done = [&]() { return __all_sync(0xffffffffu, !(p0.T > 1.0e-4f) && !(p1.T > 1.0e-4f)); };
+    if (all_done()) return;  // nothing inside the image in this block
     prefetch(0);
 
     for (uint32_t b = 0; b < num_batches; b++) {
@@ -111,60 +182,25 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             const float *row = rows + s * ROW;
             const float4 A = *reinterpret_cast<const float4 *>(row);      // mx my a b
             const float4 B = *reinterpret_cast<const float4 *>(row + 4);  // c opac r g
-            const float col_b = row[8];
-            const float dx = A.x - px, dy = A.y - py;
-            const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
-            const float gaussian = __expf(-sigma);
-            const float oa = B.y * gaussian;
-            const float alpha = fminf(0.999f, oa);
-            float w_cut = 1.0f;
-            bool contrib;
-            if (SMOOTH) {
-                w_cut = cutoff_weight(alpha);
-                contrib = T > 1.0e-4f && sigma >= 0.0f && w_cut > 0.0f;
-            } else {
-                contrib = T > 1.0e-4f && sigma >= 0.0f && alpha >= ALPHA_CUTOFF_MID;
-            }
-            const float alpha_eff = alpha * w_cut;
-            const float next_T = T * (1.0f - alpha_eff);
-            const bool stop = contrib && next_T <= 1.0e-4f;
-            if (stop) { T = 0.0f; contrib = false; }
-            if (!__any_sync(0xffffffffu, contrib)) {
-                if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, !(T > 1.0e-4f))) bits = 0;
+            const float dx = A.x - px, dy0 = A.y - py0, dy1 = dy0 - 4.0f;
+            const float adx2 = A.z * dx * dx, bdx = A.w * dx;
+            const float sigma0 = 0.5f * (adx2 + B.x * dy0 * dy0) + bdx * dy0;
+            const float sigma1 = 0.5f * (adx2 + B.x * dy1 * dy1) + bdx * dy1;
+            float ga0, oa0, al0, wc0, nt0, ga1, oa1, al1, wc1, nt1;
+            bool st0, st1;
+            const bool c0 = bwd_test<SMOOTH>(p0, sigma0, B.y, ga0, oa0, al0, wc0, nt0, st0);
+            const bool c1 = bwd_test<SMOOTH>(p1, sigma1, B.y, ga1, oa1, al1, wc1, nt1, st1);
+            const bool any_stop = __any_sync(0xffffffffu, st0 || st1);
+            if (!__any_sync(0xffffffffu, c0 || c1)) {
+                if (any_stop && all_done()) bits = 0;
                 continue;
             }
             float g[10];
 #pragma unroll
             for (int i = 0; i < 10; i++) g[i] = 0.0f;
-            if (contrib) {
-                const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cbl = fmaxf(col_b, 0.0f);
-                const float vis = alpha_eff * T;
-                g[5] = (B.z >= 0.0f) ? vis * vo_r : 0.0f;
-                g[6] = (B.w >= 0.0f) ? vis * vo_g : 0.0f;
-                g[7] = (col_b >= 0.0f) ? vis * vo_b : 0.0f;
-                const float ra = __fdividef(1.0f, 1.0f - alpha_eff);
-                const float dot_rgb = ((T * cr - rem_r) * vo_r + (T * cg - rem_g) * vo_g + (T * cbl - rem_b) * vo_b) * ra;
-                const float v_alpha_eff = dot_rgb + vo_w * ra;
-                float v_alpha = v_alpha_eff;
-                if (SMOOTH) v_alpha = v_alpha_eff * (w_cut + alpha * cutoff_weight_deriv(alpha));
-                const float v_sigma = -alpha * v_alpha;
-                const float vxy_x = v_sigma * (A.z * dx + A.w * dy);
-                const float vxy_y = v_sigma * (A.w * dx + B.x * dy);
-                if (oa <= 0.999f) {
-                    g[0] = vxy_x;
-                    g[1] = vxy_y;
-                    g[2] = 0.5f * v_sigma * dx * dx;
-                    g[3] = v_sigma * dx * dy;
-                    g[4] = 0.5f * v_sigma * dy * dy;
-                    g[8] = v_alpha * gaussian;
-                    const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
-                    g[9] = sqrtf(sx * sx + sy * sy) * inv_fa;
-                }
-                rem_r -= vis * cr;
-                rem_g -= vis * cg;
-                rem_b -= vis * cbl;
-                T = next_T;
-            }
+            const float col_b = row[8];
+            if (c0) bwd_accumulate<SMOOTH>(p0, g, dx, dy0, A.z, A.w, B.x, B.z, B.w, col_b, ga0, oa0, al0, wc0, nt0, img_wf, img_hf);
+            if (c1) bwd_accumulate<SMOOTH>(p1, g, dx, dy1, A.z, A.w, B.x, B.z, B.w, col_b, ga1, oa1, al1, wc1, nt1, img_wf, img_hf);
             // ---- reduce-scatter 10 values over 32 lanes: 5+3+2+1+1 shuffles
             float a5[6];
 #pragma unroll
@@ -198,9 +234,9 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
             const uint32_t id = __shfl_sync(0xffffffffu, my_id, s);
             if (owner && d1 != 0.0f) atomicAdd(v_combined + (size_t)id * BG_VCOMBINED_STRIDE + slot, d1);
-            if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, !(T > 1.0e-4f))) bits = 0;
+            if (any_stop && all_done()) bits = 0;
         }
-        if (__all_sync(0xffffffffu, !(T > 1.0e-4f))) break;
+        if (all_done()) break;
         __syncwarp();
     }
     cp_async_wait<0>();
@@ -213,11 +249,11 @@ cudaError_t launch_rasterize_bwd(cudaStream_t s, bool smooth, uint32_t num_tiles
     RasterBwdUniforms u;
     u.tiles_x = tiles_x; u.img_w = w; u.img_h = h; u.bg_r = bg[0]; u.bg_g = bg[1]; u.bg_b = bg[2];
     if (smooth)
-        rasterize_bwd_kernel<true><<<num_tiles, 256, 0, s>>>(cgid_from_isect, tile_offsets, projected,
+        rasterize_bwd_kernel<true><<<num_tiles, RASTER_THREADS, 0, s>>>(cgid_from_isect, tile_offsets, projected,
                                                              (const float4 *)out_img, (const float4 *)v_output,
                                                              v_combined, u);
     else
-        rasterize_bwd_kernel<false><<<num_tiles, 256, 0, s>>>(cgid_from_isect, tile_offsets, projected,
+        rasterize_bwd_kernel<false><<<num_tiles, RASTER_THREADS, 0, s>>>(cgid_from_isect, tile_offsets, projected,
                                                               (const float4 *)out_img, (const float4 *)v_output,
                                                               v_combined, u);
     return cudaGetLastError();

@@ -1,20 +1,22 @@
 // raster_common.cuh -- pieces shared by the forward and backward blend kernels.
 //
-// Tile = 16x16 pixels = one CTA of 256 threads.  Warp k owns the 8x4 pixel block
-//   origin (8*(k&1), 4*(k>>1)), lane l -> pixel (l&7, l>>3) inside the block.
+// Tile = 16x16 pixels = one CTA of 128 threads.  Warp k owns the 8x8 pixel block with origin
+//   (8*(k&1), 8*(k>>1)); lane l owns the two pixels (l&7, l>>3) and (l&7, (l>>3)+4) of the block.
 // Every warp walks the tile's depth-ordered splat list on its own, 32 splats at a time: lane l
 // fetches the 48-byte projected row of splat l with three 16-byte cp.async (LDGSTS) into the
-// warp's double-buffered shared staging area, tests that splat against the warp's 8x4 block
+// warp's double-buffered shared staging area, tests that splat against the warp's 8x8 block
 // (exact minimum of the conic over the rectangle of pixel centres), and the ballot of the
 // survivors is then consumed bit by bit, in order.  Blend order -- and therefore the result -- is
 // exactly the reference's, pairs that cannot reach alpha >= 1/255 anywhere in the block are never
 // evaluated, and no block-wide barrier sits inside the loop: a warp whose 32 pixels are saturated
-// retires at once, the next batch's loads overlap the current batch's math.
+// retires at once (a warp's 64 pixels), the next batch's loads overlap the current batch's math.
 #pragma once
 #include "bg_common.cuh"
 
 namespace bg {
 
+constexpr int RASTER_WARPS = 4;
+constexpr int RASTER_THREADS = RASTER_WARPS * 32;
 constexpr int WB = 32;                    // splats per warp batch
 constexpr int ROW = BG_PROJECTED_STRIDE;  // 12 floats
 
