@@ -45,36 +45,46 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Streams `nvidia-smi -lms 100` for one GPU; keeps the samples that fall inside marked timed regions."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+        self.gpu, self.rows, self.windows, self.proc = gpu_index, [], [], None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        self._stop_evt.set()
+        time.sleep(0.15)
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=5)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        inside = [r for (t, r) in self.rows if any(a <= t <= b + 0.1 for a, b in self.windows)] or [r for _, r in self.rows[-3:]]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in inside if len(r) >= 7 and num(r[0]) is not None]
+        mx = [num(r[1]) for r in inside if len(r) >= 7 and num(r[1]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(inside)}
 
 
 def scene_np():
@@ -109,14 +119,17 @@ def run_reference(args):
     from oracle import oracle as orc
     cam, tr, sh, op, v_out = scene_np()
     u = build_uniforms(cam, IMG_W, IMG_H)
-    for _ in range(args.warmup):
-        cpu_oracle_pass(u, tr, sh, op, v_out)
-    t = [cpu_oracle_pass(u, tr, sh, op, v_out) for _ in range(args.steps)]
-    total = sum(t)
-    ms = total / args.steps * 1e3
+    # One "step" of this arm is one full fwd+bwd pass of the workload on the host cores (seconds each).
+    # The number of timed passes is bounded so that the whole run stays within a few minutes whatever
+    # --steps says; ms_per_step is the mean over the passes actually timed.
+    t_first = cpu_oracle_pass(u, tr, sh, op, v_out)  # warm-up (page-in, thread pool)
+    n_pass = max(1, min(args.steps, int(150.0 / max(t_first, 1e-3))))
+    t = [cpu_oracle_pass(u, tr, sh, op, v_out) for _ in range(n_pass)]
+    ms = sum(t) / n_pass * 1e3
     val = IMG_W * IMG_H / (ms * 1e-3) / 1e6
     cores = orc.num_threads()
-    sample = f"{args.steps} full fwd+bwd passes of the same 1M-Gaussian 1080p scene (OpenMP, {cores} threads)"
+    sample = (f"{n_pass} full fwd+bwd passes of the same 1M-Gaussian 1080p scene timed (of {args.steps} steps requested; "
+              f"bounded to ~150 s), OpenMP, {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -131,8 +144,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
@@ -207,17 +220,21 @@ def main():
 
     def timed(fn, steps):
         barrier()
+        w0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
         barrier()
+        sampler.mark(w0, time.time())
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up
     for _ in range(args.warmup):
         out, g = step_device()
@@ -227,8 +244,6 @@ def main():
     per_tile = toff[..., 1] - toff[..., 0]
     T = per_tile.size
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms_dev = timed(lambda i: step_device(), args.steps)
     # ---- e2e: host input, copies inside the timed region
     stage(0)
@@ -244,7 +259,6 @@ def main():
         R.rasterize_bwd(out, v_out)
     ms_bwd = timed(lambda i: R.rasterize_bwd(out, v_out), args.steps) / args.steps
     ms_fwd_all = timed(lambda i: R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top), args.steps) / args.steps
-    clocks = sampler.stop()
 
     ms_step = ms_dev / args.steps
     value = world * P / (ms_step * 1e-3) / 1e6
@@ -273,7 +287,7 @@ def main():
                 "note": "upstream-gradient image uploaded from pinned host memory every step (double-buffered on a copy stream), "
                         "gradient checksums + counters read back; Gaussian parameters stay resident as in the reference trainer"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
-        "clocks": clocks,
+        "clocks": None,
         "roofline": {"bound": "hbm", "kernel": "rasterize_bwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": algo_bytes, "kernel_ms": ms_bwd,
@@ -282,6 +296,18 @@ def main():
                      "pipeline_fwd_bwd": {"algorithmic_bytes": b_fwd + b_bwd, "achieved": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9,
                                           "frac": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9 / peak, "forward_ms": ms_fwd_all}},
     }
+    if world == 1 and not args.no_train:
+        # secondary figure of the metric: full train step (render + L1/SSIM loss + backward + Adam x3 + stats/noise)
+        import brush_b200.train as T
+        gt = torch.randint(0, 2 ** 31 - 1, (IMG_H, IMG_W), dtype=torch.int32, device=dev) | (255 << 24)
+        splats = T.Splats(ttr.clone(), tsh.clone(), top.clone())
+        trainer = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
+        batch = T.SceneBatch(img_packed=gt, camera=cam)
+        for _ in range(3):
+            trainer.step(batch, splats)
+        ms_train = timed(lambda i: trainer.step(batch, splats), args.steps) / args.steps
+        line["train"] = {"iters_per_s": 1e3 / ms_train, "ms_per_iter": ms_train,
+                         "note": "SplatTrainer.step, 1 view/step, GT resident on the device, refine() not included"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         u = build_uniforms(cam0, IMG_W, IMG_H)
@@ -290,6 +316,7 @@ def main():
         dt = sum(cpu_oracle_pass(u, tr, sh, op, v_out_np) for _ in range(reps)) / reps
         line["cpu_baseline"] = {"value": P / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                                 "sample": f"{reps} full fwd+bwd passes of the same scene on the host cores (oracle/, OpenMP)"}
+    line["clocks"] = sampler.stop()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -224,7 +224,8 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     BG_CUDA(cudaMemsetAsync(c->tile_offsets, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
     if (bwd_info && n > 0) BG_CUDA(cudaMemsetAsync(visible, 0, (size_t)n * sizeof(float), s));
 
-    const int pgrid = c->sm_count * 4;
+    const int pgrid = c->sm_count * 5;   // project_cull: 256-thread CTAs, 48 regs
+    const int vgrid = c->sm_count * 8;   // project_visible_emit: 128-thread CTAs, 26 KB smem
     uint32_t *counters = c->ctl + CTL_COUNTERS;
     // K1: cull + compaction in index order
     BG_CUDA(launch_project_cull(s, pgrid, mip != 0, transforms, raw_opac, n, *cam, w, h, tiles_x, tiles_y,
@@ -244,7 +245,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
                                c->max_isect, counters + 2, c->ctl + CTL_TICKETS + TK_SCAN, c->lb_scan, next_epoch(c)));
     // K2+K3
     if (n > 0)
-        BG_CUDA(launch_project_visible_emit(s, pgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
+        BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
                                             tiles_x, tiles_y, c->projected, c->isect_key[0], c->isect_val[0],
                                             c->max_isect, c->cgid_from_gid, c->hit_masks, c->ctl));
     // tile sort on bits = 32 - clz(num_tiles)

@@ -169,12 +169,15 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             max_radius[gid] = r.radius;  // zero for culled splats (render_aux.rs:76-78)
             cgid_from_gid[gid] = 0xFFFFFFFFu;  // overwritten for visible splats by project_visible_emit
         }
-        warp_count_tiles(r, s_hits + (threadIdx.x & ~31u), s_mask + (threadIdx.x & ~31u));
+        // The visible count is known before the (expensive) tile walk: publish the tile aggregate
+        // first, count tiles, and only then look back -- by then the predecessors have published,
+        // so the chained scan adds no stall.
         uint32_t total;
         uint32_t local = block_exclusive_scan(r.visible ? 1u : 0u, s_scan, &total);
+        unsigned long long *st = lb_state + tile;
+        if (threadIdx.x == 0) lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total);
+        warp_count_tiles(r, s_hits + (threadIdx.x & ~31u), s_mask + (threadIdx.x & ~31u));
         if (threadIdx.x < 32) {
-            unsigned long long *st = lb_state + tile;
-            if (threadIdx.x == 0) lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total);
             uint32_t prefix = (tile == 0) ? 0u : lb_lookback_warp(lb_state, tile, epoch);
             if (threadIdx.x == 0) {
                 if (tile != 0) lb_store(st, epoch, LB_INCLUSIVE, prefix + total);

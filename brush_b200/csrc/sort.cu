@@ -118,17 +118,26 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
             }
             my_count = sum;
         }
-        // ---- publish aggregate, look back (thread d serves digit d)
+        // ---- publish the aggregate (thread d serves digit d), then reorder the tile in shared memory;
+        // only after that look back.  The reorder frees the key/value registers, so the look-back can
+        // keep LB_BATCH independent loads in flight: in steady state a tile sits behind ~gridDim
+        // predecessors that only hold aggregates, and a serial walk would cost one L2 round trip each.
         unsigned long long *st = lb_state + (size_t)tile * RADIX + threadIdx.x;
         lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, my_count);
         uint32_t bin_total;
         uint32_t bin_start = block_exclusive_scan(my_count, s_scan, &bin_total);
+        s_bin_start[threadIdx.x] = bin_start;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            uint32_t d = (key[i] >> shift) & mask;
+            uint32_t pos = s_bin_start[d] + s_warp_hist[wid * RADIX + d] + rank[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];
+        }
         uint32_t prefix = 0;
         if (tile != 0) {
-            // Serial look-back costs one L2 round trip per predecessor; in the first wave every
-            // running tile has ~gridDim predecessors that only hold aggregates.  Issue LB_BATCH
-            // independent loads per round and consume them in order.
-            constexpr int LB_BATCH = 8;
+            constexpr int LB_BATCH = 16;
             int64_t t = (int64_t)tile - 1;
             bool done_lb = false;
             while (!done_lb) {
@@ -155,17 +164,7 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
             }
             lb_store(st, epoch, LB_INCLUSIVE, prefix + my_count);
         }
-        s_bin_start[threadIdx.x] = bin_start;
         s_bin_dst[threadIdx.x] = (int64_t)s_digit_base[threadIdx.x] + (int64_t)prefix - (int64_t)bin_start;
-        __syncthreads();
-        // ---- reorder inside the tile through shared memory
-#pragma unroll
-        for (int i = 0; i < SORT_ITEMS; i++) {
-            uint32_t d = (key[i] >> shift) & mask;
-            uint32_t pos = s_bin_start[d] + s_warp_hist[wid * RADIX + d] + rank[i];
-            s_keys[pos] = key[i];
-            s_vals[pos] = val[i];
-        }
         __syncthreads();
         // ---- coalesced scatter: consecutive positions of one bin go to consecutive addresses
         for (uint32_t j = threadIdx.x; j < tile_count; j += SORT_THREADS) {
