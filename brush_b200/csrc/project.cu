@@ -263,8 +263,11 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
 }
 
 // K2 + K3.  One thread per visible Gaussian in depth order (compact gid = position in the
-// depth-sorted list).  128 threads per CTA; each warp stages the SH rows of its 32 Gaussians in
-// shared memory with coalesced loads, then every lane evaluates its own row.
+// depth-sorted list).  Every lane gathers its own parameter rows (the gather is by sorted global id,
+// so neighbouring lanes touch unrelated rows anyway): the 192-byte SH row as twelve independent
+// 128-bit loads (whole 32-byte sectors are consumed, 17 loads in flight per thread), no shared-memory
+// staging and no barriers -- the kernel is bound by gather latency, so memory-level parallelism is
+// what counts (ncu: long-scoreboard stalls dominated the staged version).
 constexpr int VIS_THREADS = 128;
 
 template <bool MIP, int DEG>
@@ -277,15 +280,10 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                             uint32_t *__restrict__ cgid_from_gid, const unsigned long long *__restrict__ hit_masks,
                             uint32_t *__restrict__ ctl) {
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
-    constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B: 128-bit staging
-    constexpr int S4 = (KF / 4) | 1;                     // odd float4 stride: conflict-free LDS.128 per lane
-    constexpr int STRIDE = VEC4 ? S4 * 4 : ((KF % 2 == 0) ? KF + 1 : KF);
-    __shared__ __align__(16) float s_sh[VIS_THREADS * STRIDE];
+    constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B are 16-byte aligned
     __shared__ uint32_t s_tile;
     const uint32_t nvis = ctl[CTL_COUNTERS + 0];
     const uint32_t num_tiles = (nvis + VIS_THREADS - 1) / VIS_THREADS;
-    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    float *wsh = s_sh + wid * 32 * STRIDE;
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&ctl[CTL_TICKETS + TK_VISIBLE], 1u);
         __syncthreads();
@@ -293,31 +291,21 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         if (tile >= num_tiles) break;
         const uint32_t cgid = tile * VIS_THREADS + threadIdx.x;
         const bool active = cgid < nvis;
-        const uint32_t gid = active ? __ldg(gid_sorted + cgid) : 0u;
-        // ---- stage SH rows (warp cooperative, coalesced inside each row)
-        {
-            const uint32_t warp_first = tile * VIS_THREADS + wid * 32;
-            const uint32_t rows = (warp_first < nvis) ? min(32u, nvis - warp_first) : 0u;
+        if (active) {
+            const uint32_t gid = __ldg(gid_sorted + cgid);
+            float coef[KF];
             if (VEC4) {
-                constexpr uint32_t R4 = KF / 4;
-                const uint32_t total4 = rows * R4;
-                float4 *wsh4 = reinterpret_cast<float4 *>(wsh);
-                for (uint32_t j = lane; j < ((total4 + 31u) & ~31u); j += 32) {
-                    uint32_t row = j / R4, c4 = j - row * R4;
-                    uint32_t g = __shfl_sync(0xffffffffu, gid, row & 31u);
-                    if (j < total4) wsh4[row * S4 + c4] = __ldg(reinterpret_cast<const float4 *>(sh + (size_t)g * KF) + c4);
+                const float4 *row4 = reinterpret_cast<const float4 *>(sh + (size_t)gid * KF);
+#pragma unroll
+                for (int i = 0; i < KF / 4; i++) {
+                    float4 q = __ldg(row4 + i);
+                    coef[4 * i] = q.x; coef[4 * i + 1] = q.y; coef[4 * i + 2] = q.z; coef[4 * i + 3] = q.w;
                 }
             } else {
-                const uint32_t total = rows * KF;
-                for (uint32_t j = lane; j < ((total + 31u) & ~31u); j += 32) {
-                    uint32_t row = j / KF, col = j - row * KF;
-                    uint32_t g = __shfl_sync(0xffffffffu, gid, row & 31u);
-                    if (j < total) wsh[row * STRIDE + col] = __ldg(sh + (size_t)g * KF + col);
-                }
+                const float *row = sh + (size_t)gid * KF;
+#pragma unroll
+                for (int i = 0; i < KF; i++) coef[i] = __ldg(row + i);
             }
-            __syncwarp();
-        }
-        if (active) {
             const float2 *t2 = reinterpret_cast<const float2 *>(transforms + (size_t)gid * 10);
             float2 a0 = __ldg(t2), a1 = __ldg(t2 + 1), a2 = __ldg(t2 + 2), a3 = __ldg(t2 + 3), a4 = __ldg(t2 + 4);
             V3 mean = mk3(a0.x, a0.y, a1.x);
@@ -333,19 +321,6 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             float mx, my;
             project_pinhole(mean_c, u, mx, my);
             V3 vdir = normalize(sub(mean, mk3(u.cam_pos[0], u.cam_pos[1], u.cam_pos[2])));
-            float coef[KF];
-            if (VEC4) {
-                const float4 *row4 = reinterpret_cast<const float4 *>(wsh) + lane * S4;
-#pragma unroll
-                for (int i = 0; i < KF / 4; i++) {
-                    float4 q = row4[i];
-                    coef[4 * i] = q.x; coef[4 * i + 1] = q.y; coef[4 * i + 2] = q.z; coef[4 * i + 3] = q.w;
-                }
-            } else {
-                const float *row = wsh + lane * STRIDE;
-#pragma unroll
-                for (int i = 0; i < KF; i++) coef[i] = row[i];
-            }
             V3 raw = sh_to_color<DEG>([&](int i) { return coef[i]; }, vdir);
             float cr = raw.x + 0.5f, cg = raw.y + 0.5f, cb = raw.z + 0.5f;
             cr = clampf(is_finite(cr) ? cr : 0.0f, -100.0f, 100.0f);

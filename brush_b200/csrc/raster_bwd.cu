@@ -73,39 +73,48 @@ __device__ __forceinline__ bool bwd_test(BwdPixel &p, float sigma, float opac, f
     return contrib;
 }
 
-// Adds one contributing pair's terms to the lane's partial sums g[0..9] and advances the pixel state.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Adds one pair's terms to the lane's partial sums g[0..9] and advances the pixel state.  Branch-free:
+// a pair that does not contribute (c == false) is multiplied out, so both pixels of a lane run the same
+// instruction stream.  cr/cg/cb = max(colour, 0); gr/gg/gb = 1 where the raw colour is >= 0 (the
+// colour VJP gate, rasterize_backwards.rs:335-337).
 template <bool SMOOTH>
-__device__ __forceinline__ void bwd_accumulate(BwdPixel &p, float *g, float dx, float dy, float ca, float cb, float cc,
-                                               float raw_r, float raw_g, float raw_b, float gaussian, float oa,
-                                               float alpha, float w_cut, float next_T, float img_wf, float img_hf) {
-    const float cr = fmaxf(raw_r, 0.0f), cg = fmaxf(raw_g, 0.0f), cbl = fmaxf(raw_b, 0.0f);
+__device__ __forceinline__ void bwd_accumulate(BwdPixel &p, float *g, bool c, float dx, float dy, float ca, float cb,
+                                               float cc, float cr, float cg, float cbl, float gr, float gg, float gb,
+                                               float gaussian, float oa, float alpha, float w_cut, float next_T,
+                                               float img_wf, float img_hf) {
+    const float wf = c ? 1.0f : 0.0f;
     const float alpha_eff = alpha * w_cut;
-    const float vis = alpha_eff * p.T;
-    g[5] += (raw_r >= 0.0f) ? vis * p.vo_r : 0.0f;
-    g[6] += (raw_g >= 0.0f) ? vis * p.vo_g : 0.0f;
-    g[7] += (raw_b >= 0.0f) ? vis * p.vo_b : 0.0f;
-    const float ra = __fdividef(1.0f, 1.0f - alpha_eff);
-    const float dot_rgb = ((p.T * cr - p.rem_r) * p.vo_r + (p.T * cg - p.rem_g) * p.vo_g + (p.T * cbl - p.rem_b) * p.vo_b) * ra;
-    const float v_alpha_eff = dot_rgb + p.vo_w * ra;
-    float v_alpha = v_alpha_eff;
-    if (SMOOTH) v_alpha = v_alpha_eff * (w_cut + alpha * cutoff_weight_deriv(alpha));
-    const float v_sigma = -alpha * v_alpha;
-    const float vxy_x = v_sigma * (ca * dx + cb * dy);
-    const float vxy_y = v_sigma * (cb * dx + cc * dy);
-    if (oa <= 0.999f) {
-        g[0] += vxy_x;
-        g[1] += vxy_y;
-        g[2] += 0.5f * v_sigma * dx * dx;
-        g[3] += v_sigma * dx * dy;
-        g[4] += 0.5f * v_sigma * dy * dy;
-        g[8] += v_alpha * gaussian;
-        const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
-        g[9] += sqrtf(sx * sx + sy * sy) * p.inv_fa;
-    }
-    p.rem_r -= vis * cr;
-    p.rem_g -= vis * cg;
-    p.rem_b -= vis * cbl;
-    p.T = next_T;
+    const float vis = alpha_eff * p.T * wf;
+    g[5] = fmaf(gr * vis, p.vo_r, g[5]);
+    g[6] = fmaf(gg * vis, p.vo_g, g[6]);
+    g[7] = fmaf(gb * vis, p.vo_b, g[7]);
+    const float ra = rcp_approx(1.0f - alpha_eff);
+    float dot = fmaf(p.T, cr, -p.rem_r) * p.vo_r;
+    dot = fmaf(fmaf(p.T, cg, -p.rem_g), p.vo_g, dot);
+    dot = fmaf(fmaf(p.T, cbl, -p.rem_b), p.vo_b, dot);
+    float v_alpha = (dot + p.vo_w) * ra * wf;
+    if (SMOOTH) v_alpha *= (w_cut + alpha * cutoff_weight_deriv(alpha));
+    // alpha-saturated pairs keep only the colour gradient (rasterize_backwards.rs:357-372)
+    const float v_alpha_g = (oa <= 0.999f) ? v_alpha : 0.0f;
+    const float v_sigma = -alpha * v_alpha_g;
+    const float vsx = v_sigma * dx, vsy = v_sigma * dy;
+    const float vxy_x = fmaf(ca, vsx, cb * vsy);
+    const float vxy_y = fmaf(cb, vsx, cc * vsy);
+    g[0] += vxy_x;
+    g[1] += vxy_y;
+    g[2] = fmaf(0.5f * vsx, dx, g[2]);
+    g[3] = fmaf(vsx, dy, g[3]);
+    g[4] = fmaf(0.5f * vsy, dy, g[4]);
+    g[8] = fmaf(v_alpha_g, gaussian, g[8]);
+    const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
+    g[9] = fmaf(sqrt_approx(fmaf(sx, sx, sy * sy)), p.inv_fa, g[9]);
+    p.rem_r = fmaf(-vis, cr, p.rem_r);
+    p.rem_g = fmaf(-vis, cg, p.rem_g);
+    p.rem_b = fmaf(-vis, cbl, p.rem_b);
+    p.T = c ? next_T : p.T;
 }
 
 template <bool SMOOTH>
@@ -199,8 +208,10 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
 #pragma unroll
             for (int i = 0; i < 10; i++) g[i] = 0.0f;
             const float col_b = row[8];
-            if (c0) bwd_accumulate<SMOOTH>(p0, g, dx, dy0, A.z, A.w, B.x, B.z, B.w, col_b, ga0, oa0, al0, wc0, nt0, img_wf, img_hf);
-            if (c1) bwd_accumulate<SMOOTH>(p1, g, dx, dy1, A.z, A.w, B.x, B.z, B.w, col_b, ga1, oa1, al1, wc1, nt1, img_wf, img_hf);
+            const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cbl = fmaxf(col_b, 0.0f);
+            const float gr = (B.z >= 0.0f) ? 1.0f : 0.0f, gg = (B.w >= 0.0f) ? 1.0f : 0.0f, gb = (col_b >= 0.0f) ? 1.0f : 0.0f;
+            bwd_accumulate<SMOOTH>(p0, g, c0, dx, dy0, A.z, A.w, B.x, cr, cg, cbl, gr, gg, gb, ga0, oa0, al0, wc0, nt0, img_wf, img_hf);
+            bwd_accumulate<SMOOTH>(p1, g, c1, dx, dy1, A.z, A.w, B.x, cr, cg, cbl, gr, gg, gb, ga1, oa1, al1, wc1, nt1, img_wf, img_hf);
             // ---- reduce-scatter 10 values over 32 lanes: 5+3+2+1+1 shuffles
             float a5[6];
 #pragma unroll

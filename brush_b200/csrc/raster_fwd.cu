@@ -143,8 +143,9 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
 #endif
                 if (__any_sync(0xffffffffu, c0 || c1)) {
                     const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cb = fmaxf(row[8], 0.0f);
-                    if (c0) { p0.r += cr * vis0; p0.g += cg * vis0; p0.b += cb * vis0; }
-                    if (c1) { p1.r += cr * vis1; p1.g += cg * vis1; p1.b += cb * vis1; }
+                    const float v0 = c0 ? vis0 : 0.0f, v1 = c1 ? vis1 : 0.0f;
+                    p0.r = fmaf(cr, v0, p0.r); p0.g = fmaf(cg, v0, p0.g); p0.b = fmaf(cb, v0, p0.b);
+                    p1.r = fmaf(cr, v1, p1.r); p1.g = fmaf(cg, v1, p1.g); p1.b = fmaf(cb, v1, p1.b);
                     used |= 1u << s;
                 }
                 if (__any_sync(0xffffffffu, st0 || st1) && __all_sync(0xffffffffu, p0.done && p1.done)) bits = 0;
