@@ -71,6 +71,9 @@ SIGNATURES = {
     "bg_inclusive_scan_u32": (_I32, [_P, _P, _P, _U32, _P]),
     "bg_image_loss_forward": (_I32, [_P, _P, _P, _P, _U32, _U32, _U32, _I64, _I64, _I64, _F, _F, C.POINTER(_F), _I32, _P]),
     "bg_image_loss_backward": (_I32, [_P, _P, _P, _P, _P, _U32, _U32, _U32, _I64, _I64, _I64, _F, _F, C.POINTER(_F), _I32, _P]),
+    "bg_image_loss_num_partials": (_U32, [_U32, _U32, _U32]),
+    "bg_image_loss_fused": (_I32, [_P, _P, _P, _P, _U32, _U32, _U32, _I64, _I64, _I64, _F, _F, C.POINTER(_F), _I32,
+                                   C.POINTER(_F), _P, _P]),
     "bg_adam_step": (_I32, [_P, _P, _P, _P, _P, _P, _U64, _U32, _P, _F, _F, _F, _F, _I32, _I32]),
     "bg_refine_stats_noise": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F]),
 }

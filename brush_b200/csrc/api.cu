@@ -43,6 +43,9 @@ cudaError_t launch_image_loss_fwd(cudaStream_t, const float *, const uint32_t *,
                                   int64_t, int64_t, float, float, const float *, bool, float *);
 cudaError_t launch_image_loss_bwd(cudaStream_t, const float *, const uint32_t *, const float *, uint32_t, uint32_t,
                                   uint32_t, int64_t, int64_t, int64_t, float, float, const float *, bool, float *);
+cudaError_t launch_image_loss_fused(cudaStream_t, const float *, const uint32_t *, uint32_t, uint32_t, uint32_t, int64_t,
+                                    int64_t, int64_t, float, float, const float *, bool, const float *, float *, float *);
+uint32_t image_loss_fused_num_partials(uint32_t, uint32_t, uint32_t);
 cudaError_t launch_adam(cudaStream_t, float *, const float *, float *, float *, uint64_t, uint32_t, const float *, float,
                         float, float, float, float, float, bool, bool);
 cudaError_t launch_refine_stats_noise(cudaStream_t, uint32_t, const float *, const float *, const float *, float *,
@@ -381,6 +384,22 @@ extern "C" int32_t bg_image_loss_backward(BgContext *c, void *stream, const floa
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(launch_image_loss_bwd((cudaStream_t)stream, pred, gt, dl_dmap, channels, h, w, sc, sy, sx, l1_w, ssim_w, bg,
                                   mask != 0, dl_dpred));
+    return BG_OK;
+}
+
+extern "C" uint32_t bg_image_loss_num_partials(uint32_t channels, uint32_t h, uint32_t w) {
+    return image_loss_fused_num_partials(channels, h, w);
+}
+
+extern "C" int32_t bg_image_loss_fused(BgContext *c, void *stream, const float *pred, const uint32_t *gt,
+                                       uint32_t channels, uint32_t h, uint32_t w, int64_t sc, int64_t sy, int64_t sx,
+                                       float l1_w, float ssim_w, const float *bg, int32_t mask,
+                                       const float *chain_per_channel, float *dl_dpred, float *loss_partials) {
+    if (!c || !pred || !gt || !chain_per_channel || !dl_dpred || !loss_partials) return BG_ERR_NULL;
+    if (channels < 3 || channels > 4 || h == 0 || w == 0) { set_err("image_loss expects 3 or 4 channels and a non-empty image", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_image_loss_fused((cudaStream_t)stream, pred, gt, channels, h, w, sc, sy, sx, l1_w, ssim_w, bg,
+                                    mask != 0, chain_per_channel, dl_dpred, loss_partials));
     return BG_OK;
 }
 

@@ -273,6 +273,210 @@ image_loss_bwd_kernel(LossArgs a, Taps taps, const float *__restrict__ dl_dmap, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused train-path kernel: loss value AND dL/dpred in one pass, for the case the trainer actually
+// runs (train.rs:254-260: loss = mean of the map, i.e. dL/dmap is one constant per channel).
+// Equivalent to image_loss_forward + mean + image_loss_backward, without materialising the loss map,
+// without re-blurring in a second kernel, and with 32x32 tiles: the (tile+halo)^2 / tile^2
+// recomputation factor of the separable window drops from 6.3 (16x16 tiles) to 3.9, and every
+// thread slides the 11-tap window over a run of outputs so each staged value is read once.
+// Window sums keep the reference's order (pairs d = 1..5, then the centre tap).
+// Per-block partial sums of the weighted map go to loss_partials (summed by the caller in a fixed
+// order, so the scalar is reproducible run to run).
+constexpr int FT = 32;            // tile edge
+constexpr int FE = FT + 4 * HALO; // 52: staged inputs
+constexpr int FP = FT + 2 * HALO; // 42: region where SSIM partials are needed
+constexpr int F_BUF_A = FE * FE * 2;      // inputs (pred, gt_eff); later chain*partials [FP*FP*3]
+constexpr int F_BUF_B = FE * FP * 5;      // first h-blur [FE rows][FP cols][5]; later second h-blur [FP][FT][3]
+constexpr int F_THREADS = 256;
+
+struct Chain4 { float c[4]; };
+
+__global__ void __launch_bounds__(F_THREADS, 3)
+image_loss_fused_kernel(LossArgs a, Taps taps, Chain4 chain, float *__restrict__ dl_dpred,
+                        float *__restrict__ loss_partials) {
+    extern __shared__ float f_smem[];
+    float *buf_a = f_smem, *buf_b = f_smem + F_BUF_A;
+    __shared__ float s_red[F_THREADS / 32];
+    const uint32_t c = blockIdx.z;
+    const int t = threadIdx.x;
+    const int tile_x0 = blockIdx.x * FT, tile_y0 = blockIdx.y * FT;
+    const int W = (int)a.w, H = (int)a.h;
+    auto out_at = [&](uint32_t ch, int y, int x) -> float & {
+        return dl_dpred[(int64_t)ch * a.sc + (int64_t)y * a.sy + (int64_t)x * a.sx];
+    };
+    float loss_acc = 0.0f;
+    const float chain_c = chain.c[c];
+    if (c == 3) {  // alpha-match channel: |pred.a - gt.a|, no window (lib.rs:215-227, 393-414)
+        for (int i = t; i < FT * FT; i += F_THREADS) {
+            int y = tile_y0 + i / FT, x = tile_x0 + i % FT;
+            if (x < W && y < H) {
+                float ga = ld_gt_a(a, y, x);
+                float diff = ld_pred(a, 3, y, x) - ga;
+                float v = fabsf(diff), ch = chain_c;
+                if (a.mask) { v *= ga; ch *= ga; }
+                loss_acc += v;
+                out_at(3, y, x) = (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f)) * ch;
+            }
+        }
+    } else {
+        const float bg_c = a.composite ? a.bg[c] : 0.0f;
+        // ---- P0: stage (pred, gt_eff) with a 2*HALO border, zero padded
+        for (int i = t; i < FE * FE; i += F_THREADS) {
+            int ly = i / FE, lx = i - ly * FE;
+            int gy = tile_y0 + ly - 2 * HALO, gx = tile_x0 + lx - 2 * HALO;
+            buf_a[i * 2] = ld_pred(a, c, gy, gx);
+            buf_a[i * 2 + 1] = ld_gt_eff(a, c, gy, gx, bg_c);
+        }
+        __syncthreads();
+        // ---- P1: horizontal window over FE rows x FP columns, 6 outputs per work item
+        for (int item = t; item < FE * 7; item += F_THREADS) {
+            const int row = item / 7, run = item - row * 7;
+            float2 v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = *reinterpret_cast<const float2 *>(&buf_a[(row * FE + run * 6 + k) * 2]);
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int d = 1; d <= 5; d++) {
+                    const float wd = taps.w[5 - d];
+                    const float2 l = v[j + 5 - d], r = v[j + 5 + d];
+                    BG_BLUR5_PAIR(o, l.x, l.y, r.x, r.y, wd)
+                }
+                const float2 cc = v[j + 5];
+                const float wc = taps.w[5];
+                o[0] += cc.x * wc; o[1] += cc.x * cc.x * wc; o[2] += cc.y * wc; o[3] += cc.y * cc.y * wc; o[4] += cc.x * cc.y * wc;
+                float *dst = &buf_b[(row * FP + run * 6 + j) * 5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) dst[k] = o[k];
+            }
+        }
+        __syncthreads();
+        // ---- P2: vertical window + SSIM partials on the FP x FP region, 6 rows per work item
+        for (int item = t; item < 7 * FP; item += F_THREADS) {
+            const int run = item / FP, px_ = item - run * FP;
+            float o[6][5];
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+#pragma unroll
+                for (int k = 0; k < 5; k++) o[j][k] = 0.0f;
+            // out[j] = sum_d w_d (in[j+5-d] + in[j+5+d]) + w_c in[j+5]; accumulate in the reference order by
+            // streaming the 16 input rows once per distance d (pairs) -- keep 16 rows x 5 in registers
+            float in[16][5];
+#pragma unroll
+            for (int r = 0; r < 16; r++)
+#pragma unroll
+                for (int k = 0; k < 5; k++) in[r][k] = buf_b[((run * 6 + r) * FP + px_) * 5 + k];
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+#pragma unroll
+                for (int d = 1; d <= 5; d++) {
+                    const float wd = taps.w[5 - d];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) o[j][k] += (in[j + 5 - d][k] + in[j + 5 + d][k]) * wd;
+                }
+#pragma unroll
+                for (int k = 0; k < 5; k++) o[j][k] += in[j + 5][k] * taps.w[5];
+            }
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const int py_ = run * 6 + j;
+                const float mu1 = o[j][0], mu2 = o[j][2];
+                const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
+                const float s1 = fmaxf(0.0f, o[j][1] - mu1_sq), s2 = fmaxf(0.0f, o[j][3] - mu2_sq);
+                const float s12 = o[j][4] - mu1 * mu2;
+                const float A = mu1_sq + mu2_sq + SSIM_C1, B = s1 + s2 + SSIM_C2;
+                const float c_top = 2.0f * mu1 * mu2 + SSIM_C1, d_top = 2.0f * s12 + SSIM_C2;
+                const float inv_ab = 1.0f / (A * B);
+                const float cd = c_top * d_top * inv_ab;
+                const bool clamped = cd < -1.0f || cd > 1.0f;
+                const float dmu1 = clamped ? 0.0f : 2.0f * mu2 * inv_ab * (d_top - c_top) - 2.0f * mu1 * cd * (1.0f / A - 1.0f / B);
+                const float ds1 = clamped ? 0.0f : -cd / B;
+                const float ds12 = clamped ? 0.0f : 2.0f * c_top * inv_ab;
+                const int gy = tile_y0 + py_ - HALO, gx = tile_x0 + px_ - HALO;
+                float ch = 0.0f;
+                if (gy >= 0 && gx >= 0 && gy < H && gx < W) {
+                    ch = chain_c;
+                    float ga = 1.0f;
+                    if (a.mask) { ga = ld_gt_a(a, gy, gx); ch *= ga; }
+                    // SSIM part of the loss value for the pixels this tile owns
+                    if (py_ >= HALO && py_ < HALO + FT && px_ >= HALO && px_ < HALO + FT)
+                        loss_acc += a.ssim_w * fminf(fmaxf(cd, -1.0f), 1.0f) * ga;
+                }
+                float *dst = &buf_a[(py_ * FP + px_) * 3];
+                dst[0] = dmu1 * ch; dst[1] = ds1 * ch; dst[2] = ds12 * ch;
+            }
+        }
+        __syncthreads();
+        // ---- P3: second horizontal window: FP rows x FT columns, 8 outputs per work item
+        for (int item = t; item < FP * 4; item += F_THREADS) {
+            const int row = item / 4, run = item - row * 4;
+            float v[18][3];
+#pragma unroll
+            for (int k = 0; k < 18; k++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) v[k][q] = buf_a[(row * FP + run * 8 + k) * 3 + q];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float o[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int d = 1; d <= 5; d++) {
+                    const float wd = taps.w[5 - d];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) o[q] += (v[j + 5 - d][q] + v[j + 5 + d][q]) * wd;
+                }
+#pragma unroll
+                for (int q = 0; q < 3; q++) o[q] += v[j + 5][q] * taps.w[5];
+                float *dst = &buf_b[(row * FT + run * 8 + j) * 3];
+                dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+            }
+        }
+        __syncthreads();
+        // ---- P4: second vertical window, L1 term, write dL/dpred: 4 pixels (one column segment) per thread
+        {
+            const int x = t & 31, y0 = (t >> 5) * 4;
+            float in[14][3];
+#pragma unroll
+            for (int r = 0; r < 14; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) in[r][q] = buf_b[((y0 + r) * FT + x) * 3 + q];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int gy = tile_y0 + y0 + j, gx = tile_x0 + x;
+                if (gy < H && gx < W) {
+                    float sm[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int d = 1; d <= 5; d++) {
+                        const float wd = taps.w[5 - d];
+#pragma unroll
+                        for (int q = 0; q < 3; q++) sm[q] += (in[j + 5 - d][q] + in[j + 5 + d][q]) * wd;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; q++) sm[q] += in[j + 5][q] * taps.w[5];
+                    const float p1 = ld_pred(a, c, gy, gx), ge = ld_gt_eff(a, c, gy, gx, bg_c);
+                    const float ssim_grad = sm[0] + (2.0f * p1) * sm[1] + ge * sm[2];
+                    const float diff = p1 - ge;
+                    const float l1_sign = diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f);
+                    float chc = chain_c, ga = 1.0f;
+                    if (a.mask) { ga = ld_gt_a(a, gy, gx); chc *= ga; }
+                    loss_acc += a.l1_w * fabsf(diff) * ga;
+                    out_at(c, gy, gx) = a.ssim_w * ssim_grad + a.l1_w * l1_sign * chc;
+                }
+            }
+        }
+    }
+    // ---- block sum of the map values (fixed order), one partial per block
+    for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+    if ((t & 31) == 0) s_red[t >> 5] = loss_acc;
+    __syncthreads();
+    if (t == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < F_THREADS / 32; i++) s += s_red[i];
+        loss_partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
+}
+
 static Taps make_taps() {
     // brush-loss/src/lib.rs:55-68: f32 arithmetic on the host, sigma = 1.5, normalised to sum 1.
     Taps t;
@@ -313,6 +517,25 @@ cudaError_t launch_image_loss_bwd(cudaStream_t s, const float *pred, const uint3
     image_loss_bwd_kernel<<<grid, block, 0, s>>>(make_args(pred, gt, h, w, sc, sy, sx, l1_w, ssim_w, bg, mask),
                                                  make_taps(), dl_dmap, dl_dpred);
     return cudaGetLastError();
+}
+
+cudaError_t launch_image_loss_fused(cudaStream_t s, const float *pred, const uint32_t *gt, uint32_t c, uint32_t h,
+                                    uint32_t w, int64_t sc, int64_t sy, int64_t sx, float l1_w, float ssim_w,
+                                    const float *bg, bool mask, const float *chain_per_channel, float *dl_dpred,
+                                    float *loss_partials) {
+    dim3 grid((w + FT - 1) / FT, (h + FT - 1) / FT, c), block(F_THREADS);
+    const size_t smem = (size_t)(F_BUF_A + F_BUF_B) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(image_loss_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    Chain4 ch;
+    for (uint32_t i = 0; i < 4; i++) ch.c[i] = i < c ? chain_per_channel[i] : 0.0f;
+    image_loss_fused_kernel<<<grid, block, smem, s>>>(make_args(pred, gt, h, w, sc, sy, sx, l1_w, ssim_w, bg, mask),
+                                                      make_taps(), ch, dl_dpred, loss_partials);
+    return cudaGetLastError();
+}
+
+uint32_t image_loss_fused_num_partials(uint32_t c, uint32_t h, uint32_t w) {
+    return ((w + FT - 1) / FT) * ((h + FT - 1) / FT) * c;
 }
 
 }  // namespace bg

@@ -41,45 +41,84 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
     }
 }
 
-// Row-reduced second moment.  One CTA handles ROWS rows: the g tile is staged in shared memory
-// (coalesced), one thread per row forms the row mean of g^2 in column order and updates v[row], then
-// all threads update m and p element-wise (coalesced).
+// Row-reduced second moment.  One CTA handles AR_ROWS rows: the g tile is staged in shared memory with
+// coalesced (128-bit when the tile allows) loads, four threads per row form the row mean of g^2 in a
+// fixed order (12-column partial sums in column order, then a two-step shuffle tree: deterministic, so
+// data-parallel ranks stay bit-identical), then all threads update m and p element-wise.
 constexpr int AR_ROWS = 64;
 
 __global__ void __launch_bounds__(256)
 adam_rowreduce_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                       float *__restrict__ v, uint64_t rows, uint32_t cols, const float *__restrict__ lr_scale,
                       AdamConsts k) {
-    extern __shared__ float s_g[];            // AR_ROWS * (cols | 1)
+    extern __shared__ __align__(16) float s_g[];   // AR_ROWS * cols (dense copy of the tile)
     __shared__ float s_v[AR_ROWS];
-    const uint32_t stride = cols | 1u;
     const uint64_t row0 = (uint64_t)blockIdx.x * AR_ROWS;
     const uint32_t nrows = (uint32_t)min((uint64_t)AR_ROWS, rows - row0);
     const uint64_t base = row0 * cols;
     const uint32_t total = nrows * cols;
-    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
-        uint32_t r = j / cols, c = j - r * cols;
-        s_g[r * stride + c] = __ldg(g + base + j);
+    const bool vec = ((base | total) & 3ull) == 0;   // tile start and length are multiples of 4 floats
+    if (vec) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(g + base);
+        float4 *s4 = reinterpret_cast<float4 *>(s_g);
+        for (uint32_t j = threadIdx.x; j < (total >> 2); j += blockDim.x) s4[j] = __ldg(g4 + j);
+    } else {
+        for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) s_g[j] = __ldg(g + base + j);
     }
     __syncthreads();
-    if (threadIdx.x < nrows) {
-        const float *gr = s_g + threadIdx.x * stride;
+    {   // 4 threads per row; partial sums over a quarter of the columns each, in column order
+        const uint32_t r = threadIdx.x >> 2, part = threadIdx.x & 3u;
         float s = 0.0f;
-        for (uint32_t c = 0; c < cols; c++) s += gr[c] * gr[c];
-        float mean_sq = s / (float)cols;
-        float vv = k.first ? mean_sq * k.f2 : v[row0 + threadIdx.x] * k.beta2 + mean_sq * k.f2;
-        v[row0 + threadIdx.x] = vv;
-        s_v[threadIdx.x] = vv;
+        if (r < nrows) {
+            const uint32_t per = (cols + 3u) >> 2;
+            const uint32_t c0 = part * per, c1 = min(cols, c0 + per);
+            const float *gr = s_g + r * cols;
+            for (uint32_t c = c0; c < c1; c++) s += gr[c] * gr[c];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0 && r < nrows) {
+            float mean_sq = s / (float)cols;
+            float vv = k.first ? mean_sq * k.f2 : v[row0 + r] * k.beta2 + mean_sq * k.f2;
+            v[row0 + r] = vv;
+            s_v[r] = vv;
+        }
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
-        uint32_t r = j / cols, c = j - r * cols;
-        float gg = s_g[r * stride + c];
-        uint64_t i = base + j;
-        float mm = k.first ? gg * k.f1 : m[i] * k.beta1 + gg * k.f1;
-        m[i] = mm;
-        float step = lr_scale ? __ldg(lr_scale + c) * k.lr : k.lr;
-        p[i] = adam_update(p[i], gg, mm, s_v[r], k, step);
+    if (vec && (cols & 3u) == 0) {
+        const uint32_t c4n = cols >> 2;
+        float4 *p4 = reinterpret_cast<float4 *>(p + base);
+        float4 *m4 = reinterpret_cast<float4 *>(m + base);
+        const float4 *s4 = reinterpret_cast<const float4 *>(s_g);
+        for (uint32_t j = threadIdx.x; j < (total >> 2); j += blockDim.x) {
+            const uint32_t r = j / c4n, c = (j - r * c4n) << 2;
+            const float4 gg = s4[j];
+            float4 mm = m4[j], pp = p4[j];
+            const float vv = s_v[r];
+            float st[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) st[q] = lr_scale ? __ldg(lr_scale + c + q) * k.lr : k.lr;
+            mm.x = k.first ? gg.x * k.f1 : mm.x * k.beta1 + gg.x * k.f1;
+            mm.y = k.first ? gg.y * k.f1 : mm.y * k.beta1 + gg.y * k.f1;
+            mm.z = k.first ? gg.z * k.f1 : mm.z * k.beta1 + gg.z * k.f1;
+            mm.w = k.first ? gg.w * k.f1 : mm.w * k.beta1 + gg.w * k.f1;
+            pp.x = adam_update(pp.x, gg.x, mm.x, vv, k, st[0]);
+            pp.y = adam_update(pp.y, gg.y, mm.y, vv, k, st[1]);
+            pp.z = adam_update(pp.z, gg.z, mm.z, vv, k, st[2]);
+            pp.w = adam_update(pp.w, gg.w, mm.w, vv, k, st[3]);
+            m4[j] = mm;
+            p4[j] = pp;
+        }
+    } else {
+        for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+            uint32_t r = j / cols, c = j - r * cols;
+            float gg = s_g[j];
+            uint64_t i = base + j;
+            float mm = k.first ? gg * k.f1 : m[i] * k.beta1 + gg * k.f1;
+            m[i] = mm;
+            float step = lr_scale ? __ldg(lr_scale + c) * k.lr : k.lr;
+            p[i] = adam_update(p[i], gg, mm, s_v[r], k, step);
+        }
     }
 }
 
@@ -90,8 +129,7 @@ cudaError_t launch_adam(cudaStream_t s, float *p, const float *g, float *m, floa
     k.lr = lr; k.beta1 = beta1; k.beta2 = beta2; k.eps = eps; k.f1 = 1.0f - beta1; k.f2 = 1.0f - beta2;
     k.bc1 = bc1; k.bc2 = bc2; k.first = first ? 1 : 0;
     if (reduce_v && cols > 1) {
-        const uint32_t stride = cols | 1u;
-        const size_t smem = (size_t)AR_ROWS * stride * sizeof(float);
+        const size_t smem = (size_t)AR_ROWS * cols * sizeof(float);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(adam_rowreduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

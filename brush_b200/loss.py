@@ -72,6 +72,30 @@ def image_loss_backward(ctx: RenderContext, pred_hwc: torch.Tensor, gt_packed: t
     return out_hwc
 
 
+def image_loss_fused(ctx: RenderContext, pred_hwc: torch.Tensor, gt_packed: torch.Tensor, channels: int,
+                     cfg: ImageLossConfig, chain_per_channel, out_hwc: Optional[torch.Tensor] = None):
+    """Train-path fusion (bg_image_loss_fused): for a loss that is a weighted mean of the map
+    (train.rs:254-260) returns (dL/dpred [h,w,c'], loss scalar tensor) in one kernel pass.
+    chain_per_channel[c] = dL/dmap of channel c; loss = sum_c chain[c] * sum(map[c])."""
+    lib = _lib.load()
+    h, w = pred_hwc.shape[0], pred_hwc.shape[1]
+    if gt_packed.shape != (h, w):
+        raise ValueError("gt_packed height/width must match pred")
+    sc, sy, sx = _strides_hwc(pred_hwc)
+    if out_hwc is None:
+        out_hwc = torch.zeros_like(pred_hwc) if pred_hwc.shape[2] > channels else torch.empty_like(pred_hwc)
+    n_part = int(lib.bg_image_loss_num_partials(channels, h, w))
+    partials = torch.empty((channels, n_part // channels), dtype=torch.float32, device=pred_hwc.device)
+    chain = (C.c_float * channels)(*[float(x) for x in chain_per_channel])
+    _lib.check(lib.bg_image_loss_fused(ctx.handle, _stream_ptr(ctx.device), pred_hwc.data_ptr(), gt_packed.data_ptr(),
+                                       channels, h, w, sc, sy, sx, cfg.l1_weight, cfg.ssim_weight, _bg_ptr(cfg),
+                                       int(cfg.mask), chain, out_hwc.data_ptr(), partials.data_ptr()),
+               "bg_image_loss_fused")
+    weights = torch.tensor([float(x) for x in chain_per_channel], dtype=torch.float32, device=pred_hwc.device)
+    loss = (partials.sum(dim=1) * weights).sum()
+    return out_hwc, loss
+
+
 class _ImageLoss(torch.autograd.Function):
     @staticmethod
     def forward(fctx, pred_hwc, gt_packed, ctx, channels, cfg):

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from .camera import Camera
-from .loss import ImageLossConfig, image_loss_backward, image_loss_forward
+from .loss import ImageLossConfig, image_loss_fused
 from .render import PASS_BACKWARD, RenderContext, _stream_ptr, project_bwd, rasterize_bwd, render_splats
 
 
@@ -114,6 +114,8 @@ class SplatTrainer:
         self.step_count = 0
         self.grad_hook = grad_hook  # called with the gradient tensors before Adam (DP all-reduce)
         self._state = None
+        self._v_output = None
+        self._v_output_ch = 0
         self._gen = torch.Generator(device=ctx.device)
         self._gen.manual_seed(config.seed)
         self._host_rng = np.random.default_rng(config.seed)
@@ -169,18 +171,14 @@ class SplatTrainer:
         composite = background if (batch.has_alpha and any(b != 0.0 for b in background)) else None
         lcfg = ImageLossConfig(l1_w, ssim_w, composite, batch.masked_alpha)
         channels = 4 if do_alpha_match else 3
-        loss_map = image_loss_forward(self.ctx, out.out_img, gt_packed, channels, lcfg)
-        # loss = mean over [h,w,3] (+ alpha mean * weight) (train.rs:254-260); dL/dmap is a constant per channel
+        # loss = mean over [h,w,3] (+ alpha mean * weight) (train.rs:254-260): dL/dmap is one constant per
+        # channel, so value and gradient come from the fused kernel in one pass.
         npx = float(img_h * img_w)
-        if do_alpha_match:
-            loss = loss_map[:3].mean() + loss_map[3].mean() * cfg.match_alpha_weight
-            dl = torch.empty((4, img_h, img_w), dtype=torch.float32, device=dev)
-            dl[:3] = 1.0 / (3.0 * npx)
-            dl[3] = cfg.match_alpha_weight / npx
-        else:
-            loss = loss_map.mean()
-            dl = torch.full((3, img_h, img_w), 1.0 / (3.0 * npx), dtype=torch.float32, device=dev)
-        v_output = image_loss_backward(self.ctx, out.out_img, gt_packed, dl, channels, lcfg)
+        chain = [1.0 / (3.0 * npx)] * 3 + ([cfg.match_alpha_weight / npx] if do_alpha_match else [])
+        if self._v_output is None or self._v_output.shape != out.out_img.shape or self._v_output_ch != channels:
+            self._v_output = torch.zeros_like(out.out_img)   # channel 3 stays zero unless alpha matching
+            self._v_output_ch = channels
+        v_output, loss = image_loss_fused(self.ctx, out.out_img, gt_packed, channels, lcfg, chain, self._v_output)
         v_combined = rasterize_bwd(out, v_output)
         v_t, v_sh, v_o, v_r = project_bwd(out, splats.transforms, splats.sh_coeffs, splats.raw_opacities, v_combined)
         if self.grad_hook is not None:

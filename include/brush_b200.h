@@ -159,6 +159,18 @@ int32_t bg_image_loss_backward(BgContext *ctx, void *stream, const float *pred, 
                                int64_t stride_c, int64_t stride_y, int64_t stride_x, float l1_weight,
                                float ssim_weight, const float *bg, int32_t mask, float *dl_dpred);
 
+/* Train-path fusion of the two calls above for a mean-reduced loss (brush-train/src/train.rs:254-260:
+ * loss = mean(map) [+ match_alpha_weight * mean(alpha map)], so dL/dmap is one constant per channel):
+ * writes dL/dpred and per-block partial sums of the loss map in ONE pass.  chain_per_channel: host
+ * float[channels] (= dL/dmap per channel).  loss_partials: device float[bg_image_loss_num_partials()];
+ * sum of partials of channel blocks = sum of that channel's map.  Partials are laid out channel-major:
+ * partials[ch * (n/channels) .. (ch+1) * (n/channels)). */
+uint32_t bg_image_loss_num_partials(uint32_t channels, uint32_t h, uint32_t w);
+int32_t bg_image_loss_fused(BgContext *ctx, void *stream, const float *pred, const uint32_t *gt_packed,
+                            uint32_t channels, uint32_t h, uint32_t w, int64_t stride_c, int64_t stride_y,
+                            int64_t stride_x, float l1_weight, float ssim_weight, const float *bg, int32_t mask,
+                            const float *chain_per_channel, float *dl_dpred, float *loss_partials);
+
 /* Replaces AdamScaled::step for one parameter tensor, brush-train/src/adam_scaled.rs:75-165.
  * p,g,m: [rows,cols]; v: [rows,cols], or [rows] when reduce_v (second moment = row mean of g^2).
  * lr_scale_per_col: device [cols] or null.  t: 1-based step count (t == 1 initialises the moments). */

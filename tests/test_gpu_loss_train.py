@@ -59,6 +59,30 @@ def test_image_loss_forward_backward(rt, h, w, channels, bg, mask):
         assert (gg[3] == 0).all()
 
 
+@pytest.mark.parametrize("h,w,channels,bg,mask", [(64, 64, 3, None, False), (45, 77, 3, None, False), (97, 130, 4, (0.2, 0.4, 0.6), False),
+                                                  (33, 31, 4, None, True), (200, 311, 3, None, False)])
+def test_image_loss_fused_matches_forward_mean_and_backward(rt, h, w, channels, bg, mask):
+    """bg_image_loss_fused == image_loss_forward -> weighted mean -> image_loss_backward (train.rs:238-260)."""
+    pred, packed = _case(h, w, 3 * h + w, alpha=channels == 4 or mask or bg is not None)
+    d = rt.ctx.device
+    cfg = rt.L.ImageLossConfig(0.8, -0.2, bg, mask)
+    tp = torch.from_numpy(pred).to(d)
+    tg = torch.from_numpy(packed.view(np.int32)).to(d)
+    npx = float(h * w)
+    chain = [1.0 / (3 * npx)] * 3 + ([0.1 / npx] if channels == 4 else [])
+    g, loss = rt.L.image_loss_fused(rt.ctx, tp, tg, channels, cfg, chain)
+    pred_chw = np.ascontiguousarray(pred.transpose(2, 0, 1)[:channels])
+    om = rt.orc.image_loss_forward(pred_chw, packed, 0.8, -0.2, bg=bg, mask=mask)
+    exp_loss = sum(chain[c] * om[c].astype(np.float64).sum() for c in range(channels))
+    assert abs(float(loss.item()) - exp_loss) <= 2e-5 * max(1.0, abs(exp_loss))
+    dl = np.stack([np.full((h, w), chain[c], np.float32) for c in range(channels)])
+    og = rt.orc.image_loss_backward(pred_chw, packed, dl, 0.8, -0.2, bg=bg, mask=mask)
+    gg = g.cpu().numpy().transpose(2, 0, 1)
+    assert np.abs(gg[:channels] - og).max() < 2e-5 * max(np.abs(og).max(), 1e-12)
+    if channels == 3:
+        assert (gg[3] == 0).all()
+
+
 def test_image_loss_chw_layout_equals_hwc(rt):
     """The reference feeds a CHW-permuted tensor (lib.rs:1076); strides make both layouts equivalent."""
     pred, packed = _case(48, 52, 7)

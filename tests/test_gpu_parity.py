@@ -283,3 +283,67 @@ def test_error_codes(rt):
                              torch.zeros(0, device=d), background=(0.25, 0.5, 0.75))
     img = out.out_img.cpu().numpy()
     assert out.num_visible == 0 and np.allclose(img[..., :3], [0.25, 0.5, 0.75]) and (img[..., 3] == 0).all()
+
+
+def _full_size_check(rt, n, w, h, scale_shift, seed):
+    """BASELINE.json full-size configs: direct oracle comparison (the C oracle needs only seconds even at
+    these sizes) plus size-independent properties of the intermediate structures."""
+    import brush_b200.render as R
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=16, seed=seed, scale_shift=scale_shift)
+    ctx = R.RenderContext(n, w, h, 0)
+    try:
+        d = ctx.device
+        ttr, tsh, top = (torch.from_numpy(x).to(d) for x in (tr, sh, op))
+        out = R.render_splats(ctx, cam, (w, h), ttr, tsh, top)
+        V, I = out.num_visible, out.num_intersections
+        assert out.intersection_overflow == 0
+        out.validate_counts()
+        # --- properties that hold at any size
+        depths = out.depths().cpu().numpy()
+        assert (np.diff(depths) >= 0).all(), "depth order"
+        tiles = _u32(out.tile_id_from_isect()).astype(np.int64)
+        assert (np.diff(tiles) >= 0).all(), "tile order"
+        cg = _u32(out.compact_gid_from_isect()).astype(np.int64)
+        same = tiles[1:] == tiles[:-1]
+        assert (np.diff(cg)[same] > 0).all(), "depth order inside every tile (stable tile sort)"
+        T = out.state.tiles_x * out.state.tiles_y
+        counts = np.bincount(tiles, minlength=T)
+        toff = _u32(out.tile_offsets()).reshape(-1, 2).astype(np.int64)
+        starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        nz = counts > 0
+        np.testing.assert_array_equal(toff[nz, 0], starts[nz])
+        assert ((toff[:, 1] - toff[:, 0]) <= counts).all() and ((toff[:, 1] >= toff[:, 0])).all()
+        gids = _u32(out.global_from_compact_gid()).astype(np.int64)
+        assert len(np.unique(gids)) == V and gids.max() < n
+        img = out.out_img.cpu().numpy()
+        assert np.isfinite(img).all() and img[..., 3].min() >= 0 and img[..., 3].max() <= 1.0
+        vis = out.visible.cpu().numpy()
+        assert set(np.unique(vis)) <= {0.0, 1.0} and vis[np.setdiff1d(np.arange(n), gids)].sum() == 0
+        # --- oracle
+        o = rt.orc.render_forward(rt.build_uniforms(cam, w, h), w, h, tr, sh, op)
+        _check_forward_exact(rt, out, o)
+        _img_close(img, o.out_img)
+        v_out = random_v_output(h, w)
+        _, ovt, ovsh, ovo, ovr = rt.orc.render_backward(o, v_out)
+        vc = R.rasterize_bwd(out, torch.from_numpy(v_out).to(d))
+        vt, vsh, vo, vr = R.project_bwd(out, ttr, tsh, top, vc)
+        for g, r, nm in ((vt, ovt, "v_transforms"), (vsh, ovsh, "v_sh"), (vo, ovo, "v_raw_opac"), (vr, ovr, "v_refine")):
+            g = g.cpu().numpy()
+            assert np.isfinite(g).all()
+            rel = np.linalg.norm(g.astype(np.float64) - r) / max(np.linalg.norm(r.astype(np.float64)), 1e-30)
+            assert rel <= 1e-3, f"{nm}: relative L2 {rel:.3e}"
+        return V, I
+    finally:
+        ctx.close()
+
+
+def test_full_size_config1_1m_1080p(rt):
+    """BASELINE.json configs[1]: 1M Gaussians, 1920x1080, forward + backward."""
+    V, I = _full_size_check(rt, 1_000_000, 1920, 1080, 0.0, 0xB2000001)
+    assert V > 900_000 and I > 5_000_000
+
+
+def test_full_size_config3_4m_4k(rt):
+    """BASELINE.json configs[3]: 4M Gaussians, 3840x2160 (log-scales + ln 2): sort / scan / blend stress."""
+    V, I = _full_size_check(rt, 4_000_000, 3840, 2160, math.log(2.0), 0xB2000003)
+    assert V > 3_600_000 and I > 20_000_000
