@@ -15,9 +15,11 @@ namespace bg {
 // project.cu
 cudaError_t launch_project_cull(cudaStream_t, int, bool, const float *, const float *, uint32_t, const BgCamera &,
                                 uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *, uint32_t *, float *,
-                                uint32_t *, unsigned long long *, uint32_t *, unsigned long long *, uint32_t);
+                                uint32_t *, unsigned long long *, uint32_t *, unsigned long long *, const uint32_t *,
+                                uint32_t);
 cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, const uint32_t *,
-                               uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *, unsigned long long *, uint32_t);
+                               uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *, unsigned long long *,
+                               const uint32_t *, uint32_t);
 cudaError_t launch_project_visible_emit(cudaStream_t, int, bool, int, const float *, const float *, const float *,
                                         const uint32_t *, const uint32_t *, const BgCamera &, uint32_t, uint32_t,
                                         float *, uint32_t *, uint32_t *, uint32_t, uint32_t *, const unsigned long long *,
@@ -28,7 +30,8 @@ cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, con
                               uint32_t *);
 cudaError_t launch_onesweep_pass(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *,
                                  uint32_t, const uint32_t *, uint32_t, uint32_t, const uint32_t *, uint32_t *,
-                                 unsigned long long *, uint32_t);
+                                 unsigned long long *, const uint32_t *, uint32_t);
+cudaError_t launch_bump_epoch(cudaStream_t, uint32_t *);
 uint32_t sort_tile_size();
 // raster_fwd.cu / raster_bwd.cu / project_bwd.cu
 cudaError_t launch_rasterize_fwd(cudaStream_t, bool, bool, uint32_t, const uint32_t *, uint32_t *, const float *,
@@ -73,7 +76,7 @@ struct BgContext {
     int sm_count = 0;
     uint32_t max_n = 0, max_w = 0, max_h = 0, max_tiles = 0;
     uint32_t max_isect = 0;
-    uint32_t epoch = 1;
+    uint32_t *epoch_dev = nullptr;          // device word: look-back epoch base, bumped on the stream per call
     uint64_t arena_bytes = 0;
     // device arena
     uint32_t *ctl = nullptr;               // CTL_WORDS u32 (forward pipeline), then CTL_WORDS (standalone ops)
@@ -93,11 +96,8 @@ struct BgContext {
     int depth_out = 0, isect_out = 0;
 };
 
-static uint32_t next_epoch(BgContext *c) {
-    c->epoch++;
-    if (c->epoch >= (1u << 30)) c->epoch = 1;  // words of 2^30 launches ago are long overwritten
-    return c->epoch;
-}
+// Launch indices inside one API call (each look-back chain of a call gets its own epoch).
+enum EpochSlots : uint32_t { EP_PROJECT = 0, EP_DEPTH_SORT = 1 /* ..4 */, EP_SCAN = 5, EP_TILE_SORT = 6 /* ..9 */ };
 
 extern "C" uint32_t bg_abi_version(void) { return BG_ABI_VERSION; }
 extern "C" const char *bg_last_error_string(void) { return g_err; }
@@ -116,7 +116,7 @@ extern "C" int32_t bg_ctx_destroy(BgContext *c) {
     cudaSetDevice(c->device);
     void *ptrs[] = {c->ctl, c->depth_key[0], c->depth_key[1], c->depth_val[0], c->depth_val[1], c->counts, c->cum,
                     c->cgid_from_gid, c->hit_masks, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
-                    c->tile_offsets, c->lb_scan, c->lb_sort};
+                    c->tile_offsets, c->lb_scan, c->lb_sort, c->epoch_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->counters_host) cudaFreeHost(c->counters_host);
@@ -162,11 +162,13 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
     ok = ok && arena_alloc(c, &c->tile_offsets, (uint64_t)c->max_tiles * 2) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->lb_scan, c->lb_scan_words) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->lb_sort, c->lb_sort_words) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->epoch_dev, 1) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&c->counters_host, 16 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
         ok = cudaMemset(c->lb_scan, 0, c->lb_scan_words * 8) == cudaSuccess &&
              cudaMemset(c->lb_sort, 0, c->lb_sort_words * 8) == cudaSuccess &&
-             cudaMemset(c->ctl, 0, 2 * CTL_WORDS * 4) == cudaSuccess;
+             cudaMemset(c->ctl, 0, 2 * CTL_WORDS * 4) == cudaSuccess &&
+             cudaMemset(c->epoch_dev, 0, 4) == cudaSuccess;
     }
     if (!ok) {
         set_err("bg_ctx_create: arena allocation", cudaGetLastError());
@@ -184,7 +186,8 @@ extern "C" uint64_t bg_ctx_arena_bytes(const BgContext *c) { return c ? c->arena
 // result lands in (keys[out_idx], vals[out_idx]) where out_idx is returned.  `hist` must be zero.
 static int32_t run_sort(BgContext *c, cudaStream_t s, const uint32_t *key_in, const uint32_t *val_in,
                         uint32_t *keys[2], uint32_t *vals[2], uint32_t n_host, const uint32_t *n_dev, uint32_t bits,
-                        uint32_t *hist, uint32_t *tickets /* [1 + passes] zeroed */, int first_dst, int *out_idx) {
+                        uint32_t *hist, uint32_t *tickets /* [1 + passes] zeroed */, int first_dst, uint32_t epoch_slot0,
+                        int *out_idx) {
     const uint32_t passes = (bits + 7) / 8;
     *out_idx = first_dst;
     if (passes == 0 || n_host == 0) return BG_OK;
@@ -195,7 +198,7 @@ static int32_t run_sort(BgContext *c, cudaStream_t s, const uint32_t *key_in, co
     for (uint32_t p = 0; p < passes; p++) {
         const uint32_t shift = p * 8, width = std::min(8u, bits - shift);
         BG_CUDA(launch_onesweep_pass(s, c->sm_count * 3, kin, vin, keys[dst], vals[dst], n_host, n_dev, shift, width,
-                                     hist + p * 256, tickets + 1 + p, c->lb_sort, next_epoch(c)));
+                                     hist + p * 256, tickets + 1 + p, c->lb_sort, c->epoch_dev, epoch_slot0 + p));
         kin = keys[dst]; vin = vals[dst];
         *out_idx = dst;
         dst ^= 1;
@@ -223,6 +226,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
 
+    BG_CUDA(launch_bump_epoch(s, c->epoch_dev));
     BG_CUDA(cudaMemsetAsync(c->ctl, 0, CTL_WORDS * sizeof(uint32_t), s));
     BG_CUDA(cudaMemsetAsync(c->tile_offsets, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
     if (bwd_info && n > 0) BG_CUDA(cudaMemsetAsync(visible, 0, (size_t)n * sizeof(float), s));
@@ -233,19 +237,19 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     // K1: cull + compaction in index order
     BG_CUDA(launch_project_cull(s, pgrid, mip != 0, transforms, raw_opac, n, *cam, w, h, tiles_x, tiles_y,
                                 c->depth_key[0], c->depth_val[0], c->counts, max_radius, c->cgid_from_gid, c->hit_masks, c->ctl,
-                                c->lb_scan, next_epoch(c)));
+                                c->lb_scan, c->epoch_dev, EP_PROJECT));
     // depth sort: 32-bit keys, 4 passes, (0)->(1)->(0)->(1)->(0)
     int dout = 0;
     {
         int32_t r = run_sort(c, s, c->depth_key[0], c->depth_val[0], c->depth_key, c->depth_val, n, counters + 0, 32,
-                             c->ctl + CTL_HIST_DEPTH, c->ctl + CTL_TICKETS + TK_DEPTH_HIST, 1, &dout);
+                             c->ctl + CTL_HIST_DEPTH, c->ctl + CTL_TICKETS + TK_DEPTH_HIST, 1, EP_DEPTH_SORT, &dout);
         if (r != BG_OK) return r;
     }
     c->depth_out = dout;
     const uint32_t *gid_sorted = c->depth_val[dout];
     // gather counts + inclusive scan -> cum, num_intersections
     BG_CUDA(launch_gather_scan(s, c->sm_count * 2, c->counts, gid_sorted, n, counters + 0, c->cum, counters + 1,
-                               c->max_isect, counters + 2, c->ctl + CTL_TICKETS + TK_SCAN, c->lb_scan, next_epoch(c)));
+                               c->max_isect, counters + 2, c->ctl + CTL_TICKETS + TK_SCAN, c->lb_scan, c->epoch_dev, EP_SCAN));
     // K2+K3
     if (n > 0)
         BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
@@ -260,7 +264,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
         const int first_dst = 1;
         int32_t r = run_sort(c, s, c->isect_key[0], c->isect_val[0], c->isect_key, c->isect_val, c->max_isect,
                              counters + 1, bits, c->ctl + CTL_HIST_TILE, c->ctl + CTL_TICKETS + TK_TILE_HIST, first_dst,
-                             &iout);
+                             EP_TILE_SORT, &iout);
         if (r != BG_OK) return r;
         (void)passes;
     }
@@ -328,6 +332,7 @@ extern "C" int32_t bg_radix_argsort_u32(BgContext *c, void *stream, const uint32
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
     uint32_t *ctl2 = c->ctl + CTL_WORDS;
+    BG_CUDA(launch_bump_epoch(s, c->epoch_dev));
     BG_CUDA(cudaMemsetAsync(ctl2, 0, CTL_WORDS * sizeof(uint32_t), s));
     const uint32_t passes = (bits + 7) / 8;
     if (passes == 0) {
@@ -344,7 +349,7 @@ extern "C" int32_t bg_radix_argsort_u32(BgContext *c, void *stream, const uint32
     const int first_dst = (passes & 1u) ? 0 : 1;  // so that the last pass writes into (keys_out, vals_out)
     int out_idx = 0;
     int32_t r = run_sort(c, s, keys, vals, kb, vb, n, n_dev, bits, ctl2 + CTL_HIST_DEPTH, ctl2 + CTL_TICKETS, first_dst,
-                         &out_idx);
+                         EP_DEPTH_SORT, &out_idx);
     if (r != BG_OK) return r;
     if (out_idx != 0) { set_err("internal: sort parity", cudaSuccess); return BG_ERR_INVALID; }
     return BG_OK;
@@ -358,9 +363,10 @@ extern "C" int32_t bg_inclusive_scan_u32(BgContext *c, void *stream, const uint3
     BG_CUDA(cudaSetDevice(c->device));
     if ((uint64_t)(n + 2047) / 2048 > c->lb_scan_words) { set_err("bg_inclusive_scan_u32: n exceeds context capacity", cudaSuccess); return BG_ERR_CAPACITY; }
     uint32_t *ctl2 = c->ctl + CTL_WORDS;
+    BG_CUDA(launch_bump_epoch(s, c->epoch_dev));
     BG_CUDA(cudaMemsetAsync(ctl2 + CTL_TICKETS, 0, 48 * sizeof(uint32_t), s));
     BG_CUDA(launch_gather_scan(s, c->sm_count * 2, in, nullptr, n, nullptr, out, nullptr, 0xFFFFFFFFu, nullptr,
-                               ctl2 + CTL_TICKETS, c->lb_scan, next_epoch(c)));
+                               ctl2 + CTL_TICKETS, c->lb_scan, c->epoch_dev, EP_SCAN));
     return BG_OK;
 }
 

@@ -132,7 +132,10 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
                     uint32_t *__restrict__ counts_by_gid, float *__restrict__ max_radius,
                     uint32_t *__restrict__ cgid_from_gid, unsigned long long *__restrict__ hit_masks,
                     uint32_t *__restrict__ ctl,
-                    unsigned long long *__restrict__ lb_state, uint32_t epoch) {
+                    unsigned long long *__restrict__ lb_state, const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
+    // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
+    // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
+    const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
     __shared__ __align__(16) float s_rows[PROJ_THREADS * 10];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile, s_prefix;
@@ -207,7 +210,10 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
                    uint32_t n_host, const uint32_t *__restrict__ n_dev, uint32_t *__restrict__ out,
                    uint32_t *__restrict__ total_out /* nullable */, uint32_t capacity,
                    uint32_t *__restrict__ overflow_flag /* nullable */, uint32_t *__restrict__ ticket,
-                   unsigned long long *__restrict__ lb_state, uint32_t epoch) {
+                   unsigned long long *__restrict__ lb_state, const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
+    // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
+    // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
+    const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile, s_prefix;
     const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
@@ -413,24 +419,24 @@ cudaError_t launch_project_cull(cudaStream_t s, int grid, bool mip, const float 
                                 uint32_t n, const BgCamera &u, uint32_t w, uint32_t h, uint32_t tx, uint32_t ty,
                                 uint32_t *depth_keys, uint32_t *gids, uint32_t *counts, float *max_radius,
                                 uint32_t *cgid_from_gid, unsigned long long *hit_masks, uint32_t *ctl,
-                                unsigned long long *lb, uint32_t epoch) {
+                                unsigned long long *lb, const uint32_t *epoch_base, uint32_t epoch_off) {
     if (n == 0) return cudaSuccess;
     if (mip)
         project_cull_kernel<true><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
-                                                                 gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch);
+                                                                 gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch_base, epoch_off);
     else
         project_cull_kernel<false><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
-                                                                  gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch);
+                                                                  gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch_base, epoch_off);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather_scan(cudaStream_t s, int grid, const uint32_t *in, const uint32_t *gather_idx,
                                uint32_t n_host, const uint32_t *n_dev, uint32_t *out, uint32_t *total_out,
                                uint32_t capacity, uint32_t *overflow_flag, uint32_t *ticket,
-                               unsigned long long *lb, uint32_t epoch) {
+                               unsigned long long *lb, const uint32_t *epoch_base, uint32_t epoch_off) {
     if (n_host == 0) return cudaSuccess;
     gather_scan_kernel<<<grid, SCAN_THREADS, 0, s>>>(in, gather_idx, n_host, n_dev, out, total_out, capacity,
-                                                     overflow_flag, ticket, lb, epoch);
+                                                     overflow_flag, ticket, lb, epoch_base, epoch_off);
     return cudaGetLastError();
 }
 

@@ -50,7 +50,10 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
                      const uint32_t *__restrict__ n_dev, uint32_t shift, uint32_t width,
                      const uint32_t *__restrict__ hist /* this pass: [256] */, uint32_t *__restrict__ ticket,
-                     unsigned long long *__restrict__ lb_state, uint32_t epoch) {
+                     unsigned long long *__restrict__ lb_state, const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
+    // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
+    // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
+    const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
     __shared__ uint32_t s_keys[SORT_TILE];
     __shared__ uint32_t s_vals[SORT_TILE];
     __shared__ uint32_t s_warp_hist[(SORT_THREADS / 32) * RADIX];
@@ -197,12 +200,20 @@ cudaError_t launch_radix_hist(cudaStream_t s, int grid, const uint32_t *keys, ui
 cudaError_t launch_onesweep_pass(cudaStream_t s, int grid, const uint32_t *keys_in, const uint32_t *vals_in,
                                  uint32_t *keys_out, uint32_t *vals_out, uint32_t n_host, const uint32_t *n_dev,
                                  uint32_t shift, uint32_t width, const uint32_t *hist, uint32_t *ticket,
-                                 unsigned long long *lb, uint32_t epoch) {
+                                 unsigned long long *lb, const uint32_t *epoch_base, uint32_t epoch_off) {
     onesweep_pass_kernel<<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift, width,
-                                                       hist, ticket, lb, epoch);
+                                                       hist, ticket, lb, epoch_base, epoch_off);
     return cudaGetLastError();
 }
 
 uint32_t sort_tile_size() { return SORT_TILE; }
 
+}  // namespace bg
+
+namespace bg {
+__global__ void bump_epoch_kernel(uint32_t *epoch_base) { *epoch_base = (*epoch_base + 1u) & 0x01FFFFFFu; }
+cudaError_t launch_bump_epoch(cudaStream_t s, uint32_t *epoch_base) {
+    bump_epoch_kernel<<<1, 1, 0, s>>>(epoch_base);
+    return cudaGetLastError();
+}
 }  // namespace bg

@@ -16,11 +16,35 @@ import torch
 import torch.distributed as dist
 
 
+class FlatGradients:
+    """One allocation holding v_transforms [n,10] | v_sh [n,k,3] | v_raw_opac [n]: project_bwd writes
+    straight into the views, the all-reduce runs once over `flat` with no packing copies."""
+
+    def __init__(self, n: int, k: int, device):
+        self.n, self.k = n, k
+        self.flat = torch.empty(n * (10 + 3 * k + 1), dtype=torch.float32, device=device)
+        o0, o1 = n * 10, n * 10 + n * 3 * k
+        self.v_t = self.flat[:o0].view(n, 10)
+        self.v_sh = self.flat[o0:o1].view(n, k, 3)
+        self.v_o = self.flat[o1:].view(n)
+        self.v_r = torch.empty(n, dtype=torch.float32, device=device)  # refine weight: MAX-reduced separately
+
+    def outputs(self):
+        return self.v_t, self.v_sh, self.v_o, self.v_r
+
+
 class ViewShardedReducer:
     def __init__(self, num_views_total: int, group=None):
         self.views = num_views_total
         self.group = group
         self._flat = None
+
+    def reduce_flat(self, fg: FlatGradients) -> None:
+        """In place on fg.flat: sum over ranks / views, ONE collective, no copies."""
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(fg.flat, op=dist.ReduceOp.SUM, group=self.group)
+        if self.views != 1:
+            fg.flat.mul_(1.0 / self.views)
 
     def _flat_buf(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
         total = sum(t.numel() for t in tensors)

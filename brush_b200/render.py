@@ -93,7 +93,10 @@ class RenderOutput:
     _event: torch.cuda.Event = field(default=None, repr=False)
 
     def _counters(self):
-        self._event.synchronize()
+        if self._event is not None:
+            self._event.synchronize()
+        else:  # rendered while a CUDA graph was being captured: the values belong to the latest replay
+            torch.cuda.synchronize(self.ctx.device)
         return self.state.counters_host
 
     @property
@@ -168,8 +171,10 @@ def render_splats(ctx: RenderContext, camera, img_size, transforms: torch.Tensor
                               out_img.data_ptr(), visible.data_ptr() if visible is not None else None,
                               max_radius.data_ptr(), C.byref(st)),
         "bg_render_forward")
-    ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream(dev))
+    ev = None
+    if not torch.cuda.is_current_stream_capturing():
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
     return RenderOutput(out_img=out_img, visible=visible, max_radius=max_radius, state=st, cam=cam, uniforms=uniforms,
                         background=tuple(float(b) for b in background), ctx=ctx, _event=ev)
 
@@ -194,8 +199,10 @@ def rasterize_bwd(out: RenderOutput, v_output: torch.Tensor, smooth_cutoff: Opti
     return v_combined
 
 
-def project_bwd(out: RenderOutput, transforms, sh_coeffs, raw_opacities, v_combined):
-    """SplatBwdOps::project_bwd (bwd/render_bwd.rs:102-171) -> (v_transforms, v_coeffs, v_raw_opac, v_refine_weight)."""
+def project_bwd(out: RenderOutput, transforms, sh_coeffs, raw_opacities, v_combined, outputs=None):
+    """SplatBwdOps::project_bwd (bwd/render_bwd.rs:102-171) -> (v_transforms, v_coeffs, v_raw_opac, v_refine_weight).
+    `outputs`: optional preallocated (v_t [n,10], v_sh [n,k,3], v_o [n], v_r [n]) -- e.g. views of one flat
+    buffer so that data-parallel training can all-reduce all gradients with a single collective."""
     lib = _lib.load()
     transforms = _f32c(transforms, "transforms")
     sh_coeffs = _f32c(sh_coeffs, "sh_coeffs")
@@ -203,10 +210,16 @@ def project_bwd(out: RenderOutput, transforms, sh_coeffs, raw_opacities, v_combi
     v_combined = _f32c(v_combined, "v_combined")
     dev = out.ctx.device
     n, k = int(out.state.n), int(out.state.k)
-    v_t = torch.empty((n, 10), dtype=torch.float32, device=dev)
-    v_sh = torch.empty((n, k, 3), dtype=torch.float32, device=dev)
-    v_o = torch.empty((n,), dtype=torch.float32, device=dev)
-    v_r = torch.empty((n,), dtype=torch.float32, device=dev)
+    if outputs is not None:
+        v_t, v_sh, v_o, v_r = outputs
+        for t_, shp in ((v_t, (n, 10)), (v_sh, (n, k, 3)), (v_o, (n,)), (v_r, (n,))):
+            if tuple(t_.shape) != shp or t_.dtype != torch.float32 or not t_.is_contiguous():
+                raise ValueError("project_bwd outputs must be contiguous float32 tensors of the documented shapes")
+    else:
+        v_t = torch.empty((n, 10), dtype=torch.float32, device=dev)
+        v_sh = torch.empty((n, k, 3), dtype=torch.float32, device=dev)
+        v_o = torch.empty((n,), dtype=torch.float32, device=dev)
+        v_r = torch.empty((n,), dtype=torch.float32, device=dev)
     _lib.check(
         lib.bg_project_backward(out.ctx.handle, _stream_ptr(dev), C.byref(out.cam), C.byref(out.state),
                                 transforms.data_ptr(), sh_coeffs.data_ptr(), raw_opacities.data_ptr(),

@@ -68,3 +68,14 @@ def test_reducer_single_process_is_scale_only():
     g = [torch.ones(4, 10), torch.ones(4, 2, 3) * 2, torch.ones(4) * 3]
     ViewShardedReducer(num_views_total=4).reduce_gradients(g)
     assert torch.allclose(g[0], torch.full((4, 10), 0.25)) and torch.allclose(g[2], torch.full((4,), 0.75))
+
+
+def test_flat_gradients_views_alias_one_buffer():
+    from brush_b200.dp import FlatGradients, ViewShardedReducer
+    fg = FlatGradients(5, 4, "cpu")
+    v_t, v_sh, v_o, v_r = fg.outputs()
+    v_t.fill_(1.0); v_sh.fill_(2.0); v_o.fill_(3.0)
+    assert fg.flat.numel() == 5 * (10 + 12 + 1)
+    assert fg.flat[:50].eq(1).all() and fg.flat[50:110].eq(2).all() and fg.flat[110:].eq(3).all()
+    ViewShardedReducer(num_views_total=2).reduce_flat(fg)
+    assert torch.allclose(v_sh, torch.full_like(v_sh, 1.0)) and torch.allclose(v_o, torch.full_like(v_o, 1.5))
