@@ -189,3 +189,28 @@ def test_train_step_first_update_matches_oracle(rt):
     close(splats.transforms.cpu().numpy()[:, 3:7], p_t[:, 3:7], vt[:, 3:7], 2e-3)
     close(splats.raw_opacities.cpu().numpy(), p_o, vo, 0.012)
     close(splats.sh_coeffs.cpu().numpy()[:, 0], p_sh.reshape(n, 4, 3)[:, 0], vsh[:, 0], 2e-3)
+
+
+def test_train_refine_train_cycle(rt):
+    """integration.rs:185-312 style: steps, a refine that changes N, more steps; everything stays finite and
+    the optimizer / refine-record state follows the new size."""
+    n, w, h = 20_000, 192, 128
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=4, seed=42)
+    op[:500] = -9.0  # dead splats: pruned at refine, budget re-used by splits
+    d = rt.ctx.device
+    tgt = rt.R.render_splats(rt.ctx, cam, (w, h), *(torch.from_numpy(x).to(d) for x in (tr, sh, op)), rpass=0)
+    gt = (tgt.out_img | (255 << 24)).clone()
+    splats = rt.T.Splats(*(torch.from_numpy(x.copy()).to(d) for x in (tr, sh + 0.1, op)))
+    trainer = rt.T.SplatTrainer(rt.T.TrainConfig(total_train_iters=1000, refine_every=5), rt.ctx, rt.T.bounds_from_pos(0.8, tr[:, :3]))
+    batch = rt.T.SceneBatch(img_packed=gt, camera=cam)
+    for _ in range(5):
+        trainer.step(batch, splats)
+    stats = trainer.refine(5, splats)
+    assert stats.num_pruned >= 500 and stats.total_splats == splats.num_splats()
+    assert stats.num_added > 0
+    for _ in range(5):
+        st = trainer.step(batch, splats)
+    assert np.isfinite(float(st.loss.item()))
+    for t in (splats.transforms, splats.sh_coeffs, splats.raw_opacities):
+        assert torch.isfinite(t).all() and t.shape[0] == stats.total_splats
+    assert trainer._state["m_t"].shape[0] == stats.total_splats
