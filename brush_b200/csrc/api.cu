@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 
@@ -220,6 +221,10 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
     const bool bwd_info = pass != BG_PASS_FORWARD;
     if (bwd_info && n > 0 && !visible) return BG_ERR_NULL;
+    if ((((uintptr_t)transforms) | ((uintptr_t)sh) | ((uintptr_t)raw_opac) | ((uintptr_t)out_img)) & 15u) {
+        set_err("bg_render_forward: arrays must be 16-byte aligned (bulk / 128-bit access)", cudaSuccess);
+        return BG_ERR_INVALID;
+    }
     const uint32_t tiles_x = (w + TILE_W - 1) / TILE_W, tiles_y = (h + TILE_W - 1) / TILE_W;
     const uint32_t num_tiles = tiles_x * tiles_y;
     if (n > c->max_n || num_tiles > c->max_tiles) { set_err("bg_render_forward: exceeds context capacity", cudaSuccess); return BG_ERR_CAPACITY; }

@@ -12,8 +12,8 @@
 //     them from the control block;
 //   * compaction of visible Gaussians is a single-pass decoupled look-back in index order --
 //     deterministic, unlike the reference's atomic slot (project_forward.rs:122-124);
-//   * the [n,10] AoS rows are staged through shared memory with 128-bit loads, the gathered SH
-//     rows with coalesced warp-cooperative loads, so every DRAM sector that is fetched is used.
+//   * the [n,10] AoS rows of a tile are staged with one TMA bulk copy (cp.async.bulk + mbarrier),
+//     double buffered; gathered rows (SH, transforms by sorted id) are read as whole 32-byte sectors.
 #include "bg_project.cuh"
 
 namespace bg {
@@ -136,29 +136,45 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
     // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
     // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
     const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
-    __shared__ __align__(16) float s_rows[PROJ_THREADS * 10];
+    // [n,10] AoS rows of a tile are one contiguous 10 KB block: staged with ONE TMA bulk copy
+    // (cp.async.bulk -> UBLKCP) completing on an mbarrier, double buffered so the next tile's rows land
+    // while this tile is processed.
+    __shared__ __align__(128) float s_rows_buf[2][PROJ_THREADS * 10];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_scan[33];
-    __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_tile, s_tile_next, s_prefix;
     __shared__ uint32_t s_hits[PROJ_THREADS];
     __shared__ unsigned long long s_mask[PROJ_THREADS];
     const uint32_t num_tiles = (n + PROJ_THREADS - 1) / PROJ_THREADS;
-    while (true) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl[CTL_TICKETS + TK_PROJECT], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= num_tiles) break;
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+    auto issue = [&](uint32_t t, uint32_t b) {  // thread 0: start the bulk copy of tile t into buffer b
+        const uint32_t tb = t * PROJ_THREADS;
+        const uint32_t bytes = (min((uint32_t)PROJ_THREADS, n - tb) * 40u) & ~15u;
+        mbar_expect_tx(&s_bar[b], bytes);
+        tma_bulk_g2s(s_rows_buf[b], transforms + (size_t)tb * 10, bytes, &s_bar[b]);
+    };
+    if (threadIdx.x == 0) {
+        uint32_t t = atomicAdd(&ctl[CTL_TICKETS + TK_PROJECT], 1u);
+        s_tile = t;
+        if (t < num_tiles) issue(t, 0);
+    }
+    __syncthreads();
+    uint32_t tile = s_tile, buf = 0, phase0 = 0, phase1 = 0;
+    while (tile < num_tiles) {
+        if (threadIdx.x == 0) {
+            uint32_t t = atomicAdd(&ctl[CTL_TICKETS + TK_PROJECT], 1u);
+            s_tile_next = t;
+            if (t < num_tiles) issue(t, buf ^ 1u);
+        }
         const uint32_t base = tile * PROJ_THREADS;
         const uint32_t rows = min((uint32_t)PROJ_THREADS, n - base);
-        // stage rows*10 floats: 128-bit loads for the bulk, scalar tail
-        {
-            const float *src = transforms + (size_t)base * 10;
-            const uint32_t nf = rows * 10, nv = nf >> 2;
-            const float4 *src4 = reinterpret_cast<const float4 *>(src);
-            float4 *dst4 = reinterpret_cast<float4 *>(s_rows);
-            for (uint32_t i = threadIdx.x; i < nv; i += PROJ_THREADS) dst4[i] = __ldg(src4 + i);
-            for (uint32_t i = (nv << 2) + threadIdx.x; i < nf; i += PROJ_THREADS) s_rows[i] = __ldg(src + i);
+        float *s_rows = s_rows_buf[buf];
+        if (buf == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&s_bar[1], phase1); phase1 ^= 1u; }
+        if (threadIdx.x == rows - 1) {  // the bulk copy moves whole 16-byte units: an odd row count leaves 8 bytes
+            const uint32_t nf = rows * 10, covered = ((rows * 40u) & ~15u) >> 2;
+            for (uint32_t i = covered; i < nf; i++) s_rows[i] = __ldg(transforms + (size_t)base * 10 + i);
         }
-        __syncthreads();
         const uint32_t gid = base + threadIdx.x;
         CullResult r;
         r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
@@ -196,7 +212,9 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             counts_by_gid[gid] = r.tiles;
             hit_masks[gid] = r.mask;
         }
-        __syncthreads();
+        tile = s_tile_next;
+        buf ^= 1u;
+        __syncthreads();  // everyone has read s_tile_next / s_prefix / this buffer before they are reused
     }
 }
 
