@@ -178,13 +178,26 @@ def main():
     v_out_host = torch.from_numpy(v_out_np).pin_memory()
     P = IMG_W * IMG_H
 
-    from brush_b200.dp import FlatGradients, ViewShardedReducer
-    fg = FlatGradients(N_SPLATS, SH_K, dev)          # gradients live in one flat buffer: one collective per step
+    from brush_b200.dp import FactoredGradients, FlatGradients, ShFactoredReducer, ViewShardedReducer
+    # N>1: view-sharded DP.  Default exchange is SH-factored (all-reduce 44 N B + all-gather 12 N B per rank and a
+    # local rebuild of v_sh); BG_DP_DENSE=1 selects the plain all-reduce of the dense (44+12K) N B gradient.
+    factored = world > 1 and os.environ.get("BG_DP_DENSE") is None
     reducer = ViewShardedReducer(num_views_total=world)
+    if factored:
+        fg = FactoredGradients(N_SPLATS, SH_K, world, dev)
+        fred = ShFactoredReducer(ctx, world)
+        cam_positions = [rank_camera(cam0, r).position for r in range(world)]
+        project_bwd = R.project_bwd_factored
+    else:
+        fg = FlatGradients(N_SPLATS, SH_K, dev)      # gradients live in one flat buffer: one collective per step
+        project_bwd = R.project_bwd
 
     def allreduce(g):
         if world > 1:
-            reducer.reduce_flat(fg)                   # SUM over ranks, 1/views scaling
+            if factored:
+                fred.reduce(fg, ttr, cam_positions)
+            else:
+                reducer.reduce_flat(fg)               # SUM over ranks, 1/views scaling
             reducer.reduce_stats(g[3], last_out[0].visible, last_out[0].max_radius)
 
     last_out = [None]
@@ -193,7 +206,7 @@ def main():
         out = R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top)
         last_out[0] = out
         vc = R.rasterize_bwd(out, v_out)
-        g = R.project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
+        g = project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
         allreduce(g)
         return out, g
 
@@ -215,8 +228,9 @@ def main():
             stage(i + 1)  # next step's upload overlaps this step's kernels
         last_out[0] = out
         vc = R.rasterize_bwd(out, vo)
-        g = R.project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
+        g = project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
         allreduce(g)
+        g = fg.gradients() if factored else g
         res = torch.stack([g[0].sum(), g[1].sum(), g[2].sum(), g[3].sum()])
         result_host[:4].copy_(res, non_blocking=True)  # D2H of the step's result
         return out
@@ -311,13 +325,14 @@ def main():
         "config": {"workload": WORKLOAD, "n_gaussians": N_SPLATS, "width": IMG_W, "height": IMG_H, "sh_k": SH_K,
                    "num_visible": V, "num_intersections": I, "splats_per_tile_mean": float(per_tile.mean()),
                    "splats_per_tile_max": int(per_tile.max()),
-                   "parallelism": "single GPU" if world == 1 else f"view-sharded dp{world}, one NCCL all-reduce of the dense gradients per step",
+                   "parallelism": "single GPU" if world == 1 else (f"view-sharded dp{world}, SH-factored exchange: all-reduce 44N B + all-gather 12N B/rank, v_sh rebuilt locally"
+                                                                           if factored else f"view-sharded dp{world}, one NCCL all-reduce of the dense gradients per step"),
                    "launch": "one CUDA graph replay per step" if graph is not None else "eager launches",
                    "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 33 MB images per step vs 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(v_out_host.numel() * 4), "d2h_bytes_per_step": 16 + 16,
                 "note": "upstream-gradient image uploaded from pinned host memory every step (double-buffered on a copy stream), "
                         "gradient checksums + counters read back; Gaussian parameters stay resident as in the reference trainer"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP + (1 if factored else 0)) * args.steps,
         "clocks": None,
         "roofline": {"bound": "hbm", "kernel": "rasterize_bwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -41,7 +41,9 @@ cudaError_t launch_rasterize_bwd(cudaStream_t, bool, uint32_t, const uint32_t *,
                                  const float *, const float *, float *, uint32_t, uint32_t, uint32_t, const float *);
 cudaError_t launch_project_bwd(cudaStream_t, bool, int, const float *, const float *, const float *,
                                const uint32_t *, const float *, uint32_t, const BgCamera &, float *, float *, float *,
-                               float *);
+                               float *, float *);
+cudaError_t launch_sh_grad_from_views(cudaStream_t, int, const float *, const float *, uint32_t, const float *, uint32_t,
+                                      float, float *);
 // loss.cu / optim.cu
 cudaError_t launch_image_loss_fwd(cudaStream_t, const float *, const uint32_t *, uint32_t, uint32_t, uint32_t, int64_t,
                                   int64_t, int64_t, float, float, const float *, bool, float *);
@@ -322,7 +324,36 @@ extern "C" int32_t bg_project_backward(BgContext *c, void *stream, const BgCamer
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,
-                               st->n, *cam, v_transforms, v_sh, v_raw_opac, v_refine));
+                               st->n, *cam, v_transforms, v_sh, v_raw_opac, v_refine, nullptr));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_project_backward_factored(BgContext *c, void *stream, const BgCamera *cam, const BgRenderState *st,
+                                                const float *transforms, const float *sh, const float *raw_opac,
+                                                const float *v_combined, float *v_transforms, float *v_color,
+                                                float *v_raw_opac, float *v_refine) {
+    if (!c || !cam || !st || !v_combined || !v_transforms || !v_color || !v_raw_opac || !v_refine) return BG_ERR_NULL;
+    if (st->n > 0 && (!transforms || !sh || !raw_opac)) return BG_ERR_NULL;
+    const int deg = sh_degree_from_k(st->k);
+    if (deg < 0) return BG_ERR_INVALID;
+    if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,
+                               st->n, *cam, v_transforms, nullptr, v_raw_opac, v_refine, v_color));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_sh_grad_from_views(BgContext *c, void *stream, uint32_t n, uint32_t k, const float *transforms,
+                                         const float *cam_positions, uint32_t views, const float *v_color_all,
+                                         float out_scale, float *v_sh) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!transforms || !cam_positions || !v_color_all || !v_sh) return BG_ERR_NULL;
+    const int deg = sh_degree_from_k(k);
+    if (deg < 0 || views == 0 || views > 16) { set_err("bg_sh_grad_from_views: k must be a square <= 25, 1 <= views <= 16", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_sh_grad_from_views((cudaStream_t)stream, deg, transforms, v_color_all, n, cam_positions, views, out_scale, v_sh));
     return BG_OK;
 }
 

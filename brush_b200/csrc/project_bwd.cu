@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(PB_THREADS)
 project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
                    const float *__restrict__ raw_opac, const uint32_t *__restrict__ cgid_from_gid,
                    const float *__restrict__ v_combined, uint32_t n, BgCamera u, float *__restrict__ v_transforms,
-                   float *__restrict__ v_sh, float *__restrict__ v_raw_opac, float *__restrict__ v_refine) {
+                   float *__restrict__ v_sh, float *__restrict__ v_raw_opac, float *__restrict__ v_refine,
+                   float *__restrict__ v_color_out /* nullable: factored mode, see sh_grad_from_views_kernel */) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int KF = K * 3;
     constexpr int STRIDE = (KF % 2 == 0) ? KF + 1 : KF;
@@ -275,14 +276,20 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         vt[7] = v_scale.x; vt[8] = v_scale.y; vt[9] = v_scale.z;
     }
     __syncthreads();  // all SH rows consumed; reuse the staging area for the gradient rows
+    const bool factored = v_color_out != nullptr;
     if (in_range) {
-        float *row = s_stage + threadIdx.x * STRIDE;
+        if (!factored) {
+            float *row = s_stage + threadIdx.x * STRIDE;
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            float yk = any ? Y[k] : 0.0f;
-            row[3 * k] = v_color.x * yk;
-            row[3 * k + 1] = v_color.y * yk;
-            row[3 * k + 2] = v_color.z * yk;
+            for (int k = 0; k < K; k++) {
+                float yk = any ? Y[k] : 0.0f;
+                row[3 * k] = v_color.x * yk;
+                row[3 * k + 1] = v_color.y * yk;
+                row[3 * k + 2] = v_color.z * yk;
+            }
+        } else {  // the SH gradient of one view is the outer product Y(dir) x v_color: ship only v_color
+            float *row = s_stage + threadIdx.x * 3;
+            row[0] = any ? v_color.x : 0.0f; row[1] = any ? v_color.y : 0.0f; row[2] = any ? v_color.z : 0.0f;
         }
 #pragma unroll
         for (int i = 0; i < 10; i++) s_vt[threadIdx.x * 10 + i] = vt[i];
@@ -291,26 +298,105 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
     }
     __syncthreads();
     {   // coalesced write-out of the dense gradient rows
-        float *dst = v_sh + (size_t)base * KF;
-        const uint32_t total = rows * KF;
-        for (uint32_t j = threadIdx.x; j < total; j += PB_THREADS) {
-            uint32_t r = j / KF, c = j - r * KF;
-            dst[j] = s_stage[r * STRIDE + c];
+        if (!factored) {
+            float *dst = v_sh + (size_t)base * KF;
+            const uint32_t total = rows * KF;
+            for (uint32_t j = threadIdx.x; j < total; j += PB_THREADS) {
+                uint32_t r = j / KF, c = j - r * KF;
+                dst[j] = s_stage[r * STRIDE + c];
+            }
+        } else {
+            float *dst = v_color_out + (size_t)base * 3;
+            for (uint32_t j = threadIdx.x; j < rows * 3; j += PB_THREADS) dst[j] = s_stage[j];
         }
         float *dt = v_transforms + (size_t)base * 10;
         for (uint32_t j = threadIdx.x; j < rows * 10; j += PB_THREADS) dt[j] = s_vt[j];
     }
 }
 
+// View-factored SH gradient for data-parallel training.  v_sh of ONE view is rank one per Gaussian:
+// v_sh[g,k,:] = Y_k(dir(mean_g, cam_v)) * v_color_v[g,:] (kernels/sh.rs:265-355).  Instead of all-reducing
+// the dense [n,K,3] tensor (192 B per Gaussian at K=16), ranks all-gather the 12-byte v_color rows of
+// their views and every rank rebuilds sum_v Y_k(dir_v) v_color_v locally, in view order (so all ranks
+// get bit-identical sums).  Exchange volume drops 16x for this tensor; the result equals the all-reduce
+// up to f32 summation order.
+struct ViewCams { float pos[16][3]; uint32_t count; };
+
+template <int DEG>
+__global__ void __launch_bounds__(PB_THREADS)
+sh_grad_from_views_kernel(const float *__restrict__ transforms, const float *__restrict__ v_color_all /* [views,n,3] */,
+                          uint32_t n, ViewCams cams, float out_scale, float *__restrict__ v_sh) {
+    constexpr int K = (DEG + 1) * (DEG + 1);
+    constexpr int KF = K * 3;
+    constexpr int STRIDE = (KF % 2 == 0) ? KF + 1 : KF;
+    __shared__ float s_stage[PB_THREADS * STRIDE];
+    const uint32_t base = blockIdx.x * PB_THREADS;
+    const uint32_t rows = min((uint32_t)PB_THREADS, n - base);
+    const uint32_t gid = base + threadIdx.x;
+    if (threadIdx.x < rows) {
+        float acc[KF];
+#pragma unroll
+        for (int i = 0; i < KF; i++) acc[i] = 0.0f;
+        const float *t = transforms + (size_t)gid * 10;
+        const V3 mean = mk3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
+        for (uint32_t v = 0; v < cams.count; v++) {
+            const float *vc = v_color_all + ((size_t)v * n + gid) * 3;
+            const float cr = __ldg(vc), cg = __ldg(vc + 1), cb = __ldg(vc + 2);
+            if (cr == 0.0f && cg == 0.0f && cb == 0.0f) continue;
+            V3 u_world = sub(mean, mk3(cams.pos[v][0], cams.pos[v][1], cams.pos[v][2]));
+            V3 vdir = scale(u_world, 1.0f / length(u_world));
+            float Y[K];
+            sh_basis<DEG>(vdir, Y);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                acc[3 * k] += cr * Y[k];
+                acc[3 * k + 1] += cg * Y[k];
+                acc[3 * k + 2] += cb * Y[k];
+            }
+        }
+        float *row = s_stage + threadIdx.x * STRIDE;
+#pragma unroll
+        for (int i = 0; i < KF; i++) row[i] = acc[i] * out_scale;
+    }
+    __syncthreads();
+    float *dst = v_sh + (size_t)base * KF;
+    const uint32_t total = rows * KF;
+    for (uint32_t j = threadIdx.x; j < total; j += PB_THREADS) {
+        uint32_t r = j / KF, c = j - r * KF;
+        dst[j] = s_stage[r * STRIDE + c];
+    }
+}
+
+cudaError_t launch_sh_grad_from_views(cudaStream_t s, int deg, const float *transforms, const float *v_color_all,
+                                      uint32_t n, const float *cam_pos_host, uint32_t views, float out_scale,
+                                      float *v_sh) {
+    if (n == 0) return cudaSuccess;
+    if (views > 16) return cudaErrorInvalidValue;
+    ViewCams cams;
+    cams.count = views;
+    for (uint32_t v = 0; v < views; v++)
+        for (int i = 0; i < 3; i++) cams.pos[v][i] = cam_pos_host[v * 3 + i];
+    const int grid = (int)((n + PB_THREADS - 1) / PB_THREADS);
+    switch (deg) {
+        case 0: sh_grad_from_views_kernel<0><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
+        case 1: sh_grad_from_views_kernel<1><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
+        case 2: sh_grad_from_views_kernel<2><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
+        case 3: sh_grad_from_views_kernel<3><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
+        case 4: sh_grad_from_views_kernel<4><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 template <bool MIP>
 static cudaError_t launch_pb_deg(cudaStream_t s, int deg, const float *transforms, const float *sh,
                                  const float *raw_opac, const uint32_t *cgid_from_gid, const float *v_combined,
                                  uint32_t n, const BgCamera &u, float *v_transforms, float *v_sh, float *v_raw_opac,
-                                 float *v_refine) {
+                                 float *v_refine, float *v_color_out) {
     const int grid = (int)((n + PB_THREADS - 1) / PB_THREADS);
 #define BG_LAUNCH_PB(D)                                                                                         \
     project_bwd_kernel<MIP, D><<<grid, PB_THREADS, 0, s>>>(transforms, sh, raw_opac, cgid_from_gid, v_combined, n, u, \
-                                                           v_transforms, v_sh, v_raw_opac, v_refine)
+                                                           v_transforms, v_sh, v_raw_opac, v_refine, v_color_out)
     switch (deg) {
         case 0: BG_LAUNCH_PB(0); break;
         case 1: BG_LAUNCH_PB(1); break;
@@ -326,12 +412,12 @@ static cudaError_t launch_pb_deg(cudaStream_t s, int deg, const float *transform
 cudaError_t launch_project_bwd(cudaStream_t s, bool mip, int deg, const float *transforms, const float *sh,
                                const float *raw_opac, const uint32_t *cgid_from_gid, const float *v_combined,
                                uint32_t n, const BgCamera &u, float *v_transforms, float *v_sh, float *v_raw_opac,
-                               float *v_refine) {
+                               float *v_refine, float *v_color_out) {
     if (n == 0) return cudaSuccess;
     return mip ? launch_pb_deg<true>(s, deg, transforms, sh, raw_opac, cgid_from_gid, v_combined, n, u, v_transforms,
-                                     v_sh, v_raw_opac, v_refine)
+                                     v_sh, v_raw_opac, v_refine, v_color_out)
                : launch_pb_deg<false>(s, deg, transforms, sh, raw_opac, cgid_from_gid, v_combined, n, u, v_transforms,
-                                      v_sh, v_raw_opac, v_refine);
+                                      v_sh, v_raw_opac, v_refine, v_color_out);
 }
 
 }  // namespace bg

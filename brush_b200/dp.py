@@ -33,6 +33,51 @@ class FlatGradients:
         return self.v_t, self.v_sh, self.v_o, self.v_r
 
 
+class FactoredGradients:
+    """Exchange buffers of the SH-factored scheme: `small` = v_transforms [n,10] | v_raw_opac [n] (all-reduced),
+    `v_color` [n,3] (this rank's view; all-gathered into `v_color_all` [views,n,3]), `v_sh` [n,k,3] (rebuilt
+    locally).  Per step a rank sends 44 n + 12 n bytes instead of (44 + 12 k) n."""
+
+    def __init__(self, n: int, k: int, views: int, device):
+        self.n, self.k, self.views = n, k, views
+        self.small = torch.empty(n * 11, dtype=torch.float32, device=device)
+        self.v_t = self.small[:n * 10].view(n, 10)
+        self.v_o = self.small[n * 10:].view(n)
+        self.v_color = torch.empty((n, 3), dtype=torch.float32, device=device)
+        self.v_color_all = torch.empty((views, n, 3), dtype=torch.float32, device=device)
+        self.v_sh = torch.empty((n, k, 3), dtype=torch.float32, device=device)
+        self.v_r = torch.empty(n, dtype=torch.float32, device=device)
+
+    def outputs(self):
+        """For render.project_bwd_factored(outputs=...)."""
+        return self.v_t, self.v_color, self.v_o, self.v_r
+
+    def gradients(self):
+        return self.v_t, self.v_sh, self.v_o, self.v_r
+
+
+class ShFactoredReducer:
+    """One view per rank.  all-reduce(small) + all-gather(v_color) + local rebuild of v_sh in view order, so
+    every rank ends with bit-identical gradients (a property a ring all-reduce also has, but here it follows
+    from the fixed summation order of bg_sh_grad_from_views)."""
+
+    def __init__(self, ctx, num_views_total: int, group=None):
+        self.ctx, self.views, self.group = ctx, num_views_total, group
+
+    def reduce(self, fg: FactoredGradients, transforms: torch.Tensor, cam_positions) -> None:
+        from .render import sh_grad_from_views
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi:
+            dist.all_gather_into_tensor(fg.v_color_all.view(-1), fg.v_color.view(-1), group=self.group)
+            dist.all_reduce(fg.small, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            fg.v_color_all[0].copy_(fg.v_color)
+        inv = 1.0 / self.views
+        sh_grad_from_views(self.ctx, transforms, fg.k, cam_positions, fg.v_color_all, inv, out=fg.v_sh)
+        if self.views != 1:
+            fg.small.mul_(inv)
+
+
 class ViewShardedReducer:
     def __init__(self, num_views_total: int, group=None):
         self.views = num_views_total

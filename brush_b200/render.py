@@ -228,6 +228,58 @@ def project_bwd(out: RenderOutput, transforms, sh_coeffs, raw_opacities, v_combi
     return v_t, v_sh, v_o, v_r
 
 
+def project_bwd_factored(out: RenderOutput, transforms, sh_coeffs, raw_opacities, v_combined, outputs=None):
+    """bg_project_backward_factored: project_bwd with the view's SH gradient left in its rank-one form.
+    Returns (v_transforms [n,10], v_color [n,3], v_raw_opac [n], v_refine_weight [n]); the dense
+    v_sh = Y(dir) x v_color is rebuilt by sh_grad_from_views after the views' v_color rows are gathered."""
+    lib = _lib.load()
+    transforms = _f32c(transforms, "transforms")
+    sh_coeffs = _f32c(sh_coeffs, "sh_coeffs")
+    raw_opacities = _f32c(raw_opacities, "raw_opacities")
+    v_combined = _f32c(v_combined, "v_combined")
+    dev = out.ctx.device
+    n = int(out.state.n)
+    if outputs is not None:
+        v_t, v_c, v_o, v_r = outputs
+        for t_, shp in ((v_t, (n, 10)), (v_c, (n, 3)), (v_o, (n,)), (v_r, (n,))):
+            if tuple(t_.shape) != shp or t_.dtype != torch.float32 or not t_.is_contiguous():
+                raise ValueError("project_bwd_factored outputs must be contiguous float32 tensors of the documented shapes")
+    else:
+        v_t = torch.empty((n, 10), dtype=torch.float32, device=dev)
+        v_c = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        v_o = torch.empty((n,), dtype=torch.float32, device=dev)
+        v_r = torch.empty((n,), dtype=torch.float32, device=dev)
+    _lib.check(
+        lib.bg_project_backward_factored(out.ctx.handle, _stream_ptr(dev), C.byref(out.cam), C.byref(out.state),
+                                         transforms.data_ptr(), sh_coeffs.data_ptr(), raw_opacities.data_ptr(),
+                                         v_combined.data_ptr(), v_t.data_ptr(), v_c.data_ptr(), v_o.data_ptr(),
+                                         v_r.data_ptr()),
+        "bg_project_backward_factored")
+    return v_t, v_c, v_o, v_r
+
+
+def sh_grad_from_views(ctx: RenderContext, transforms, k: int, cam_positions, v_color_all, out_scale: float = 1.0,
+                       out=None):
+    """bg_sh_grad_from_views: v_sh [n,k,3] = out_scale * sum_v Y(dir(mean, cam_positions[v])) x v_color_all[v].
+    cam_positions: sequence of `views` world-space camera positions; v_color_all: [views, n, 3]."""
+    lib = _lib.load()
+    transforms = _f32c(transforms, "transforms")
+    v_color_all = _f32c(v_color_all, "v_color_all")
+    views, n = int(v_color_all.shape[0]), int(v_color_all.shape[1])
+    pos = [float(x) for p in cam_positions for x in p]
+    if len(pos) != 3 * views:
+        raise ValueError("cam_positions must hold one xyz per view of v_color_all")
+    if out is None:
+        out = torch.empty((n, k, 3), dtype=torch.float32, device=transforms.device)
+    elif tuple(out.shape) != (n, k, 3) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 [n,k,3] tensor")
+    arr = (C.c_float * len(pos))(*pos)
+    _lib.check(lib.bg_sh_grad_from_views(ctx.handle, _stream_ptr(ctx.device), n, k, transforms.data_ptr(), arr, views,
+                                         v_color_all.data_ptr(), float(out_scale), out.data_ptr()),
+               "bg_sh_grad_from_views")
+    return out
+
+
 class RenderFunction(torch.autograd.Function):
     """Autograd glue: forward = render, backward = rasterize_bwd + project_bwd (bwd/burn_glue.rs:121-182).
     The refine weight gradient is returned through the `refine_weight_holder` input, as in the reference."""
