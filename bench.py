@@ -268,7 +268,9 @@ def main():
 
     # The step is ~20 short launches; replaying it as one CUDA graph removes the host launch gaps
     # (the library keeps nothing launch-specific on the host: counters and look-back epochs live on the device).
-    use_graph = world == 1 and os.environ.get("BG_BENCH_NO_GRAPH") is None
+    # N>1 runs eager: the step contains NCCL collectives.  Capturing them (BG_BENCH_GRAPH_DP=1) HUNG at N=2 when
+    # tried (two collectives on NCCL's internal stream inside one graph), so it stays an experiment, off by default.
+    use_graph = os.environ.get("BG_BENCH_NO_GRAPH") is None and (world == 1 or os.environ.get("BG_BENCH_GRAPH_DP", "0") == "1")
     graph = None
     if use_graph:
         try:

@@ -67,6 +67,9 @@ SIGNATURES = {
                                  C.POINTER(_F), _I32, _P, _P, _P, C.POINTER(BgRenderState)]),
     "bg_rasterize_backward": (_I32, [_P, _P, C.POINTER(BgRenderState), _P, _P, C.POINTER(_F), _I32, _P, _U32]),
     "bg_project_backward": (_I32, [_P, _P, C.POINTER(BgCamera), C.POINTER(BgRenderState), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bg_compute_min_scale": (_I32, [_P, _P, _U32, _P, _P, _U32, _F, _P]),
+    "bg_fold_min_scale_forward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),
+    "bg_fold_min_scale_backward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),
     "bg_project_backward_factored": (_I32, [_P, _P, C.POINTER(BgCamera), C.POINTER(BgRenderState), _P, _P, _P, _P, _P, _P, _P, _P]),
     "bg_sh_grad_from_views": (_I32, [_P, _P, _U32, _U32, _P, C.POINTER(_F), _U32, _P, _F, _P]),
     "bg_radix_argsort_u32": (_I32, [_P, _P, _P, _P, _U32, _P, _U32, _P, _P]),

@@ -42,6 +42,9 @@ cudaError_t launch_rasterize_bwd(cudaStream_t, bool, uint32_t, const uint32_t *,
 cudaError_t launch_project_bwd(cudaStream_t, bool, int, const float *, const float *, const float *,
                                const uint32_t *, const float *, uint32_t, const BgCamera &, float *, float *, float *,
                                float *, float *);
+cudaError_t launch_min_scale(cudaStream_t, uint32_t, const float *, const float *, uint32_t, float, float *);
+cudaError_t launch_fold_min_scale_fwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
+cudaError_t launch_fold_min_scale_bwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
 cudaError_t launch_sh_grad_from_views(cudaStream_t, int, const float *, const float *, uint32_t, const float *, uint32_t,
                                       float, float *);
 // loss.cu / optim.cu
@@ -485,5 +488,39 @@ extern "C" int32_t bg_refine_stats_noise(BgContext *c, void *stream, uint32_t n,
     BG_CUDA(launch_refine_stats_noise((cudaStream_t)stream, n, v_refine, visible, max_radius, refine_weight_norm,
                                       vis_weight, max_screen_size, transforms, raw_opac, noise, noise_scale,
                                       median_scale));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_compute_min_scale(BgContext *c, void *stream, uint32_t n, const float *transforms,
+                                        const float *view_cams, uint32_t views, float factor, float *f_out) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!transforms || !view_cams || !f_out) return BG_ERR_NULL;
+    if (views == 0 || !(factor > 0.0f)) { set_err("bg_compute_min_scale: needs views > 0 and factor > 0 (the reference returns None)", cudaSuccess); return BG_ERR_INVALID; }
+    if ((uintptr_t)view_cams % 16) { set_err("bg_compute_min_scale: view_cams must be 16-byte aligned", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_min_scale((cudaStream_t)stream, n, transforms, view_cams, views, factor, f_out));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_fold_min_scale_forward(BgContext *c, void *stream, uint32_t n, const float *transforms,
+                                             const float *raw_opac, const float *f, float *transforms_out,
+                                             float *raw_opac_out) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!transforms || !raw_opac || !f || !transforms_out || !raw_opac_out) return BG_ERR_NULL;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_fold_min_scale_fwd((cudaStream_t)stream, n, transforms, raw_opac, f, transforms_out, raw_opac_out));
+    return BG_OK;
+}
+
+extern "C" int32_t bg_fold_min_scale_backward(BgContext *c, void *stream, uint32_t n, const float *transforms,
+                                              const float *raw_opac, const float *f, float *v_transforms,
+                                              float *v_raw_opac) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!transforms || !raw_opac || !f || !v_transforms || !v_raw_opac) return BG_ERR_NULL;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_fold_min_scale_bwd((cudaStream_t)stream, n, transforms, raw_opac, f, v_transforms, v_raw_opac));
     return BG_OK;
 }

@@ -7,6 +7,8 @@
 //     and writes p,m,v (28 B/element, 20 B/element + 8 B/row when v is row-reduced).
 //   refine_stats_noise_kernel <- RefineRecord::gather_stats (brush-train/src/stats.rs:40-50) and the
 //       mean-noise update (brush-train/src/train.rs:389-416).
+//   min_scale_kernel / fold_min_scale_{fwd,bwd}_kernel <- compute_min_scale (train.rs:102-125) and
+//       fold_min_scale (brush-render/src/gaussian_splats.rs:86-111): the Mip-Splatting 3D filter floor.
 #include <algorithm>
 
 #include "bg_common.cuh"
@@ -177,6 +179,116 @@ cudaError_t launch_refine_stats_noise(cudaStream_t s, uint32_t n, const float *v
     const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n + 255) / 256, 148ull * 16);
     refine_stats_noise_kernel<<<grid, 256, 0, s>>>(n, v_refine, visible, max_radius, refine_norm, vis_weight, max_screen,
                                                    transforms, raw_opac, noise, noise_scale, median_scale);
+    return cudaGetLastError();
+}
+
+// f_i = sqrt(factor) * min_v(|mean_i - cam_v| / max(focal_v, 1e-6))      (train.rs:102-125)
+// cams: [views,4] = (x, y, z, focal_px) on the device.
+__global__ void __launch_bounds__(256)
+min_scale_kernel(uint32_t n, const float *__restrict__ transforms, const float *__restrict__ cams, uint32_t views,
+                 float sqrt_factor, float *__restrict__ f_out) {
+    __shared__ float4 s_cam[256];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (i < n) { mx = __ldg(transforms + (size_t)i * 10); my = __ldg(transforms + (size_t)i * 10 + 1); mz = __ldg(transforms + (size_t)i * 10 + 2); }
+    float best = 0.f;
+    bool have = false;
+    for (uint32_t base = 0; base < views; base += 256) {
+        const uint32_t cnt = min(256u, views - base);
+        __syncthreads();
+        if (threadIdx.x < cnt) s_cam[threadIdx.x] = __ldg(reinterpret_cast<const float4 *>(cams) + base + threadIdx.x);
+        __syncthreads();
+        for (uint32_t v = 0; v < cnt; v++) {
+            const float4 c = s_cam[v];
+            const float dx = mx - c.x, dy = my - c.y, dz = mz - c.z;
+            const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            const float ratio = dist / fmaxf(c.w, 1e-6f);
+            best = have ? fminf(best, ratio) : ratio;
+            have = true;
+        }
+    }
+    if (i < n) f_out[i] = best * sqrt_factor;
+}
+
+struct FoldTerms { float s2[3], s2f[3], coef, sig, opac; bool in_range; };
+
+__device__ __forceinline__ FoldTerms fold_terms(const float *ls, float raw, float f) {
+    FoldTerms t;
+    const float f2 = f * f;
+    float det1 = 1.f, det2 = 1.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        t.s2[a] = expf(2.0f * ls[a]);
+        t.s2f[a] = t.s2[a] + f2;
+    }
+    det1 = t.s2[0] * t.s2[1] * t.s2[2];
+    det2 = t.s2f[0] * t.s2f[1] * t.s2f[2];
+    t.coef = sqrtf(det1 / det2);
+    t.sig = 1.0f / (1.0f + expf(-raw));
+    const float o = t.sig * t.coef;
+    t.in_range = o >= 1e-6f && o <= 1.0f - 1e-6f;
+    t.opac = fminf(fmaxf(o, 1e-6f), 1.0f - 1e-6f);
+    return t;
+}
+
+// transforms_out may alias transforms (bake_min_scale, gaussian_splats.rs:245-252).
+__global__ void __launch_bounds__(256)
+fold_min_scale_fwd_kernel(uint32_t n, const float *transforms, const float *raw_opac, const float *__restrict__ f,
+                          float *transforms_out, float *raw_opac_out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float row[10];
+#pragma unroll
+        for (int c = 0; c < 10; c++) row[c] = transforms[(size_t)i * 10 + c];
+        const FoldTerms t = fold_terms(row + 7, raw_opac[i], __ldg(f + i));
+#pragma unroll
+        for (int a = 0; a < 3; a++) row[7 + a] = 0.5f * logf(t.s2f[a]);
+#pragma unroll
+        for (int c = 0; c < 10; c++) transforms_out[(size_t)i * 10 + c] = row[c];
+        raw_opac_out[i] = logf(t.opac / (1.0f - t.opac));
+    }
+}
+
+// Chain the gradients w.r.t. the folded (log-scale, raw opacity) back to the learned ones, in place:
+//   v_ls_a  = v_ls'_a * s2_a/(s2_a+f2) + v_coef * coef * f2/(s2_a+f2)
+//   v_raw   = v_opac * coef * sig (1-sig),   v_opac = v_raw' / (opac (1-opac)) inside the clamp, else 0
+//   v_coef  = v_opac * sig
+__global__ void __launch_bounds__(256)
+fold_min_scale_bwd_kernel(uint32_t n, const float *__restrict__ transforms, const float *__restrict__ raw_opac,
+                          const float *__restrict__ f, float *__restrict__ v_transforms, float *__restrict__ v_raw_opac) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float ls[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) ls[a] = __ldg(transforms + (size_t)i * 10 + 7 + a);
+        const float fi = __ldg(f + i);
+        const FoldTerms t = fold_terms(ls, __ldg(raw_opac + i), fi);
+        const float v_rawf = v_raw_opac[i];
+        const float v_opac = t.in_range ? v_rawf / (t.opac * (1.0f - t.opac)) : 0.0f;
+        const float v_coef = v_opac * t.sig;
+        v_raw_opac[i] = v_opac * t.coef * (t.sig * (1.0f - t.sig));
+        const float f2 = fi * fi;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float g = v_transforms[(size_t)i * 10 + 7 + a];
+            v_transforms[(size_t)i * 10 + 7 + a] = g * (t.s2[a] / t.s2f[a]) + v_coef * t.coef * (f2 / t.s2f[a]);
+        }
+    }
+}
+
+static unsigned grid_for(uint32_t n) { return (unsigned)std::min<uint64_t>(((uint64_t)n + 255) / 256, 148ull * 16); }
+
+cudaError_t launch_min_scale(cudaStream_t s, uint32_t n, const float *transforms, const float *cams, uint32_t views,
+                             float factor, float *f_out) {
+    min_scale_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, transforms, cams, views, sqrtf(factor), f_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_fold_min_scale_fwd(cudaStream_t s, uint32_t n, const float *transforms, const float *raw_opac,
+                                      const float *f, float *transforms_out, float *raw_opac_out) {
+    fold_min_scale_fwd_kernel<<<grid_for(n), 256, 0, s>>>(n, transforms, raw_opac, f, transforms_out, raw_opac_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_fold_min_scale_bwd(cudaStream_t s, uint32_t n, const float *transforms, const float *raw_opac,
+                                      const float *f, float *v_transforms, float *v_raw_opac) {
+    fold_min_scale_bwd_kernel<<<grid_for(n), 256, 0, s>>>(n, transforms, raw_opac, f, v_transforms, v_raw_opac);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,12 @@ provides memory, streams and (for N>1) torch.distributed.
                          without replacement runs on the GPU (seeded Efraimidis-Spirakis keys + top-k)
                          instead of a full host readback + rand::sample_weighted (multinomial.rs:1-26).
 
-Out of scope here: LPIPS, the Mip-Splatting 3D-filter floor (min_scale; needs the dataset's view list).
+  Splats.min_scale / set_view_cams <- the Mip-Splatting 3D-filter floor: compute_min_scale (train.rs:102-125),
+                         fold_min_scale / bake_min_scale (gaussian_splats.rs:86-111, 245-252); the floor is folded
+                         into scales/opacity for every render, its gradient chained back in place, baked at the
+                         start of refine() and recomputed at its end while progress < 0.9 (train.rs:437, 641-647).
+
+Out of scope here: LPIPS.
 """
 from __future__ import annotations
 
@@ -32,7 +37,8 @@ import torch
 from . import _lib
 from .camera import Camera
 from .loss import ImageLossConfig, image_loss_fused
-from .render import PASS_BACKWARD, RenderContext, _stream_ptr, project_bwd, rasterize_bwd, render_splats
+from .render import (PASS_BACKWARD, RenderContext, _stream_ptr, project_bwd, project_bwd_factored, rasterize_bwd,
+                     render_splats, sh_grad_from_views)
 
 
 @dataclass
@@ -66,9 +72,51 @@ class Splats:
     transforms: torch.Tensor      # [N,10]
     sh_coeffs: torch.Tensor       # [N,K,3]
     raw_opacities: torch.Tensor   # [N]
+    min_scale: Optional[torch.Tensor] = None   # [N] world-space scale floor (gaussian_splats.rs:73), a constant
 
     def num_splats(self) -> int:
         return self.transforms.shape[0]
+
+    def folded(self, ctx: RenderContext):
+        """(transforms, raw_opacities) as the renderer must see them (gaussian_splats.rs:212-223, 379-384)."""
+        if self.min_scale is None:
+            return self.transforms, self.raw_opacities
+        return fold_min_scale(ctx, self.transforms, self.raw_opacities, self.min_scale)
+
+    def bake_min_scale(self, ctx: RenderContext) -> None:
+        """Splats::bake_min_scale (gaussian_splats.rs:245-252): fold permanently, in place, and drop the floor."""
+        if self.min_scale is not None:
+            fold_min_scale(ctx, self.transforms, self.raw_opacities, self.min_scale, out=(self.transforms, self.raw_opacities))
+            self.min_scale = None
+
+
+def fold_min_scale(ctx: RenderContext, transforms, raw_opac, f, out=None):
+    lib = _lib.load()
+    n = transforms.shape[0]
+    t_out, o_out = out if out is not None else (torch.empty_like(transforms), torch.empty_like(raw_opac))
+    _lib.check(lib.bg_fold_min_scale_forward(ctx.handle, _stream_ptr(ctx.device), n, transforms.data_ptr(), raw_opac.data_ptr(),
+                                             f.data_ptr(), t_out.data_ptr(), o_out.data_ptr()), "bg_fold_min_scale_forward")
+    return t_out, o_out
+
+
+def fold_min_scale_backward(ctx: RenderContext, transforms, raw_opac, f, v_transforms, v_raw_opac) -> None:
+    """In place: gradients w.r.t. the folded values -> w.r.t. the learned ones."""
+    lib = _lib.load()
+    _lib.check(lib.bg_fold_min_scale_backward(ctx.handle, _stream_ptr(ctx.device), transforms.shape[0], transforms.data_ptr(),
+                                              raw_opac.data_ptr(), f.data_ptr(), v_transforms.data_ptr(),
+                                              v_raw_opac.data_ptr()), "bg_fold_min_scale_backward")
+
+
+def compute_min_scale(ctx: RenderContext, transforms, view_cams: torch.Tensor, factor: float) -> Optional[torch.Tensor]:
+    """compute_min_scale (train.rs:102-125).  view_cams: device [views,4] = (x, y, z, focal_px)."""
+    if factor <= 0.0 or view_cams is None or view_cams.shape[0] == 0:
+        return None
+    lib = _lib.load()
+    f = torch.empty(transforms.shape[0], dtype=torch.float32, device=transforms.device)
+    _lib.check(lib.bg_compute_min_scale(ctx.handle, _stream_ptr(ctx.device), transforms.shape[0], transforms.data_ptr(),
+                                        view_cams.data_ptr(), view_cams.shape[0], float(factor), f.data_ptr()),
+               "bg_compute_min_scale")
+    return f
 
 
 @dataclass
@@ -120,6 +168,8 @@ class RefineStats:
     total_splats: int
 
 
+MIN_SCALE_FREEZE_FRAC = 0.9   # train.rs:37
+MIN_SCALE_FACTOR = 0.1        # train.rs:44
 MIN_OPACITY = 1.0 / 255.0
 BOUND_PERCENTILE = 0.8
 FRAC_1_SQRT_2 = 0.7071067811865476
@@ -192,6 +242,14 @@ class SplatTrainer:
         self._gen = torch.Generator(device=ctx.device if ctx is not None else "cpu")
         self._gen.manual_seed(config.seed)
         self._host_rng = np.random.default_rng(config.seed)
+        self.view_cams: Optional[torch.Tensor] = None
+        self._views_buf = None
+
+    def set_view_cams(self, view_cams) -> None:
+        """train.rs:172-174.  view_cams: sequence of ((x, y, z), focal_px) of the training views."""
+        rows = [[float(c[0][0]), float(c[0][1]), float(c[0][2]), float(c[1])] for c in view_cams]
+        dev = self.ctx.device if self.ctx is not None else "cpu"
+        self.view_cams = torch.tensor(rows, dtype=torch.float32, device=dev).reshape(-1, 4) if rows else None
 
     # -- optimizer state (train.rs:300-326, adam_scaled.rs)
     def _ensure_state(self, s: Splats):
@@ -236,8 +294,9 @@ class SplatTrainer:
         background = self.sample_background()
         median_scale = self.bounds.median_size()
 
-        out = render_splats(self.ctx, batch.camera, (img_w, img_h), splats.transforms, splats.sh_coeffs,
-                            splats.raw_opacities, mip=cfg.render_mip, background=background, rpass=PASS_BACKWARD)
+        r_transforms, r_raw_opac = splats.folded(self.ctx)   # 3D-filter floor folded in (bwd/burn_glue.rs:260-270)
+        out = render_splats(self.ctx, batch.camera, (img_w, img_h), r_transforms, splats.sh_coeffs,
+                            r_raw_opac, mip=cfg.render_mip, background=background, rpass=PASS_BACKWARD)
         # loss config (train.rs:220-249)
         l1_w, ssim_w = (1.0 - cfg.ssim_weight, -cfg.ssim_weight) if self.ssim_enabled else (1.0, 0.0)
         do_alpha_match = batch.has_alpha and not batch.masked_alpha and cfg.match_alpha_weight > 0.0
@@ -253,30 +312,125 @@ class SplatTrainer:
             self._v_output_ch = channels
         v_output, loss = image_loss_fused(self.ctx, out.out_img, gt_packed, channels, lcfg, chain, self._v_output)
         v_combined = rasterize_bwd(out, v_output)
-        v_t, v_sh, v_o, v_r = project_bwd(out, splats.transforms, splats.sh_coeffs, splats.raw_opacities, v_combined)
+        v_t, v_sh, v_o, v_r = project_bwd(out, r_transforms, splats.sh_coeffs, r_raw_opac, v_combined)
+        if splats.min_scale is not None:
+            fold_min_scale_backward(self.ctx, splats.transforms, splats.raw_opacities, splats.min_scale, v_t, v_o)
         if self.grad_hook is not None:
             self.grad_hook((v_t, v_sh, v_o, v_r, out.visible, out.max_radius))
 
-        # learning rates (train.rs:328-350)
+        lr_mean = self._apply_updates(splats, v_t, v_sh, v_o, v_r, out.visible, out.max_radius, median_scale)
+        return TrainStepStats(num_visible_event=out, lr_mean=lr_mean, loss=loss)
+
+
+    # ------------------------------------------------------------------------------------------------
+    def step_views(self, batches: Sequence[SceneBatch], splats: Splats, group=None) -> TrainStepStats:
+        """One optimizer step over several views (BASELINE config [4]): the loss is the mean of the
+        per-view losses, i.e. the step equals accumulating the views' gradients sequentially on one GPU.
+        Under torch.distributed every rank passes ITS views (the same count on every rank); ranks exchange
+        the SH-factored gradients (dp.FactoredGradients: all-reduce 44 N B, all-gather 12 N B per view, v_sh
+        rebuilt locally in global view order), so all ranks apply bit-identical updates.  At most 16 views
+        per step in total."""
+        import torch.distributed as dist
+        cfg = self.config
+        self._ensure_state(splats)
+        st = self._state
+        self.step_count += 1
+        dev = self.ctx.device
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        world = dist.get_world_size(group) if multi else 1
+        local = len(batches)
+        views = local * world
+        if local == 0 or views > 16:
+            raise ValueError("step_views needs 1..16 views per step in total")
+        n, k = splats.num_splats(), splats.sh_coeffs.shape[1]
+        fb = self._views_buf
+        if fb is None or fb["n"] != n or fb["views"] != views or fb["local"] != local:
+            z = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+            fb = self._views_buf = dict(n=n, views=views, local=local, small=z(n * 11), tmp=z(n * 11), v_color=z(local, n, 3),
+                                        v_color_all=z(views, n, 3), v_sh=z(n, k, 3), v_r=z(n), v_r_acc=z(n), vis=z(n), rad=z(n),
+                                        cam_pos=z(views, 3))
+        small, tmp = fb["small"], fb["tmp"]
+        acc_t, acc_o = small[:n * 10].view(n, 10), small[n * 10:]
+        tmp_t, tmp_o = tmp[:n * 10].view(n, 10), tmp[n * 10:]
+        background = self.sample_background()          # shared seed: identical on every rank
+        median_scale = self.bounds.median_size()
+        r_transforms, r_raw_opac = splats.folded(self.ctx)
+        l1_w, ssim_w = (1.0 - cfg.ssim_weight, -cfg.ssim_weight) if self.ssim_enabled else (1.0, 0.0)
+        loss_sum = None
+        out = None
+        for i, batch in enumerate(batches):
+            img_h, img_w = batch.img_size()
+            gt_packed = batch.img_packed.to(dev, non_blocking=True)
+            out = render_splats(self.ctx, batch.camera, (img_w, img_h), r_transforms, splats.sh_coeffs, r_raw_opac,
+                                mip=cfg.render_mip, background=background, rpass=PASS_BACKWARD)
+            do_alpha_match = batch.has_alpha and not batch.masked_alpha and cfg.match_alpha_weight > 0.0
+            composite = background if (batch.has_alpha and any(b != 0.0 for b in background)) else None
+            lcfg = ImageLossConfig(l1_w, ssim_w, composite, batch.masked_alpha)
+            channels = 4 if do_alpha_match else 3
+            npx = float(img_h * img_w)
+            chain = [1.0 / (3.0 * npx)] * 3 + ([cfg.match_alpha_weight / npx] if do_alpha_match else [])
+            if self._v_output is None or self._v_output.shape != out.out_img.shape or self._v_output_ch != channels:
+                self._v_output = torch.zeros_like(out.out_img)
+                self._v_output_ch = channels
+            v_output, loss = image_loss_fused(self.ctx, out.out_img, gt_packed, channels, lcfg, chain, self._v_output)
+            loss_sum = loss if loss_sum is None else loss_sum + loss
+            v_combined = rasterize_bwd(out, v_output)
+            first = i == 0
+            project_bwd_factored(out, r_transforms, splats.sh_coeffs, r_raw_opac, v_combined,
+                                 outputs=(acc_t if first else tmp_t, fb["v_color"][i], acc_o if first else tmp_o,
+                                          fb["v_r_acc"] if first else fb["v_r"]))
+            if first:
+                fb["vis"].copy_(out.visible)
+                fb["rad"].copy_(out.max_radius)
+            else:                                       # gather_stats over the local views (stats.rs:40-50)
+                small.add_(tmp)
+                torch.maximum(fb["v_r_acc"], fb["v_r"], out=fb["v_r_acc"])
+                fb["vis"].add_(out.visible)
+                torch.maximum(fb["rad"], out.max_radius, out=fb["rad"])
+        # ---- exchange: global view index = rank * local + i
+        my_pos = torch.tensor([list(b.camera.position) for b in batches], dtype=torch.float32)
+        if multi:
+            dist.all_gather_into_tensor(fb["v_color_all"].view(-1), fb["v_color"].view(-1), group=group)
+            dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group)
+            mx = torch.stack([fb["v_r_acc"], fb["rad"]])
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+            fb["v_r_acc"].copy_(mx[0]); fb["rad"].copy_(mx[1])
+            dist.all_reduce(fb["vis"], op=dist.ReduceOp.SUM, group=group)
+            gathered = fb["cam_pos"]
+            dist.all_gather_into_tensor(gathered.view(-1), my_pos.to(dev).view(-1), group=group)
+            cam_positions = gathered.cpu().tolist()
+        else:
+            fb["v_color_all"].copy_(fb["v_color"])
+            cam_positions = my_pos.tolist()
+        inv = 1.0 / views
+        sh_grad_from_views(self.ctx, r_transforms, k, cam_positions, fb["v_color_all"], inv, out=fb["v_sh"])
+        if views != 1:
+            small.mul_(inv)
+        if splats.min_scale is not None:
+            fold_min_scale_backward(self.ctx, splats.transforms, splats.raw_opacities, splats.min_scale, acc_t, acc_o)
+        loss_mean = loss_sum * (1.0 / local)
+        lr_mean = self._apply_updates(splats, acc_t, fb["v_sh"], acc_o, fb["v_r_acc"], fb["vis"], fb["rad"], median_scale)
+        return TrainStepStats(num_visible_event=out, lr_mean=lr_mean, loss=loss_mean)
+
+    def _apply_updates(self, splats, v_t, v_sh, v_o, v_r, visible, max_radius, median_scale) -> float:
+        """Adam on the three parameter tensors, refine statistics, mean noise (train.rs:300-416)."""
+        cfg, st, dev = self.config, self._state, self.ctx.device
         lr_mean = cfg.lr_mean * self.lr_mean_decay ** (self.step_count - 1) * float(median_scale)
         lr_vals = np.array([lr_mean] * 3 + [cfg.lr_rotation] * 4 + [cfg.lr_scale] * 3, np.float32)
         st["t_lr"].copy_(torch.from_numpy(lr_vals), non_blocking=True)
         self._adam(splats.transforms, v_t, st["m_t"], st["v_t"], 1.0, st["t_lr"], False)
         self._adam(splats.sh_coeffs, v_sh, st["m_sh"], st["v_sh"], cfg.lr_coeffs_dc, st["sh_lr_scale"], True)
         self._adam(splats.raw_opacities, v_o, st["m_o"], st["v_o"], cfg.lr_opac, None, False)
-
-        # refine stats + noise on the updated opacities (train.rs:280-298, 389-416)
         n = splats.num_splats()
         noise = torch.randn((n, 3), dtype=torch.float32, device=dev, generator=self._gen)
         lib = _lib.load()
-        _lib.check(lib.bg_refine_stats_noise(self.ctx.handle, _stream_ptr(dev), n, v_r.data_ptr(), out.visible.data_ptr(),
-                                             out.max_radius.data_ptr(), st["refine_norm"].data_ptr(),
+        _lib.check(lib.bg_refine_stats_noise(self.ctx.handle, _stream_ptr(dev), n, v_r.data_ptr(), visible.data_ptr(),
+                                             max_radius.data_ptr(), st["refine_norm"].data_ptr(),
                                              st["vis_weight"].data_ptr(), st["max_screen"].data_ptr(),
                                              splats.transforms.data_ptr(), splats.raw_opacities.data_ptr(),
                                              noise.data_ptr(), float(np.float32(lr_mean) * np.float32(cfg.mean_noise_weight)),
                                              float(median_scale)), "bg_refine_stats_noise")
-        return TrainStepStats(num_visible_event=out, lr_mean=lr_mean, loss=loss)
-
+        return lr_mean
 
     # ------------------------------------------------------------------------------------------------
     def refine(self, iteration: int, splats: Splats) -> RefineStats:
@@ -287,6 +441,9 @@ class SplatTrainer:
             raise RuntimeError("Can only refine after optimizer is initialized")
         st = self._state
         dev = splats.transforms.device
+        # refine manipulates the canonical params: bake the current floor first (train.rs:432-437)
+        if splats.min_scale is not None:
+            splats.bake_min_scale(self.ctx)
         max_allowed = float(np.max(self.bounds.extent)) * 100.0
 
         # ---- prune mask (train.rs:487-535)
@@ -389,5 +546,9 @@ class SplatTrainer:
         splats.transforms = splats.transforms.contiguous()
         splats.sh_coeffs = splats.sh_coeffs.contiguous()
         splats.raw_opacities = splats.raw_opacities.contiguous()
+        # fresh 3D-filter floor against the new positions / count (train.rs:641-647)
+        progress = iteration / float(max(cfg.total_train_iters, 1))
+        if progress < MIN_SCALE_FREEZE_FRAC and self.view_cams is not None and self.ctx is not None:
+            splats.min_scale = compute_min_scale(self.ctx, splats.transforms, self.view_cams, MIN_SCALE_FACTOR)
         return RefineStats(num_added=refine_count, num_split_oversized=num_oversized, num_split_high_grad=num_high_grad,
                            num_pruned=pruned, num_pruned_non_finite=num_non_finite, total_splats=n_new)

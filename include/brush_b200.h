@@ -134,6 +134,27 @@ int32_t bg_project_backward(BgContext *ctx, void *stream, const BgCamera *cam, c
                             const float *v_combined, float *v_transforms, float *v_sh, float *v_raw_opac,
                             float *v_refine);
 
+/* Mip-Splatting 3D smoothing filter (scale floor).
+ * bg_compute_min_scale  <- compute_min_scale (brush-train/src/train.rs:102-125):
+ *     f[i] = sqrt(factor) * min_v(|mean_i - cam_v| / max(focal_v, 1e-6)); view_cams: DEVICE [views,4] =
+ *     (x, y, z, focal_px), 16-byte aligned.  views == 0 or factor <= 0 is BG_ERR_INVALID (the reference
+ *     returns None: the caller simply has no floor).
+ * bg_fold_min_scale_forward <- fold_min_scale (brush-render/src/gaussian_splats.rs:86-111): scales become
+ *     sqrt(s^2+f^2), opacity is multiplied by sqrt(det(s^2)/det(s^2+f^2)) and clamped to [1e-6, 1-1e-6];
+ *     outputs may alias the inputs (Splats::bake_min_scale, :245-252).
+ * bg_fold_min_scale_backward: what burn's autodiff derives for that fold.  IN PLACE: on entry
+ *     v_transforms[:,7:10] / v_raw_opac hold the gradients w.r.t. the FOLDED values (as written by
+ *     bg_project_backward on a render of the folded parameters), on exit w.r.t. the learned ones.
+ *     transforms / raw_opac are the learned (un-folded) parameters; f is a constant. */
+int32_t bg_compute_min_scale(BgContext *ctx, void *stream, uint32_t n, const float *transforms,
+                             const float *view_cams, uint32_t views, float factor, float *f_out);
+int32_t bg_fold_min_scale_forward(BgContext *ctx, void *stream, uint32_t n, const float *transforms,
+                                  const float *raw_opac, const float *f, float *transforms_out,
+                                  float *raw_opac_out);
+int32_t bg_fold_min_scale_backward(BgContext *ctx, void *stream, uint32_t n, const float *transforms,
+                                   const float *raw_opac, const float *f, float *v_transforms,
+                                   float *v_raw_opac);
+
 /* View-sharded data parallelism (the reference is single-device).  The SH part of the
  * gradient of ONE view is rank one per Gaussian: v_sh[g,k,:] = Y_k(dir(mean_g, camera)) * v_color[g,:]
  * (kernels/sh.rs:265-355).  bg_project_backward_factored is bg_project_backward without the dense v_sh:

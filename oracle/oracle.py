@@ -86,6 +86,12 @@ def lib():
         L.orc_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
         L.orc_adam_step.restype = None
+        L.orc_compute_min_scale.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p]
+        L.orc_compute_min_scale.restype = None
+        L.orc_fold_min_scale_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_fold_min_scale_fwd.restype = None
+        L.orc_fold_min_scale_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_fold_min_scale_bwd.restype = None
         L.orc_expf_det.argtypes = [C.c_float]
         L.orc_expf_det.restype = C.c_float
         L.orc_logf_det.argtypes = [C.c_float]
@@ -250,6 +256,30 @@ def adam_step(p, g, m, v, lr, t, lr_scale_per_col=None, beta1=0.9, beta2=0.999, 
         assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
     s = _f32(lr_scale_per_col) if lr_scale_per_col is not None else None
     lib().orc_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), rows, cols, _ptr(s), lr, beta1, beta2, eps, t, int(reduce_v))
+
+
+def compute_min_scale(transforms, view_cams, factor):
+    """compute_min_scale (train.rs:102-125).  view_cams: [views,4] = x, y, z, focal_px."""
+    t, c = _f32(transforms), _f32(view_cams).reshape(-1, 4)
+    out = np.empty(t.shape[0], dtype=np.float32)
+    lib().orc_compute_min_scale(_ptr(t), t.shape[0], _ptr(c), c.shape[0], factor, _ptr(out))
+    return out
+
+
+def fold_min_scale(transforms, raw_opac, f):
+    """fold_min_scale (gaussian_splats.rs:86-111) -> (transforms', raw_opac')."""
+    t, o, ff = _f32(transforms), _f32(raw_opac), _f32(f)
+    to, oo = np.empty_like(t), np.empty_like(o)
+    lib().orc_fold_min_scale_fwd(_ptr(t), _ptr(o), _ptr(ff), t.shape[0], _ptr(to), _ptr(oo))
+    return to, oo
+
+
+def fold_min_scale_backward(transforms, raw_opac, f, v_transforms_folded, v_raw_opac_folded):
+    """Reverse-mode chain of fold_min_scale -> (v_transforms, v_raw_opac) w.r.t. the learned parameters."""
+    t, o, ff = _f32(transforms), _f32(raw_opac), _f32(f)
+    vt, vo = _f32(v_transforms_folded).copy(), _f32(v_raw_opac_folded).copy()
+    lib().orc_fold_min_scale_bwd(_ptr(t), _ptr(o), _ptr(ff), t.shape[0], _ptr(vt), _ptr(vo))
+    return vt, vo
 
 
 def expf_det(x: float) -> float:

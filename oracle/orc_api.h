@@ -88,6 +88,16 @@ void orc_adam_step(float *p, const float *g, float *m, float *v, uint64_t rows, 
                    const float *lr_scale_per_col, float lr, float beta1, float beta2, float eps, int t,
                    int reduce_v);
 
+/* Mip-Splatting 3D filter floor: compute_min_scale (brush-train/src/train.rs:102-125), fold_min_scale
+ * (brush-render/src/gaussian_splats.rs:86-111) and the reverse-mode chain of the fold (in place on the
+ * gradients w.r.t. the folded values).  view_cams: [views,4] = x, y, z, focal_px. */
+void orc_compute_min_scale(const float *transforms, uint32_t n, const float *view_cams, uint32_t views, float factor,
+                           float *f_out);
+void orc_fold_min_scale_fwd(const float *transforms, const float *raw_opac, const float *f, uint32_t n,
+                            float *transforms_out, float *raw_opac_out);
+void orc_fold_min_scale_bwd(const float *transforms, const float *raw_opac, const float *f, uint32_t n,
+                            float *v_transforms, float *v_raw_opac);
+
 float orc_expf_det(float x);
 float orc_logf_det(float x);
 int orc_num_threads(void);

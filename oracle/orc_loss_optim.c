@@ -291,3 +291,79 @@ void orc_adam_step(float *p, const float *g, float *m, float *v, uint64_t rows, 
         }
     }
 }
+
+/* ---- Mip-Splatting 3D filter floor ------------------------------------------------------------
+ * orc_compute_min_scale follows compute_min_scale (brush-train/src/train.rs:102-125);
+ * orc_fold_min_scale_fwd follows fold_min_scale (brush-render/src/gaussian_splats.rs:86-111) op by op;
+ * orc_fold_min_scale_bwd is the reverse-mode chain of those ops, written out un-simplified (one
+ * statement per burn op), i.e. what burn's autodiff evaluates.  view_cams: [views,4] = x,y,z,focal. */
+void orc_compute_min_scale(const float *transforms, uint32_t n, const float *view_cams, uint32_t views, float factor,
+                           float *f_out) {
+    const float sf = sqrtf(factor);
+#pragma omp parallel for schedule(static)
+    for (uint32_t i = 0; i < n; i++) {
+        const float *t = transforms + (size_t)i * 10;
+        float best = 0.0f;
+        for (uint32_t v = 0; v < views; v++) {
+            const float *c = view_cams + (size_t)v * 4;
+            float dx = t[0] - c[0], dy = t[1] - c[1], dz = t[2] - c[2];
+            float dist = sqrtf((dx * dx + dy * dy) + dz * dz);
+            float ratio = dist / fmaxf(c[3], 1e-6f);
+            best = (v == 0) ? ratio : fminf(best, ratio);
+        }
+        f_out[i] = best * sf;
+    }
+}
+
+void orc_fold_min_scale_fwd(const float *transforms, const float *raw_opac, const float *f, uint32_t n,
+                            float *transforms_out, float *raw_opac_out) {
+#pragma omp parallel for schedule(static)
+    for (uint32_t i = 0; i < n; i++) {
+        const float *t = transforms + (size_t)i * 10;
+        float *o = transforms_out + (size_t)i * 10;
+        float f2 = f[i] * f[i];
+        float s2[3], s2f[3];
+        for (int a = 0; a < 3; a++) { s2[a] = expf(t[7 + a] * 2.0f); s2f[a] = s2[a] + f2; }
+        for (int c = 0; c < 7; c++) o[c] = t[c];
+        for (int a = 0; a < 3; a++) o[7 + a] = logf(s2f[a]) * 0.5f;
+        float det1 = s2[0] * s2[1] * s2[2], det2 = s2f[0] * s2f[1] * s2f[2];
+        float coef = sqrtf(det1 / det2);
+        float sig = 1.0f / (1.0f + expf(-raw_opac[i]));
+        float opac = fminf(fmaxf(sig * coef, 1e-6f), 1.0f - 1e-6f);
+        raw_opac_out[i] = logf(opac / (1.0f - opac));
+    }
+}
+
+void orc_fold_min_scale_bwd(const float *transforms, const float *raw_opac, const float *f, uint32_t n,
+                            float *v_transforms, float *v_raw_opac) {
+#pragma omp parallel for schedule(static)
+    for (uint32_t i = 0; i < n; i++) {
+        const float *t = transforms + (size_t)i * 10;
+        float *vt = v_transforms + (size_t)i * 10;
+        float f2 = f[i] * f[i];
+        float s2[3], s2f[3];
+        for (int a = 0; a < 3; a++) { s2[a] = expf(t[7 + a] * 2.0f); s2f[a] = s2[a] + f2; }
+        float det1 = s2[0] * s2[1] * s2[2], det2 = s2f[0] * s2f[1] * s2f[2];
+        float r = det1 / det2;
+        float coef = sqrtf(r);
+        float sig = 1.0f / (1.0f + expf(-raw_opac[i]));
+        float pre = sig * coef;
+        float opac = fminf(fmaxf(pre, 1e-6f), 1.0f - 1e-6f);
+        /* raw' = log(q), q = opac / (1 - opac) */
+        float one_m = 1.0f - opac;
+        float q = opac / one_m;
+        float v_q = v_raw_opac[i] / q;
+        float v_opac = v_q / one_m + v_q * opac / (one_m * one_m);
+        float v_pre = (pre >= 1e-6f && pre <= 1.0f - 1e-6f) ? v_opac : 0.0f; /* clamp passes gradient inside the range */
+        float v_sig = v_pre * coef, v_coef = v_pre * sig;
+        v_raw_opac[i] = v_sig * (sig * (1.0f - sig));
+        float v_r = v_coef * 0.5f / coef;
+        float v_det1 = v_r / det2, v_det2 = -v_r * det1 / (det2 * det2);
+        for (int a = 0; a < 3; a++) {
+            int b = (a + 1) % 3, c = (a + 2) % 3;
+            float v_s2f = v_det2 * (s2f[b] * s2f[c]) + vt[7 + a] * 0.5f / s2f[a]; /* det2 product; log*0.5 */
+            float v_s2 = v_det1 * (s2[b] * s2[c]) + v_s2f;                          /* det1 product; s2 + f2 */
+            vt[7 + a] = v_s2 * s2[a] * 2.0f;                                        /* exp(2 ls) */
+        }
+    }
+}

@@ -214,3 +214,126 @@ def test_train_refine_train_cycle(rt):
     for t in (splats.transforms, splats.sh_coeffs, splats.raw_opacities):
         assert torch.isfinite(t).all() and t.shape[0] == stats.total_splats
     assert trainer._state["m_t"].shape[0] == stats.total_splats
+
+
+def test_min_scale_kernels_vs_oracle(rt):
+    """compute_min_scale / fold_min_scale (+ its reverse-mode chain) through the C ABI vs the oracle."""
+    n = 50_000
+    rng = np.random.default_rng(3)
+    tr = np.zeros((n, 10), np.float32)
+    tr[:, 0:3] = rng.uniform(-3, 3, (n, 3))
+    tr[:, 3:7] = rng.uniform(-1, 1, (n, 4))
+    tr[:, 7:10] = rng.uniform(np.log(0.004), np.log(0.3), (n, 3))
+    op = rng.uniform(-3, 4, n).astype(np.float32)
+    cams = np.concatenate([rng.uniform(-5, 5, (300, 3)), rng.uniform(400, 1800, (300, 1))], 1).astype(np.float32)
+    d = rt.ctx.device
+    ttr, top, tc = torch.from_numpy(tr).to(d), torch.from_numpy(op).to(d), torch.from_numpy(cams).to(d)
+    f = rt.T.compute_min_scale(rt.ctx, ttr, tc, 0.1)
+    of = rt.orc.compute_min_scale(tr, cams, 0.1)
+    np.testing.assert_allclose(f.cpu().numpy(), of, rtol=1e-6)
+    assert rt.T.compute_min_scale(rt.ctx, ttr, tc[:0], 0.1) is None and rt.T.compute_min_scale(rt.ctx, ttr, tc, 0.0) is None
+    f8 = (f * 8.0).contiguous()
+    t2, o2 = rt.T.fold_min_scale(rt.ctx, ttr, top, f8)
+    ot2, oo2 = rt.orc.fold_min_scale(tr, op, of * np.float32(8.0))
+    assert torch.equal(t2[:, :7], ttr[:, :7])
+    np.testing.assert_allclose(t2.cpu().numpy(), ot2, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(o2.cpu().numpy(), oo2, rtol=1e-5, atol=1e-5)
+    vt = rng.normal(size=tr.shape).astype(np.float32)
+    vo = rng.normal(size=op.shape).astype(np.float32)
+    gvt, gvo = torch.from_numpy(vt).to(d), torch.from_numpy(vo).to(d)
+    rt.T.fold_min_scale_backward(rt.ctx, ttr, top, f8, gvt, gvo)
+    ovt, ovo = rt.orc.fold_min_scale_backward(tr, op, of * np.float32(8.0), vt, vo)
+    np.testing.assert_allclose(gvt.cpu().numpy(), ovt, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(gvo.cpu().numpy(), ovo, rtol=2e-4, atol=2e-5)
+    # bake: in place, floor dropped
+    s = rt.T.Splats(ttr.clone(), torch.zeros((n, 1, 3), device=d), top.clone(), min_scale=f8)
+    s.bake_min_scale(rt.ctx)
+    assert s.min_scale is None and torch.equal(s.transforms, t2) and torch.equal(s.raw_opacities, o2)
+
+
+def test_train_with_min_scale_floor(rt):
+    """The floor is folded in for the render, its gradient chained back, baked at refine and recomputed after
+    (train.rs:432-437, 641-647): a step with a floor of zero equals a step without one."""
+    n, w, h = 20_000, 192, 128
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=4, seed=7)
+    d = rt.ctx.device
+    tgt = rt.R.render_splats(rt.ctx, cam, (w, h), *(torch.from_numpy(x).to(d) for x in (tr, sh, op)), rpass=0)
+    gt = (tgt.out_img | (255 << 24)).clone()
+    batch = rt.T.SceneBatch(img_packed=gt, camera=cam)
+    cfg = rt.T.TrainConfig(total_train_iters=1000, background_noise_strength=0.0, mean_noise_weight=0.0)
+
+    def run(min_scale):
+        s = rt.T.Splats(*(torch.from_numpy(x.copy()).to(d) for x in (tr, sh + 0.1, op)), min_scale=min_scale)
+        grads = []
+        t = rt.T.SplatTrainer(cfg, rt.ctx, rt.T.bounds_from_pos(0.8, tr[:, :3]),
+                              grad_hook=lambda g: grads.extend(x.clone() for x in g[:3]))
+        t.step(batch, s)
+        return grads
+
+    g_ref = run(None)
+    g_zero = run(torch.zeros(n, dtype=torch.float32, device=d))
+    # f = 0: the fold is an exp/log round trip only -> the same gradients up to f32 rounding
+    for a, b in zip(g_zero, g_ref):
+        rel = (a.double() - b.double()).norm() / b.double().norm()
+        assert rel < 1e-3, rel
+    # a real floor: trains, refines, floor re-attached with the new N
+    s = rt.T.Splats(*(torch.from_numpy(x.copy()).to(d) for x in (tr, sh + 0.1, op)))
+    t = rt.T.SplatTrainer(rt.T.TrainConfig(total_train_iters=1000), rt.ctx, rt.T.bounds_from_pos(0.8, tr[:, :3]))
+    focal = 0.5 * w / np.tan(0.5 * cam.fov_x)
+    t.set_view_cams([(cam.position, focal), ((0.5, 0.0, -1.0), focal)])
+    s.min_scale = rt.T.compute_min_scale(rt.ctx, s.transforms, t.view_cams, rt.T.MIN_SCALE_FACTOR)
+    for _ in range(4):
+        st = t.step(batch, s)
+    stats = t.refine(4, s)
+    assert s.min_scale is not None and s.min_scale.shape[0] == stats.total_splats == s.num_splats()
+    for _ in range(3):
+        st = t.step(batch, s)
+    assert np.isfinite(float(st.loss.item()))
+    assert all(torch.isfinite(x).all() for x in (s.transforms, s.sh_coeffs, s.raw_opacities, s.min_scale))
+
+
+def test_step_views_equals_sequential_accumulation(rt):
+    """SURVEY 8e parity definition: the multi-view step equals the single-GPU step that accumulates the views'
+    gradients sequentially (mean over views), up to f32 summation order."""
+    import math
+    from brush_b200.camera import Camera
+    n, w, h = 20_000, 192, 128
+    cam0, tr, sh, op = synthetic_scene(n, w, h, k=9, seed=21)
+    a = math.radians(4.0) / 2.0
+    cam1 = Camera(position=(0.1, -0.05, 0.0), rotation=(0.0, math.sin(a), 0.0, math.cos(a)), fov_x=cam0.fov_x, fov_y=cam0.fov_y,
+                  center_uv=cam0.center_uv)
+    d = rt.ctx.device
+    dev_params = lambda: [torch.from_numpy(x.copy()).to(d) for x in (tr, sh, op)]
+    batches = []
+    for cam in (cam0, cam1):
+        tgt = rt.R.render_splats(rt.ctx, cam, (w, h), *dev_params(), rpass=0)
+        batches.append(rt.T.SceneBatch(img_packed=(tgt.out_img | (255 << 24)).clone(), camera=cam))
+    cfg = rt.T.TrainConfig(total_train_iters=1000, background_noise_strength=0.0, mean_noise_weight=0.0)
+    captured = {}
+
+    class Capture(rt.T.SplatTrainer):
+        def _apply_updates(self, splats, v_t, v_sh, v_o, v_r, visible, max_radius, median_scale):
+            captured.update(v_t=v_t.clone(), v_sh=v_sh.clone(), v_o=v_o.clone(), v_r=v_r.clone(), vis=visible.clone(),
+                            rad=max_radius.clone())
+            return super()._apply_updates(splats, v_t, v_sh, v_o, v_r, visible, max_radius, median_scale)
+
+    bounds = rt.T.bounds_from_pos(0.8, tr[:, :3])
+    p = dev_params()
+    sh_start = p[1] + 0.1
+    multi = rt.T.Splats(p[0].clone(), sh_start.clone(), p[2].clone())
+    st = Capture(cfg, rt.ctx, bounds).step_views(batches, multi)
+    got = dict(captured)
+    per_view = []
+    for b in batches:
+        s1 = rt.T.Splats(p[0].clone(), sh_start.clone(), p[2].clone())
+        Capture(cfg, rt.ctx, bounds).step(b, s1)
+        per_view.append(dict(captured))
+    for key in ("v_t", "v_sh", "v_o"):
+        want = (per_view[0][key].double() + per_view[1][key].double()) / 2.0
+        rel = (got[key].double() - want).norm() / want.norm()
+        assert rel < 1e-5, (key, rel)
+    assert torch.equal(got["v_r"], torch.maximum(per_view[0]["v_r"], per_view[1]["v_r"]))
+    assert torch.equal(got["vis"], per_view[0]["vis"] + per_view[1]["vis"])
+    assert torch.equal(got["rad"], torch.maximum(per_view[0]["rad"], per_view[1]["rad"]))
+    assert np.isfinite(float(st.loss.item()))
+    assert all(torch.isfinite(x).all() for x in (multi.transforms, multi.sh_coeffs, multi.raw_opacities))
