@@ -16,7 +16,7 @@ BG_OK, BG_ERR_NULL, BG_ERR_INVALID, BG_ERR_CUDA, BG_ERR_CAPACITY, BG_ERR_UNSUPPO
 PASS_FORWARD, PASS_BACKWARD, PASS_BACKWARD_SMOOTH = 0, 1, 2
 PROJECTED_STRIDE = 12
 VCOMBINED_STRIDE = 10
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _STATUS_NAMES = {1: "BG_ERR_NULL", 2: "BG_ERR_INVALID", 3: "BG_ERR_CUDA", 4: "BG_ERR_CAPACITY", 5: "BG_ERR_UNSUPPORTED"}
 
@@ -35,6 +35,7 @@ class BgCamera(C.Structure):
         ("lim_pos_x", C.c_float), ("lim_pos_y", C.c_float), ("lim_neg_x", C.c_float), ("lim_neg_y", C.c_float),
         ("half_max_render_fov", C.c_float),
         ("camera_model", C.c_uint32),
+        ("model_params", C.c_float * 8),
     ]
 
 
@@ -124,4 +125,6 @@ def camera_struct(u) -> BgCamera:
     c.lim_pos_x, c.lim_pos_y, c.lim_neg_x, c.lim_neg_y = u.lim_pos_x, u.lim_pos_y, u.lim_neg_x, u.lim_neg_y
     c.half_max_render_fov = u.half_max_render_fov
     c.camera_model = u.camera_model
+    for i, v in enumerate(getattr(u, "model_params", ())):
+        c.model_params[i] = float(v)
     return c

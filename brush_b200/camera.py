@@ -2,8 +2,11 @@
 
 Follows /root/reference/crates/brush-render/src/camera.rs:
   Camera                         camera.rs:11-82
-  fov_to_focal / focal_to_fov    camera.rs:85-119  (f64, radians)
-  calculate_jacobian_clamp_limits camera.rs:200-254 (pinhole branch)
+  fov_to_focal / focal_to_fov    camera.rs:85-198  (f64, radians; all four camera models)
+  calculate_jacobian_clamp_limits camera.rs:200-254
+  camera models                  kernels/camera_model/mod.rs:32-39: `camera_model` is the model id and
+                                 `model_params` its distortion coefficients (KB4: k1..k4; RT8: k1..k6, p1, p2;
+                                 thin-prism fisheye: k1..k4, p1, p2, sx1, sy1)
 and the uniform construction of render.rs:70-99 (ProjectUniforms).
 
 `world_to_local` restates glam 0.30's `Affine3A::from_rotation_translation(..).inverse()`
@@ -19,17 +22,104 @@ import numpy as np
 
 F32 = np.float32
 
-PINHOLE = 0
+PINHOLE, KANNALA_BRANDT_4, RADIAL_TANGENTIAL_8, THIN_PRISM_FISHEYE = 0, 1, 2, 3
+MODEL_PARAM_COUNT = {PINHOLE: 0, KANNALA_BRANDT_4: 4, RADIAL_TANGENTIAL_8: 8, THIN_PRISM_FISHEYE: 8}
 
 
-def fov_to_focal(fov: float, pixels: int) -> float:
-    """camera.rs:85-101, pinhole branch.  f64 in, f64 out."""
-    return (float(pixels) / 2.0) / math.tan(fov / 2.0)
+def _kb4_d(theta: float, k) -> float:
+    """camera.rs:121-130 (coefficients are f32 in the reference, widened to f64)."""
+    t2 = theta * theta
+    t3 = t2 * theta
+    t5 = t3 * t2
+    t7 = t5 * t2
+    t9 = t7 * t2
+    return theta + k[0] * t3 + k[1] * t5 + k[2] * t7 + k[3] * t9
 
 
-def focal_to_fov(focal: float, pixels: int) -> float:
-    """camera.rs:104-119, pinhole branch."""
-    return 2.0 * math.atan((float(pixels) / 2.0) / focal)
+def _kb4_dd(theta: float, k) -> float:
+    t2 = theta * theta
+    t4 = t2 * t2
+    t6 = t4 * t2
+    t8 = t6 * t2
+    return 1.0 + 3.0 * k[0] * t2 + 5.0 * k[1] * t4 + 7.0 * k[2] * t6 + 9.0 * k[3] * t8
+
+
+def _kb4_invert_d(target: float, k) -> float:
+    """camera.rs:146-169: Newton on d(theta) = target, theta in [0, pi]."""
+    if target <= 0.0:
+        return 0.0
+    theta = min(target, math.pi - 1e-6)
+    for _ in range(50):
+        f = _kb4_d(theta, k) - target
+        fp = _kb4_dd(theta, k)
+        if abs(fp) < 1e-12:
+            break
+        nxt = min(max(theta - f / fp, 0.0), math.pi)
+        if abs(nxt - theta) < 1e-12:
+            theta = nxt
+            break
+        theta = nxt
+    return theta
+
+
+def _rt8_radial(r: float, p) -> float:
+    """camera.rs:172-180."""
+    r2 = r * r
+    r4 = r2 * r2
+    r6 = r4 * r2
+    return (1.0 + p[0] * r2 + p[1] * r4 + p[2] * r6) / (1.0 + p[3] * r2 + p[4] * r4 + p[5] * r6)
+
+
+def rt8_undistort_radius(r_d: float, p) -> float:
+    """camera.rs:184-198: fixed-point iteration r = r_d / radial(r)."""
+    r = r_d
+    for _ in range(30):
+        factor = _rt8_radial(r, p)
+        if abs(factor) < 1e-12:
+            break
+        r_new = r_d / factor
+        if abs(r_new - r) < 1e-12:
+            r = r_new
+            break
+        r = r_new
+    return r
+
+
+def _params64(model_params, camera_model=None):
+    if camera_model is not None and len(model_params) != MODEL_PARAM_COUNT.get(camera_model, -1):
+        raise ValueError("model_params does not match the camera model")
+    return [float(F32(v)) for v in model_params]
+
+
+def fov_to_focal(fov: float, pixels: int, camera_model: int = PINHOLE, model_params=()) -> float:
+    """camera.rs:85-101.  f64 in, f64 out."""
+    half = fov / 2.0
+    p = _params64(model_params, camera_model)
+    if camera_model == PINHOLE:
+        projected = math.tan(half)
+    elif camera_model in (KANNALA_BRANDT_4, THIN_PRISM_FISHEYE):
+        projected = _kb4_d(half, p)
+    elif camera_model == RADIAL_TANGENTIAL_8:
+        r = math.tan(half)
+        projected = r * _rt8_radial(r, p)
+    else:
+        raise ValueError("unknown camera model")
+    return (float(pixels) / 2.0) / projected
+
+
+def focal_to_fov(focal: float, pixels: int, camera_model: int = PINHOLE, model_params=()) -> float:
+    """camera.rs:104-119."""
+    r_norm = (float(pixels) / 2.0) / focal
+    p = _params64(model_params, camera_model)
+    if camera_model == PINHOLE:
+        half = math.atan(r_norm)
+    elif camera_model in (KANNALA_BRANDT_4, THIN_PRISM_FISHEYE):
+        half = _kb4_invert_d(r_norm, p)
+    elif camera_model == RADIAL_TANGENTIAL_8:
+        half = math.atan(rt8_undistort_radius(r_norm, p))
+    else:
+        raise ValueError("unknown camera model")
+    return 2.0 * half
 
 
 def _mat3_from_quat_xyzw(q) -> np.ndarray:
@@ -66,13 +156,15 @@ class Camera:
     fov_y: float = 0.0
     center_uv: tuple = (0.5, 0.5)
     camera_model: int = PINHOLE
+    model_params: tuple = ()
 
     def is_valid(self) -> bool:
         vals = [self.fov_x, self.fov_y, *self.center_uv, *self.position, *self.rotation]
         return all(math.isfinite(float(v)) for v in vals)
 
     def focal(self, img_w: int, img_h: int):
-        return (F32(fov_to_focal(self.fov_x, img_w)), F32(fov_to_focal(self.fov_y, img_h)))
+        return (F32(fov_to_focal(self.fov_x, img_w, self.camera_model, self.model_params)),
+                F32(fov_to_focal(self.fov_y, img_h, self.camera_model, self.model_params)))
 
     def center(self, img_w: int, img_h: int):
         return (F32(self.center_uv[0]) * F32(img_w), F32(self.center_uv[1]) * F32(img_h))
@@ -110,6 +202,7 @@ class ProjectUniforms:
     lim_neg_y: float
     half_max_render_fov: float
     camera_model: int = PINHOLE
+    model_params: tuple = ()
     img_w: int = 0
     img_h: int = 0
 
@@ -120,10 +213,19 @@ def build_uniforms(camera: Camera, img_w: int, img_h: int) -> ProjectUniforms:
     fx, fy = camera.focal(img_w, img_h)
     cx, cy = camera.center(img_w, img_h)
     wf, hf = F32(img_w), F32(img_h)
+    model = camera.camera_model
+    if len(camera.model_params) != MODEL_PARAM_COUNT.get(model, -1):
+        raise ValueError("camera.model_params does not match the camera model")
     lim_pos_x = (F32(1.15) * wf - cx) / fx
     lim_pos_y = (F32(1.15) * hf - cy) / fy
     lim_neg_x = (F32(-0.15) * wf - cx) / fx
     lim_neg_y = (F32(-0.15) * hf - cy) / fy
+    if model == RADIAL_TANGENTIAL_8:        # bound the UNDISTORTED coordinate (camera.rs:229-243)
+        p64 = _params64(camera.model_params)
+        und = lambda e: F32(rt8_undistort_radius(abs(float(e)), p64)) * F32(np.sign(e))
+        lim_pos_x, lim_pos_y, lim_neg_x, lim_neg_y = und(lim_pos_x), und(lim_pos_y), und(lim_neg_x), und(lim_neg_y)
+    elif model in (KANNALA_BRANDT_4, THIN_PRISM_FISHEYE):   # fisheye Jacobians are not clamped (camera.rs:244-247)
+        lim_pos_x = lim_pos_y = lim_neg_x = lim_neg_y = F32(0.0)
     hyp = F32(math.hypot(float(F32(camera.fov_x)), float(F32(camera.fov_y))))
     half = F32(min(float(hyp * F32(1.05)), float(F32(2.0) * F32(math.pi) - F32(1e-6)))) * F32(0.5)
     return ProjectUniforms(
@@ -134,5 +236,6 @@ def build_uniforms(camera: Camera, img_w: int, img_h: int) -> ProjectUniforms:
         lim_neg_x=float(lim_neg_x), lim_neg_y=float(lim_neg_y),
         half_max_render_fov=float(half),
         camera_model=camera.camera_model,
+        model_params=tuple(float(F32(v)) for v in camera.model_params),
         img_w=img_w, img_h=img_h,
     )

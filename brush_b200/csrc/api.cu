@@ -223,7 +223,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     const int deg = sh_degree_from_k(k);
     if (deg < 0) { set_err("Invalid nr. of sh bases", cudaSuccess); return BG_ERR_INVALID; }
     if (pass < 0 || pass > 2) { set_err("invalid pass", cudaSuccess); return BG_ERR_INVALID; }
-    if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
+    if (cam->camera_model > BG_CAMERA_THIN_PRISM_FISHEYE) return BG_ERR_UNSUPPORTED;
     const bool bwd_info = pass != BG_PASS_FORWARD;
     if (bwd_info && n > 0 && !visible) return BG_ERR_NULL;
     if ((((uintptr_t)transforms) | ((uintptr_t)sh) | ((uintptr_t)raw_opac) | ((uintptr_t)out_img)) & 15u) {
@@ -323,7 +323,7 @@ extern "C" int32_t bg_project_backward(BgContext *c, void *stream, const BgCamer
     if (st->n > 0 && (!transforms || !sh || !raw_opac)) return BG_ERR_NULL;
     const int deg = sh_degree_from_k(st->k);
     if (deg < 0) return BG_ERR_INVALID;
-    if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
+    if (cam->camera_model > BG_CAMERA_THIN_PRISM_FISHEYE) return BG_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,
@@ -339,7 +339,7 @@ extern "C" int32_t bg_project_backward_factored(BgContext *c, void *stream, cons
     if (st->n > 0 && (!transforms || !sh || !raw_opac)) return BG_ERR_NULL;
     const int deg = sh_degree_from_k(st->k);
     if (deg < 0) return BG_ERR_INVALID;
-    if (cam->camera_model != BG_CAMERA_PINHOLE) return BG_ERR_UNSUPPORTED;
+    if (cam->camera_model > BG_CAMERA_THIN_PRISM_FISHEYE) return BG_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,

@@ -9,6 +9,7 @@
 #pragma once
 #include "bg_common.cuh"
 #include "bg_math.cuh"
+#include "bg_camera.cuh"
 
 namespace bg {
 
@@ -39,9 +40,27 @@ __device__ __forceinline__ M23 jacobian_pinhole(V3 p, const BgCamera &u) {
     j.c2 = mk2(-dx * cxn, -dy * cyn);
     return j;
 }
+// DISTORTED = false: pinhole, resolved at compile time (all BASELINE configs); true: the three distorted models,
+// selected by the uniform u.camera_model (the reference specialises per model AND per coefficient set).
+template <bool DISTORTED>
+__device__ __forceinline__ M23 project_jacobian(V3 p, const BgCamera &u) {
+    if (DISTORTED) return jacobian_distorted(p, u);
+    return jacobian_pinhole(p, u);
+}
+template <bool DISTORTED>
+__device__ __forceinline__ void project_mean(V3 p, const BgCamera &u, float &ox, float &oy) {
+    if (DISTORTED) project_distorted(p, u, ox, oy);
+    else project_pinhole(p, u, ox, oy);
+}
+template <bool DISTORTED>
+__device__ __forceinline__ bool in_front(V3 mean_c, const BgCamera &u) {  // project_forward.rs:47-61
+    if (DISTORTED) return in_front_distorted(mean_c, u);
+    return !(mean_c.z < 0.01f);
+}
+template <bool DISTORTED>
 __device__ __forceinline__ S2 calc_cov2d(V3 scl, Q4 quat, V3 mean_c, const BgCamera &u) {
     M3 ns = mul_diag(mul(view_rotation(u), quat_to_mat3(quat)), scl);
-    M23 v = mul(jacobian_pinhole(mean_c, u), ns);
+    M23 v = mul(project_jacobian<DISTORTED>(mean_c, u), ns);
     S2 raw = gram(v);
     const float lim = 1.0e18f;
     float ma = max_abs(raw);

@@ -32,7 +32,7 @@ struct CullResult {
 };
 
 // Everything of project_forward up to the tile bbox (project_forward.rs:43-117).
-template <bool MIP>
+template <bool MIP, bool DIST>
 __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, const BgCamera &u, uint32_t img_w,
                                                uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y) {
     CullResult r;
@@ -41,7 +41,7 @@ __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, c
     r.min_x = r.min_y = r.bbw = r.ntiles = 0;
     V3 mean_c = world_to_cam(mk3(t[0], t[1], t[2]), u);
     if (!(is_finite(mean_c) && mean_c.z <= 1.0e10f)) return r;
-    if (mean_c.z < 0.01f) return r;
+    if (!in_front<DIST>(mean_c, u)) return r;
     V3 scl = mk3(det_expf(t[7]), det_expf(t[8]), det_expf(t[9]));
     if (!is_finite(scl)) return r;
     Q4 qu; qu.w = t[3]; qu.x = t[4]; qu.y = t[5]; qu.z = t[6];
@@ -49,13 +49,13 @@ __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, c
     if (!(qn >= 1.0e-6f && is_finite(qn))) return r;
     if (!is_finite(raw_opac)) return r;
     Q4 quat = normalize(qu);
-    S2 raw_cov = calc_cov2d(scl, quat, mean_c, u);
+    S2 raw_cov = calc_cov2d<DIST>(scl, quat, mean_c, u);
     float comp;
     S2 cov = compensate_cov2d<MIP>(raw_cov, comp);
     float opac = det_sigmoid(raw_opac) * comp;
     if (!is_finite(cov)) return r;
     float mx, my;
-    project_pinhole(mean_c, u, mx, my);
+    project_mean<DIST>(mean_c, u, mx, my);
     if (!(opac >= 1.0f / 255.0f)) return r;
     float pt = det_logf(opac * 255.0f);
     S2 conic = inverse(cov);
@@ -124,7 +124,7 @@ __device__ __forceinline__ void warp_count_tiles(CullResult &r, uint32_t *w_hits
 }
 
 // K1.  One thread per Gaussian, 256 Gaussians per tile, persistent CTAs.
-template <bool MIP>
+template <bool MIP, bool DIST>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_cull_kernel(const float *__restrict__ transforms, const float *__restrict__ raw_opac, uint32_t n,
                     BgCamera u, uint32_t img_w, uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y,
@@ -184,7 +184,7 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             float t[10];
 #pragma unroll
             for (int j = 0; j < 10; j++) t[j] = s_rows[threadIdx.x * 10 + j];
-            r = cull_one<MIP>(t, __ldg(raw_opac + gid), u, img_w, img_h, tiles_x, tiles_y);
+            r = cull_one<MIP, DIST>(t, __ldg(raw_opac + gid), u, img_w, img_h, tiles_x, tiles_y);
             max_radius[gid] = r.radius;  // zero for culled splats (render_aux.rs:76-78)
             cgid_from_gid[gid] = 0xFFFFFFFFu;  // overwritten for visible splats by project_visible_emit
         }
@@ -294,7 +294,7 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
 // what counts (ncu: long-scoreboard stalls dominated the staged version).
 constexpr int VIS_THREADS = 128;
 
-template <bool MIP, int DEG>
+template <bool MIP, int DEG, bool DIST>
 __global__ void __launch_bounds__(VIS_THREADS)
 project_visible_emit_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
                             const float *__restrict__ raw_opac, const uint32_t *__restrict__ gid_sorted,
@@ -337,13 +337,13 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             V3 scl = mk3(det_expf(a3.y), det_expf(a4.x), det_expf(a4.y));
             Q4 quat = normalize(qu);
             V3 mean_c = world_to_cam(mean, u);
-            S2 raw_cov = calc_cov2d(scl, quat, mean_c, u);
+            S2 raw_cov = calc_cov2d<DIST>(scl, quat, mean_c, u);
             float comp;
             S2 cov = compensate_cov2d<MIP>(raw_cov, comp);
             float opac = det_sigmoid(__ldg(raw_opac + gid)) * comp;
             S2 conic = inverse(cov);
             float mx, my;
-            project_pinhole(mean_c, u, mx, my);
+            project_mean<DIST>(mean_c, u, mx, my);
             V3 vdir = normalize(sub(mean, mk3(u.cam_pos[0], u.cam_pos[1], u.cam_pos[2])));
             V3 raw = sh_to_color<DEG>([&](int i) { return coef[i]; }, vdir);
             float cr = raw.x + 0.5f, cg = raw.y + 0.5f, cb = raw.z + 0.5f;
@@ -439,12 +439,13 @@ cudaError_t launch_project_cull(cudaStream_t s, int grid, bool mip, const float 
                                 uint32_t *cgid_from_gid, unsigned long long *hit_masks, uint32_t *ctl,
                                 unsigned long long *lb, const uint32_t *epoch_base, uint32_t epoch_off) {
     if (n == 0) return cudaSuccess;
-    if (mip)
-        project_cull_kernel<true><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
-                                                                 gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch_base, epoch_off);
-    else
-        project_cull_kernel<false><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys,
-                                                                  gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch_base, epoch_off);
+    const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
+#define BG_LAUNCH_CULL(M, D)                                                                                       \
+    project_cull_kernel<M, D><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys, \
+                                                            gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch_base, epoch_off)
+    if (mip) { if (dist) BG_LAUNCH_CULL(true, true); else BG_LAUNCH_CULL(true, false); }
+    else     { if (dist) BG_LAUNCH_CULL(false, true); else BG_LAUNCH_CULL(false, false); }
+#undef BG_LAUNCH_CULL
     return cudaGetLastError();
 }
 
@@ -464,8 +465,11 @@ static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const f
                                       const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
                                       uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
                                       uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl) {
-#define BG_LAUNCH_VIS(D)                                                                                          \
-    project_visible_emit_kernel<MIP, D><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
+    const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
+#define BG_LAUNCH_VIS(D)                                                                                                   \
+    if (dist) project_visible_emit_kernel<MIP, D, true><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl); \
+    else project_visible_emit_kernel<MIP, D, false><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
                                                                      tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl)
     switch (deg) {
         case 0: BG_LAUNCH_VIS(0); break;

@@ -172,7 +172,7 @@ __device__ __forceinline__ V3 sh_viewdir_vjp(const float *S, V3 v) {
 
 constexpr int PB_THREADS = 128;
 
-template <bool MIP, int DEG>
+template <bool MIP, int DEG, bool DIST>
 __global__ void __launch_bounds__(PB_THREADS)
 project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
                    const float *__restrict__ raw_opac, const uint32_t *__restrict__ cgid_from_gid,
@@ -249,7 +249,7 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         V3 mean_c = world_to_cam(mean, u);
         M3 rm = quat_to_mat3(quat);
         M3 m = mul_diag(rm, scl);
-        S2 raw_cov = calc_cov2d(scl, quat, mean_c, u);
+        S2 raw_cov = calc_cov2d<DIST>(scl, quat, mean_c, u);
         float comp;
         S2 cov = compensate_cov2d<MIP>(raw_cov, comp);
         float osig = det_sigmoid(__ldg(raw_opac + gid));
@@ -263,8 +263,9 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         S3 covar = outer_self(m);
         M3 view_rot = view_rotation(u);
         S3 cov_c = congruence(covar, view_rot);
-        M23 jac = jacobian_pinhole(mean_c, u);
-        V3 v_mean_c = projection_vjp_pinhole(jac, mean_c, cov_c, u, v_cov2d, mk2(rg[0], rg[1]));
+        M23 jac = project_jacobian<DIST>(mean_c, u);
+        V3 v_mean_c = DIST ? projection_vjp_distorted(jac, mean_c, cov_c, u, v_cov2d, mk2(rg[0], rg[1]))
+                           : projection_vjp_pinhole(jac, mean_c, cov_c, u, v_cov2d, mk2(rg[0], rg[1]));
         S3 vcc = tcongruence(jac, v_cov2d);
         V3 v_mean = add(tmul(view_rot, v_mean_c), v_mean_sh);
         M3 v_m = mul(scale(tcongruence(vcc, view_rot), 2.0f), m);
@@ -394,8 +395,11 @@ static cudaError_t launch_pb_deg(cudaStream_t s, int deg, const float *transform
                                  uint32_t n, const BgCamera &u, float *v_transforms, float *v_sh, float *v_raw_opac,
                                  float *v_refine, float *v_color_out) {
     const int grid = (int)((n + PB_THREADS - 1) / PB_THREADS);
-#define BG_LAUNCH_PB(D)                                                                                         \
-    project_bwd_kernel<MIP, D><<<grid, PB_THREADS, 0, s>>>(transforms, sh, raw_opac, cgid_from_gid, v_combined, n, u, \
+    const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
+#define BG_LAUNCH_PB(D)                                                                                                 \
+    if (dist) project_bwd_kernel<MIP, D, true><<<grid, PB_THREADS, 0, s>>>(transforms, sh, raw_opac, cgid_from_gid, v_combined, n, u, \
+                                                           v_transforms, v_sh, v_raw_opac, v_refine, v_color_out);      \
+    else project_bwd_kernel<MIP, D, false><<<grid, PB_THREADS, 0, s>>>(transforms, sh, raw_opac, cgid_from_gid, v_combined, n, u, \
                                                            v_transforms, v_sh, v_raw_opac, v_refine, v_color_out)
     switch (deg) {
         case 0: BG_LAUNCH_PB(0); break;

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 1u
+#define BG_ABI_VERSION 2u
 
 /* f32 lanes per projected splat.  Lanes 0..8 are the reference layout
  * (kernels/helpers.rs:49-53: xy_x, xy_y, conic_x, conic_y, conic_z, color_a,
@@ -57,8 +57,17 @@ typedef enum {
 /* gaussian_splats.rs:27-48 RasterPass */
 typedef enum { BG_PASS_FORWARD = 0, BG_PASS_BACKWARD = 1, BG_PASS_BACKWARD_SMOOTH = 2 } BgPass;
 
-/* kernels/camera_model/mod.rs:32-39 CameraModel (only pinhole is built) */
-typedef enum { BG_CAMERA_PINHOLE = 0 } BgCameraModel;
+/* kernels/camera_model/mod.rs:32-39 CameraModel.  The reference bakes the distortion coefficients into the
+ * kernel at compile time; here they travel in BgCamera.model_params:
+ *   KANNALA_BRANDT_4    (kannala_brandt_4.rs:10-16)      k1 k2 k3 k4
+ *   RADIAL_TANGENTIAL_8 (radial_tangential_8.rs:12-21)   k1 k2 k3 k4 k5 k6 p1 p2
+ *   THIN_PRISM_FISHEYE  (thin_prism_fisheye.rs:25-31)    k1 k2 k3 k4 p1 p2 sx1 sy1 */
+typedef enum {
+    BG_CAMERA_PINHOLE = 0,
+    BG_CAMERA_KANNALA_BRANDT_4 = 1,
+    BG_CAMERA_RADIAL_TANGENTIAL_8 = 2,
+    BG_CAMERA_THIN_PRISM_FISHEYE = 3
+} BgCameraModel;
 
 /* Host struct.  Mirror of ProjectUniforms (shaders.rs:17-66, kernels/types.rs:51-80) minus the
  * sizes that are passed as arguments.  viewmat = camera.world_to_local(), top 3 rows, column
@@ -70,6 +79,7 @@ typedef struct {
     float lim_pos_x, lim_pos_y, lim_neg_x, lim_neg_y;  /* JacobianClampLimits, camera.rs:200-254 */
     float half_max_render_fov;                         /* render.rs:70-71 */
     uint32_t camera_model;                             /* BgCameraModel */
+    float model_params[8];                             /* distortion coefficients of camera_model, zero padded */
 } BgCamera;
 
 /* Saved forward state handed to the backward calls: mirror of the non-image fields of

@@ -27,6 +27,7 @@ class OrcCamera(C.Structure):
         ("lim_pos_x", C.c_float), ("lim_pos_y", C.c_float), ("lim_neg_x", C.c_float), ("lim_neg_y", C.c_float),
         ("half_max_render_fov", C.c_float),
         ("camera_model", C.c_uint32),
+        ("model_params", C.c_float * 8),
     ]
 
 
@@ -112,6 +113,8 @@ def camera_struct(u) -> OrcCamera:
     c.lim_pos_x, c.lim_pos_y, c.lim_neg_x, c.lim_neg_y = u.lim_pos_x, u.lim_pos_y, u.lim_neg_x, u.lim_neg_y
     c.half_max_render_fov = u.half_max_render_fov
     c.camera_model = u.camera_model
+    for i, v in enumerate(getattr(u, "model_params", ())):
+        c.model_params[i] = float(v)
     return c
 
 

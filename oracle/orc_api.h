@@ -29,7 +29,8 @@ typedef struct {
     float cam_pos[3];
     float lim_pos_x, lim_pos_y, lim_neg_x, lim_neg_y;
     float half_max_render_fov;
-    uint32_t camera_model; /* 0 = pinhole (only model restated so far) */
+    uint32_t camera_model;  /* 0 pinhole, 1 Kannala-Brandt 4, 2 radial-tangential 8, 3 thin-prism fisheye */
+    float model_params[8];  /* distortion coefficients, see orc_camera.h */
 } OrcCamera;
 
 enum { ORC_PASS_FORWARD = 0, ORC_PASS_BACKWARD = 1, ORC_PASS_BACKWARD_SMOOTH = 2 };
@@ -100,6 +101,7 @@ void orc_fold_min_scale_bwd(const float *transforms, const float *raw_opac, cons
 
 float orc_expf_det(float x);
 float orc_logf_det(float x);
+float orc_atan2f_det(float y, float x); /* y >= 0 */
 int orc_num_threads(void);
 
 #ifdef __cplusplus

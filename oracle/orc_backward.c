@@ -14,6 +14,7 @@
  */
 #include "orc_api.h"
 #include "orc_math.h"
+#include "orc_camera.h"
 
 #include <stdlib.h>
 
@@ -315,19 +316,6 @@ static inline omat3 view_rotation(const OrcCamera *u) {
     return m;
 }
 
-/* kernels/camera_model/pinhole.rs:32-56 (same as forward) */
-static inline omat2x3 jacobian_pinhole(ovec3 p, const OrcCamera *u) {
-    float inv_z = 1.0f / p.z;
-    float dx = u->fx * inv_z, dy = u->fy * inv_z;
-    float clamped_x = orc_clamp(p.x * inv_z, u->lim_neg_x, u->lim_pos_x);
-    float clamped_y = orc_clamp(p.y * inv_z, u->lim_neg_y, u->lim_pos_y);
-    omat2x3 j;
-    j.c0 = v2(dx, 0.0f);
-    j.c1 = v2(0.0f, dy);
-    j.c2 = v2(-dx * clamped_x, -dy * clamped_y);
-    return j;
-}
-
 /* kernels/camera_model/pinhole.rs:58-123 */
 static ovec3 projection_vjp_pinhole(omat2x3 jac, ovec3 mean_c, osym3 cov_c, const OrcCamera *u, osym2 v_cov2d,
                                     ovec2 v_mean2d) {
@@ -416,8 +404,14 @@ void orc_project_backward(const OrcCamera *cam, const OrcRender *r, const float 
         osym2 v_cov2d = inverse2x2_vjp(conic_inv, v_inv);
         osym3 covar = m3_outer_product_self(m);
         osym3 cov_c = s3_congruence(covar, view_rot);
-        omat2x3 jac = jacobian_pinhole(mean_c, cam);
-        ovec3 v_mean_c = projection_vjp_pinhole(jac, mean_c, cov_c, cam, v_cov2d, v2(v_mean2d_x, v_mean2d_y));
+        omat2x3 jac = orc_cam_jacobian(mean_c, cam);
+        ovec3 v_mean_c; /* camera_model/mod.rs:84-136 */
+        switch (cam->camera_model) {
+            case ORC_CAM_KB4: v_mean_c = cam_vjp_kb4(jac, mean_c, cov_c, cam, v_cov2d, v2(v_mean2d_x, v_mean2d_y), cam->model_params); break;
+            case ORC_CAM_RT8: v_mean_c = cam_vjp_rt8(mean_c, cov_c, cam, v_cov2d, v2(v_mean2d_x, v_mean2d_y), cam->model_params); break;
+            case ORC_CAM_TPF: v_mean_c = cam_vjp_tpf(jac, mean_c, cov_c, cam, v_cov2d, v2(v_mean2d_x, v_mean2d_y), cam->model_params); break;
+            default: v_mean_c = projection_vjp_pinhole(jac, mean_c, cov_c, cam, v_cov2d, v2(v_mean2d_x, v_mean2d_y)); break;
+        }
         osym3 vcc = m23_transpose_congruence_sym2(jac, v_cov2d);
         ovec3 v_mean = v3_add(m3_transpose_mul_vec3(view_rot, v_mean_c), v_mean_from_sh);
         omat3 v_m = s3_mul_mat3(s3_scale(s3_transpose_congruence(vcc, view_rot), 2.0f), m);

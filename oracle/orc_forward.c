@@ -15,6 +15,7 @@
  */
 #include "orc_api.h"
 #include "orc_math.h"
+#include "orc_camera.h"
 
 #include <stdlib.h>
 #ifdef _OPENMP
@@ -49,31 +50,10 @@ static inline ovec3 world_to_cam(ovec3 mean, const OrcCamera *u) {
     return v3_add(m3_mul_vec3(view_rotation(u), mean), view_translation(u));
 }
 
-/* kernels/camera_model/pinhole.rs:24-30 */
-static inline void project_pinhole(ovec3 p, const OrcCamera *u, float *ox, float *oy) {
-    float inv_z = 1.0f / p.z;
-    *ox = u->fx * p.x * inv_z + u->cx;
-    *oy = u->fy * p.y * inv_z + u->cy;
-}
-
-/* kernels/camera_model/pinhole.rs:32-56 */
-static inline omat2x3 jacobian_pinhole(ovec3 p, const OrcCamera *u) {
-    float inv_z = 1.0f / p.z;
-    float dx = u->fx * inv_z;
-    float dy = u->fy * inv_z;
-    float clamped_x = orc_clamp(p.x * inv_z, u->lim_neg_x, u->lim_pos_x);
-    float clamped_y = orc_clamp(p.y * inv_z, u->lim_neg_y, u->lim_pos_y);
-    omat2x3 j;
-    j.c0 = v2(dx, 0.0f);
-    j.c1 = v2(0.0f, dy);
-    j.c2 = v2(-dx * clamped_x, -dy * clamped_y);
-    return j;
-}
-
 /* kernels/helpers.rs:145-174 */
 osym2 orc_calc_cov2d(ovec3 scale, oquat quat, ovec3 mean_c, const OrcCamera *u) {
     omat3 ns = m3_mul_diag(m3_mul_mat3(view_rotation(u), q_to_mat3(quat)), scale);
-    omat2x3 jac = jacobian_pinhole(mean_c, u);
+    omat2x3 jac = orc_cam_jacobian(mean_c, u);
     omat2x3 v = m23_mul_mat3(jac, ns);
     osym2 raw = m23_gram(v);
     float lim = 1.0e18f;
@@ -317,7 +297,7 @@ OrcRender *orc_render_forward(const OrcCamera *cam, uint32_t w, uint32_t h, uint
         const float *t = transforms + (size_t)gi * 10;
         ovec3 mean_c = world_to_cam(v3(t[0], t[1], t[2]), cam);
         if (!(v3_is_finite(mean_c) && mean_c.z <= 1.0e10f)) continue;
-        if (mean_c.z < 0.01f) continue;
+        if (!orc_cam_in_front(mean_c, cam)) continue; /* project_forward.rs:47-61 */
         ovec3 scale = v3(orc_expf(t[7]), orc_expf(t[8]), orc_expf(t[9]));
         if (!v3_is_finite(scale)) continue;
         oquat qu = {t[3], t[4], t[5], t[6]};
@@ -332,7 +312,7 @@ OrcRender *orc_render_forward(const OrcCamera *cam, uint32_t w, uint32_t h, uint
         float opac = orc_sigmoid(ro) * filter_comp;
         if (!s2_is_finite(cov)) continue;
         float mx, my;
-        project_pinhole(mean_c, cam, &mx, &my);
+        orc_cam_project(mean_c, cam, &mx, &my);
         if (!(opac >= 1.0f / 255.0f)) continue;
         float power_threshold = orc_logf(opac * 255.0f);
         osym2 conic = s2_inverse(cov);
@@ -391,7 +371,7 @@ OrcRender *orc_render_forward(const OrcCamera *cam, uint32_t w, uint32_t h, uint
         float opac = orc_sigmoid(raw_opac[gi]) * filter_comp;
         osym2 conic = s2_inverse(cov);
         float mx, my;
-        project_pinhole(mean_c, cam, &mx, &my);
+        orc_cam_project(mean_c, cam, &mx, &my);
         ovec3 v = v3_normalize(v3_sub(mean, cam_pos));
         ovec3 raw = orc_sh_to_color(sh + (size_t)gi * k * 3, sh_degree, v);
         float cr = raw.x + 0.5f, cg = raw.y + 0.5f, cb = raw.z + 0.5f;
@@ -534,3 +514,5 @@ void orc_render_free(OrcRender *r) {
     free(r->tile_id_from_isect); free(r->cgid_from_isect); free(r->tile_offsets); free(r->tile_offsets_untrimmed);
     free(r);
 }
+
+float orc_atan2f_det(float y, float x) { return orc_atan2f(y, x); }

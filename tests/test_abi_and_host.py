@@ -46,7 +46,7 @@ def test_null_and_invalid_arguments_return_status_codes():
 
 def test_struct_layouts_match_header():
     from brush_b200 import _lib
-    assert ctypes.sizeof(_lib.BgCamera) == 4 * (12 + 4 + 3 + 4 + 1 + 1)
+    assert ctypes.sizeof(_lib.BgCamera) == 4 * (12 + 4 + 3 + 4 + 1 + 1 + 8)
     assert _lib.BgRenderState.n.offset == 9 * 8
 
 

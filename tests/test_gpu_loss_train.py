@@ -332,7 +332,8 @@ def test_step_views_equals_sequential_accumulation(rt):
         want = (per_view[0][key].double() + per_view[1][key].double()) / 2.0
         rel = (got[key].double() - want).norm() / want.norm()
         assert rel < 1e-5, (key, rel)
-    assert torch.equal(got["v_r"], torch.maximum(per_view[0]["v_r"], per_view[1]["v_r"]))
+    # the refine weight comes out of f32 atomics in the blend backward: equal up to summation order
+    torch.testing.assert_close(got["v_r"], torch.maximum(per_view[0]["v_r"], per_view[1]["v_r"]), rtol=1e-4, atol=1e-7)
     assert torch.equal(got["vis"], per_view[0]["vis"] + per_view[1]["vis"])
     assert torch.equal(got["rad"], torch.maximum(per_view[0]["rad"], per_view[1]["rad"]))
     assert np.isfinite(float(st.loss.item()))
