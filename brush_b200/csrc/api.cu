@@ -326,6 +326,10 @@ extern "C" int32_t bg_project_backward(BgContext *c, void *stream, const BgCamer
     if (cam->camera_model > BG_CAMERA_THIN_PRISM_FISHEYE) return BG_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
+    if (((uintptr_t)sh | (uintptr_t)v_sh) % 16) {
+        set_err("bg_project_backward: sh and v_sh must be 16-byte aligned (128-bit row access)", cudaSuccess);
+        return BG_ERR_INVALID;
+    }
     BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,
                                st->n, *cam, v_transforms, v_sh, v_raw_opac, v_refine, nullptr));
     return BG_OK;
@@ -342,6 +346,10 @@ extern "C" int32_t bg_project_backward_factored(BgContext *c, void *stream, cons
     if (cam->camera_model > BG_CAMERA_THIN_PRISM_FISHEYE) return BG_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
+    if ((uintptr_t)sh % 16) {
+        set_err("bg_project_backward_factored: sh must be 16-byte aligned (128-bit row access)", cudaSuccess);
+        return BG_ERR_INVALID;
+    }
     BG_CUDA(launch_project_bwd(s, st->mip != 0, deg, transforms, sh, raw_opac, st->compact_from_global_gid, v_combined,
                                st->n, *cam, v_transforms, nullptr, v_raw_opac, v_refine, v_color));
     return BG_OK;

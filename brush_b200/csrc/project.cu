@@ -78,12 +78,10 @@ __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, c
 // count_contributing_tiles (helpers.rs:203-222) for the 32 Gaussians of a warp at once.  A per-thread
 // walk costs the warp the LARGEST bbox among its lanes; here the warp's candidate tiles are flattened
 // into one list and tested 32 at a time, whoever they belong to (binary search of the owner over the
-// exclusive prefix of the per-lane tile counts).  Hit counts and hit bits go to the owner through
-// shared-memory atomics.  `w_hits` / `w_mask`: this warp's 32-entry scratch arrays.
-__device__ __forceinline__ void warp_count_tiles(CullResult &r, uint32_t *w_hits, unsigned long long *w_mask) {
+// exclusive prefix of the per-lane tile counts).  Hit counts and the 64-bit hit mask are collected by the
+// owner lane from the ballot of each round.
+__device__ __forceinline__ void warp_count_tiles(CullResult &r) {
     const uint32_t lane = threadIdx.x & 31u;
-    w_hits[lane] = 0;
-    w_mask[lane] = 0ull;
     uint32_t incl = r.ntiles;
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -91,7 +89,8 @@ __device__ __forceinline__ void warp_count_tiles(CullResult &r, uint32_t *w_hits
     }
     const uint32_t pre = incl - r.ntiles;
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    __syncwarp();
+    uint32_t hits_count = 0;
+    unsigned long long mask = 0ull;
     for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t j = base + lane;
         uint32_t own = 0;  // largest lane whose exclusive prefix is <= j
@@ -110,17 +109,25 @@ __device__ __forceinline__ void warp_count_tiles(CullResult &r, uint32_t *w_hits
         const float pt = __shfl_sync(0xffffffffu, r.pt, own);
         const uint32_t min_x = __shfl_sync(0xffffffffu, r.min_x, own), min_y = __shfl_sync(0xffffffffu, r.min_y, own);
         const uint32_t bbw = __shfl_sync(0xffffffffu, r.bbw, own);
+        bool hit = false;
         if (j < total) {
             const uint32_t ry = local / bbw, rx = local - ry * bbw;
-            if (tile_hit(min_x + rx, min_y + ry, mx, my, conic, pt)) {
-                atomicAdd(&w_hits[own], 1u);
-                if (local < 64u) atomicOr(&w_mask[own], 1ull << local);
-            }
+            hit = tile_hit(min_x + rx, min_y + ry, mx, my, conic, pt);
+        }
+        // Owners collect their results from the ballot: the tiles of lane L's splat are the list positions
+        // [pre, pre + ntiles), i.e. the lanes [s, e) of this round -- no atomics, nothing leaves registers.
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        const uint32_t lo = max(pre, base), hi = min(pre + r.ntiles, base + 32u);
+        if (hi > lo) {
+            const uint32_t sft = lo - base, len = hi - lo;
+            const uint32_t seg = (hits >> sft) & (len >= 32u ? 0xffffffffu : ((1u << len) - 1u));
+            hits_count += __popc(seg);
+            const uint32_t local0 = lo - pre;  // tile index (inside the bbox) of the segment's first lane
+            if (local0 < 64u) mask |= (unsigned long long)seg << local0;
         }
     }
-    __syncwarp();
-    r.tiles = w_hits[lane];
-    r.mask = w_mask[lane];
+    r.tiles = hits_count;
+    r.mask = mask;
 }
 
 // K1.  One thread per Gaussian, 256 Gaussians per tile, persistent CTAs.
@@ -143,8 +150,6 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile, s_tile_next, s_prefix;
-    __shared__ uint32_t s_hits[PROJ_THREADS];
-    __shared__ unsigned long long s_mask[PROJ_THREADS];
     const uint32_t num_tiles = (n + PROJ_THREADS - 1) / PROJ_THREADS;
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
@@ -195,7 +200,7 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
         uint32_t local = block_exclusive_scan(r.visible ? 1u : 0u, s_scan, &total);
         unsigned long long *st = lb_state + tile;
         if (threadIdx.x == 0) lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total);
-        warp_count_tiles(r, s_hits + (threadIdx.x & ~31u), s_mask + (threadIdx.x & ~31u));
+        warp_count_tiles(r);
         if (threadIdx.x < 32) {
             uint32_t prefix = (tile == 0) ? 0u : lb_lookback_warp(lb_state, tile, epoch);
             if (threadIdx.x == 0) {
@@ -411,23 +416,40 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
 }
 
 // K4.  tile_offsets must be zeroed by the caller (render.rs:232-236).
+__device__ __forceinline__ void tile_boundary(uint32_t i, uint32_t tid, uint32_t prev, uint32_t n, uint32_t num_tiles,
+                                              uint32_t *__restrict__ tile_offsets) {
+    if (tid >= num_tiles) return;
+    if (i == n - 1) tile_offsets[tid * 2 + 1] = i + 1;
+    if (i == 0) {
+        tile_offsets[tid * 2] = 0;
+    } else if (tid != prev) {
+        if (prev < num_tiles) tile_offsets[prev * 2 + 1] = i;
+        tile_offsets[tid * 2] = i;
+    }
+}
+
+// Four sorted ids per thread (one 128-bit load + the predecessor word): the kernel is a pure stream with a rare
+// scattered store, so the only thing that matters is keeping enough loads in flight.
 __global__ void __launch_bounds__(256)
 tile_offsets_kernel(const uint32_t *__restrict__ tile_ids, const uint32_t *__restrict__ ctl, uint32_t num_tiles,
                     uint32_t *__restrict__ tile_offsets) {
     const uint32_t n = ctl[CTL_COUNTERS + 1];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t tid = __ldg(tile_ids + i);
-        if (tid < num_tiles) {
-            if (i == n - 1) tile_offsets[tid * 2 + 1] = i + 1;
-            if (i == 0) {
-                tile_offsets[tid * 2] = 0;
-            } else {
-                uint32_t prev = __ldg(tile_ids + i - 1);
-                if (tid != prev) {
-                    if (prev < num_tiles) tile_offsets[prev * 2 + 1] = i;
-                    tile_offsets[tid * 2] = i;
-                }
-            }
+    const uint32_t groups = (n + 3u) / 4u;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const uint32_t i0 = g * 4u;
+        uint32_t v[4];
+        if (i0 + 4u <= n) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(tile_ids) + g);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = (i0 + e < n) ? __ldg(tile_ids + i0 + e) : 0xFFFFFFFFu;
+        }
+        uint32_t prev = (i0 == 0) ? 0xFFFFFFFFu : __ldg(tile_ids + i0 - 1);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (i0 + e < n) tile_boundary(i0 + e, v[e], prev, n, num_tiles, tile_offsets);
+            prev = v[e];
         }
     }
 }

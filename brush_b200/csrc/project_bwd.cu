@@ -181,9 +181,10 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
                    float *__restrict__ v_color_out /* nullable: factored mode, see sh_grad_from_views_kernel */) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int KF = K * 3;
-    constexpr int STRIDE = (KF % 2 == 0) ? KF + 1 : KF;
-    // one staging area, used first for the SH rows (in) and then for the SH gradient rows (out)
-    __shared__ float s_stage[PB_THREADS * STRIDE];
+    // SH rows in and SH gradient rows out go straight between registers and global memory, one row per thread
+    // (128-bit accesses when the row is a multiple of 16 bytes): consecutive threads own consecutive rows, so a
+    // warp's 12 accesses cover one contiguous 6 KB span and every fetched sector is used out of L1.
+    constexpr bool VEC4 = (KF % 4) == 0;
     __shared__ __align__(16) float s_vt[PB_THREADS * 10];
     const uint32_t base = blockIdx.x * PB_THREADS;
     const uint32_t rows = min((uint32_t)PB_THREADS, n - base);
@@ -205,17 +206,6 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
     bool any = false;
 #pragma unroll
     for (int i = 0; i < 10; i++) any = any || (rg[i] != 0.0f);
-
-    // ---- stage this CTA's SH rows (contiguous in memory: fully coalesced)
-    {
-        const float *src = sh + (size_t)base * KF;
-        const uint32_t total = rows * KF;
-        for (uint32_t j = threadIdx.x; j < total; j += PB_THREADS) {
-            uint32_t r = j / KF, c = j - r * KF;
-            s_stage[r * STRIDE + c] = __ldg(src + j);
-        }
-    }
-    __syncthreads();
 
     float vt[10];
 #pragma unroll
@@ -239,9 +229,24 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         V3 vdir = scale(u_world, 1.0f / u_len);
         sh_basis<DEG>(vdir, Y);
         float S[K];
-        const float *row = s_stage + threadIdx.x * STRIDE;
+        if (DEG > 0) {   // S_k = coeff_k . v_color; degree 0 has no view-direction dependence: its row is never read
+            float row[KF];
+            const float *src = sh + (size_t)gid * KF;
+            if (VEC4) {
 #pragma unroll
-        for (int k = 0; k < K; k++) S[k] = dot(mk3(row[3 * k], row[3 * k + 1], row[3 * k + 2]), v_color);
+                for (int q = 0; q < KF / 4; q++) {
+                    float4 t = __ldg(reinterpret_cast<const float4 *>(src) + q);
+                    row[4 * q] = t.x; row[4 * q + 1] = t.y; row[4 * q + 2] = t.z; row[4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < KF; q++) row[q] = __ldg(src + q);
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) S[k] = dot(mk3(row[3 * k], row[3 * k + 1], row[3 * k + 2]), v_color);
+        } else {
+            S[0] = 0.0f;
+        }
         V3 v_v_sh = sh_viewdir_vjp<DEG>(S, vdir);
         float vdv = dot(vdir, v_v_sh);
         V3 v_mean_sh = scale(sub(v_v_sh, scale(vdir, vdv)), 1.0f / u_len);
@@ -276,11 +281,10 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         vt[3] = v_q.w; vt[4] = v_q.x; vt[5] = v_q.y; vt[6] = v_q.z;
         vt[7] = v_scale.x; vt[8] = v_scale.y; vt[9] = v_scale.z;
     }
-    __syncthreads();  // all SH rows consumed; reuse the staging area for the gradient rows
     const bool factored = v_color_out != nullptr;
     if (in_range) {
         if (!factored) {
-            float *row = s_stage + threadIdx.x * STRIDE;
+            float row[KF];
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 float yk = any ? Y[k] : 0.0f;
@@ -288,9 +292,18 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
                 row[3 * k + 1] = v_color.y * yk;
                 row[3 * k + 2] = v_color.z * yk;
             }
+            float *dst = v_sh + (size_t)gid * KF;
+            if (VEC4) {
+#pragma unroll
+                for (int q = 0; q < KF / 4; q++)
+                    reinterpret_cast<float4 *>(dst)[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < KF; q++) dst[q] = row[q];
+            }
         } else {  // the SH gradient of one view is the outer product Y(dir) x v_color: ship only v_color
-            float *row = s_stage + threadIdx.x * 3;
-            row[0] = any ? v_color.x : 0.0f; row[1] = any ? v_color.y : 0.0f; row[2] = any ? v_color.z : 0.0f;
+            float *dst = v_color_out + (size_t)gid * 3;
+            dst[0] = any ? v_color.x : 0.0f; dst[1] = any ? v_color.y : 0.0f; dst[2] = any ? v_color.z : 0.0f;
         }
 #pragma unroll
         for (int i = 0; i < 10; i++) s_vt[threadIdx.x * 10 + i] = vt[i];
@@ -298,18 +311,7 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         v_refine[gid] = v_refine_out;
     }
     __syncthreads();
-    {   // coalesced write-out of the dense gradient rows
-        if (!factored) {
-            float *dst = v_sh + (size_t)base * KF;
-            const uint32_t total = rows * KF;
-            for (uint32_t j = threadIdx.x; j < total; j += PB_THREADS) {
-                uint32_t r = j / KF, c = j - r * KF;
-                dst[j] = s_stage[r * STRIDE + c];
-            }
-        } else {
-            float *dst = v_color_out + (size_t)base * 3;
-            for (uint32_t j = threadIdx.x; j < rows * 3; j += PB_THREADS) dst[j] = s_stage[j];
-        }
+    {   // coalesced write-out of the [rows,10] gradient block
         float *dt = v_transforms + (size_t)base * 10;
         for (uint32_t j = threadIdx.x; j < rows * 10; j += PB_THREADS) dt[j] = s_vt[j];
     }

@@ -22,11 +22,13 @@ class FlatGradients:
 
     def __init__(self, n: int, k: int, device):
         self.n, self.k = n, k
-        self.flat = torch.empty(n * (10 + 3 * k + 1), dtype=torch.float32, device=device)
-        o0, o1 = n * 10, n * 10 + n * 3 * k
-        self.v_t = self.flat[:o0].view(n, 10)
-        self.v_sh = self.flat[o0:o1].view(n, k, 3)
-        self.v_o = self.flat[o1:].view(n)
+        up4 = lambda x: (x + 3) // 4 * 4                # every segment starts 16-byte aligned (128-bit row access)
+        o0 = up4(n * 10)
+        o1 = o0 + up4(n * 3 * k)
+        self.flat = torch.zeros(o1 + n, dtype=torch.float32, device=device)
+        self.v_t = self.flat[:n * 10].view(n, 10)
+        self.v_sh = self.flat[o0:o0 + n * 3 * k].view(n, k, 3)
+        self.v_o = self.flat[o1:o1 + n].view(n)
         self.v_r = torch.empty(n, dtype=torch.float32, device=device)  # refine weight: MAX-reduced separately
 
     def outputs(self):

@@ -75,7 +75,9 @@ def test_flat_gradients_views_alias_one_buffer():
     fg = FlatGradients(5, 4, "cpu")
     v_t, v_sh, v_o, v_r = fg.outputs()
     v_t.fill_(1.0); v_sh.fill_(2.0); v_o.fill_(3.0)
-    assert fg.flat.numel() == 5 * (10 + 12 + 1)
-    assert fg.flat[:50].eq(1).all() and fg.flat[50:110].eq(2).all() and fg.flat[110:].eq(3).all()
+    # segments start on 16-byte boundaries (n*10 = 50 floats is padded to 52)
+    assert fg.flat.numel() == 52 + 60 + 5
+    assert fg.flat[:50].eq(1).all() and fg.flat[50:52].eq(0).all() and fg.flat[52:112].eq(2).all() and fg.flat[112:].eq(3).all()
+    assert all(t.data_ptr() % 16 == 0 for t in (v_t, v_sh, v_o))
     ViewShardedReducer(num_views_total=2).reduce_flat(fg)
     assert torch.allclose(v_sh, torch.full_like(v_sh, 1.0)) and torch.allclose(v_o, torch.full_like(v_o, 1.5))
