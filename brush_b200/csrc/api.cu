@@ -24,7 +24,7 @@ cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32
 cudaError_t launch_project_visible_emit(cudaStream_t, int, bool, int, const float *, const float *, const float *,
                                         const uint32_t *, const uint32_t *, const BgCamera &, uint32_t, uint32_t,
                                         float *, uint32_t *, uint32_t *, uint32_t, uint32_t *, const unsigned long long *,
-                                        uint32_t *);
+                                        uint32_t *, uint32_t);
 cudaError_t launch_tile_offsets(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, uint32_t *);
 // sort.cu
 cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, const uint32_t *, uint32_t, uint32_t,
@@ -193,12 +193,12 @@ extern "C" uint64_t bg_ctx_arena_bytes(const BgContext *c) { return c ? c->arena
 static int32_t run_sort(BgContext *c, cudaStream_t s, const uint32_t *key_in, const uint32_t *val_in,
                         uint32_t *keys[2], uint32_t *vals[2], uint32_t n_host, const uint32_t *n_dev, uint32_t bits,
                         uint32_t *hist, uint32_t *tickets /* [1 + passes] zeroed */, int first_dst, uint32_t epoch_slot0,
-                        int *out_idx) {
+                        int *out_idx, bool hist_ready = false /* the producer of the keys already counted the digits */) {
     const uint32_t passes = (bits + 7) / 8;
     *out_idx = first_dst;
     if (passes == 0 || n_host == 0) return BG_OK;
     const int grid = c->sm_count * 4;
-    BG_CUDA(launch_radix_hist(s, grid, key_in, n_host, n_dev, bits, passes, hist));
+    if (!hist_ready) BG_CUDA(launch_radix_hist(s, grid, key_in, n_host, n_dev, bits, passes, hist));
     const uint32_t *kin = key_in, *vin = val_in;
     int dst = first_dst;
     for (uint32_t p = 0; p < passes; p++) {
@@ -252,7 +252,8 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     int dout = 0;
     {
         int32_t r = run_sort(c, s, c->depth_key[0], c->depth_val[0], c->depth_key, c->depth_val, n, counters + 0, 32,
-                             c->ctl + CTL_HIST_DEPTH, c->ctl + CTL_TICKETS + TK_DEPTH_HIST, 1, EP_DEPTH_SORT, &dout);
+                             c->ctl + CTL_HIST_DEPTH, c->ctl + CTL_TICKETS + TK_DEPTH_HIST, 1, EP_DEPTH_SORT, &dout,
+                             /*hist_ready=*/true);   // counted by project_cull
         if (r != BG_OK) return r;
     }
     c->depth_out = dout;
@@ -260,21 +261,21 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     // gather counts + inclusive scan -> cum, num_intersections
     BG_CUDA(launch_gather_scan(s, c->sm_count * 2, c->counts, gid_sorted, n, counters + 0, c->cum, counters + 1,
                                c->max_isect, counters + 2, c->ctl + CTL_TICKETS + TK_SCAN, c->lb_scan, c->epoch_dev, EP_SCAN));
-    // K2+K3
-    if (n > 0)
-        BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
-                                            tiles_x, tiles_y, c->projected, c->isect_key[0], c->isect_val[0],
-                                            c->max_isect, c->cgid_from_gid, c->hit_masks, c->ctl));
     // tile sort on bits = 32 - clz(num_tiles)
     uint32_t bits = 0;
     while (bits < 32 && (num_tiles >> bits) != 0) bits++;
+    // K2+K3 (also counts the tile-key digits for the sort when they fit two passes)
+    if (n > 0)
+        BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
+                                            tiles_x, tiles_y, c->projected, c->isect_key[0], c->isect_val[0],
+                                            c->max_isect, c->cgid_from_gid, c->hit_masks, c->ctl, bits));
     int iout = 0;
     {
         const uint32_t passes = (bits + 7) / 8;
         const int first_dst = 1;
         int32_t r = run_sort(c, s, c->isect_key[0], c->isect_val[0], c->isect_key, c->isect_val, c->max_isect,
                              counters + 1, bits, c->ctl + CTL_HIST_TILE, c->ctl + CTL_TICKETS + TK_TILE_HIST, first_dst,
-                             EP_TILE_SORT, &iout);
+                             EP_TILE_SORT, &iout, /*hist_ready=*/n > 0 && bits <= 16);
         if (r != BG_OK) return r;
         (void)passes;
     }

@@ -150,8 +150,12 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile, s_tile_next, s_prefix;
+    // digit histograms of the depth keys for the four one-sweep passes that follow: counted here, where the keys
+    // are produced, instead of by a separate pass over them
+    __shared__ uint32_t s_dhist[4 * 256];
     const uint32_t num_tiles = (n + PROJ_THREADS - 1) / PROJ_THREADS;
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    for (uint32_t i = threadIdx.x; i < 4 * 256; i += PROJ_THREADS) s_dhist[i] = 0;
     __syncthreads();
     auto issue = [&](uint32_t t, uint32_t b) {  // thread 0: start the bulk copy of tile t into buffer b
         const uint32_t tb = t * PROJ_THREADS;
@@ -212,7 +216,10 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
         __syncthreads();
         if (r.visible) {
             uint32_t slot = s_prefix + local;
-            depth_keys[slot] = __float_as_uint(r.depth);  // z >= 0.01: float order == uint order
+            const uint32_t dk = __float_as_uint(r.depth);  // z >= 0.01: float order == uint order
+            depth_keys[slot] = dk;
+#pragma unroll
+            for (int p = 0; p < 4; p++) atomicAdd(&s_dhist[p * 256 + ((dk >> (8 * p)) & 255u)], 1u);
             gids[slot] = gid;
             counts_by_gid[gid] = r.tiles;
             hit_masks[gid] = r.mask;
@@ -220,6 +227,11 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
         tile = s_tile_next;
         buf ^= 1u;
         __syncthreads();  // everyone has read s_tile_next / s_prefix / this buffer before they are reused
+    }
+    uint32_t *hist = ctl + CTL_HIST_DEPTH;
+    for (uint32_t i = threadIdx.x; i < 4 * 256; i += PROJ_THREADS) {
+        const uint32_t c = s_dhist[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -307,10 +319,24 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                             float *__restrict__ projected, uint32_t *__restrict__ tile_keys,
                             uint32_t *__restrict__ isect_vals, uint32_t isect_capacity,
                             uint32_t *__restrict__ cgid_from_gid, const unsigned long long *__restrict__ hit_masks,
-                            uint32_t *__restrict__ ctl) {
+                            uint32_t *__restrict__ ctl, uint32_t tile_bits) {
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
     constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B are 16-byte aligned
+    constexpr uint32_t EMIT_BUF = 1024;                  // staged (tile id, owner) pairs per warp
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_emit_keys[(VIS_THREADS / 32) * EMIT_BUF];
+    __shared__ uint8_t s_emit_own[(VIS_THREADS / 32) * EMIT_BUF];
+    // digit histograms of the emitted tile keys for the one-sweep passes of the tile sort (<= 2 passes: < 65536 tiles)
+    __shared__ uint32_t s_thist[2 * 256];
+    const uint32_t hist_passes = (tile_bits <= 16u) ? (tile_bits + 7u) / 8u : 0u;   // else the sort counts itself
+    const uint32_t hi_mask = (tile_bits > 8u) ? ((1u << min(8u, tile_bits - 8u)) - 1u) : 0u;
+    const uint32_t lo_mask = (1u << min(8u, tile_bits)) - 1u;
+    for (uint32_t i = threadIdx.x; i < 2 * 256; i += VIS_THREADS) s_thist[i] = 0;
+    __syncthreads();
+    auto count_key = [&](uint32_t key) {
+        if (hist_passes > 0) atomicAdd(&s_thist[key & lo_mask], 1u);
+        if (hist_passes > 1) atomicAdd(&s_thist[256 + ((key >> 8) & hi_mask)], 1u);
+    };
     const uint32_t nvis = ctl[CTL_COUNTERS + 0];
     const uint32_t num_tiles = (nvis + VIS_THREADS - 1) / VIS_THREADS;
     while (true) {
@@ -320,6 +346,11 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         if (tile >= num_tiles) break;
         const uint32_t cgid = tile * VIS_THREADS + threadIdx.x;
         const bool active = cgid < nvis;
+        TileBox bb;
+        bb.min_x = bb.min_y = bb.max_x = bb.max_y = 0;
+        uint32_t base = 0, budget = 0, e_gid = 0;
+        float e_mx = 0.f, e_my = 0.f, e_pt = 0.f;
+        S2 e_conic; e_conic.c00 = e_conic.c01 = e_conic.c11 = 0.f;
         if (active) {
             const uint32_t gid = __ldg(gid_sorted + cgid);
             float coef[KF];
@@ -361,17 +392,44 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             dst[1] = make_float4(conic.c11, opac, cr, cg);
             dst[2] = make_float4(cb, pt, 0.0f, 0.0f);
             cgid_from_gid[gid] = cgid;
-            // ---- emit (tile id, compact gid) pairs (map_gaussians.rs:26-79)
+            // ---- (tile id, compact gid) pairs (map_gaussians.rs:26-79)
             float ex, ey;
             bbox_extent(conic, pt, ex, ey);
-            TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
-            uint32_t base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
-            uint32_t budget = __ldg(cum + cgid) - base;
+            bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
+            base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
+            budget = __ldg(cum + cgid) - base;
+            e_mx = mx; e_my = my; e_conic = conic; e_pt = pt;
+            e_gid = gid;
+        }
+        // The output slots of a warp's 32 splats are one contiguous range [base(lane 0), base + budget of lane 31):
+        // the keys are gathered in a per-warp shared-memory buffer and written out with coalesced stores (the
+        // owner's compact id goes out the same way).  Warps whose splats cover more tiles than the buffer holds
+        // (rare: very large splats) write directly.
+        const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+        const uint32_t warp_base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t last_end = __shfl_sync(0xffffffffu, base + budget, 31);
+        // inactive lanes carry base = budget = 0: take the end of the last active lane instead
+        uint32_t end_here = active ? base + budget : 0u;
+        for (int o = 16; o > 0; o >>= 1) end_here = max(end_here, __shfl_xor_sync(0xffffffffu, end_here, o));
+        (void)last_end;
+        const uint32_t warp_total = end_here - warp_base;
+        const bool staged = warp_total <= EMIT_BUF;
+        uint32_t *wkeys = s_emit_keys + wid * EMIT_BUF;
+        uint8_t *wown = s_emit_own + wid * EMIT_BUF;
+        if (active) {
+            const uint32_t off = base - warp_base;
+            auto put = [&](uint32_t h, uint32_t key) {
+                if (staged) { wkeys[off + h] = key; wown[off + h] = (uint8_t)lane; }
+                else {
+                    uint32_t o = base + h;
+                    if (o < isect_capacity) { tile_keys[o] = key; isect_vals[o] = cgid; count_key(key); }
+                }
+            };
             uint32_t hits = 0;
             const uint32_t bbw = bb.max_x - bb.min_x, bbh = bb.max_y - bb.min_y;
             if (bbw * bbh <= 64u) {
                 // the counting pass left the hit bits of this bbox: no tile test is repeated here
-                unsigned long long m = __ldg(hit_masks + gid);
+                unsigned long long m = __ldg(hit_masks + e_gid);
                 const unsigned long long row_mask = (bbw >= 64u) ? ~0ull : ((1ull << bbw) - 1ull);
                 uint32_t row_key = bb.min_x + bb.min_y * tiles_x;
                 for (uint32_t ry = 0; ry < bbh && hits < budget; ry++, m = (bbw >= 64u) ? 0ull : (m >> bbw), row_key += tiles_x) {
@@ -379,23 +437,15 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                     while (rb && hits < budget) {
                         uint32_t rx = (uint32_t)__ffsll((long long)rb) - 1u;
                         rb &= rb - 1ull;
-                        uint32_t o = base + hits;
-                        if (o < isect_capacity) {
-                            tile_keys[o] = row_key + rx;
-                            isect_vals[o] = cgid;
-                        }
+                        put(hits, row_key + rx);
                         hits++;
                     }
                 }
             } else {
                 for (uint32_t ty = bb.min_y; ty < bb.max_y && hits < budget; ty++) {
                     for (uint32_t tx = bb.min_x; tx < bb.max_x && hits < budget; tx++) {
-                        if (tile_hit(tx, ty, mx, my, conic, pt)) {
-                            uint32_t o = base + hits;
-                            if (o < isect_capacity) {
-                                tile_keys[o] = tx + ty * tiles_x;
-                                isect_vals[o] = cgid;
-                            }
+                        if (tile_hit(tx, ty, e_mx, e_my, e_conic, e_pt)) {
+                            put(hits, tx + ty * tiles_x);
                             hits++;
                         }
                     }
@@ -403,15 +453,27 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             }
             // same tile_hit as the counting pass => hits == budget; keep the reference's padding
             // so that no slot is ever left unwritten.
-            for (uint32_t pad = hits; pad < budget; pad++) {
-                uint32_t o = base + pad;
+            for (uint32_t pad = hits; pad < budget; pad++) put(pad, tiles_x * tiles_y);
+        }
+        __syncwarp();
+        if (staged) {
+            const uint32_t cg0 = tile * VIS_THREADS + (threadIdx.x & ~31u);
+            for (uint32_t j = lane; j < warp_total; j += 32) {
+                const uint32_t o = warp_base + j;
                 if (o < isect_capacity) {
-                    tile_keys[o] = tiles_x * tiles_y;
-                    isect_vals[o] = cgid;
+                    const uint32_t key = wkeys[j];
+                    tile_keys[o] = key;
+                    isect_vals[o] = cg0 + wown[j];
+                    count_key(key);
                 }
             }
         }
         __syncthreads();
+    }
+    uint32_t *hist = ctl + CTL_HIST_TILE;
+    for (uint32_t i = threadIdx.x; i < hist_passes * 256; i += VIS_THREADS) {
+        const uint32_t c = s_thist[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -486,13 +548,14 @@ static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const f
                                       const float *raw_opac, const uint32_t *gid_sorted, const uint32_t *cum,
                                       const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
                                       uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
-                                      uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl) {
+                                      uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl,
+                                      uint32_t tile_bits) {
     const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
 #define BG_LAUNCH_VIS(D)                                                                                                   \
     if (dist) project_visible_emit_kernel<MIP, D, true><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
-                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl); \
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits); \
     else project_visible_emit_kernel<MIP, D, false><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
-                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl)
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits)
     switch (deg) {
         case 0: BG_LAUNCH_VIS(0); break;
         case 1: BG_LAUNCH_VIS(1); break;
@@ -509,11 +572,12 @@ cudaError_t launch_project_visible_emit(cudaStream_t s, int grid, bool mip, int 
                                         const float *sh, const float *raw_opac, const uint32_t *gid_sorted,
                                         const uint32_t *cum, const BgCamera &u, uint32_t tx, uint32_t ty,
                                         float *projected, uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
-                                        uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl) {
+                                        uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl,
+                                        uint32_t tile_bits) {
     return mip ? launch_visible_deg<true>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty, projected,
-                                          tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl)
+                                          tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits)
                : launch_visible_deg<false>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty,
-                                           projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl);
+                                           projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits);
 }
 
 cudaError_t launch_tile_offsets(cudaStream_t s, int grid, const uint32_t *tile_ids, const uint32_t *ctl,

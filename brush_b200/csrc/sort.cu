@@ -29,26 +29,25 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n_host, const uint
     const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
     for (uint32_t i = threadIdx.x; i < passes * RADIX; i += SORT_THREADS) s_hist[i] = 0;
     __syncthreads();
-    // Runs of equal digits inside a warp (tile ids arrive sorted by splat, so the high digit is one long run)
-    // are added with ONE shared-memory atomic by the run's first lane instead of serialising 32 of them.
+    // Pure stream + shared-memory atomics: four keys per 128-bit load keep enough loads in flight.
+    // (Aggregating runs of equal digits with shuffles/ballots before the atomic measured SLOWER.)
     const uint32_t stride = gridDim.x * SORT_THREADS;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t wbase = blockIdx.x * SORT_THREADS + (threadIdx.x & ~31u); wbase < n; wbase += stride) {
-        const uint32_t i = wbase + lane;
-        const bool valid = i < n;   // invalid lanes only at the top of the last warp
-        const uint32_t k = valid ? __ldg(keys + i) : 0u;
+    const uint32_t tid = blockIdx.x * SORT_THREADS + threadIdx.x;
+    auto add_key = [&](uint32_t k) {
         for (uint32_t p = 0; p < passes; p++) {
-            const uint32_t shift = p * 8, width = min(8u, bits - shift);
-            const uint32_t d = (k >> shift) & ((1u << width) - 1u);
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
-            const bool head = valid && (lane == 0 || d != prev);
-            const uint32_t heads = __ballot_sync(0xffffffffu, head || !valid);
-            if (head) {
-                const uint32_t above = heads & ~((2u << lane) - 1u);
-                const uint32_t run = (above ? (uint32_t)__ffs(above) - 1u : 32u) - lane;
-                atomicAdd(&s_hist[p * RADIX + d], run);
-            }
+            uint32_t shift = p * 8, width = min(8u, bits - shift);
+            atomicAdd(&s_hist[p * RADIX + ((k >> shift) & ((1u << width) - 1u))], 1u);
         }
+    };
+    if ((reinterpret_cast<uintptr_t>(keys) & 15u) == 0) {
+        const uint32_t groups = n / 4u;
+        for (uint32_t g = tid; g < groups; g += stride) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(keys) + g);
+            add_key(q.x); add_key(q.y); add_key(q.z); add_key(q.w);
+        }
+        for (uint32_t i = groups * 4u + tid; i < n; i += stride) add_key(__ldg(keys + i));
+    } else {
+        for (uint32_t i = tid; i < n; i += stride) add_key(__ldg(keys + i));
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < passes * RADIX; i += SORT_THREADS) {
