@@ -304,15 +304,22 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
 }
 
 // K2 + K3.  One thread per visible Gaussian in depth order (compact gid = position in the
-// depth-sorted list).  Every lane gathers its own parameter rows (the gather is by sorted global id,
-// so neighbouring lanes touch unrelated rows anyway): the 192-byte SH row as twelve independent
-// 128-bit loads (whole 32-byte sectors are consumed, 17 loads in flight per thread), no shared-memory
-// staging and no barriers -- the kernel is bound by gather latency, so memory-level parallelism is
-// what counts (ncu: long-scoreboard stalls dominated the staged version).
+// depth-sorted list); WARPS are the unit of work (a ticket = 32 consecutive compact ids), so the loop has no
+// block barrier.  Every lane gathers its own parameter rows (the gather is by sorted global id, so
+// neighbouring lanes touch unrelated rows anyway): the 192-byte SH row as twelve independent 128-bit loads.
+// The kernel is bound by gather latency (ncu: long-scoreboard on the first use of the rows), hence:
+//   * the NEXT ticket and its global ids are fetched at the top of an iteration, and the rows they point at are
+//     pulled into L2 with cp.async.bulk.prefetch.L2 while the current splats are processed;
+//   * the (tile id, compact gid) pairs of a warp -- one contiguous output range -- are gathered in shared memory
+//     and written with coalesced stores; bboxes larger than the 64-bit hit mask are tested by the whole warp.
 constexpr int VIS_THREADS = 128;
 
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {  // p 16-byte aligned, bytes % 16 == 0
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <bool MIP, int DEG, bool DIST>
-__global__ void __launch_bounds__(VIS_THREADS)
+__global__ void __launch_bounds__(VIS_THREADS, 6)
 project_visible_emit_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
                             const float *__restrict__ raw_opac, const uint32_t *__restrict__ gid_sorted,
                             const uint32_t *__restrict__ cum, BgCamera u, uint32_t tiles_x, uint32_t tiles_y,
@@ -323,7 +330,6 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
     constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B are 16-byte aligned
     constexpr uint32_t EMIT_BUF = 1024;                  // staged (tile id, owner) pairs per warp
-    __shared__ uint32_t s_tile;
     __shared__ uint32_t s_emit_keys[(VIS_THREADS / 32) * EMIT_BUF];
     __shared__ uint8_t s_emit_own[(VIS_THREADS / 32) * EMIT_BUF];
     // digit histograms of the emitted tile keys for the one-sweep passes of the tile sort (<= 2 passes: < 65536 tiles)
@@ -338,21 +344,35 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         if (hist_passes > 1) atomicAdd(&s_thist[256 + ((key >> 8) & hi_mask)], 1u);
     };
     const uint32_t nvis = ctl[CTL_COUNTERS + 0];
-    const uint32_t num_tiles = (nvis + VIS_THREADS - 1) / VIS_THREADS;
-    while (true) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl[CTL_TICKETS + TK_VISIBLE], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= num_tiles) break;
-        const uint32_t cgid = tile * VIS_THREADS + threadIdx.x;
+    const uint32_t num_tickets = (nvis + 31u) / 32u;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t *wkeys = s_emit_keys + wid * EMIT_BUF;
+    uint8_t *wown = s_emit_own + wid * EMIT_BUF;
+    auto take_ticket = [&]() {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ctl[CTL_TICKETS + TK_VISIBLE], 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    uint32_t ticket = take_ticket();
+    uint32_t gid = 0;
+    if (ticket < num_tickets && ticket * 32u + lane < nvis) gid = __ldg(gid_sorted + ticket * 32u + lane);
+    while (ticket < num_tickets) {
+        const uint32_t cgid = ticket * 32u + lane;
         const bool active = cgid < nvis;
+        // next ticket: its ids are on their way while this ticket's rows are gathered
+        const uint32_t ticket_next = take_ticket();
+        const bool next_active = ticket_next < num_tickets && ticket_next * 32u + lane < nvis;
+        uint32_t gid_next = 0;
+        if (next_active) gid_next = __ldg(gid_sorted + ticket_next * 32u + lane);
+
         TileBox bb;
         bb.min_x = bb.min_y = bb.max_x = bb.max_y = 0;
-        uint32_t base = 0, budget = 0, e_gid = 0;
+        uint32_t base = 0, budget = 0;
+        unsigned long long hitm = 0ull;
         float e_mx = 0.f, e_my = 0.f, e_pt = 0.f;
         S2 e_conic; e_conic.c00 = e_conic.c01 = e_conic.c11 = 0.f;
         if (active) {
-            const uint32_t gid = __ldg(gid_sorted + cgid);
             float coef[KF];
             if (VEC4) {
                 const float4 *row4 = reinterpret_cast<const float4 *>(sh + (size_t)gid * KF);
@@ -368,6 +388,10 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             }
             const float2 *t2 = reinterpret_cast<const float2 *>(transforms + (size_t)gid * 10);
             float2 a0 = __ldg(t2), a1 = __ldg(t2 + 1), a2 = __ldg(t2 + 2), a3 = __ldg(t2 + 3), a4 = __ldg(t2 + 4);
+            const float ro = __ldg(raw_opac + gid);
+            hitm = __ldg(hit_masks + gid);
+            base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
+            budget = __ldg(cum + cgid) - base;
             V3 mean = mk3(a0.x, a0.y, a1.x);
             Q4 qu; qu.w = a1.y; qu.x = a2.x; qu.y = a2.y; qu.z = a3.x;
             V3 scl = mk3(det_expf(a3.y), det_expf(a4.x), det_expf(a4.y));
@@ -376,7 +400,7 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             S2 raw_cov = calc_cov2d<DIST>(scl, quat, mean_c, u);
             float comp;
             S2 cov = compensate_cov2d<MIP>(raw_cov, comp);
-            float opac = det_sigmoid(__ldg(raw_opac + gid)) * comp;
+            float opac = det_sigmoid(ro) * comp;
             S2 conic = inverse(cov);
             float mx, my;
             project_mean<DIST>(mean_c, u, mx, my);
@@ -396,80 +420,101 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             float ex, ey;
             bbox_extent(conic, pt, ex, ey);
             bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
-            base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
-            budget = __ldg(cum + cgid) - base;
             e_mx = mx; e_my = my; e_conic = conic; e_pt = pt;
-            e_gid = gid;
         }
-        // The output slots of a warp's 32 splats are one contiguous range [base(lane 0), base + budget of lane 31):
-        // the keys are gathered in a per-warp shared-memory buffer and written out with coalesced stores (the
-        // owner's compact id goes out the same way).  Warps whose splats cover more tiles than the buffer holds
-        // (rare: very large splats) write directly.
-        const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+        // pull the next ticket's rows towards L2 (the ids have arrived by now)
+        if (next_active) {
+            const char *srow = reinterpret_cast<const char *>(sh + (size_t)gid_next * KF);
+            const char *trow = reinterpret_cast<const char *>(transforms + (size_t)gid_next * 10);
+            if (VEC4) prefetch_l2_bulk(srow, KF * 4);
+            prefetch_l2_bulk(reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(trow) & ~(uintptr_t)15), 48);
+        }
+        // The output slots of a warp's 32 splats are one contiguous range [base(lane 0), end(last active lane)).
         const uint32_t warp_base = __shfl_sync(0xffffffffu, base, 0);
-        const uint32_t last_end = __shfl_sync(0xffffffffu, base + budget, 31);
-        // inactive lanes carry base = budget = 0: take the end of the last active lane instead
         uint32_t end_here = active ? base + budget : 0u;
         for (int o = 16; o > 0; o >>= 1) end_here = max(end_here, __shfl_xor_sync(0xffffffffu, end_here, o));
-        (void)last_end;
         const uint32_t warp_total = end_here - warp_base;
         const bool staged = warp_total <= EMIT_BUF;
-        uint32_t *wkeys = s_emit_keys + wid * EMIT_BUF;
-        uint8_t *wown = s_emit_own + wid * EMIT_BUF;
-        if (active) {
-            const uint32_t off = base - warp_base;
-            auto put = [&](uint32_t h, uint32_t key) {
-                if (staged) { wkeys[off + h] = key; wown[off + h] = (uint8_t)lane; }
-                else {
-                    uint32_t o = base + h;
-                    if (o < isect_capacity) { tile_keys[o] = key; isect_vals[o] = cgid; count_key(key); }
-                }
-            };
+        const uint32_t off = base - warp_base;
+        const uint32_t bbw = bb.max_x - bb.min_x, bbh = bb.max_y - bb.min_y;
+        const bool big = active && bbw * bbh > 64u;
+        auto put = [&](uint32_t slot_off, uint32_t slot_base, uint32_t owner_lane, uint32_t h, uint32_t key) {
+            if (staged) { wkeys[slot_off + h] = key; wown[slot_off + h] = (uint8_t)owner_lane; }
+            else {
+                uint32_t o = slot_base + h;
+                if (o < isect_capacity) { tile_keys[o] = key; isect_vals[o] = ticket * 32u + owner_lane; count_key(key); }
+            }
+        };
+        if (active && !big) {
+            // the counting pass left the hit bits of this bbox: no tile test is repeated here
             uint32_t hits = 0;
-            const uint32_t bbw = bb.max_x - bb.min_x, bbh = bb.max_y - bb.min_y;
-            if (bbw * bbh <= 64u) {
-                // the counting pass left the hit bits of this bbox: no tile test is repeated here
-                unsigned long long m = __ldg(hit_masks + e_gid);
-                const unsigned long long row_mask = (bbw >= 64u) ? ~0ull : ((1ull << bbw) - 1ull);
-                uint32_t row_key = bb.min_x + bb.min_y * tiles_x;
-                for (uint32_t ry = 0; ry < bbh && hits < budget; ry++, m = (bbw >= 64u) ? 0ull : (m >> bbw), row_key += tiles_x) {
-                    unsigned long long rb = m & row_mask;
-                    while (rb && hits < budget) {
-                        uint32_t rx = (uint32_t)__ffsll((long long)rb) - 1u;
-                        rb &= rb - 1ull;
-                        put(hits, row_key + rx);
-                        hits++;
-                    }
-                }
-            } else {
-                for (uint32_t ty = bb.min_y; ty < bb.max_y && hits < budget; ty++) {
-                    for (uint32_t tx = bb.min_x; tx < bb.max_x && hits < budget; tx++) {
-                        if (tile_hit(tx, ty, e_mx, e_my, e_conic, e_pt)) {
-                            put(hits, tx + ty * tiles_x);
-                            hits++;
-                        }
-                    }
+            unsigned long long m = hitm;
+            const unsigned long long row_mask = (bbw >= 64u) ? ~0ull : ((1ull << bbw) - 1ull);
+            uint32_t row_key = bb.min_x + bb.min_y * tiles_x;
+            for (uint32_t ry = 0; ry < bbh && hits < budget; ry++, m = (bbw >= 64u) ? 0ull : (m >> bbw), row_key += tiles_x) {
+                unsigned long long rb = m & row_mask;
+                while (rb && hits < budget) {
+                    uint32_t rx = (uint32_t)__ffsll((long long)rb) - 1u;
+                    rb &= rb - 1ull;
+                    put(off, base, lane, hits, row_key + rx);
+                    hits++;
                 }
             }
-            // same tile_hit as the counting pass => hits == budget; keep the reference's padding
-            // so that no slot is ever left unwritten.
-            for (uint32_t pad = hits; pad < budget; pad++) put(pad, tiles_x * tiles_y);
+            // same hits as the counting pass => hits == budget; keep the reference's padding so that no slot is
+            // ever left unwritten.
+            for (uint32_t pad = hits; pad < budget; pad++) put(off, base, lane, pad, tiles_x * tiles_y);
+        }
+        // bboxes beyond the 64-bit mask (0.3 % of the splats of the 1M/1080p scene, 75+ tiles each): the whole
+        // warp tests 32 tiles of one such splat at a time instead of one lane walking them alone.
+        uint32_t bigs = __ballot_sync(0xffffffffu, big);
+        while (bigs) {
+            const uint32_t L = (uint32_t)__ffs(bigs) - 1u;
+            bigs &= bigs - 1u;
+            const float mx = __shfl_sync(0xffffffffu, e_mx, L), my = __shfl_sync(0xffffffffu, e_my, L);
+            S2 conic;
+            conic.c00 = __shfl_sync(0xffffffffu, e_conic.c00, L);
+            conic.c01 = __shfl_sync(0xffffffffu, e_conic.c01, L);
+            conic.c11 = __shfl_sync(0xffffffffu, e_conic.c11, L);
+            const float pt = __shfl_sync(0xffffffffu, e_pt, L);
+            const uint32_t min_x = __shfl_sync(0xffffffffu, bb.min_x, L), min_y = __shfl_sync(0xffffffffu, bb.min_y, L);
+            const uint32_t w_ = __shfl_sync(0xffffffffu, bbw, L), h_ = __shfl_sync(0xffffffffu, bbh, L);
+            const uint32_t off_l = __shfl_sync(0xffffffffu, off, L), base_l = __shfl_sync(0xffffffffu, base, L);
+            const uint32_t budget_l = __shfl_sync(0xffffffffu, budget, L);
+            const uint32_t ntile = w_ * h_;
+            uint32_t cnt = 0;
+            for (uint32_t j0 = 0; j0 < ntile; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                bool hit = false;
+                uint32_t key = 0;
+                if (j < ntile) {
+                    const uint32_t ry = j / w_, rx = j - ry * w_;
+                    hit = tile_hit(min_x + rx, min_y + ry, mx, my, conic, pt);
+                    key = (min_x + rx) + (min_y + ry) * tiles_x;
+                }
+                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                const uint32_t pos = cnt + __popc(hb & lt_mask);
+                if (hit && pos < budget_l) put(off_l, base_l, L, pos, key);
+                cnt += __popc(hb);
+            }
+            for (uint32_t pad = min(cnt, budget_l) + lane; pad < budget_l; pad += 32) put(off_l, base_l, L, pad, tiles_x * tiles_y);
         }
         __syncwarp();
         if (staged) {
-            const uint32_t cg0 = tile * VIS_THREADS + (threadIdx.x & ~31u);
             for (uint32_t j = lane; j < warp_total; j += 32) {
                 const uint32_t o = warp_base + j;
                 if (o < isect_capacity) {
                     const uint32_t key = wkeys[j];
                     tile_keys[o] = key;
-                    isect_vals[o] = cg0 + wown[j];
+                    isect_vals[o] = ticket * 32u + wown[j];
                     count_key(key);
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
+        ticket = ticket_next;
+        gid = gid_next;
     }
+    __syncthreads();
     uint32_t *hist = ctl + CTL_HIST_TILE;
     for (uint32_t i = threadIdx.x; i < hist_passes * 256; i += VIS_THREADS) {
         const uint32_t c = s_thist[i];
