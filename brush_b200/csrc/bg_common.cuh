@@ -87,6 +87,18 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100): one whole 32-byte sector per lane, so a row-per-lane
+// gather does not depend on L1 keeping half-used sectors between two 128-bit loads.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float *p, float *o) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float *p, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -329,6 +329,8 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                             uint32_t *__restrict__ ctl, uint32_t tile_bits) {
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
     constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B are 16-byte aligned
+    constexpr bool VEC8 = (KF % 8) == 0;                 // 192 B rows: six 256-bit loads when the base is 32-byte aligned
+    const bool sh_align32 = (reinterpret_cast<uintptr_t>(sh) & 31u) == 0;
     constexpr uint32_t EMIT_BUF = 1024;                  // staged (tile id, owner) pairs per warp
     __shared__ uint32_t s_emit_keys[(VIS_THREADS / 32) * EMIT_BUF];
     __shared__ uint8_t s_emit_own[(VIS_THREADS / 32) * EMIT_BUF];
@@ -374,7 +376,11 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         S2 e_conic; e_conic.c00 = e_conic.c01 = e_conic.c11 = 0.f;
         if (active) {
             float coef[KF];
-            if (VEC4) {
+            if (VEC8 && sh_align32) {
+                const float *row = sh + (size_t)gid * KF;
+#pragma unroll
+                for (int i = 0; i < KF / 8; i++) ldg256(row + 8 * i, coef + 8 * i);
+            } else if (VEC4) {
                 const float4 *row4 = reinterpret_cast<const float4 *>(sh + (size_t)gid * KF);
 #pragma unroll
                 for (int i = 0; i < KF / 4; i++) {

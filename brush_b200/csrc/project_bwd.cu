@@ -185,6 +185,9 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
     // (128-bit accesses when the row is a multiple of 16 bytes): consecutive threads own consecutive rows, so a
     // warp's 12 accesses cover one contiguous 6 KB span and every fetched sector is used out of L1.
     constexpr bool VEC4 = (KF % 4) == 0;
+    constexpr bool VEC8 = (KF % 8) == 0;   // 256-bit accesses when the arrays are 32-byte aligned
+    const bool in32 = (reinterpret_cast<uintptr_t>(sh) & 31u) == 0;
+    const bool out32 = (reinterpret_cast<uintptr_t>(v_sh) & 31u) == 0;
     __shared__ __align__(16) float s_vt[PB_THREADS * 10];
     const uint32_t base = blockIdx.x * PB_THREADS;
     const uint32_t rows = min((uint32_t)PB_THREADS, n - base);
@@ -232,7 +235,10 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
         if (DEG > 0) {   // S_k = coeff_k . v_color; degree 0 has no view-direction dependence: its row is never read
             float row[KF];
             const float *src = sh + (size_t)gid * KF;
-            if (VEC4) {
+            if (VEC8 && in32) {
+#pragma unroll
+                for (int q = 0; q < KF / 8; q++) ldg256(src + 8 * q, row + 8 * q);
+            } else if (VEC4) {
 #pragma unroll
                 for (int q = 0; q < KF / 4; q++) {
                     float4 t = __ldg(reinterpret_cast<const float4 *>(src) + q);
@@ -293,7 +299,10 @@ project_bwd_kernel(const float *__restrict__ transforms, const float *__restrict
                 row[3 * k + 2] = v_color.z * yk;
             }
             float *dst = v_sh + (size_t)gid * KF;
-            if (VEC4) {
+            if (VEC8 && out32) {
+#pragma unroll
+                for (int q = 0; q < KF / 8; q++) stg256(dst + 8 * q, row + 8 * q);
+            } else if (VEC4) {
 #pragma unroll
                 for (int q = 0; q < KF / 4; q++)
                     reinterpret_cast<float4 *>(dst)[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);

@@ -119,7 +119,7 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
                 hit = block_may_hit(A.x, A.y, A.z, A.w, B.x, pt + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f), rx0, rx1, ry0, ry1);
             }
             uint32_t bits = __ballot_sync(0xffffffffu, hit);
-            uint32_t used = 0;
+            uint32_t used_l = 0;
 #ifdef BG_STATS
             st_tested += count; st_iters += __popc(bits);
 #endif
@@ -141,15 +141,17 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
                 { uint32_t m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
                   st_pairs += __popc(m0) + __popc(m1); st_useful += (m0 | m1) ? 1 : 0; }
 #endif
-                if (__any_sync(0xffffffffu, c0 || c1)) {
-                    const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cb = fmaxf(row[8], 0.0f);
-                    const float v0 = c0 ? vis0 : 0.0f, v1 = c1 ? vis1 : 0.0f;
-                    p0.r = fmaf(cr, v0, p0.r); p0.g = fmaf(cg, v0, p0.g); p0.b = fmaf(cb, v0, p0.b);
-                    p1.r = fmaf(cr, v1, p1.r); p1.g = fmaf(cg, v1, p1.g); p1.b = fmaf(cb, v1, p1.b);
-                    used |= 1u << s;
-                }
-                if (__any_sync(0xffffffffu, st0 || st1) && __all_sync(0xffffffffu, p0.done && p1.done)) bits = 0;
+                // No votes inside the splat loop: after the exact block cull nearly every surviving splat has a
+                // contributing lane, so the blend runs unconditionally (weights are zero where it does not apply),
+                // each lane remembers which splats its pixels used, and "all pixels saturated" is checked once per
+                // batch (saturated pixels ignore the remaining splats of the batch; nothing they do is observable).
+                const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cb = fmaxf(row[8], 0.0f);
+                const float v0 = c0 ? vis0 : 0.0f, v1 = c1 ? vis1 : 0.0f;
+                p0.r = fmaf(cr, v0, p0.r); p0.g = fmaf(cg, v0, p0.g); p0.b = fmaf(cb, v0, p0.b);
+                p1.r = fmaf(cr, v1, p1.r); p1.g = fmaf(cg, v1, p1.g); p1.b = fmaf(cb, v1, p1.b);
+                if (c0 || c1) used_l |= 1u << s;
             }
+            const uint32_t used = __reduce_or_sync(0xffffffffu, used_l);
             if (BWD_INFO && ((used >> lane) & 1u)) {
                 visible[__ldg(gid_from_cgid + my_id)] = 1.0f;
                 last_useful = batch_start + lane + 1;
