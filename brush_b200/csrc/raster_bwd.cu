@@ -78,19 +78,20 @@ __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.appro
 
 // Adds one pair's terms to the lane's partial sums g[0..9] and advances the pixel state.  Branch-free:
 // a pair that does not contribute (c == false) is multiplied out, so both pixels of a lane run the same
-// instruction stream.  cr/cg/cb = max(colour, 0); gr/gg/gb = 1 where the raw colour is >= 0 (the
-// colour VJP gate, rasterize_backwards.rs:335-337).
+// instruction stream.  cr/cg/cb = max(colour, 0).
 template <bool SMOOTH>
 __device__ __forceinline__ void bwd_accumulate(BwdPixel &p, float *g, bool c, float dx, float dy, float ca, float cb,
-                                               float cc, float cr, float cg, float cbl, float gr, float gg, float gb,
+                                               float cc, float cr, float cg, float cbl,
                                                float gaussian, float oa, float alpha, float w_cut, float next_T,
                                                float img_wf, float img_hf) {
     const float wf = c ? 1.0f : 0.0f;
     const float alpha_eff = alpha * w_cut;
     const float vis = alpha_eff * p.T * wf;
-    g[5] = fmaf(gr * vis, p.vo_r, g[5]);
-    g[6] = fmaf(gg * vis, p.vo_g, g[6]);
-    g[7] = fmaf(gb * vis, p.vo_b, g[7]);
+    // colour sums are accumulated ungated and the 0.5 of the conic diagonal is left out: both are per-splat
+    // constants, applied once to the lane's partial sums before the reduction
+    g[5] = fmaf(vis, p.vo_r, g[5]);
+    g[6] = fmaf(vis, p.vo_g, g[6]);
+    g[7] = fmaf(vis, p.vo_b, g[7]);
     const float ra = rcp_approx(1.0f - alpha_eff);
     float dot = fmaf(p.T, cr, -p.rem_r) * p.vo_r;
     dot = fmaf(fmaf(p.T, cg, -p.rem_g), p.vo_g, dot);
@@ -105,9 +106,9 @@ __device__ __forceinline__ void bwd_accumulate(BwdPixel &p, float *g, bool c, fl
     const float vxy_y = fmaf(cb, vsx, cc * vsy);
     g[0] += vxy_x;
     g[1] += vxy_y;
-    g[2] = fmaf(0.5f * vsx, dx, g[2]);
+    g[2] = fmaf(vsx, dx, g[2]);
     g[3] = fmaf(vsx, dy, g[3]);
-    g[4] = fmaf(0.5f * vsy, dy, g[4]);
+    g[4] = fmaf(vsy, dy, g[4]);
     g[8] = fmaf(v_alpha_g, gaussian, g[8]);
     const float sx = vxy_x * img_wf, sy = vxy_y * img_hf;
     g[9] = fmaf(sqrt_approx(fmaf(sx, sx, sy * sy)), p.inv_fa, g[9]);
@@ -209,9 +210,12 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             for (int i = 0; i < 10; i++) g[i] = 0.0f;
             const float col_b = row[8];
             const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cbl = fmaxf(col_b, 0.0f);
-            const float gr = (B.z >= 0.0f) ? 1.0f : 0.0f, gg = (B.w >= 0.0f) ? 1.0f : 0.0f, gb = (col_b >= 0.0f) ? 1.0f : 0.0f;
-            bwd_accumulate<SMOOTH>(p0, g, c0, dx, dy0, A.z, A.w, B.x, cr, cg, cbl, gr, gg, gb, ga0, oa0, al0, wc0, nt0, img_wf, img_hf);
-            bwd_accumulate<SMOOTH>(p1, g, c1, dx, dy1, A.z, A.w, B.x, cr, cg, cbl, gr, gg, gb, ga1, oa1, al1, wc1, nt1, img_wf, img_hf);
+            bwd_accumulate<SMOOTH>(p0, g, c0, dx, dy0, A.z, A.w, B.x, cr, cg, cbl, ga0, oa0, al0, wc0, nt0, img_wf, img_hf);
+            bwd_accumulate<SMOOTH>(p1, g, c1, dx, dy1, A.z, A.w, B.x, cr, cg, cbl, ga1, oa1, al1, wc1, nt1, img_wf, img_hf);
+            g[2] *= 0.5f; g[4] *= 0.5f;
+            g[5] = (B.z >= 0.0f) ? g[5] : 0.0f;   // colour VJP gate (rasterize_backwards.rs:335-337)
+            g[6] = (B.w >= 0.0f) ? g[6] : 0.0f;
+            g[7] = (col_b >= 0.0f) ? g[7] : 0.0f;
             // ---- reduce-scatter 10 values over 32 lanes: 5+3+2+1+1 shuffles
             float a5[6];
 #pragma unroll
