@@ -29,7 +29,7 @@ cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, con
                               uint32_t *);
 cudaError_t launch_onesweep_pass(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *,
                                  uint32_t, const uint32_t *, uint32_t, uint32_t, const uint32_t *, uint32_t *,
-                                 unsigned long long *, const uint32_t *, uint32_t);
+                                 unsigned long long *, unsigned long long *, const uint32_t *, uint32_t);
 cudaError_t launch_bump_epoch(cudaStream_t, uint32_t *);
 uint32_t sort_tile_size();
 // raster_fwd.cu / raster_bwd.cu / project_bwd.cu
@@ -95,7 +95,7 @@ struct BgContext {
     uint32_t *tile_offsets = nullptr;
     unsigned long long *lb_scan = nullptr;  // look-back words for project/scan kernels
     unsigned long long *lb_sort = nullptr;  // look-back words for the sort passes: [tiles][256]
-    uint64_t lb_scan_words = 0, lb_sort_words = 0;
+    uint64_t lb_scan_words = 0, lb_sort_words = 0, lb_sort_tile_words = 0;
     uint32_t *counters_host = nullptr;      // pinned [4]
     // last forward (for state pointers)
     int depth_out = 0, isect_out = 0;
@@ -149,7 +149,8 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
     c->sm_count = prop.multiProcessorCount;
     const uint64_t n = max_splats, I = c->max_isect;
     const uint64_t sort_tiles = (std::max<uint64_t>(n, I) + sort_tile_size() - 1) / sort_tile_size() + 1;
-    c->lb_sort_words = sort_tiles * 256;
+    c->lb_sort_tile_words = sort_tiles * 256;
+    c->lb_sort_words = c->lb_sort_tile_words + (sort_tiles / 16 + 2) * 256;   // tile counts + group totals
     c->lb_scan_words = (n + 255) / 256 + 64;
     bool ok = true;
     ok = ok && arena_alloc(c, &c->ctl, 2 * CTL_WORDS) == cudaSuccess;
@@ -204,7 +205,8 @@ static int32_t run_sort(BgContext *c, cudaStream_t s, const uint32_t *key_in, co
     for (uint32_t p = 0; p < passes; p++) {
         const uint32_t shift = p * 8, width = std::min(8u, bits - shift);
         BG_CUDA(launch_onesweep_pass(s, c->sm_count * 3, kin, vin, keys[dst], vals[dst], n_host, n_dev, shift, width,
-                                     hist + p * 256, tickets + 1 + p, c->lb_sort, c->epoch_dev, epoch_slot0 + p));
+                                     hist + p * 256, tickets + 1 + p, c->lb_sort, c->lb_sort + c->lb_sort_tile_words, c->epoch_dev,
+                                     epoch_slot0 + p));
         kin = keys[dst]; vin = vals[dst];
         *out_idx = dst;
         dst ^= 1;

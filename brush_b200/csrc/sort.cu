@@ -56,13 +56,14 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n_host, const uint
     }
 }
 
-// One digit pass.  lb_state: [num_tiles][256] look-back words for this pass.
+// One digit pass.  lb_state: [num_tiles][256] tile counts, lb_group: [ceil(num_tiles/16)][256] group totals.
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
                      const uint32_t *__restrict__ n_dev, uint32_t shift, uint32_t width,
                      const uint32_t *__restrict__ hist /* this pass: [256] */, uint32_t *__restrict__ ticket,
-                     unsigned long long *__restrict__ lb_state, const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
+                     unsigned long long *__restrict__ lb_state, unsigned long long *__restrict__ lb_group,
+                     const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
     // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
     // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
     const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
@@ -144,11 +145,15 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
             my_count = sum;
         }
         // ---- publish the aggregate (thread d serves digit d), then reorder the tile in shared memory;
-        // only after that look back.  The reorder frees the key/value registers, so the look-back can
-        // keep LB_BATCH independent loads in flight: in steady state a tile sits behind ~gridDim
-        // predecessors that only hold aggregates, and a serial walk would cost one L2 round trip each.
+        // only after that look back.  Two-level decoupled look-back: tile words only ever hold the tile's own
+        // count; a tile sums the counts of the earlier tiles of its group of LB_GROUP (one batch of independent
+        // loads), the group's last tile publishes the group total, and the group totals are chained with the
+        // usual aggregate -> inclusive protocol.  A 1M-key sort runs all its ~230 tiles at once: with a flat chain
+        // the last tile walked ~230 predecessors, 16 per L2 round trip; now any tile needs about three round trips.
+        constexpr uint32_t LB_GROUP = 16;
+        const uint32_t grp = tile / LB_GROUP, r = tile % LB_GROUP;
         unsigned long long *st = lb_state + (size_t)tile * RADIX + threadIdx.x;
-        lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, my_count);
+        lb_store(st, epoch, LB_AGGREGATE, my_count);
         uint32_t bin_total;
         uint32_t bin_start = block_exclusive_scan(my_count, s_scan, &bin_total);
         s_bin_start[threadIdx.x] = bin_start;
@@ -160,17 +165,36 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
             s_keys[pos] = key[i];
             s_vals[pos] = val[i];
         }
-        uint32_t prefix = 0;
-        if (tile != 0) {
+        uint32_t in_group = 0;
+        {
+            unsigned long long w[LB_GROUP - 1];
+#pragma unroll
+            for (uint32_t q = 0; q < LB_GROUP - 1; q++)
+                w[q] = (q < r) ? lb_load(lb_state + (size_t)(tile - 1u - q) * RADIX + threadIdx.x) : 0ull;
+#pragma unroll
+            for (uint32_t q = 0; q < LB_GROUP - 1; q++) {
+                if (q < r) {
+                    while (lb_status(w[q], epoch) == LB_INVALID)
+                        w[q] = lb_load(lb_state + (size_t)(tile - 1u - q) * RADIX + threadIdx.x);
+                    in_group += lb_value(w[q]);
+                }
+            }
+        }
+        const bool closes_group = (r == LB_GROUP - 1u) || (tile == num_tiles - 1u);
+        const uint32_t group_total = in_group + my_count;
+        unsigned long long *gst = lb_group + (size_t)grp * RADIX + threadIdx.x;
+        if (closes_group) lb_store(gst, epoch, grp == 0 ? LB_INCLUSIVE : LB_AGGREGATE, group_total);
+        uint32_t gprefix = 0;
+        if (grp != 0) {
             constexpr int LB_BATCH = 16;
-            int64_t t = (int64_t)tile - 1;
+            int64_t t = (int64_t)grp - 1;
             bool done_lb = false;
             while (!done_lb) {
                 unsigned long long w[LB_BATCH];
 #pragma unroll
                 for (int q = 0; q < LB_BATCH; q++) {
                     int64_t tt = t - q;
-                    w[q] = (tt >= 0) ? lb_load(lb_state + (size_t)tt * RADIX + threadIdx.x) : 0ull;
+                    w[q] = (tt >= 0) ? lb_load(lb_group + (size_t)tt * RADIX + threadIdx.x) : 0ull;
                 }
 #pragma unroll
                 for (int q = 0; q < LB_BATCH; q++) {
@@ -179,16 +203,17 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
                     if (tt < 0) { done_lb = true; break; }
                     uint32_t stt = lb_status(w[q], epoch);
                     while (stt == LB_INVALID) {  // not published yet: wait on this one word
-                        w[q] = lb_load(lb_state + (size_t)tt * RADIX + threadIdx.x);
+                        w[q] = lb_load(lb_group + (size_t)tt * RADIX + threadIdx.x);
                         stt = lb_status(w[q], epoch);
                     }
-                    prefix += lb_value(w[q]);
+                    gprefix += lb_value(w[q]);
                     if (stt == LB_INCLUSIVE) done_lb = true;
                 }
                 t -= LB_BATCH;
             }
-            lb_store(st, epoch, LB_INCLUSIVE, prefix + my_count);
+            if (closes_group) lb_store(gst, epoch, LB_INCLUSIVE, gprefix + group_total);
         }
+        const uint32_t prefix = gprefix + in_group;
         s_bin_dst[threadIdx.x] = (int64_t)s_digit_base[threadIdx.x] + (int64_t)prefix - (int64_t)bin_start;
         __syncthreads();
         // ---- coalesced scatter: consecutive positions of one bin go to consecutive addresses
@@ -212,9 +237,10 @@ cudaError_t launch_radix_hist(cudaStream_t s, int grid, const uint32_t *keys, ui
 cudaError_t launch_onesweep_pass(cudaStream_t s, int grid, const uint32_t *keys_in, const uint32_t *vals_in,
                                  uint32_t *keys_out, uint32_t *vals_out, uint32_t n_host, const uint32_t *n_dev,
                                  uint32_t shift, uint32_t width, const uint32_t *hist, uint32_t *ticket,
-                                 unsigned long long *lb, const uint32_t *epoch_base, uint32_t epoch_off) {
+                                 unsigned long long *lb, unsigned long long *lb_group, const uint32_t *epoch_base,
+                                 uint32_t epoch_off) {
     onesweep_pass_kernel<<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift, width,
-                                                       hist, ticket, lb, epoch_base, epoch_off);
+                                                       hist, ticket, lb, lb_group, epoch_base, epoch_off);
     return cudaGetLastError();
 }
 
