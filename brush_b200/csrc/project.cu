@@ -232,8 +232,8 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
 // consecutive compact ids), so the loop has no block barrier.
 //   * Every lane gathers its own parameter rows (the gather is by sorted global id, so neighbouring lanes touch
 //     unrelated rows anyway): the 192-byte SH row as six 256-bit loads.  The kernel is bound by gather latency, so
-//     the rows of the ticket that the grid will reach one iteration from now are pulled into L2 with
-//     cp.async.bulk.prefetch.L2 while the current splats are processed.
+//     the NEXT ticket and its ids are fetched at the top of an iteration and the rows they point at are pulled
+//     into L2 with cp.async.bulk.prefetch.L2 while the current splats are processed.
 //   * Tile intersection (helpers.rs:203-264, map_gaussians.rs:26-79): the candidate tiles of the warp's 32 splats
 //     are flattened into one list and tested 32 at a time, whoever they belong to (binary search of the owner over
 //     the exclusive prefix of the per-lane bbox sizes) -- a per-thread walk would cost the warp its LARGEST bbox.
@@ -331,16 +331,15 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             }
         }
     };
-    // Tickets are taken when they are processed, NOT one iteration ahead: a ticket that is reserved but not yet
-    // counted holds up the offsets of every later ticket.  The L2 prefetch therefore targets the ticket that some
-    // warp of the grid will take about one iteration from now (ticket + number of warps in the grid).
-    const uint32_t pf_dist = gridDim.x * (VIS_THREADS / 32);
     uint32_t ticket = take_ticket();
+    uint32_t gid = 0;
+    if (ticket < num_tickets && ticket * 32u + lane < nvis) gid = __ldg(gid_sorted + ticket * 32u + lane);
     // the ticket whose pairs are staged and waiting for their offset
     bool pend = false, pend_closer = false;
     uint32_t pend_ticket = 0, pend_cnt = 0, pend_total = 0, cur = 0;
     while (ticket < num_tickets || pend) {
         const bool have = ticket < num_tickets;
+        uint32_t ticket_next = ticket, gid_next = 0;
         uint32_t cnt = 0, group_total = 0;
         bool closer = false, staged_ok = false;
         uint32_t *wkeys = wkeys_base + cur * EMIT_BUF;
@@ -348,11 +347,10 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         if (have) {
         const uint32_t cgid = ticket * 32u + lane;
         const bool active = cgid < nvis;
-        const uint32_t gid = active ? __ldg(gid_sorted + cgid) : 0u;
-        const uint32_t far = ticket + pf_dist;
-        const bool next_active = far < num_tickets && far * 32u + lane < nvis;
-        uint32_t gid_next = 0;
-        if (next_active) gid_next = __ldg(gid_sorted + far * 32u + lane);
+        // next ticket: its ids are on their way while this ticket's rows are gathered
+        ticket_next = take_ticket();
+        const bool next_active = ticket_next < num_tickets && ticket_next * 32u + lane < nvis;
+        if (next_active) gid_next = __ldg(gid_sorted + ticket_next * 32u + lane);
 
         uint32_t min_x = 0, min_y = 0, bbw = 0, ntiles = 0;
         float e_mx = 0.f, e_my = 0.f, e_pt = 0.f;
@@ -409,7 +407,7 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             ntiles = (bb.max_y - bb.min_y) * bbw;
             e_mx = mx; e_my = my; e_conic = conic; e_pt = pt;
         }
-        // pull the rows of a ticket one grid-iteration ahead towards L2 (its ids have arrived by now)
+        // pull the next ticket's rows towards L2 (the ids have arrived by now)
         if (next_active) {
             const char *srow = reinterpret_cast<const char *>(sh + (size_t)gid_next * KF);
             const char *trow = reinterpret_cast<const char *>(transforms + (size_t)gid_next * 10);
@@ -497,7 +495,7 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         pend = have && staged_ok;
         pend_ticket = ticket; pend_cnt = cnt; pend_closer = closer; pend_total = group_total;
         cur ^= 1u;
-        if (have) ticket = take_ticket();
+        if (have) { ticket = ticket_next; gid = gid_next; }
     }
     __syncthreads();
     uint32_t *hist = ctl + CTL_HIST_TILE;

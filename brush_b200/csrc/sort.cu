@@ -17,11 +17,8 @@
 namespace bg {
 
 constexpr int SORT_THREADS = 256;
-// Keys per thread: 16 (4096-key tiles) for large inputs -- fewest look-back words, best coalescing; 4 (1024-key
-// tiles) when the input is small enough that 4096-key tiles would leave most SMs with a single tile and a
-// 16-deep serial ranking chain (the depth sort of ~1M keys ran 230 tiles on 148 SMs: latency-bound, not HBM-bound).
-constexpr int SORT_ITEMS_LARGE = 16, SORT_ITEMS_SMALL = 4;
-constexpr uint32_t SORT_SMALL_MAX = 1u << 21;   // inputs up to 2M keys use the small tiles
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int RADIX = 256;
 
 // hist[p*256 + d] += #keys whose p-th digit is d, for p < passes.
@@ -60,7 +57,6 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n_host, const uint
 }
 
 // One digit pass.  lb_state: [num_tiles][256] tile counts, lb_group: [ceil(num_tiles/16)][256] group totals.
-template <int SORT_ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
@@ -70,7 +66,6 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
                      const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
     // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
     // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
-    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
     __shared__ uint32_t s_keys[SORT_TILE];
     __shared__ uint32_t s_vals[SORT_TILE];
@@ -244,21 +239,12 @@ cudaError_t launch_onesweep_pass(cudaStream_t s, int grid, const uint32_t *keys_
                                  uint32_t shift, uint32_t width, const uint32_t *hist, uint32_t *ticket,
                                  unsigned long long *lb, unsigned long long *lb_group, const uint32_t *epoch_base,
                                  uint32_t epoch_off) {
-    // the tile size follows the CAPACITY n_host (the device-side count n_dev can only be smaller)
-    if (n_host <= SORT_SMALL_MAX)
-        onesweep_pass_kernel<SORT_ITEMS_SMALL><<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev,
-                                                                             shift, width, hist, ticket, lb, lb_group, epoch_base, epoch_off);
-    else
-        onesweep_pass_kernel<SORT_ITEMS_LARGE><<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev,
-                                                                             shift, width, hist, ticket, lb, lb_group, epoch_base, epoch_off);
+    onesweep_pass_kernel<<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift, width,
+                                                       hist, ticket, lb, lb_group, epoch_base, epoch_off);
     return cudaGetLastError();
 }
 
-// look-back tiles needed for a sort of up to n keys (capacity)
-uint64_t sort_num_tiles(uint64_t n) {
-    const uint64_t tile = (n <= SORT_SMALL_MAX) ? SORT_THREADS * SORT_ITEMS_SMALL : SORT_THREADS * SORT_ITEMS_LARGE;
-    return (n + tile - 1) / tile + 1;
-}
+uint32_t sort_tile_size() { return SORT_TILE; }
 
 }  // namespace bg
 
