@@ -22,7 +22,7 @@ cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32
 cudaError_t launch_project_visible_emit(cudaStream_t, int, bool, int, const float *, const float *, const float *,
                                         const uint32_t *, const BgCamera &, uint32_t, uint32_t, float *, uint32_t *,
                                         uint32_t *, uint32_t, uint32_t *, uint32_t *, uint32_t, unsigned long long *,
-                                        unsigned long long *, unsigned long long *, const uint32_t *, uint32_t);
+                                        unsigned long long *, const uint32_t *, uint32_t);
 cudaError_t launch_tile_offsets(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, uint32_t *);
 // sort.cu
 cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, const uint32_t *, uint32_t, uint32_t,
@@ -88,7 +88,7 @@ struct BgContext {
     uint32_t *depth_val[2] = {nullptr, nullptr};
     uint32_t *cgid_from_gid = nullptr;
     unsigned long long *lb_emit = nullptr;  // look-back words of project_visible_emit: [tickets] + [ticket groups]
-    uint64_t lb_emit_warp_words = 0, lb_emit_group_words = 0, lb_emit_words = 0;
+    uint64_t lb_emit_warp_words = 0, lb_emit_words = 0;
     float *projected = nullptr;
     uint32_t *isect_key[2] = {nullptr, nullptr};
     uint32_t *isect_val[2] = {nullptr, nullptr};
@@ -161,8 +161,7 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
         ok = ok && arena_alloc(c, &c->isect_val[i], I) == cudaSuccess;
     }
     c->lb_emit_warp_words = ((uint64_t)n + 31) / 32 + 64;
-    c->lb_emit_group_words = c->lb_emit_warp_words / 32 + 64;
-    c->lb_emit_words = c->lb_emit_warp_words + 2 * c->lb_emit_group_words;   // ticket counts | group totals | group accumulators
+    c->lb_emit_words = c->lb_emit_warp_words + c->lb_emit_warp_words / 32 + 64;
     ok = ok && arena_alloc(c, &c->lb_emit, c->lb_emit_words) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->cgid_from_gid, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->projected, n * BG_PROJECTED_STRIDE) == cudaSuccess;
@@ -243,8 +242,6 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     BG_CUDA(cudaMemsetAsync(c->ctl, 0, CTL_WORDS * sizeof(uint32_t), s));
     BG_CUDA(cudaMemsetAsync(c->tile_offsets, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
     if (bwd_info && n > 0) BG_CUDA(cudaMemsetAsync(visible, 0, (size_t)n * sizeof(float), s));
-    unsigned long long *group_acc = c->lb_emit + c->lb_emit_warp_words + c->lb_emit_group_words;
-    BG_CUDA(cudaMemsetAsync(group_acc, 0, ((size_t)n / 1024 + 2) * sizeof(unsigned long long), s));
 
     const int pgrid = c->sm_count * 8;   // project_cull: 256-thread CTAs, 39 regs, 25 KB smem
     const int vgrid = c->sm_count * 6;   // project_visible_emit: 128-thread CTAs, ~80 regs
@@ -272,7 +269,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
         BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, *cam, tiles_x,
                                             tiles_y, c->projected, c->isect_key[0], c->isect_val[0], c->max_isect,
                                             c->cgid_from_gid, c->ctl, bits, c->lb_emit, c->lb_emit + c->lb_emit_warp_words,
-                                            group_acc, c->epoch_dev, EP_SCAN));
+                                            c->epoch_dev, EP_SCAN));
     int iout = 0;
     {
         const uint32_t passes = (bits + 7) / 8;

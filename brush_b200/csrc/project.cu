@@ -239,16 +239,12 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
 //     the exclusive prefix of the per-lane bbox sizes) -- a per-thread walk would cost the warp its LARGEST bbox.
 //     Each tile is tested ONCE (the reference counts in project_forward and tests again in map_gaussians): the
 //     hits go, in order, into a per-warp shared-memory list.
-//   * The output offset of a ticket is the exclusive prefix of the hit counts of all earlier tickets (the
+//   * The output offset of the warp is the exclusive prefix of the hit counts of all earlier tickets (the
 //     reference: int_gather + prefix_sum, render.rs:185-187), obtained by a two-level decoupled look-back over L2:
-//     each warp publishes its count and adds it to its group's (32 tickets) accumulator with one 64-bit atomic
-//     (count of finished tickets | sum); whoever completes a group publishes the group total, and the group totals
-//     are chained (aggregate -> inclusive).  The offset of a ticket = chained total of the earlier groups + counts
-//     of the earlier tickets of its own group.
-//   * Software pipelining hides the chain: a warp stages the pairs of ticket t in shared memory, then processes
-//     its NEXT ticket, and only then resolves the offset of t and writes its pairs out (coalesced stores; the
-//     tile-key digits are counted for the sort on the way).  By then the earlier tickets have long published, so
-//     nobody spins (ncu on the unpipelined version: 60 % of the stall samples sat in the look-back polls).
+//     each warp publishes its count, sums the counts of the earlier warps of its group of 32 tickets, the last
+//     warp of a group publishes the group total, and the group totals are chained.  Any warp waits for at most a
+//     few L2 round trips however many warps are in flight.
+//   * The list is then written out with coalesced stores, and the tile-key digits are counted for the sort.
 constexpr int VIS_THREADS = 128;
 constexpr uint32_t EMIT_GROUP = 32;   // tickets per look-back group
 
@@ -265,16 +261,15 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                             uint32_t *__restrict__ isect_vals, uint32_t isect_capacity,
                             uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl, uint32_t tile_bits,
                             unsigned long long *__restrict__ lb_warp, unsigned long long *__restrict__ lb_group,
-                            unsigned long long *__restrict__ group_acc /* zeroed: [finished tickets:32 | hits:32] */,
                             const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
     const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
     constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B are 16-byte aligned
     constexpr bool VEC8 = (KF % 8) == 0;                 // 192 B rows: six 256-bit loads when the base is 32-byte aligned
     const bool sh_align32 = (reinterpret_cast<uintptr_t>(sh) & 31u) == 0;
-    constexpr uint32_t EMIT_BUF = 768;                   // staged (tile id, owner) pairs per warp and buffer
-    __shared__ uint32_t s_emit_keys[(VIS_THREADS / 32) * 2 * EMIT_BUF];
-    __shared__ uint8_t s_emit_own[(VIS_THREADS / 32) * 2 * EMIT_BUF];
+    constexpr uint32_t EMIT_BUF = 1024;                  // staged (tile id, owner) pairs per warp
+    __shared__ uint32_t s_emit_keys[(VIS_THREADS / 32) * EMIT_BUF];
+    __shared__ uint8_t s_emit_own[(VIS_THREADS / 32) * EMIT_BUF];
     // digit histograms of the emitted tile keys for the one-sweep passes of the tile sort (<= 2 passes: < 65536 tiles)
     __shared__ uint32_t s_thist[2 * 256];
     const uint32_t hist_passes = (tile_bits <= 16u) ? (tile_bits + 7u) / 8u : 0u;   // else the sort counts itself
@@ -290,66 +285,23 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
     const uint32_t num_tickets = (nvis + 31u) / 32u;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t *wkeys_base = s_emit_keys + wid * 2 * EMIT_BUF;
-    uint8_t *wown_base = s_emit_own + wid * 2 * EMIT_BUF;
+    uint32_t *wkeys = s_emit_keys + wid * EMIT_BUF;
+    uint8_t *wown = s_emit_own + wid * EMIT_BUF;
     auto take_ticket = [&]() {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&ctl[CTL_TICKETS + TK_VISIBLE], 1u);
         return __shfl_sync(0xffffffffu, t, 0);
     };
-    // offset of ticket t (all lanes): chained total of the earlier groups + counts of the earlier tickets of its group;
-    // if this warp completed the group (`closer`), the group word is upgraded to INCLUSIVE; the last ticket writes
-    // num_intersections (render.rs:146-168 reads it back; here it stays on the device)
-    auto resolve = [&](uint32_t t, uint32_t cnt_t, bool closer, uint32_t group_total) -> uint32_t {
-        const uint32_t grp = t / EMIT_GROUP, r = t % EMIT_GROUP;
-        uint32_t v = 0;
-        if (lane < r) {
-            const unsigned long long *w = lb_warp + (t - 1u - lane);
-            unsigned long long word = lb_load(w);
-            while (lb_status(word, epoch) == LB_INVALID) word = lb_load(w);
-            v = lb_value(word);
-        }
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const uint32_t group_prefix = (grp == 0) ? 0u : lb_lookback_warp(lb_group, grp, epoch);
-        if (closer && grp != 0 && lane == 0) lb_store(lb_group + grp, epoch, LB_INCLUSIVE, group_prefix + group_total);
-        const uint32_t off = group_prefix + v;
-        if (t == num_tickets - 1u && lane == 0) {
-            uint32_t tot = off + cnt_t;
-            if (tot > isect_capacity) { ctl[CTL_COUNTERS + 2] = tot; tot = isect_capacity; }
-            ctl[CTL_COUNTERS + 1] = tot;
-        }
-        return off;
-    };
-    auto write_out = [&](uint32_t t, uint32_t cnt_t, uint32_t off, const uint32_t *keys, const uint8_t *own) {
-        for (uint32_t j = lane; j < cnt_t; j += 32) {
-            const uint32_t o = off + j;
-            if (o < isect_capacity) {
-                const uint32_t key = keys[j];
-                tile_keys[o] = key;
-                isect_vals[o] = t * 32u + own[j];
-                count_key(key);
-            }
-        }
-    };
     uint32_t ticket = take_ticket();
     uint32_t gid = 0;
     if (ticket < num_tickets && ticket * 32u + lane < nvis) gid = __ldg(gid_sorted + ticket * 32u + lane);
-    // the ticket whose pairs are staged and waiting for their offset
-    bool pend = false, pend_closer = false;
-    uint32_t pend_ticket = 0, pend_cnt = 0, pend_total = 0, cur = 0;
-    while (ticket < num_tickets || pend) {
-        const bool have = ticket < num_tickets;
-        uint32_t ticket_next = ticket, gid_next = 0;
-        uint32_t cnt = 0, group_total = 0;
-        bool closer = false, staged_ok = false;
-        uint32_t *wkeys = wkeys_base + cur * EMIT_BUF;
-        uint8_t *wown = wown_base + cur * EMIT_BUF;
-        if (have) {
+    while (ticket < num_tickets) {
         const uint32_t cgid = ticket * 32u + lane;
         const bool active = cgid < nvis;
         // next ticket: its ids are on their way while this ticket's rows are gathered
-        ticket_next = take_ticket();
+        const uint32_t ticket_next = take_ticket();
         const bool next_active = ticket_next < num_tickets && ticket_next * 32u + lane < nvis;
+        uint32_t gid_next = 0;
         if (next_active) gid_next = __ldg(gid_sorted + ticket_next * 32u + lane);
 
         uint32_t min_x = 0, min_y = 0, bbw = 0, ntiles = 0;
@@ -424,7 +376,7 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         const uint32_t pre = incl - ntiles;
         const uint32_t total_cand = __shfl_sync(0xffffffffu, incl, 31);
         auto run_tests = [&](bool direct, uint32_t out_base) -> uint32_t {
-            uint32_t c = 0;
+            uint32_t cnt = 0;
             for (uint32_t base = 0; base < total_cand; base += 32) {
                 const uint32_t j = base + lane;
                 uint32_t own = 0;  // largest lane whose exclusive prefix is <= j
@@ -451,7 +403,7 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                     key = (mnx + rx) + (mny + ry) * tiles_x;
                 }
                 const uint32_t hb = __ballot_sync(0xffffffffu, hit);
-                const uint32_t pos = c + __popc(hb & lt_mask);
+                const uint32_t pos = cnt + __popc(hb & lt_mask);
                 if (hit) {
                     if (!direct) {
                         if (pos < EMIT_BUF) { wkeys[pos] = key; wown[pos] = (uint8_t)own; }
@@ -460,42 +412,54 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                         if (o < isect_capacity) { tile_keys[o] = key; isect_vals[o] = ticket * 32u + own; count_key(key); }
                     }
                 }
-                c += __popc(hb);
+                cnt += __popc(hb);
             }
-            return c;
+            return cnt;
         };
-        cnt = run_tests(false, 0u);
-        // ---- publish the count; add it to the group accumulator; whoever completes the group publishes its total
-        const uint32_t grp = ticket / EMIT_GROUP;
-        if (lane == 0) {
-            lb_store(lb_warp + ticket, epoch, LB_AGGREGATE, cnt);
-            const uint32_t group_size = min(EMIT_GROUP, num_tickets - grp * EMIT_GROUP);
-            const unsigned long long old = atomicAdd(group_acc + grp, (1ull << 32) | (unsigned long long)cnt);
-            if ((uint32_t)(old >> 32) + 1u == group_size) {
-                closer = true;
-                group_total = (uint32_t)old + cnt;
-                lb_store(lb_group + grp, epoch, grp == 0 ? LB_INCLUSIVE : LB_AGGREGATE, group_total);
+        const uint32_t cnt = run_tests(false, 0u);
+        // ---- output offset: two-level decoupled look-back over the tickets
+        const uint32_t grp = ticket / EMIT_GROUP, r = ticket % EMIT_GROUP;
+        if (lane == 0) lb_store(lb_warp + ticket, epoch, LB_AGGREGATE, cnt);
+        uint32_t in_group = 0;
+        {
+            uint32_t v = 0;
+            if (lane < r) {
+                const unsigned long long *w = lb_warp + (ticket - 1u - lane);
+                unsigned long long word = lb_load(w);
+                while (lb_status(word, epoch) == LB_INVALID) word = lb_load(w);
+                v = lb_value(word);
             }
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            in_group = v;
         }
-        closer = __shfl_sync(0xffffffffu, closer ? 1u : 0u, 0) != 0u;
-        group_total = __shfl_sync(0xffffffffu, group_total, 0);
-        staged_ok = cnt <= EMIT_BUF;
-        if (!staged_ok) {  // rare (very large splats): resolve now, test again and write straight to global memory
-            const uint32_t off = resolve(ticket, cnt, closer, group_total);
-            run_tests(true, off);
+        const bool closes_group = (r == EMIT_GROUP - 1u) || (ticket == num_tickets - 1u);
+        const uint32_t group_total = in_group + cnt;
+        if (closes_group && lane == 0) lb_store(lb_group + grp, epoch, grp == 0 ? LB_INCLUSIVE : LB_AGGREGATE, group_total);
+        const uint32_t group_prefix = (grp == 0) ? 0u : lb_lookback_warp(lb_group, grp, epoch);
+        if (closes_group && grp != 0 && lane == 0) lb_store(lb_group + grp, epoch, LB_INCLUSIVE, group_prefix + group_total);
+        const uint32_t warp_base = group_prefix + in_group;
+        if (ticket == num_tickets - 1u && lane == 0) {   // num_intersections (render.rs:146-168 reads it back)
+            uint32_t tot = warp_base + cnt;
+            if (tot > isect_capacity) { ctl[CTL_COUNTERS + 2] = tot; tot = isect_capacity; }
+            ctl[CTL_COUNTERS + 1] = tot;
         }
-        }  // have
         __syncwarp();
-        // ---- the previous ticket's offset is certainly known by now: write its pairs out
-        if (pend) {
-            const uint32_t off = resolve(pend_ticket, pend_cnt, pend_closer, pend_total);
-            write_out(pend_ticket, pend_cnt, off, wkeys_base + (cur ^ 1u) * EMIT_BUF, wown_base + (cur ^ 1u) * EMIT_BUF);
+        if (cnt <= EMIT_BUF) {
+            for (uint32_t j = lane; j < cnt; j += 32) {
+                const uint32_t o = warp_base + j;
+                if (o < isect_capacity) {
+                    const uint32_t key = wkeys[j];
+                    tile_keys[o] = key;
+                    isect_vals[o] = ticket * 32u + wown[j];
+                    count_key(key);
+                }
+            }
+        } else {
+            run_tests(true, warp_base);
         }
         __syncwarp();
-        pend = have && staged_ok;
-        pend_ticket = ticket; pend_cnt = cnt; pend_closer = closer; pend_total = group_total;
-        cur ^= 1u;
-        if (have) { ticket = ticket_next; gid = gid_next; }
+        ticket = ticket_next;
+        gid = gid_next;
     }
     __syncthreads();
     uint32_t *hist = ctl + CTL_HIST_TILE;
@@ -577,10 +541,10 @@ static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const f
                                       uint32_t ty, float *projected, uint32_t *tile_keys, uint32_t *isect_vals,
                                       uint32_t cap, uint32_t *cgid_from_gid, uint32_t *ctl, uint32_t tile_bits,
                                       unsigned long long *lb_warp, unsigned long long *lb_group,
-                                      unsigned long long *group_acc, const uint32_t *epoch_base, uint32_t epoch_off) {
+                                      const uint32_t *epoch_base, uint32_t epoch_off) {
     const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
 #define BG_VIS_ARGS transforms, sh, raw_opac, gid_sorted, u, tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, \
-                    ctl, tile_bits, lb_warp, lb_group, group_acc, epoch_base, epoch_off
+                    ctl, tile_bits, lb_warp, lb_group, epoch_base, epoch_off
 #define BG_LAUNCH_VIS(D)                                                                              \
     if (dist) project_visible_emit_kernel<MIP, D, true><<<grid, VIS_THREADS, 0, s>>>(BG_VIS_ARGS);   \
     else project_visible_emit_kernel<MIP, D, false><<<grid, VIS_THREADS, 0, s>>>(BG_VIS_ARGS)
@@ -602,12 +566,11 @@ cudaError_t launch_project_visible_emit(cudaStream_t s, int grid, bool mip, int 
                                         const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
                                         uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap, uint32_t *cgid_from_gid,
                                         uint32_t *ctl, uint32_t tile_bits, unsigned long long *lb_warp,
-                                        unsigned long long *lb_group, unsigned long long *group_acc,
-                                        const uint32_t *epoch_base, uint32_t epoch_off) {
+                                        unsigned long long *lb_group, const uint32_t *epoch_base, uint32_t epoch_off) {
     return mip ? launch_visible_deg<true>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, u, tx, ty, projected, tile_keys,
-                                          isect_vals, cap, cgid_from_gid, ctl, tile_bits, lb_warp, lb_group, group_acc, epoch_base, epoch_off)
+                                          isect_vals, cap, cgid_from_gid, ctl, tile_bits, lb_warp, lb_group, epoch_base, epoch_off)
                : launch_visible_deg<false>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, u, tx, ty, projected, tile_keys,
-                                           isect_vals, cap, cgid_from_gid, ctl, tile_bits, lb_warp, lb_group, group_acc, epoch_base, epoch_off);
+                                           isect_vals, cap, cgid_from_gid, ctl, tile_bits, lb_warp, lb_group, epoch_base, epoch_off);
 }
 
 cudaError_t launch_tile_offsets(cudaStream_t s, int grid, const uint32_t *tile_ids, const uint32_t *ctl,
