@@ -14,15 +14,17 @@
 
 namespace bg {
 // project.cu
-cudaError_t launch_project_cull(cudaStream_t, int, bool, const float *, const float *, uint32_t, const BgCamera &, uint32_t,
-                                uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *, float *, uint32_t *, uint32_t *,
-                                unsigned long long *, const uint32_t *, uint32_t);
-cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, const uint32_t *, uint32_t *,
-                               uint32_t *, uint32_t, uint32_t *, uint32_t *, unsigned long long *, const uint32_t *, uint32_t);
+cudaError_t launch_project_cull(cudaStream_t, int, bool, const float *, const float *, uint32_t, const BgCamera &,
+                                uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *, uint32_t *, float *,
+                                uint32_t *, unsigned long long *, uint32_t *, unsigned long long *, const uint32_t *,
+                                uint32_t);
+cudaError_t launch_gather_scan(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, const uint32_t *,
+                               uint32_t *, uint32_t *, uint32_t, uint32_t *, uint32_t *, unsigned long long *,
+                               const uint32_t *, uint32_t);
 cudaError_t launch_project_visible_emit(cudaStream_t, int, bool, int, const float *, const float *, const float *,
-                                        const uint32_t *, const BgCamera &, uint32_t, uint32_t, float *, uint32_t *,
-                                        uint32_t *, uint32_t, uint32_t *, uint32_t *, uint32_t, unsigned long long *,
-                                        unsigned long long *, const uint32_t *, uint32_t);
+                                        const uint32_t *, const uint32_t *, const BgCamera &, uint32_t, uint32_t,
+                                        float *, uint32_t *, uint32_t *, uint32_t, uint32_t *, const unsigned long long *,
+                                        uint32_t *, uint32_t);
 cudaError_t launch_tile_offsets(cudaStream_t, int, const uint32_t *, const uint32_t *, uint32_t, uint32_t *);
 // sort.cu
 cudaError_t launch_radix_hist(cudaStream_t, int, const uint32_t *, uint32_t, const uint32_t *, uint32_t, uint32_t,
@@ -86,9 +88,8 @@ struct BgContext {
     uint32_t *ctl = nullptr;               // CTL_WORDS u32 (forward pipeline), then CTL_WORDS (standalone ops)
     uint32_t *depth_key[2] = {nullptr, nullptr};
     uint32_t *depth_val[2] = {nullptr, nullptr};
-    uint32_t *cgid_from_gid = nullptr;
-    unsigned long long *lb_emit = nullptr;  // look-back words of project_visible_emit: [tickets] + [ticket groups]
-    uint64_t lb_emit_warp_words = 0, lb_emit_words = 0;
+    uint32_t *counts = nullptr, *cum = nullptr, *cgid_from_gid = nullptr;
+    unsigned long long *hit_masks = nullptr;  // per-Gaussian tile hit bits from the counting pass
     float *projected = nullptr;
     uint32_t *isect_key[2] = {nullptr, nullptr};
     uint32_t *isect_val[2] = {nullptr, nullptr};
@@ -119,8 +120,8 @@ static cudaError_t arena_alloc(BgContext *c, T **p, uint64_t count) {
 extern "C" int32_t bg_ctx_destroy(BgContext *c) {
     if (!c) return BG_ERR_NULL;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->ctl, c->depth_key[0], c->depth_key[1], c->depth_val[0], c->depth_val[1], c->lb_emit,
-                    c->cgid_from_gid, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
+    void *ptrs[] = {c->ctl, c->depth_key[0], c->depth_key[1], c->depth_val[0], c->depth_val[1], c->counts, c->cum,
+                    c->cgid_from_gid, c->hit_masks, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
                     c->tile_offsets, c->lb_scan, c->lb_sort, c->epoch_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -160,10 +161,10 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
         ok = ok && arena_alloc(c, &c->isect_key[i], I) == cudaSuccess;
         ok = ok && arena_alloc(c, &c->isect_val[i], I) == cudaSuccess;
     }
-    c->lb_emit_warp_words = ((uint64_t)n + 31) / 32 + 64;
-    c->lb_emit_words = c->lb_emit_warp_words + c->lb_emit_warp_words / 32 + 64;
-    ok = ok && arena_alloc(c, &c->lb_emit, c->lb_emit_words) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->counts, n) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->cum, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->cgid_from_gid, n) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->hit_masks, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->projected, n * BG_PROJECTED_STRIDE) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->tile_offsets, (uint64_t)c->max_tiles * 2) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->lb_scan, c->lb_scan_words) == cudaSuccess;
@@ -172,7 +173,6 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
     ok = ok && cudaHostAlloc((void **)&c->counters_host, 16 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
         ok = cudaMemset(c->lb_scan, 0, c->lb_scan_words * 8) == cudaSuccess &&
-             cudaMemset(c->lb_emit, 0, c->lb_emit_words * 8) == cudaSuccess &&
              cudaMemset(c->lb_sort, 0, c->lb_sort_words * 8) == cudaSuccess &&
              cudaMemset(c->ctl, 0, 2 * CTL_WORDS * 4) == cudaSuccess &&
              cudaMemset(c->epoch_dev, 0, 4) == cudaSuccess;
@@ -243,12 +243,12 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     BG_CUDA(cudaMemsetAsync(c->tile_offsets, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
     if (bwd_info && n > 0) BG_CUDA(cudaMemsetAsync(visible, 0, (size_t)n * sizeof(float), s));
 
-    const int pgrid = c->sm_count * 8;   // project_cull: 256-thread CTAs, 39 regs, 25 KB smem
+    const int pgrid = c->sm_count * 5;   // project_cull: 256-thread CTAs, 48 regs
     const int vgrid = c->sm_count * 6;   // project_visible_emit: 128-thread CTAs, ~80 regs
     uint32_t *counters = c->ctl + CTL_COUNTERS;
     // K1: cull + compaction in index order
     BG_CUDA(launch_project_cull(s, pgrid, mip != 0, transforms, raw_opac, n, *cam, w, h, tiles_x, tiles_y,
-                                c->depth_key[0], c->depth_val[0], max_radius, c->cgid_from_gid, c->ctl,
+                                c->depth_key[0], c->depth_val[0], c->counts, max_radius, c->cgid_from_gid, c->hit_masks, c->ctl,
                                 c->lb_scan, c->epoch_dev, EP_PROJECT));
     // depth sort: 32-bit keys, 4 passes, (0)->(1)->(0)->(1)->(0)
     int dout = 0;
@@ -260,16 +260,17 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     }
     c->depth_out = dout;
     const uint32_t *gid_sorted = c->depth_val[dout];
+    // gather counts + inclusive scan -> cum, num_intersections
+    BG_CUDA(launch_gather_scan(s, c->sm_count * 2, c->counts, gid_sorted, n, counters + 0, c->cum, counters + 1,
+                               c->max_isect, counters + 2, c->ctl + CTL_TICKETS + TK_SCAN, c->lb_scan, c->epoch_dev, EP_SCAN));
     // tile sort on bits = 32 - clz(num_tiles)
     uint32_t bits = 0;
     while (bits < 32 && (num_tiles >> bits) != 0) bits++;
-    // K2+K3: projection of the visible splats, tile intersection, scan of the hit counts (-> num_intersections),
-    // emission of the (tile, splat) pairs and the tile-key digit counts for the sort
+    // K2+K3 (also counts the tile-key digits for the sort when they fit two passes)
     if (n > 0)
-        BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, *cam, tiles_x,
-                                            tiles_y, c->projected, c->isect_key[0], c->isect_val[0], c->max_isect,
-                                            c->cgid_from_gid, c->ctl, bits, c->lb_emit, c->lb_emit + c->lb_emit_warp_words,
-                                            c->epoch_dev, EP_SCAN));
+        BG_CUDA(launch_project_visible_emit(s, vgrid, mip != 0, deg, transforms, sh, raw_opac, gid_sorted, c->cum, *cam,
+                                            tiles_x, tiles_y, c->projected, c->isect_key[0], c->isect_val[0],
+                                            c->max_isect, c->cgid_from_gid, c->hit_masks, c->ctl, bits));
     int iout = 0;
     {
         const uint32_t passes = (bits + 7) / 8;

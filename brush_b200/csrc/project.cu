@@ -23,7 +23,12 @@ constexpr int PROJ_THREADS = 256;
 struct CullResult {
     bool visible;
     float depth;
+    uint32_t tiles;
     float radius;
+    unsigned long long mask;  // hit bits of the bbox tiles, row major, valid when the bbox has <= 64 tiles
+    // screen-space footprint, consumed by the warp-cooperative tile count
+    float mx, my, c00, c01, c11, pt;
+    uint32_t min_x, min_y, bbw, ntiles;
 };
 
 // Everything of project_forward up to the tile bbox (project_forward.rs:43-117).
@@ -31,7 +36,9 @@ template <bool MIP, bool DIST>
 __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, const BgCamera &u, uint32_t img_w,
                                                uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y) {
     CullResult r;
-    r.visible = false; r.depth = 0.0f; r.radius = 0.0f;
+    r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
+    r.mx = r.my = r.c00 = r.c01 = r.c11 = r.pt = 0.0f;
+    r.min_x = r.min_y = r.bbw = r.ntiles = 0;
     V3 mean_c = world_to_cam(mk3(t[0], t[1], t[2]), u);
     if (!(is_finite(mean_c) && mean_c.z <= 1.0e10f)) return r;
     if (!in_front<DIST>(mean_c, u)) return r;
@@ -58,10 +65,69 @@ __device__ __forceinline__ CullResult cull_one(const float *t, float raw_opac, c
     float wf = (float)img_w, hf = (float)img_h;
     bool on_screen = mx + ex > 0.0f && mx - ex < wf && my + ey > 0.0f && my - ey < hf;
     if (!on_screen) return r;
+    TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
     r.visible = true;
     r.depth = mean_c.z;
     r.radius = fmaxf(ex / wf, ey / hf);
+    r.mx = mx; r.my = my; r.c00 = conic.c00; r.c01 = conic.c01; r.c11 = conic.c11; r.pt = pt;
+    r.min_x = bb.min_x; r.min_y = bb.min_y; r.bbw = bb.max_x - bb.min_x;
+    r.ntiles = (bb.max_y - bb.min_y) * r.bbw;
     return r;
+}
+
+// count_contributing_tiles (helpers.rs:203-222) for the 32 Gaussians of a warp at once.  A per-thread
+// walk costs the warp the LARGEST bbox among its lanes; here the warp's candidate tiles are flattened
+// into one list and tested 32 at a time, whoever they belong to (binary search of the owner over the
+// exclusive prefix of the per-lane tile counts).  Hit counts and the 64-bit hit mask are collected by the
+// owner lane from the ballot of each round.
+__device__ __forceinline__ void warp_count_tiles(CullResult &r) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t incl = r.ntiles;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t pre = incl - r.ntiles;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t hits_count = 0;
+    unsigned long long mask = 0ull;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        uint32_t own = 0;  // largest lane whose exclusive prefix is <= j
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            uint32_t cand = own + step;
+            uint32_t pc = __shfl_sync(0xffffffffu, pre, cand & 31u);
+            if (pc <= j) own = cand;
+        }
+        const uint32_t local = j - __shfl_sync(0xffffffffu, pre, own);
+        const float mx = __shfl_sync(0xffffffffu, r.mx, own), my = __shfl_sync(0xffffffffu, r.my, own);
+        S2 conic;
+        conic.c00 = __shfl_sync(0xffffffffu, r.c00, own);
+        conic.c01 = __shfl_sync(0xffffffffu, r.c01, own);
+        conic.c11 = __shfl_sync(0xffffffffu, r.c11, own);
+        const float pt = __shfl_sync(0xffffffffu, r.pt, own);
+        const uint32_t min_x = __shfl_sync(0xffffffffu, r.min_x, own), min_y = __shfl_sync(0xffffffffu, r.min_y, own);
+        const uint32_t bbw = __shfl_sync(0xffffffffu, r.bbw, own);
+        bool hit = false;
+        if (j < total) {
+            const uint32_t ry = local / bbw, rx = local - ry * bbw;
+            hit = tile_hit(min_x + rx, min_y + ry, mx, my, conic, pt);
+        }
+        // Owners collect their results from the ballot: the tiles of lane L's splat are the list positions
+        // [pre, pre + ntiles), i.e. the lanes [s, e) of this round -- no atomics, nothing leaves registers.
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        const uint32_t lo = max(pre, base), hi = min(pre + r.ntiles, base + 32u);
+        if (hi > lo) {
+            const uint32_t sft = lo - base, len = hi - lo;
+            const uint32_t seg = (hits >> sft) & (len >= 32u ? 0xffffffffu : ((1u << len) - 1u));
+            hits_count += __popc(seg);
+            const uint32_t local0 = lo - pre;  // tile index (inside the bbox) of the segment's first lane
+            if (local0 < 64u) mask |= (unsigned long long)seg << local0;
+        }
+    }
+    r.tiles = hits_count;
+    r.mask = mask;
 }
 
 // K1.  One thread per Gaussian, 256 Gaussians per tile, persistent CTAs.
@@ -69,8 +135,10 @@ template <bool MIP, bool DIST>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_cull_kernel(const float *__restrict__ transforms, const float *__restrict__ raw_opac, uint32_t n,
                     BgCamera u, uint32_t img_w, uint32_t img_h, uint32_t tiles_x, uint32_t tiles_y,
-                    uint32_t *__restrict__ depth_keys, uint32_t *__restrict__ gids, float *__restrict__ max_radius,
-                    uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl,
+                    uint32_t *__restrict__ depth_keys, uint32_t *__restrict__ gids,
+                    uint32_t *__restrict__ counts_by_gid, float *__restrict__ max_radius,
+                    uint32_t *__restrict__ cgid_from_gid, unsigned long long *__restrict__ hit_masks,
+                    uint32_t *__restrict__ ctl,
                     unsigned long long *__restrict__ lb_state, const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
     // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
     // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
@@ -118,7 +186,9 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
         }
         const uint32_t gid = base + threadIdx.x;
         CullResult r;
-        r.visible = false; r.depth = 0.0f; r.radius = 0.0f;
+        r.visible = false; r.depth = 0.0f; r.tiles = 0; r.radius = 0.0f; r.mask = 0ull;
+        r.mx = r.my = r.c00 = r.c01 = r.c11 = r.pt = 0.0f;
+        r.min_x = r.min_y = r.bbw = r.ntiles = 0;
         if (threadIdx.x < rows) {
             float t[10];
 #pragma unroll
@@ -127,10 +197,14 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             max_radius[gid] = r.radius;  // zero for culled splats (render_aux.rs:76-78)
             cgid_from_gid[gid] = 0xFFFFFFFFu;  // overwritten for visible splats by project_visible_emit
         }
+        // The visible count is known before the (expensive) tile walk: publish the tile aggregate
+        // first, count tiles, and only then look back -- by then the predecessors have published,
+        // so the chained scan adds no stall.
         uint32_t total;
         uint32_t local = block_exclusive_scan(r.visible ? 1u : 0u, s_scan, &total);
         unsigned long long *st = lb_state + tile;
         if (threadIdx.x == 0) lb_store(st, epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total);
+        warp_count_tiles(r);
         if (threadIdx.x < 32) {
             uint32_t prefix = (tile == 0) ? 0u : lb_lookback_warp(lb_state, tile, epoch);
             if (threadIdx.x == 0) {
@@ -147,6 +221,8 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
 #pragma unroll
             for (int p = 0; p < 4; p++) atomicAdd(&s_dhist[p * 256 + ((dk >> (8 * p)) & 255u)], 1u);
             gids[slot] = gid;
+            counts_by_gid[gid] = r.tiles;
+            hit_masks[gid] = r.mask;
         }
         tile = s_tile_next;
         buf ^= 1u;
@@ -227,26 +303,16 @@ gather_scan_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
     }
 }
 
-// K2 + K3 (+ count_contributing_tiles and the scan over the counts).  One thread per visible Gaussian in
-// depth order (compact gid = position in the depth-sorted list); WARPS are the unit of work (a ticket = 32
-// consecutive compact ids), so the loop has no block barrier.
-//   * Every lane gathers its own parameter rows (the gather is by sorted global id, so neighbouring lanes touch
-//     unrelated rows anyway): the 192-byte SH row as six 256-bit loads.  The kernel is bound by gather latency, so
-//     the NEXT ticket and its ids are fetched at the top of an iteration and the rows they point at are pulled
-//     into L2 with cp.async.bulk.prefetch.L2 while the current splats are processed.
-//   * Tile intersection (helpers.rs:203-264, map_gaussians.rs:26-79): the candidate tiles of the warp's 32 splats
-//     are flattened into one list and tested 32 at a time, whoever they belong to (binary search of the owner over
-//     the exclusive prefix of the per-lane bbox sizes) -- a per-thread walk would cost the warp its LARGEST bbox.
-//     Each tile is tested ONCE (the reference counts in project_forward and tests again in map_gaussians): the
-//     hits go, in order, into a per-warp shared-memory list.
-//   * The output offset of the warp is the exclusive prefix of the hit counts of all earlier tickets (the
-//     reference: int_gather + prefix_sum, render.rs:185-187), obtained by a two-level decoupled look-back over L2:
-//     each warp publishes its count, sums the counts of the earlier warps of its group of 32 tickets, the last
-//     warp of a group publishes the group total, and the group totals are chained.  Any warp waits for at most a
-//     few L2 round trips however many warps are in flight.
-//   * The list is then written out with coalesced stores, and the tile-key digits are counted for the sort.
+// K2 + K3.  One thread per visible Gaussian in depth order (compact gid = position in the
+// depth-sorted list); WARPS are the unit of work (a ticket = 32 consecutive compact ids), so the loop has no
+// block barrier.  Every lane gathers its own parameter rows (the gather is by sorted global id, so
+// neighbouring lanes touch unrelated rows anyway): the 192-byte SH row as twelve independent 128-bit loads.
+// The kernel is bound by gather latency (ncu: long-scoreboard on the first use of the rows), hence:
+//   * the NEXT ticket and its global ids are fetched at the top of an iteration, and the rows they point at are
+//     pulled into L2 with cp.async.bulk.prefetch.L2 while the current splats are processed;
+//   * the (tile id, compact gid) pairs of a warp -- one contiguous output range -- are gathered in shared memory
+//     and written with coalesced stores; bboxes larger than the 64-bit hit mask are tested by the whole warp.
 constexpr int VIS_THREADS = 128;
-constexpr uint32_t EMIT_GROUP = 32;   // tickets per look-back group
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {  // p 16-byte aligned, bytes % 16 == 0
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -256,13 +322,11 @@ template <bool MIP, int DEG, bool DIST>
 __global__ void __launch_bounds__(VIS_THREADS, 6)
 project_visible_emit_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
                             const float *__restrict__ raw_opac, const uint32_t *__restrict__ gid_sorted,
-                            BgCamera u, uint32_t tiles_x, uint32_t tiles_y,
+                            const uint32_t *__restrict__ cum, BgCamera u, uint32_t tiles_x, uint32_t tiles_y,
                             float *__restrict__ projected, uint32_t *__restrict__ tile_keys,
                             uint32_t *__restrict__ isect_vals, uint32_t isect_capacity,
-                            uint32_t *__restrict__ cgid_from_gid, uint32_t *__restrict__ ctl, uint32_t tile_bits,
-                            unsigned long long *__restrict__ lb_warp, unsigned long long *__restrict__ lb_group,
-                            const uint32_t *__restrict__ epoch_base, uint32_t epoch_off) {
-    const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
+                            uint32_t *__restrict__ cgid_from_gid, const unsigned long long *__restrict__ hit_masks,
+                            uint32_t *__restrict__ ctl, uint32_t tile_bits) {
     constexpr int KF = (DEG + 1) * (DEG + 1) * 3;        // floats per SH row
     constexpr bool VEC4 = (KF % 4) == 0;                 // rows of 48 B / 192 B are 16-byte aligned
     constexpr bool VEC8 = (KF % 8) == 0;                 // 192 B rows: six 256-bit loads when the base is 32-byte aligned
@@ -304,7 +368,10 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         uint32_t gid_next = 0;
         if (next_active) gid_next = __ldg(gid_sorted + ticket_next * 32u + lane);
 
-        uint32_t min_x = 0, min_y = 0, bbw = 0, ntiles = 0;
+        TileBox bb;
+        bb.min_x = bb.min_y = bb.max_x = bb.max_y = 0;
+        uint32_t base = 0, budget = 0;
+        unsigned long long hitm = 0ull;
         float e_mx = 0.f, e_my = 0.f, e_pt = 0.f;
         S2 e_conic; e_conic.c00 = e_conic.c01 = e_conic.c11 = 0.f;
         if (active) {
@@ -328,6 +395,9 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             const float2 *t2 = reinterpret_cast<const float2 *>(transforms + (size_t)gid * 10);
             float2 a0 = __ldg(t2), a1 = __ldg(t2 + 1), a2 = __ldg(t2 + 2), a3 = __ldg(t2 + 3), a4 = __ldg(t2 + 4);
             const float ro = __ldg(raw_opac + gid);
+            hitm = __ldg(hit_masks + gid);
+            base = (cgid == 0) ? 0u : __ldg(cum + cgid - 1);
+            budget = __ldg(cum + cgid) - base;
             V3 mean = mk3(a0.x, a0.y, a1.x);
             Q4 qu; qu.w = a1.y; qu.x = a2.x; qu.y = a2.y; qu.z = a3.x;
             V3 scl = mk3(det_expf(a3.y), det_expf(a4.x), det_expf(a4.y));
@@ -352,11 +422,10 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             dst[1] = make_float4(conic.c11, opac, cr, cg);
             dst[2] = make_float4(cb, pt, 0.0f, 0.0f);
             cgid_from_gid[gid] = cgid;
+            // ---- (tile id, compact gid) pairs (map_gaussians.rs:26-79)
             float ex, ey;
             bbox_extent(conic, pt, ex, ey);
-            const TileBox bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
-            min_x = bb.min_x; min_y = bb.min_y; bbw = bb.max_x - bb.min_x;
-            ntiles = (bb.max_y - bb.min_y) * bbw;
+            bb = tile_bbox(mx, my, ex, ey, tiles_x, tiles_y);
             e_mx = mx; e_my = my; e_conic = conic; e_pt = pt;
         }
         // pull the next ticket's rows towards L2 (the ids have arrived by now)
@@ -366,86 +435,78 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             if (VEC4) prefetch_l2_bulk(srow, KF * 4);
             prefetch_l2_bulk(reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(trow) & ~(uintptr_t)15), 48);
         }
-        // ---- flattened tile tests.  direct == false: hits go to the warp's shared-memory list (first EMIT_BUF of
-        // them); direct == true (only for warps with more hits than the list holds): straight to global memory.
-        uint32_t incl = ntiles;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
-        }
-        const uint32_t pre = incl - ntiles;
-        const uint32_t total_cand = __shfl_sync(0xffffffffu, incl, 31);
-        auto run_tests = [&](bool direct, uint32_t out_base) -> uint32_t {
-            uint32_t cnt = 0;
-            for (uint32_t base = 0; base < total_cand; base += 32) {
-                const uint32_t j = base + lane;
-                uint32_t own = 0;  // largest lane whose exclusive prefix is <= j
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    uint32_t cand = own + step;
-                    uint32_t pc = __shfl_sync(0xffffffffu, pre, cand & 31u);
-                    if (pc <= j) own = cand;
+        // The output slots of a warp's 32 splats are one contiguous range [base(lane 0), end(last active lane)).
+        const uint32_t warp_base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t end_here = active ? base + budget : 0u;
+        for (int o = 16; o > 0; o >>= 1) end_here = max(end_here, __shfl_xor_sync(0xffffffffu, end_here, o));
+        const uint32_t warp_total = end_here - warp_base;
+        const bool staged = warp_total <= EMIT_BUF;
+        const uint32_t off = base - warp_base;
+        const uint32_t bbw = bb.max_x - bb.min_x, bbh = bb.max_y - bb.min_y;
+        const bool big = active && bbw * bbh > 64u;
+        auto put = [&](uint32_t slot_off, uint32_t slot_base, uint32_t owner_lane, uint32_t h, uint32_t key) {
+            if (staged) { wkeys[slot_off + h] = key; wown[slot_off + h] = (uint8_t)owner_lane; }
+            else {
+                uint32_t o = slot_base + h;
+                if (o < isect_capacity) { tile_keys[o] = key; isect_vals[o] = ticket * 32u + owner_lane; count_key(key); }
+            }
+        };
+        if (active && !big) {
+            // the counting pass left the hit bits of this bbox: no tile test is repeated here
+            uint32_t hits = 0;
+            unsigned long long m = hitm;
+            const unsigned long long row_mask = (bbw >= 64u) ? ~0ull : ((1ull << bbw) - 1ull);
+            uint32_t row_key = bb.min_x + bb.min_y * tiles_x;
+            for (uint32_t ry = 0; ry < bbh && hits < budget; ry++, m = (bbw >= 64u) ? 0ull : (m >> bbw), row_key += tiles_x) {
+                unsigned long long rb = m & row_mask;
+                while (rb && hits < budget) {
+                    uint32_t rx = (uint32_t)__ffsll((long long)rb) - 1u;
+                    rb &= rb - 1ull;
+                    put(off, base, lane, hits, row_key + rx);
+                    hits++;
                 }
-                const uint32_t local = j - __shfl_sync(0xffffffffu, pre, own);
-                const float mx = __shfl_sync(0xffffffffu, e_mx, own), my = __shfl_sync(0xffffffffu, e_my, own);
-                S2 conic;
-                conic.c00 = __shfl_sync(0xffffffffu, e_conic.c00, own);
-                conic.c01 = __shfl_sync(0xffffffffu, e_conic.c01, own);
-                conic.c11 = __shfl_sync(0xffffffffu, e_conic.c11, own);
-                const float pt = __shfl_sync(0xffffffffu, e_pt, own);
-                const uint32_t mnx = __shfl_sync(0xffffffffu, min_x, own), mny = __shfl_sync(0xffffffffu, min_y, own);
-                const uint32_t w_ = __shfl_sync(0xffffffffu, bbw, own);
+            }
+            // same hits as the counting pass => hits == budget; keep the reference's padding so that no slot is
+            // ever left unwritten.
+            for (uint32_t pad = hits; pad < budget; pad++) put(off, base, lane, pad, tiles_x * tiles_y);
+        }
+        // bboxes beyond the 64-bit mask (0.3 % of the splats of the 1M/1080p scene, 75+ tiles each): the whole
+        // warp tests 32 tiles of one such splat at a time instead of one lane walking them alone.
+        uint32_t bigs = __ballot_sync(0xffffffffu, big);
+        while (bigs) {
+            const uint32_t L = (uint32_t)__ffs(bigs) - 1u;
+            bigs &= bigs - 1u;
+            const float mx = __shfl_sync(0xffffffffu, e_mx, L), my = __shfl_sync(0xffffffffu, e_my, L);
+            S2 conic;
+            conic.c00 = __shfl_sync(0xffffffffu, e_conic.c00, L);
+            conic.c01 = __shfl_sync(0xffffffffu, e_conic.c01, L);
+            conic.c11 = __shfl_sync(0xffffffffu, e_conic.c11, L);
+            const float pt = __shfl_sync(0xffffffffu, e_pt, L);
+            const uint32_t min_x = __shfl_sync(0xffffffffu, bb.min_x, L), min_y = __shfl_sync(0xffffffffu, bb.min_y, L);
+            const uint32_t w_ = __shfl_sync(0xffffffffu, bbw, L), h_ = __shfl_sync(0xffffffffu, bbh, L);
+            const uint32_t off_l = __shfl_sync(0xffffffffu, off, L), base_l = __shfl_sync(0xffffffffu, base, L);
+            const uint32_t budget_l = __shfl_sync(0xffffffffu, budget, L);
+            const uint32_t ntile = w_ * h_;
+            uint32_t cnt = 0;
+            for (uint32_t j0 = 0; j0 < ntile; j0 += 32) {
+                const uint32_t j = j0 + lane;
                 bool hit = false;
                 uint32_t key = 0;
-                if (j < total_cand) {
-                    const uint32_t ry = local / w_, rx = local - ry * w_;
-                    hit = tile_hit(mnx + rx, mny + ry, mx, my, conic, pt);
-                    key = (mnx + rx) + (mny + ry) * tiles_x;
+                if (j < ntile) {
+                    const uint32_t ry = j / w_, rx = j - ry * w_;
+                    hit = tile_hit(min_x + rx, min_y + ry, mx, my, conic, pt);
+                    key = (min_x + rx) + (min_y + ry) * tiles_x;
                 }
                 const uint32_t hb = __ballot_sync(0xffffffffu, hit);
                 const uint32_t pos = cnt + __popc(hb & lt_mask);
-                if (hit) {
-                    if (!direct) {
-                        if (pos < EMIT_BUF) { wkeys[pos] = key; wown[pos] = (uint8_t)own; }
-                    } else {
-                        const uint32_t o = out_base + pos;
-                        if (o < isect_capacity) { tile_keys[o] = key; isect_vals[o] = ticket * 32u + own; count_key(key); }
-                    }
-                }
+                if (hit && pos < budget_l) put(off_l, base_l, L, pos, key);
                 cnt += __popc(hb);
             }
-            return cnt;
-        };
-        const uint32_t cnt = run_tests(false, 0u);
-        // ---- output offset: two-level decoupled look-back over the tickets
-        const uint32_t grp = ticket / EMIT_GROUP, r = ticket % EMIT_GROUP;
-        if (lane == 0) lb_store(lb_warp + ticket, epoch, LB_AGGREGATE, cnt);
-        uint32_t in_group = 0;
-        {
-            uint32_t v = 0;
-            if (lane < r) {
-                const unsigned long long *w = lb_warp + (ticket - 1u - lane);
-                unsigned long long word = lb_load(w);
-                while (lb_status(word, epoch) == LB_INVALID) word = lb_load(w);
-                v = lb_value(word);
-            }
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            in_group = v;
-        }
-        const bool closes_group = (r == EMIT_GROUP - 1u) || (ticket == num_tickets - 1u);
-        const uint32_t group_total = in_group + cnt;
-        if (closes_group && lane == 0) lb_store(lb_group + grp, epoch, grp == 0 ? LB_INCLUSIVE : LB_AGGREGATE, group_total);
-        const uint32_t group_prefix = (grp == 0) ? 0u : lb_lookback_warp(lb_group, grp, epoch);
-        if (closes_group && grp != 0 && lane == 0) lb_store(lb_group + grp, epoch, LB_INCLUSIVE, group_prefix + group_total);
-        const uint32_t warp_base = group_prefix + in_group;
-        if (ticket == num_tickets - 1u && lane == 0) {   // num_intersections (render.rs:146-168 reads it back)
-            uint32_t tot = warp_base + cnt;
-            if (tot > isect_capacity) { ctl[CTL_COUNTERS + 2] = tot; tot = isect_capacity; }
-            ctl[CTL_COUNTERS + 1] = tot;
+            for (uint32_t pad = min(cnt, budget_l) + lane; pad < budget_l; pad += 32) put(off_l, base_l, L, pad, tiles_x * tiles_y);
         }
         __syncwarp();
-        if (cnt <= EMIT_BUF) {
-            for (uint32_t j = lane; j < cnt; j += 32) {
+        if (staged) {
+            for (uint32_t j = lane; j < warp_total; j += 32) {
                 const uint32_t o = warp_base + j;
                 if (o < isect_capacity) {
                     const uint32_t key = wkeys[j];
@@ -454,8 +515,6 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
                     count_key(key);
                 }
             }
-        } else {
-            run_tests(true, warp_base);
         }
         __syncwarp();
         ticket = ticket_next;
@@ -511,14 +570,14 @@ tile_offsets_kernel(const uint32_t *__restrict__ tile_ids, const uint32_t *__res
 // ---- host launchers (called from api.cu) ----
 cudaError_t launch_project_cull(cudaStream_t s, int grid, bool mip, const float *transforms, const float *raw_opac,
                                 uint32_t n, const BgCamera &u, uint32_t w, uint32_t h, uint32_t tx, uint32_t ty,
-                                uint32_t *depth_keys, uint32_t *gids, float *max_radius,
-                                uint32_t *cgid_from_gid, uint32_t *ctl,
+                                uint32_t *depth_keys, uint32_t *gids, uint32_t *counts, float *max_radius,
+                                uint32_t *cgid_from_gid, unsigned long long *hit_masks, uint32_t *ctl,
                                 unsigned long long *lb, const uint32_t *epoch_base, uint32_t epoch_off) {
     if (n == 0) return cudaSuccess;
     const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
 #define BG_LAUNCH_CULL(M, D)                                                                                       \
     project_cull_kernel<M, D><<<grid, PROJ_THREADS, 0, s>>>(transforms, raw_opac, n, u, w, h, tx, ty, depth_keys, \
-                                                            gids, max_radius, cgid_from_gid, ctl, lb, epoch_base, epoch_off)
+                                                            gids, counts, max_radius, cgid_from_gid, hit_masks, ctl, lb, epoch_base, epoch_off)
     if (mip) { if (dist) BG_LAUNCH_CULL(true, true); else BG_LAUNCH_CULL(true, false); }
     else     { if (dist) BG_LAUNCH_CULL(false, true); else BG_LAUNCH_CULL(false, false); }
 #undef BG_LAUNCH_CULL
@@ -537,17 +596,17 @@ cudaError_t launch_gather_scan(cudaStream_t s, int grid, const uint32_t *in, con
 
 template <bool MIP>
 static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const float *transforms, const float *sh,
-                                      const float *raw_opac, const uint32_t *gid_sorted, const BgCamera &u, uint32_t tx,
-                                      uint32_t ty, float *projected, uint32_t *tile_keys, uint32_t *isect_vals,
-                                      uint32_t cap, uint32_t *cgid_from_gid, uint32_t *ctl, uint32_t tile_bits,
-                                      unsigned long long *lb_warp, unsigned long long *lb_group,
-                                      const uint32_t *epoch_base, uint32_t epoch_off) {
+                                      const float *raw_opac, const uint32_t *gid_sorted, const uint32_t *cum,
+                                      const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
+                                      uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
+                                      uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl,
+                                      uint32_t tile_bits) {
     const bool dist = u.camera_model != BG_CAMERA_PINHOLE;
-#define BG_VIS_ARGS transforms, sh, raw_opac, gid_sorted, u, tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, \
-                    ctl, tile_bits, lb_warp, lb_group, epoch_base, epoch_off
-#define BG_LAUNCH_VIS(D)                                                                              \
-    if (dist) project_visible_emit_kernel<MIP, D, true><<<grid, VIS_THREADS, 0, s>>>(BG_VIS_ARGS);   \
-    else project_visible_emit_kernel<MIP, D, false><<<grid, VIS_THREADS, 0, s>>>(BG_VIS_ARGS)
+#define BG_LAUNCH_VIS(D)                                                                                                   \
+    if (dist) project_visible_emit_kernel<MIP, D, true><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits); \
+    else project_visible_emit_kernel<MIP, D, false><<<grid, VIS_THREADS, 0, s>>>(transforms, sh, raw_opac, gid_sorted, cum, u, \
+                                                                     tx, ty, projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits)
     switch (deg) {
         case 0: BG_LAUNCH_VIS(0); break;
         case 1: BG_LAUNCH_VIS(1); break;
@@ -557,20 +616,19 @@ static cudaError_t launch_visible_deg(cudaStream_t s, int grid, int deg, const f
         default: return cudaErrorInvalidValue;
     }
 #undef BG_LAUNCH_VIS
-#undef BG_VIS_ARGS
     return cudaGetLastError();
 }
 
 cudaError_t launch_project_visible_emit(cudaStream_t s, int grid, bool mip, int deg, const float *transforms,
                                         const float *sh, const float *raw_opac, const uint32_t *gid_sorted,
-                                        const BgCamera &u, uint32_t tx, uint32_t ty, float *projected,
-                                        uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap, uint32_t *cgid_from_gid,
-                                        uint32_t *ctl, uint32_t tile_bits, unsigned long long *lb_warp,
-                                        unsigned long long *lb_group, const uint32_t *epoch_base, uint32_t epoch_off) {
-    return mip ? launch_visible_deg<true>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, u, tx, ty, projected, tile_keys,
-                                          isect_vals, cap, cgid_from_gid, ctl, tile_bits, lb_warp, lb_group, epoch_base, epoch_off)
-               : launch_visible_deg<false>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, u, tx, ty, projected, tile_keys,
-                                           isect_vals, cap, cgid_from_gid, ctl, tile_bits, lb_warp, lb_group, epoch_base, epoch_off);
+                                        const uint32_t *cum, const BgCamera &u, uint32_t tx, uint32_t ty,
+                                        float *projected, uint32_t *tile_keys, uint32_t *isect_vals, uint32_t cap,
+                                        uint32_t *cgid_from_gid, const unsigned long long *hit_masks, uint32_t *ctl,
+                                        uint32_t tile_bits) {
+    return mip ? launch_visible_deg<true>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty, projected,
+                                          tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits)
+               : launch_visible_deg<false>(s, grid, deg, transforms, sh, raw_opac, gid_sorted, cum, u, tx, ty,
+                                           projected, tile_keys, isect_vals, cap, cgid_from_gid, hit_masks, ctl, tile_bits);
 }
 
 cudaError_t launch_tile_offsets(cudaStream_t s, int grid, const uint32_t *tile_ids, const uint32_t *ctl,
