@@ -1,0 +1,278 @@
+"""SceneBatch producer and COLMAP model reader, host side.
+
+  view_to_packed_data / pack_rgba <- brush-dataset/src/scene.rs:97-136 (u8 RGBA packed little endian into one int32
+                                      per pixel, byte-space premultiplication for AlphaMode::Transparent)
+  load_colmap_text                <- brush-dataset/src/formats/colmap.rs:102-303 (views sorted by image name,
+                                      subsample / max frames, w2c -> c2w, fov from focal per camera model,
+                                      missing images skipped with a warning, initial points from points3D.txt)
+  build_camera_model              <- formats/colmap.rs:305-390 (COLMAP sensor models -> pinhole / RT8 / KB4 / TPF)
+  split_eval_every                <- formats/mod.rs:135-148
+  COLMAP text grammar             <- colmap-reader (cameras.txt / images.txt / points3D.txt)
+
+The step's only host->device input is the packed [H,W] int32 image; `SceneLoader` keeps two pinned staging buffers
+so the upload of view i+1 overlaps the step on view i.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import camera as cm
+from .camera import Camera
+from .ply import SH_C0, SplatData
+
+ALPHA_MASKED, ALPHA_TRANSPARENT = "masked", "transparent"
+
+
+def pack_rgba(rgba: np.ndarray, premultiply: bool) -> np.ndarray:
+    """scene.rs:121-136.  rgba: uint8 [H,W,4] -> int32 [H,W] (r | g<<8 | b<<16 | a<<24)."""
+    px = np.ascontiguousarray(rgba, np.uint8)
+    if premultiply:
+        a = px[..., 3:4].astype(np.uint16)
+        rgb = ((px[..., :3].astype(np.uint16) * a + 127) // 255).astype(np.uint8)   # byte space, before any float
+        px = np.concatenate([rgb, px[..., 3:4]], axis=-1)
+    return np.ascontiguousarray(px).view("<u4").reshape(px.shape[0], px.shape[1]).view(np.int32)
+
+
+def view_to_packed_data(image: np.ndarray, alpha_mode: str = ALPHA_MASKED) -> Tuple[np.ndarray, bool]:
+    """scene.rs:97-119.  image: uint8 [H,W,3] or [H,W,4] (other depths: convert to RGBA8 first).
+    Returns (packed int32 [H,W], has_alpha)."""
+    if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] not in (3, 4):
+        raise ValueError("expected a uint8 [H,W,3|4] image")
+    has_alpha = image.shape[2] == 4
+    if not has_alpha:
+        image = np.concatenate([image, np.full(image.shape[:2] + (1,), 255, np.uint8)], axis=-1)
+    return pack_rgba(image, has_alpha and alpha_mode == ALPHA_TRANSPARENT), has_alpha
+
+
+# ---- COLMAP text model ------------------------------------------------------------------------------------
+@dataclass
+class ColmapCamera:
+    id: int
+    model: str
+    width: int
+    height: int
+    params: List[float]
+
+    def focal(self) -> Tuple[float, float]:
+        if self.model in ("SIMPLE_PINHOLE", "SIMPLE_RADIAL", "RADIAL", "SIMPLE_RADIAL_FISHEYE", "RADIAL_FISHEYE"):
+            return self.params[0], self.params[0]
+        return self.params[0], self.params[1]
+
+    def principal_point(self) -> Tuple[float, float]:
+        if self.model in ("SIMPLE_PINHOLE", "SIMPLE_RADIAL", "RADIAL", "SIMPLE_RADIAL_FISHEYE", "RADIAL_FISHEYE"):
+            return self.params[1], self.params[2]
+        return self.params[2], self.params[3]
+
+
+@dataclass
+class ColmapImage:
+    id: int
+    quat_wxyz: Tuple[float, float, float, float]   # world -> camera
+    tvec: Tuple[float, float, float]
+    camera_id: int
+    name: str
+
+
+def _data_lines(text: str):
+    for ln in text.splitlines():
+        s = ln.strip()
+        if s and not s.startswith("#"):
+            yield s
+
+
+def read_cameras_text(text: str) -> List[ColmapCamera]:
+    out = []
+    for s in _data_lines(text):
+        p = s.split()
+        out.append(ColmapCamera(int(p[0]), p[1], int(p[2]), int(p[3]), [float(v) for v in p[4:]]))
+    return out
+
+
+def read_images_text(text: str) -> List[ColmapImage]:
+    """Two lines per image; the second (2D points) may be empty, so blank lines are significant."""
+    out = []
+    lines = [ln for ln in text.splitlines() if not ln.lstrip().startswith("#")]
+    i = 0
+    while i < len(lines):
+        s = lines[i].strip()
+        if not s:
+            i += 1
+            continue
+        p = s.split()
+        out.append(ColmapImage(int(p[0]), tuple(float(v) for v in p[1:5]), tuple(float(v) for v in p[5:8]), int(p[8]),
+                               " ".join(p[9:])))
+        i += 2   # skip the POINTS2D line
+    return out
+
+
+def read_points3d_text(text: str):
+    xyz, rgb = [], []
+    for s in _data_lines(text):
+        p = s.split()
+        xyz.append([float(p[1]), float(p[2]), float(p[3])])
+        rgb.append([int(p[4]), int(p[5]), int(p[6])])
+    return np.array(xyz, np.float32).reshape(-1, 3), np.array(rgb, np.uint8).reshape(-1, 3)
+
+
+def build_camera_model(c: ColmapCamera):
+    """formats/colmap.rs:305-390 -> (camera_model id, model_params)."""
+    p, m = c.params, c.model
+    f32 = lambda v: float(np.float32(v))
+    if m in ("SIMPLE_PINHOLE", "PINHOLE", "FOV"):          # FOV: no matching polynomial, falls back to pinhole
+        return cm.PINHOLE, ()
+    if m == "SIMPLE_RADIAL":
+        return cm.RADIAL_TANGENTIAL_8, (f32(p[3]), 0, 0, 0, 0, 0, 0, 0)
+    if m == "RADIAL":
+        return cm.RADIAL_TANGENTIAL_8, (f32(p[3]), f32(p[4]), 0, 0, 0, 0, 0, 0)
+    if m == "OPENCV":
+        return cm.RADIAL_TANGENTIAL_8, (f32(p[4]), f32(p[5]), 0, 0, 0, 0, f32(p[6]), f32(p[7]))
+    if m == "FULL_OPENCV":
+        return cm.RADIAL_TANGENTIAL_8, (f32(p[4]), f32(p[5]), f32(p[8]), f32(p[9]), f32(p[10]), f32(p[11]), f32(p[6]), f32(p[7]))
+    if m == "SIMPLE_RADIAL_FISHEYE":
+        return cm.KANNALA_BRANDT_4, (f32(p[3]), 0, 0, 0)
+    if m == "RADIAL_FISHEYE":
+        return cm.KANNALA_BRANDT_4, (f32(p[3]), f32(p[4]), 0, 0)
+    if m == "OPENCV_FISHEYE":
+        return cm.KANNALA_BRANDT_4, (f32(p[4]), f32(p[5]), f32(p[6]), f32(p[7]))
+    if m == "THIN_PRISM_FISHEYE":
+        return cm.THIN_PRISM_FISHEYE, (f32(p[4]), f32(p[5]), f32(p[8]), f32(p[9]), f32(p[6]), f32(p[7]), f32(p[10]), f32(p[11]))
+    raise ValueError(f"unknown COLMAP camera model {m}")
+
+
+def _quat_to_mat(w, x, y, z):
+    n = math.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def camera_from_colmap(c: ColmapCamera, img: ColmapImage) -> Camera:
+    """colmap.rs:170-202: intrinsics -> fov per model, world-to-camera pose -> camera-to-world."""
+    model, params = build_camera_model(c)
+    fx, fy = c.focal()
+    fov_x = cm.focal_to_fov(fx, c.width, model, params)
+    fov_y = cm.focal_to_fov(fy, c.height, model, params)
+    cx, cy = c.principal_point()
+    qw, qx, qy, qz = img.quat_wxyz
+    R = _quat_to_mat(qw, qx, qy, qz)
+    pos = -R.T @ np.array(img.tvec, np.float64)
+    n = math.sqrt(qw * qw + qx * qx + qy * qy + qz * qz)
+    rot_c2w = (-qx / n, -qy / n, -qz / n, qw / n)            # conjugate, glam (x, y, z, w) order
+    return Camera(position=tuple(float(v) for v in pos), rotation=rot_c2w, fov_x=fov_x, fov_y=fov_y,
+                  center_uv=(float(np.float32(cx) / np.float32(c.width)), float(np.float32(cy) / np.float32(c.height))),
+                  camera_model=model, model_params=params)
+
+
+def split_eval_every(views: Sequence, eval_split_every: Optional[int]):
+    """formats/mod.rs:135-148 -> (train, eval)."""
+    train, ev = [], []
+    for i, v in enumerate(views):
+        (ev if (eval_split_every and i % eval_split_every == 0) else train).append(v)
+    return train, ev
+
+
+@dataclass
+class SceneView:
+    camera: Camera
+    image_path: str
+
+    def load_packed(self, alpha_mode: str = ALPHA_MASKED, max_resolution: Optional[int] = None):
+        from PIL import Image
+        im = Image.open(self.image_path)
+        if im.mode not in ("RGB", "RGBA"):
+            im = im.convert("RGBA" if "A" in im.getbands() else "RGB")
+        if max_resolution and max(im.size) > max_resolution:
+            s = max_resolution / max(im.size)
+            im = im.resize((max(1, round(im.size[0] * s)), max(1, round(im.size[1] * s))), Image.LANCZOS)
+        return view_to_packed_data(np.asarray(im, np.uint8), alpha_mode)
+
+
+@dataclass
+class DatasetLoadResult:
+    train: List[SceneView]
+    eval: List[SceneView]
+    init_splat: Optional[SplatData]
+    warnings: List[str] = field(default_factory=list)
+
+
+def _find(root: str, name: str) -> Optional[str]:
+    low = name.lower()
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.lower() == low:
+                return os.path.join(d, f)
+    return None
+
+
+def load_colmap_text(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
+                     eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None) -> DatasetLoadResult:
+    cam_path = _find(root, "cameras.txt")
+    if cam_path is None:
+        raise FileNotFoundError("no cameras.txt under " + root)
+    sparse = os.path.dirname(cam_path)
+    cams = {c.id: c for c in read_cameras_text(open(cam_path).read())}
+    infos = sorted(read_images_text(open(os.path.join(sparse, "images.txt")).read()), key=lambda i: i.name)
+    views, warnings = [], []
+    picked = infos[::max(int(subsample_frames or 1), 1)]
+    if max_frames is not None:
+        picked = picked[:max_frames]
+    for info in picked:
+        if info.camera_id not in cams:
+            raise ValueError(f"Image '{info.name}' references camera ID {info.camera_id} which doesn't exist in camera data")
+        path = _find(root, os.path.basename(info.name))
+        if path is None:
+            warnings.append(f"Skipped '{info.name}': image file not found")
+            continue
+        camera = camera_from_colmap(cams[info.camera_id], info)
+        if not camera.is_valid():
+            warnings.append(f"Skipped '{info.name}': camera contains nan or inf values")
+            continue
+        views.append(SceneView(camera, path))
+    train, ev = split_eval_every(views, eval_split_every)
+    init = None
+    pts = os.path.join(sparse, "points3D.txt")
+    if os.path.exists(pts):
+        xyz, rgb = read_points3d_text(open(pts).read())
+        step = max(int(subsample_points or 1), 1)
+        xyz, rgb = xyz[::step], rgb[::step]
+        if len(xyz):
+            sh = ((rgb.astype(np.float32) / np.float32(255.0)) - np.float32(0.5)) / np.float32(SH_C0)   # rgb_to_sh
+            init = SplatData(means=xyz, sh_coeffs=sh.reshape(-1, 1, 3))
+    return DatasetLoadResult(train, ev, init, warnings)
+
+
+class SceneLoader:
+    """Double-buffered pinned staging of the packed views: `next_batch()` returns a SceneBatch whose image is a
+    pinned host tensor (uploaded by SplatTrainer.step with a non-blocking copy) while the following view is decoded."""
+
+    def __init__(self, views: Sequence[SceneView], alpha_mode: str = ALPHA_MASKED, seed: int = 0):
+        self.views, self.alpha_mode = list(views), alpha_mode
+        self._rng = np.random.default_rng(seed)
+        self._order: List[int] = []
+        self._buf = [None, None]
+        self._i = 0
+
+    def next_batch(self):
+        import torch
+        from .train import SceneBatch
+        if not self._order:
+            self._order = list(self._rng.permutation(len(self.views)))
+        v = self.views[self._order.pop()]
+        packed, has_alpha = v.load_packed(self.alpha_mode)
+        slot = self._i & 1
+        self._i += 1
+        t = self._buf[slot]
+        if t is None or tuple(t.shape) != packed.shape:
+            t = torch.empty(packed.shape, dtype=torch.int32)
+            if torch.cuda.is_available():
+                t = t.pin_memory()
+            self._buf[slot] = t
+        t.copy_(torch.from_numpy(packed))
+        return SceneBatch(img_packed=t, camera=v.camera, has_alpha=has_alpha,
+                          masked_alpha=has_alpha and self.alpha_mode == ALPHA_MASKED)

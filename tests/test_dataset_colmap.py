@@ -1,0 +1,125 @@
+"""COLMAP text loader and packed-view producer, after the reference's own tests
+(brush-dataset/src/formats/colmap.rs:392-590, scene.rs:164+)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from brush_b200 import camera as cm
+from brush_b200 import dataset as ds
+
+IMG_W, IMG_H, FX, FY, CX, CY = 64, 48, 80.0, 70.0, 30.0, 20.0
+
+
+def _img1_w2c():
+    a = math.pi / 4.0                       # Quat::from_rotation_y(pi/2) = (w, x, y, z) = (cos a, 0, sin a, 0)
+    return (math.cos(a), 0.0, math.sin(a), 0.0), (1.0, 0.0, 2.0)
+
+
+def _write_dataset(root):
+    from PIL import Image
+    sparse = os.path.join(root, "sparse", "0")
+    os.makedirs(sparse)
+    open(os.path.join(sparse, "cameras.txt"), "w").write(
+        "# Camera list with one line of data per camera:\n#   CAMERA_ID, MODEL, WIDTH, HEIGHT, PARAMS[]\n"
+        f"1 PINHOLE {IMG_W} {IMG_H} {FX} {FY} {CX} {CY}\n")
+    q, t = _img1_w2c()
+    open(os.path.join(sparse, "images.txt"), "w").write(
+        "# Image list with two lines of data per image:\n#   IMAGE_ID, QW, QX, QY, QZ, TX, TY, TZ, CAMERA_ID, NAME\n"
+        "#   POINTS2D[] as (X, Y, POINT3D_ID)\n"
+        "1 1.0 0.0 0.0 0.0 1.0 2.0 3.0 1 img0.png\n\n"
+        f"2 {q[0]} {q[1]} {q[2]} {q[3]} {t[0]} {t[1]} {t[2]} 1 img1.png\n10.0 20.0 1 30.0 40.0 -1\n"
+        "3 1.0 0.0 0.0 0.0 0.0 0.0 0.0 1 img2.png\n\n"
+        "4 1.0 0.0 0.0 0.0 5.0 5.0 5.0 1 missing.png\n\n")
+    open(os.path.join(sparse, "points3D.txt"), "w").write(
+        "# 3D point list with one line of data per point:\n"
+        "1 1.5 2.5 3.5 255 0 0 0.5 1 0\n2 -1.0 0.0 1.0 0 255 0 0.5 2 1\n3 0.0 1.0 0.0 0 0 255 0.5 3 0\n"
+        "4 2.0 2.0 2.0 128 128 128 0.5 1 1\n")
+    os.makedirs(os.path.join(root, "images"))
+    for name in ("img0.png", "img1.png", "img2.png"):
+        Image.fromarray(np.full((3, 4, 3), (10, 20, 30), np.uint8)).save(os.path.join(root, "images", name))
+
+
+def test_loads_text_model(tmp_path):
+    _write_dataset(str(tmp_path))
+    r = ds.load_colmap_text(str(tmp_path))
+    assert len(r.train) == 3 and r.eval == [] and len(r.warnings) == 1 and "missing.png" in r.warnings[0]
+    cam = r.train[0].camera
+    assert cam.camera_model == cm.PINHOLE
+    assert abs(cam.fov_x - cm.focal_to_fov(FX, IMG_W)) < 1e-6 and abs(cam.fov_y - cm.focal_to_fov(FY, IMG_H)) < 1e-6
+    fx, fy = cam.focal(IMG_W, IMG_H)
+    cx, cy = cam.center(IMG_W, IMG_H)
+    assert abs(fx - FX) < 1e-3 and abs(fy - FY) < 1e-3 and abs(cx - CX) < 1e-3 and abs(cy - CY) < 1e-3
+    # sorted by name; img0: identity rotation, w2c translation (1,2,3) -> camera at (-1,-2,-3)
+    np.testing.assert_allclose(r.train[0].camera.position, (-1, -2, -3), atol=1e-4)
+    np.testing.assert_allclose(np.abs(r.train[0].camera.rotation), (0, 0, 0, 1), atol=1e-6)
+    np.testing.assert_allclose(r.train[2].camera.position, (0, 0, 0), atol=1e-6)
+    # img1: -R^T (1, 0, 2) = (2, 0, -1); rotation is the inverse of the written one
+    np.testing.assert_allclose(r.train[1].camera.position, (2.0, 0.0, -1.0), atol=1e-4)
+    q, _ = _img1_w2c()
+    np.testing.assert_allclose(r.train[1].camera.rotation, (-q[1], -q[2], -q[3], q[0]), atol=1e-6)
+    # the camera built from it maps the camera centre to the origin of its local frame
+    vm = r.train[1].camera.world_to_local().reshape(4, 3)
+    np.testing.assert_allclose(vm[:3].T @ np.array(r.train[1].camera.position) + vm[3], 0, atol=1e-5)
+    init = r.init_splat
+    assert init.num_splats() == 4 and (init.means[0] == [1.5, 2.5, 3.5]).all()
+    want = (np.array([1, 0, 0], np.float32) - np.float32(0.5)) / np.float32(0.2820947917738781)
+    np.testing.assert_array_equal(init.sh_coeffs[0, 0], want)
+    packed, has_alpha = r.train[0].load_packed()
+    assert packed.shape == (3, 4) and not has_alpha and (packed.view(np.uint32) == (10 | 20 << 8 | 30 << 16 | 255 << 24)).all()
+
+
+def test_splits_eval_views(tmp_path):
+    _write_dataset(str(tmp_path))
+    r = ds.load_colmap_text(str(tmp_path), eval_split_every=2)
+    assert len(r.train) == 1 and len(r.eval) == 2
+    np.testing.assert_allclose(r.train[0].camera.position, (2.0, 0.0, -1.0), atol=1e-4)
+    np.testing.assert_allclose(r.eval[0].camera.position, (-1, -2, -3), atol=1e-4)
+    np.testing.assert_allclose(r.eval[1].camera.position, (0, 0, 0), atol=1e-6)
+
+
+def test_colmap_camera_models_map_like_the_reference():
+    c = ds.ColmapCamera(1, "OPENCV", 100, 80, [90, 91, 50, 40, -0.1, 0.02, 1e-3, -2e-3])
+    assert ds.build_camera_model(c) == (cm.RADIAL_TANGENTIAL_8, pytest.approx((-0.1, 0.02, 0, 0, 0, 0, 1e-3, -2e-3)))
+    c = ds.ColmapCamera(1, "FULL_OPENCV", 100, 80, [90, 91, 50, 40, 1, 2, 3, 4, 5, 6, 7, 8])
+    assert ds.build_camera_model(c) == (cm.RADIAL_TANGENTIAL_8, (1, 2, 5, 6, 7, 8, 3, 4))
+    c = ds.ColmapCamera(1, "OPENCV_FISHEYE", 100, 80, [90, 91, 50, 40, 1, 2, 3, 4])
+    assert ds.build_camera_model(c) == (cm.KANNALA_BRANDT_4, (1, 2, 3, 4))
+    c = ds.ColmapCamera(1, "THIN_PRISM_FISHEYE", 100, 80, [90, 91, 50, 40, 1, 2, 3, 4, 5, 6, 7, 8])
+    assert ds.build_camera_model(c) == (cm.THIN_PRISM_FISHEYE, (1, 2, 5, 6, 3, 4, 7, 8))
+    c = ds.ColmapCamera(1, "SIMPLE_RADIAL", 100, 80, [90, 50, 40, 0.05])
+    assert c.focal() == (90, 90) and c.principal_point() == (50, 40)
+    assert ds.build_camera_model(c)[0] == cm.RADIAL_TANGENTIAL_8
+    assert ds.build_camera_model(ds.ColmapCamera(1, "FOV", 1, 1, [1, 1, 0, 0, 0.5])) == (cm.PINHOLE, ())
+    cam = ds.camera_from_colmap(ds.ColmapCamera(1, "OPENCV_FISHEYE", 640, 480, [300, 300, 320, 240, -0.01, 0.003, 0, 0]),
+                                ds.ColmapImage(1, (1, 0, 0, 0), (0, 0, 0), 1, "a.png"))
+    f = cm.fov_to_focal(cam.fov_x, 640, cam.camera_model, cam.model_params)
+    assert abs(f - 300) < 1e-6
+
+
+def test_view_to_packed_data_and_premultiplication():
+    rgb = np.arange(2 * 3 * 3, dtype=np.uint8).reshape(2, 3, 3)
+    p, has_alpha = ds.view_to_packed_data(rgb)
+    assert not has_alpha and p.dtype == np.int32
+    u = p.view(np.uint32)
+    assert (u & 0xFF == rgb[..., 0]).all() and ((u >> 8) & 0xFF == rgb[..., 1]).all() and (u >> 24 == 255).all()
+    rgba = np.array([[[200, 100, 50, 128], [255, 255, 255, 0], [7, 8, 9, 255]]], np.uint8)
+    masked, ha = ds.view_to_packed_data(rgba, ds.ALPHA_MASKED)
+    assert ha and (masked.view(np.uint32)[0] == [200 | 100 << 8 | 50 << 16 | 128 << 24, 0x00FFFFFF, 7 | 8 << 8 | 9 << 16 | 255 << 24]).all()
+    pre, _ = ds.view_to_packed_data(rgba, ds.ALPHA_TRANSPARENT)
+    mul = lambda c, a: (c * a + 127) // 255
+    assert pre.view(np.uint32)[0, 0] == (mul(200, 128) | mul(100, 128) << 8 | mul(50, 128) << 16 | 128 << 24)
+    assert pre.view(np.uint32)[0, 1] == 0 and pre.view(np.uint32)[0, 2] == masked.view(np.uint32)[0, 2]
+    with pytest.raises(ValueError):
+        ds.view_to_packed_data(np.zeros((2, 2), np.uint8))
+
+
+def test_scene_loader_cycles_through_views(tmp_path):
+    _write_dataset(str(tmp_path))
+    r = ds.load_colmap_text(str(tmp_path))
+    loader = ds.SceneLoader(r.train, seed=1)
+    seen = {loader.next_batch().camera.position for _ in range(3)}
+    assert len(seen) == 3
+    b = loader.next_batch()
+    assert tuple(b.img_packed.shape) == (3, 4) and not b.has_alpha

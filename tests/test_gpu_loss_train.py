@@ -338,3 +338,28 @@ def test_step_views_equals_sequential_accumulation(rt):
     assert torch.equal(got["rad"], torch.maximum(per_view[0]["rad"], per_view[1]["rad"]))
     assert np.isfinite(float(st.loss.item()))
     assert all(torch.isfinite(x).all() for x in (multi.transforms, multi.sh_coeffs, multi.raw_opacities))
+
+
+def test_eval_stats_vs_oracle(rt):
+    """eval.rs:22-61: PSNR / SSIM of a render against a ground-truth image, through the product kernels vs the oracle."""
+    from brush_b200.eval import eval_stats
+    n, w, h = 15_000, 160, 120
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=4, seed=31)
+    d = rt.ctx.device
+    rng = np.random.default_rng(2)
+    gt = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    splats = rt.T.Splats(*(torch.from_numpy(x).to(d) for x in (tr, sh, op)))
+    s = eval_stats(rt.ctx, splats, cam, gt)
+    from brush_b200.camera import build_uniforms
+    o = rt.orc.render_forward(build_uniforms(cam, w, h), w, h, tr, sh, op, bg=(0, 0, 0))
+    rgb = np.round(o.out_img[..., :3] * np.float32(255.0)) / np.float32(255.0)
+    packed = (gt[..., 0].astype(np.uint32) | gt[..., 1].astype(np.uint32) << 8 | gt[..., 2].astype(np.uint32) << 16 | np.uint32(255 << 24))
+    chw = np.ascontiguousarray(rgb.transpose(2, 0, 1)).astype(np.float32)
+    l1 = rt.orc.image_loss_forward(chw, packed, 1.0, 0.0)
+    psnr = 10.0 * np.log10(1.0 / np.mean(l1.astype(np.float64) ** 2))
+    ssim = float(rt.orc.image_loss_forward(chw, packed, 0.0, 1.0).astype(np.float64).mean())
+    assert abs(float(s.psnr) - psnr) < 2e-3 and abs(float(s.ssim) - ssim) < 2e-4
+    # a perfect reconstruction of its own 8-bit image: SSIM 1, PSNR very high
+    own = (s.rendered.clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
+    s2 = eval_stats(rt.ctx, splats, cam, own)
+    assert float(s2.ssim) > 0.9999 and float(s2.psnr) > 60.0
