@@ -244,7 +244,7 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     if (bwd_info && n > 0) BG_CUDA(cudaMemsetAsync(visible, 0, (size_t)n * sizeof(float), s));
 
     const int pgrid = c->sm_count * 5;   // project_cull: 256-thread CTAs, 48 regs
-    const int vgrid = c->sm_count * 8;   // project_visible_emit: 128-thread CTAs, 64 regs (launch bounds), 22.5 KB smem
+    const int vgrid = c->sm_count * 6;   // project_visible_emit: 128-thread CTAs, 80 regs (8 CTAs/SM at 64 regs spills: 143 -> 198 us)
     uint32_t *counters = c->ctl + CTL_COUNTERS;
     // K1: cull + compaction in index order
     BG_CUDA(launch_project_cull(s, pgrid, mip != 0, transforms, raw_opac, n, *cam, w, h, tiles_x, tiles_y,

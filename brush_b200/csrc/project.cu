@@ -319,7 +319,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) 
 }
 
 template <bool MIP, int DEG, bool DIST>
-__global__ void __launch_bounds__(VIS_THREADS, 8)
+__global__ void __launch_bounds__(VIS_THREADS, 6)
 project_visible_emit_kernel(const float *__restrict__ transforms, const float *__restrict__ sh,
                             const float *__restrict__ raw_opac, const uint32_t *__restrict__ gid_sorted,
                             const uint32_t *__restrict__ cum, BgCamera u, uint32_t tiles_x, uint32_t tiles_y,
