@@ -200,11 +200,9 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             bool st0, st1;
             const bool c0 = bwd_test<SMOOTH>(p0, sigma0, B.y, ga0, oa0, al0, wc0, nt0, st0);
             const bool c1 = bwd_test<SMOOTH>(p1, sigma1, B.y, ga1, oa1, al1, wc1, nt1, st1);
-            const bool any_stop = __any_sync(0xffffffffu, st0 || st1);
-            if (!__any_sync(0xffffffffu, c0 || c1)) {
-                if (any_stop && all_done()) bits = 0;
-                continue;
-            }
+            // one vote per splat: saturation of the whole block is only checked between batches (a saturated
+            // pixel ignores the remaining splats of its batch, nothing it does is observable)
+            if (!__any_sync(0xffffffffu, c0 || c1)) continue;
             float g[10];
 #pragma unroll
             for (int i = 0; i < 10; i++) g[i] = 0.0f;
@@ -249,7 +247,6 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
             const uint32_t id = __shfl_sync(0xffffffffu, my_id, s);
             if (owner && d1 != 0.0f) atomicAdd(v_combined + (size_t)id * BG_VCOMBINED_STRIDE + slot, d1);
-            if (any_stop && all_done()) bits = 0;
         }
         if (all_done()) break;
         __syncwarp();
