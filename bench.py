@@ -356,6 +356,26 @@ def main():
         ms_train = timed(lambda i: trainer.step(batch, splats), args.steps) / args.steps
         line["train"] = {"iters_per_s": 1e3 / ms_train, "ms_per_iter": ms_train,
                          "note": "SplatTrainer.step, 1 view/step, GT resident on the device, refine() not included"}
+    if not args.no_train and 8 % world == 0:
+        # BASELINE config [4] shape (at this scene's 1M Gaussians): ONE optimizer step over 8 views, views sharded over
+        # the ranks, SH-factored exchange, identical Adam update on every rank (SplatTrainer.step_views)
+        import brush_b200.train as T
+        local = 8 // world
+        batches = []
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234)
+        for v in range(local):
+            gtv = torch.randint(0, 2 ** 31 - 1, (IMG_H, IMG_W), dtype=torch.int32, device=dev, generator=g) | (255 << 24)
+            batches.append(T.SceneBatch(img_packed=gtv, camera=rank_camera(cam0, rank * local + v)))
+        splats8 = T.Splats(ttr.clone(), tsh.clone(), top.clone())
+        trainer8 = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
+        for _ in range(2):
+            trainer8.step_views(batches, splats8)
+        k8 = max(10, args.steps // 5)
+        ms8 = timed(lambda i: trainer8.step_views(batches, splats8), k8) / k8
+        line["train_8_views"] = {"iters_per_s": 1e3 / ms8, "ms_per_iter": ms8, "views_per_step": 8, "views_per_rank": local,
+                                 "note": "SplatTrainer.step_views: 8 views per optimizer step sharded over the ranks "
+                                         "(BASELINE config [4] at 1M Gaussians), SH-factored gradient exchange"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         u = build_uniforms(cam0, IMG_W, IMG_H)
