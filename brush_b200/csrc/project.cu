@@ -418,9 +418,11 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
             cb = clampf(is_finite(cb) ? cb : 0.0f, -100.0f, 100.0f);
             float pt = det_logf(opac * 255.0f);
             float4 *dst = reinterpret_cast<float4 *>(projected + (size_t)cgid * BG_PROJECTED_STRIDE);
+            const float L2E = 1.4426950408889634f;
             dst[0] = make_float4(mx, my, conic.c00, conic.c01);
             dst[1] = make_float4(conic.c11, opac, cr, cg);
-            dst[2] = make_float4(cb, pt, 0.0f, 0.0f);
+            dst[2] = make_float4(cb, (0.5f * L2E) * conic.c11, (0.5f * L2E) * conic.c00, L2E * conic.c01);
+            dst[3] = make_float4(pt, 0.0f, 0.0f, 0.0f);
             cgid_from_gid[gid] = cgid;
             // ---- (tile id, compact gid) pairs (map_gaussians.rs:26-79)
             float ex, ey;

@@ -56,7 +56,7 @@ __device__ __forceinline__ BwdPixel load_bwd_pixel(bool inside, size_t pix_id, c
 template <bool SMOOTH>
 __device__ __forceinline__ bool bwd_test(BwdPixel &p, float sigma, float opac, float &gaussian, float &oa, float &alpha,
                                          float &w_cut, float &next_T, bool &stop) {
-    gaussian = __expf(-sigma);
+    gaussian = ex2_approx(-sigma);   // sigma arrives scaled by log2(e)
     oa = opac * gaussian;
     alpha = fminf(0.999f, oa);
     w_cut = 1.0f;
@@ -159,6 +159,7 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             cp_async16(dst, src);
             cp_async16(dst + 4, src + 4);
             cp_async16(dst + 8, src + 8);
+            cp_async16(dst + 12, src + 12);
         }
         cp_async_commit();
     };
@@ -182,7 +183,7 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
         if (lane < count) {
             const float4 A = *reinterpret_cast<const float4 *>(rows + lane * ROW);
             const float2 B = *reinterpret_cast<const float2 *>(rows + lane * ROW + 4);
-            const float pt = rows[lane * ROW + 9];
+            const float pt = rows[lane * ROW + ROW_PT];
             hit = block_may_hit(A.x, A.y, A.z, A.w, B.x, pt + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f), rx0, rx1, ry0, ry1);
         }
         uint32_t bits = __ballot_sync(0xffffffffu, hit);
@@ -192,10 +193,12 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             const float *row = rows + s * ROW;
             const float4 A = *reinterpret_cast<const float4 *>(row);      // mx my a b
             const float4 B = *reinterpret_cast<const float4 *>(row + 4);  // c opac r g
+            const float4 C = *reinterpret_cast<const float4 *>(row + 8);  // b_col, then log2(e)-scaled c/2, a/2, b
             const float dx = A.x - px, dy0 = A.y - py0, dy1 = dy0 - 4.0f;
-            const float adx2 = A.z * dx * dx, bdx = A.w * dx;
-            const float sigma0 = 0.5f * (adx2 + B.x * dy0 * dy0) + bdx * dy0;
-            const float sigma1 = 0.5f * (adx2 + B.x * dy1 * dy1) + bdx * dy1;
+            const float hx = (C.z * dx) * dx, bdx = C.w * dx;
+            // sigma * log2(e): the exponent of 2^-x; its sign test is the test on sigma
+            const float sigma0 = fmaf(bdx, dy0, fmaf(C.y * dy0, dy0, hx));
+            const float sigma1 = fmaf(bdx, dy1, fmaf(C.y * dy1, dy1, hx));
             float ga0, oa0, al0, wc0, nt0, ga1, oa1, al1, wc1, nt1;
             bool st0, st1;
             const bool c0 = bwd_test<SMOOTH>(p0, sigma0, B.y, ga0, oa0, al0, wc0, nt0, st0);
@@ -206,7 +209,7 @@ rasterize_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_
             float g[10];
 #pragma unroll
             for (int i = 0; i < 10; i++) g[i] = 0.0f;
-            const float col_b = row[8];
+            const float col_b = C.x;
             const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cbl = fmaxf(col_b, 0.0f);
             bwd_accumulate<SMOOTH>(p0, g, c0, dx, dy0, A.z, A.w, B.x, cr, cg, cbl, ga0, oa0, al0, wc0, nt0, img_wf, img_hf);
             bwd_accumulate<SMOOTH>(p1, g, c1, dx, dy1, A.z, A.w, B.x, cr, cg, cbl, ga1, oa1, al1, wc1, nt1, img_wf, img_hf);

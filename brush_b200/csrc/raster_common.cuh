@@ -18,7 +18,8 @@ namespace bg {
 constexpr int RASTER_WARPS = 4;
 constexpr int RASTER_THREADS = RASTER_WARPS * 32;
 constexpr int WB = 32;                    // splats per warp batch
-constexpr int ROW = BG_PROJECTED_STRIDE;  // 12 floats
+constexpr int ROW = BG_PROJECTED_STRIDE;  // 16 floats
+constexpr int ROW_PT = 12;                // lane of ln(255 opacity), the block-cull threshold
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -60,6 +61,8 @@ __device__ __forceinline__ bool block_may_hit(float mx, float my, float a, float
     }
     return !(best > thr + 0.05f + 4.0e-6f * err);  // NaN compares false -> kept
 }
+
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // kernels/helpers.rs:26-47 (test-only smooth cutoff)
 __device__ __forceinline__ float cutoff_weight(float alpha) {

@@ -33,7 +33,7 @@ struct FwdPixel {
 
 template <bool SMOOTH>
 __device__ __forceinline__ void fwd_pair(FwdPixel &p, float sigma, float opac, float &vis_out, bool &contrib, bool &stop) {
-    const float alpha = fminf(0.999f, opac * __expf(-sigma));
+    const float alpha = fminf(0.999f, opac * ex2_approx(-sigma));   // sigma arrives scaled by log2(e)
     float alpha_eff;
     if (SMOOTH) {
         const float wc = cutoff_weight(alpha);
@@ -93,6 +93,7 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
             cp_async16(dst, src);
             cp_async16(dst + 4, src + 4);
             cp_async16(dst + 8, src + 8);
+            cp_async16(dst + 12, src + 12);
         }
         cp_async_commit();
     };
@@ -115,7 +116,7 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
             if (lane < count) {
                 const float4 A = *reinterpret_cast<const float4 *>(rows + lane * ROW);
                 const float2 B = *reinterpret_cast<const float2 *>(rows + lane * ROW + 4);
-                const float pt = rows[lane * ROW + 9];
+                const float pt = rows[lane * ROW + ROW_PT];
                 hit = block_may_hit(A.x, A.y, A.z, A.w, B.x, pt + (SMOOTH ? SMOOTH_THR_EXTRA : 0.0f), rx0, rx1, ry0, ry1);
             }
             uint32_t bits = __ballot_sync(0xffffffffu, hit);
@@ -129,10 +130,12 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
                 const float *row = rows + s * ROW;
                 const float4 A = *reinterpret_cast<const float4 *>(row);       // mx my a b
                 const float4 B = *reinterpret_cast<const float4 *>(row + 4);   // c opac r g
+                const float4 C = *reinterpret_cast<const float4 *>(row + 8);   // b_col, then log2(e)-scaled c/2, a/2, b
                 const float dx = px - A.x, dy0 = py0 - A.y, dy1 = dy0 + 4.0f;
-                const float adx2 = A.z * dx * dx, bdx = A.w * dx;
-                const float sigma0 = 0.5f * (adx2 + B.x * dy0 * dy0) + bdx * dy0;
-                const float sigma1 = 0.5f * (adx2 + B.x * dy1 * dy1) + bdx * dy1;
+                const float hx = (C.z * dx) * dx, bdx = C.w * dx;
+                // sigma * log2(e): alpha = opacity * 2^-sigma2
+                const float sigma0 = fmaf(bdx, dy0, fmaf(C.y * dy0, dy0, hx));
+                const float sigma1 = fmaf(bdx, dy1, fmaf(C.y * dy1, dy1, hx));
                 float vis0, vis1;
                 bool c0, c1, st0, st1;
                 fwd_pair<SMOOTH>(p0, sigma0, B.y, vis0, c0, st0);
@@ -145,7 +148,7 @@ rasterize_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__r
                 // contributing lane, so the blend runs unconditionally (weights are zero where it does not apply),
                 // each lane remembers which splats its pixels used, and "all pixels saturated" is checked once per
                 // batch (saturated pixels ignore the remaining splats of the batch; nothing they do is observable).
-                const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cb = fmaxf(row[8], 0.0f);
+                const float cr = fmaxf(B.z, 0.0f), cg = fmaxf(B.w, 0.0f), cb = fmaxf(C.x, 0.0f);
                 const float v0 = c0 ? vis0 : 0.0f, v1 = c1 ? vis1 : 0.0f;
                 p0.r = fmaf(cr, v0, p0.r); p0.g = fmaf(cg, v0, p0.g); p0.b = fmaf(cb, v0, p0.b);
                 p1.r = fmaf(cr, v1, p1.r); p1.g = fmaf(cg, v1, p1.g); p1.b = fmaf(cb, v1, p1.b);

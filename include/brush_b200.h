@@ -35,13 +35,14 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 2u
+#define BG_ABI_VERSION 3u
 
-/* f32 lanes per projected splat.  Lanes 0..8 are the reference layout
- * (kernels/helpers.rs:49-53: xy_x, xy_y, conic_x, conic_y, conic_z, color_a,
- * color_r, color_g, color_b); lanes 9..11 pad the row to 48 B so that a row
- * is three aligned 128-bit loads (lane 9 caches ln(255*opacity)). */
-#define BG_PROJECTED_STRIDE 12u
+/* f32 lanes per projected splat: a 64-byte row, four aligned 128-bit loads.  Lanes 0..8 are the reference
+ * layout (kernels/helpers.rs:49-53: xy_x, xy_y, conic_x, conic_y, conic_z, color_a, color_r, color_g, color_b).
+ * Lanes 9..12 are derived values cached for the blend kernels: 9 = log2(e)/2 * conic_z, 10 = log2(e)/2 * conic_x,
+ * 11 = log2(e) * conic_y (so that alpha = opacity * 2^-(l10 dx^2 + l9 dy^2 + l11 dx dy) costs three FMA-class
+ * operations and one MUFU per pixel), 12 = ln(255 * opacity) (the block-cull threshold); 13..15 pad. */
+#define BG_PROJECTED_STRIDE 16u
 /* f32 lanes per row of v_combined (bwd/burn_glue.rs:36-43). */
 #define BG_VCOMBINED_STRIDE 10u
 
