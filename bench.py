@@ -117,6 +117,8 @@ def run_reference(args):
         return 0
     from brush_b200.camera import build_uniforms
     from oracle import oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the CPU implementation on ALL the host's cores
+    orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cam, tr, sh, op, v_out = scene_np()
     u = build_uniforms(cam, IMG_W, IMG_H)
     # One "step" of this arm is one full fwd+bwd pass of the workload on the host cores (seconds each).
@@ -378,6 +380,7 @@ def main():
                                          "(BASELINE config [4] at 1M Gaussians), SH-factored gradient exchange"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
+        orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         u = build_uniforms(cam0, IMG_W, IMG_H)
         cpu_oracle_pass(u, tr, sh, op, v_out_np)
         reps = 3

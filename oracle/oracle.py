@@ -98,6 +98,8 @@ def lib():
         L.orc_logf_det.argtypes = [C.c_float]
         L.orc_logf_det.restype = C.c_float
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -295,3 +297,7 @@ def logf_det(x: float) -> float:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))

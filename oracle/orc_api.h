@@ -103,6 +103,7 @@ float orc_expf_det(float x);
 float orc_logf_det(float x);
 float orc_atan2f_det(float y, float x); /* y >= 0 */
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1 */
 
 #ifdef __cplusplus
 }
