@@ -204,11 +204,15 @@ def main():
 
     last_out = [None]
 
-    def step_device():
+    def step_compute():   # this rank's kernels (what the CUDA graph holds)
         out = R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top)
         last_out[0] = out
         vc = R.rasterize_bwd(out, v_out)
         g = project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
+        return out, g
+
+    def step_device():
+        out, g = step_compute()
         allreduce(g)
         return out, g
 
@@ -270,9 +274,9 @@ def main():
 
     # The step is ~20 short launches; replaying it as one CUDA graph removes the host launch gaps
     # (the library keeps nothing launch-specific on the host: counters and look-back epochs live on the device).
-    # N>1 runs eager: the step contains NCCL collectives.  Capturing them (BG_BENCH_GRAPH_DP=1) HUNG at N=2 when
-    # tried (two collectives on NCCL's internal stream inside one graph), so it stays an experiment, off by default.
-    use_graph = os.environ.get("BG_BENCH_NO_GRAPH") is None and (world == 1 or os.environ.get("BG_BENCH_GRAPH_DP", "0") == "1")
+    # N>1: the graph holds this rank's kernels only; the NCCL collectives of the gradient exchange are issued eagerly
+    # after each replay (capturing them too hung at N=2: two collectives on NCCL's internal stream inside one capture).
+    use_graph = os.environ.get("BG_BENCH_NO_GRAPH") is None
     graph = None
     if use_graph:
         try:
@@ -280,19 +284,24 @@ def main():
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    step_device()
+                    step_compute()
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out, g = step_device()
+                out, g = step_compute()
             for _ in range(3):
                 graph.replay()
+                allreduce(g)
             torch.cuda.synchronize(dev)
             assert out.num_visible == V and out.num_intersections == I
         except Exception as e:  # capture not possible: measure the eager loop instead
             sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing eager launches\n")
             graph = None
-    ms_dev = timed((lambda i: graph.replay()) if graph is not None else (lambda i: step_device()), args.steps)
+    def step_graph(i):
+        graph.replay()
+        allreduce(g)     # no-op at N=1
+
+    ms_dev = timed(step_graph if graph is not None else (lambda i: step_device()), args.steps)
     # ---- e2e: host input, copies inside the timed region
     stage(0)
     for i in range(2):
@@ -331,7 +340,7 @@ def main():
                    "splats_per_tile_max": int(per_tile.max()),
                    "parallelism": "single GPU" if world == 1 else (f"view-sharded dp{world}, SH-factored exchange: all-reduce 44N B + all-gather 12N B/rank, v_sh rebuilt locally"
                                                                            if factored else f"view-sharded dp{world}, one NCCL all-reduce of the dense gradients per step"),
-                   "launch": "one CUDA graph replay per step" if graph is not None else "eager launches",
+                   "launch": ("one CUDA graph replay per step" + ("" if world == 1 else " + eager NCCL exchange")) if graph is not None else "eager launches",
                    "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 33 MB images per step vs 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(v_out_host.numel() * 4), "d2h_bytes_per_step": 16 + 16,
                 "note": "upstream-gradient image uploaded from pinned host memory every step (double-buffered on a copy stream), "
