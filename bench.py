@@ -139,11 +139,31 @@ def run_reference(args):
                        "the reference needs cargo + wgpu and has no CPU path (SURVEY.md F3/F4)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner), so the
+    process-wide fd 1 is pointed at stderr for the whole run and the line goes to a private copy of the original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -398,7 +418,7 @@ def main():
                                 "sample": f"{reps} full fwd+bwd passes of the same scene on the host cores (oracle/, OpenMP)"}
     line["clocks"] = sampler.stop()
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
