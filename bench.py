@@ -111,14 +111,24 @@ def cpu_oracle_pass(u, tr, sh, op, v_out):
     return dt
 
 
+def _oracle_on_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs are the oracle on ALL the host's cores.  The
+    OpenMP default (one thread per core the runtime may use) is what a plain `python bench.py` gets; it is restored
+    by dropping the variable before the oracle's OpenMP runtime starts, with an explicit count as a fallback."""
+    os.environ.pop("OMP_NUM_THREADS", None)
+    from oracle import oracle as orc
+    if orc.num_threads() <= 1:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        orc.set_num_threads(max(1, n // 2) if n >= 4 else n)   # physical cores: SMT siblings slow this code down
+    return orc
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from brush_b200.camera import build_uniforms
-    from oracle import oracle as orc
-    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the CPU implementation on ALL the host's cores
-    orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    orc = _oracle_on_all_cores()
     cam, tr, sh, op, v_out = scene_np()
     u = build_uniforms(cam, IMG_W, IMG_H)
     # One "step" of this arm is one full fwd+bwd pass of the workload on the host cores (seconds each).
@@ -408,8 +418,7 @@ def main():
                                  "note": "SplatTrainer.step_views: 8 views per optimizer step sharded over the ranks "
                                          "(BASELINE config [4] at 1M Gaussians), SH-factored gradient exchange"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        orc = _oracle_on_all_cores()
         u = build_uniforms(cam0, IMG_W, IMG_H)
         cpu_oracle_pass(u, tr, sh, op, v_out_np)
         reps = 3
