@@ -226,11 +226,11 @@ def main():
 
     def allreduce(g):
         if world > 1:
-            if factored:
-                fred.reduce(fg, ttr, cam_positions)
+            if factored:   # gradients AND refine statistics in two collectives
+                fred.reduce(fg, ttr, cam_positions, last_out[0].visible, last_out[0].max_radius)
             else:
                 reducer.reduce_flat(fg)               # SUM over ranks, 1/views scaling
-            reducer.reduce_stats(g[3], last_out[0].visible, last_out[0].max_radius)
+                reducer.reduce_stats(g[3], last_out[0].visible, last_out[0].max_radius)
 
     last_out = [None]
 
@@ -368,7 +368,7 @@ def main():
         "config": {"workload": WORKLOAD, "n_gaussians": N_SPLATS, "width": IMG_W, "height": IMG_H, "sh_k": SH_K,
                    "num_visible": V, "num_intersections": I, "splats_per_tile_mean": float(per_tile.mean()),
                    "splats_per_tile_max": int(per_tile.max()),
-                   "parallelism": "single GPU" if world == 1 else (f"view-sharded dp{world}, SH-factored exchange: all-reduce 44N B + all-gather 12N B/rank, v_sh rebuilt locally"
+                   "parallelism": "single GPU" if world == 1 else (f"view-sharded dp{world}, SH-factored exchange: all-reduce 48N B + all-gather 20N B/rank (gradients and refine statistics), v_sh rebuilt locally"
                                                                            if factored else f"view-sharded dp{world}, one NCCL all-reduce of the dense gradients per step"),
                    "launch": ("one CUDA graph replay per step" + ("" if world == 1 else " + eager NCCL exchange")) if graph is not None else "eager launches",
                    "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 33 MB images per step vs 126 MB L2)"},

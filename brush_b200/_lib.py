@@ -72,7 +72,7 @@ SIGNATURES = {
     "bg_fold_min_scale_forward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),
     "bg_fold_min_scale_backward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),
     "bg_project_backward_factored": (_I32, [_P, _P, C.POINTER(BgCamera), C.POINTER(BgRenderState), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "bg_sh_grad_from_views": (_I32, [_P, _P, _U32, _U32, _P, C.POINTER(_F), _U32, _P, _F, _P]),
+    "bg_sh_grad_from_views": (_I32, [_P, _P, _U32, _U32, _P, C.POINTER(_F), _U32, _P, C.c_uint64, _F, _P]),
     "bg_radix_argsort_u32": (_I32, [_P, _P, _P, _P, _U32, _P, _U32, _P, _P]),
     "bg_inclusive_scan_u32": (_I32, [_P, _P, _P, _U32, _P]),
     "bg_image_loss_forward": (_I32, [_P, _P, _P, _P, _U32, _U32, _U32, _I64, _I64, _I64, _F, _F, C.POINTER(_F), _I32, _P]),

@@ -46,7 +46,7 @@ cudaError_t launch_min_scale(cudaStream_t, uint32_t, const float *, const float 
 cudaError_t launch_fold_min_scale_fwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
 cudaError_t launch_fold_min_scale_bwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
 cudaError_t launch_sh_grad_from_views(cudaStream_t, int, const float *, const float *, uint32_t, const float *, uint32_t,
-                                      float, float *);
+                                      float, float *, size_t);
 // loss.cu / optim.cu
 cudaError_t launch_image_loss_fwd(cudaStream_t, const float *, const uint32_t *, uint32_t, uint32_t, uint32_t, int64_t,
                                   int64_t, int64_t, float, float, const float *, bool, float *);
@@ -360,14 +360,16 @@ extern "C" int32_t bg_project_backward_factored(BgContext *c, void *stream, cons
 
 extern "C" int32_t bg_sh_grad_from_views(BgContext *c, void *stream, uint32_t n, uint32_t k, const float *transforms,
                                          const float *cam_positions, uint32_t views, const float *v_color_all,
-                                         float out_scale, float *v_sh) {
+                                         uint64_t view_stride, float out_scale, float *v_sh) {
     if (!c) return BG_ERR_NULL;
     if (n == 0) return BG_OK;
     if (!transforms || !cam_positions || !v_color_all || !v_sh) return BG_ERR_NULL;
     const int deg = sh_degree_from_k(k);
     if (deg < 0 || views == 0 || views > 16) { set_err("bg_sh_grad_from_views: k must be a square <= 25, 1 <= views <= 16", cudaSuccess); return BG_ERR_INVALID; }
     BG_CUDA(cudaSetDevice(c->device));
-    BG_CUDA(launch_sh_grad_from_views((cudaStream_t)stream, deg, transforms, v_color_all, n, cam_positions, views, out_scale, v_sh));
+    if (view_stride != 0 && view_stride < (uint64_t)n * 3) { set_err("bg_sh_grad_from_views: view_stride smaller than one view", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(launch_sh_grad_from_views((cudaStream_t)stream, deg, transforms, v_color_all, n, cam_positions, views, out_scale, v_sh,
+                                      view_stride ? (size_t)view_stride : (size_t)n * 3));
     return BG_OK;
 }
 

@@ -337,7 +337,7 @@ struct ViewCams { float pos[16][3]; uint32_t count; };
 template <int DEG>
 __global__ void __launch_bounds__(PB_THREADS)
 sh_grad_from_views_kernel(const float *__restrict__ transforms, const float *__restrict__ v_color_all /* [views,n,3] */,
-                          uint32_t n, ViewCams cams, float out_scale, float *__restrict__ v_sh) {
+                          uint32_t n, ViewCams cams, float out_scale, float *__restrict__ v_sh, size_t view_stride) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int KF = K * 3;
     constexpr int STRIDE = (KF % 2 == 0) ? KF + 1 : KF;
@@ -352,7 +352,7 @@ sh_grad_from_views_kernel(const float *__restrict__ transforms, const float *__r
         const float *t = transforms + (size_t)gid * 10;
         const V3 mean = mk3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
         for (uint32_t v = 0; v < cams.count; v++) {
-            const float *vc = v_color_all + ((size_t)v * n + gid) * 3;
+            const float *vc = v_color_all + (size_t)v * view_stride + (size_t)gid * 3;
             const float cr = __ldg(vc), cg = __ldg(vc + 1), cb = __ldg(vc + 2);
             if (cr == 0.0f && cg == 0.0f && cb == 0.0f) continue;
             V3 u_world = sub(mean, mk3(cams.pos[v][0], cams.pos[v][1], cams.pos[v][2]));
@@ -381,7 +381,7 @@ sh_grad_from_views_kernel(const float *__restrict__ transforms, const float *__r
 
 cudaError_t launch_sh_grad_from_views(cudaStream_t s, int deg, const float *transforms, const float *v_color_all,
                                       uint32_t n, const float *cam_pos_host, uint32_t views, float out_scale,
-                                      float *v_sh) {
+                                      float *v_sh, size_t view_stride) {
     if (n == 0) return cudaSuccess;
     if (views > 16) return cudaErrorInvalidValue;
     ViewCams cams;
@@ -390,11 +390,11 @@ cudaError_t launch_sh_grad_from_views(cudaStream_t s, int deg, const float *tran
         for (int i = 0; i < 3; i++) cams.pos[v][i] = cam_pos_host[v * 3 + i];
     const int grid = (int)((n + PB_THREADS - 1) / PB_THREADS);
     switch (deg) {
-        case 0: sh_grad_from_views_kernel<0><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
-        case 1: sh_grad_from_views_kernel<1><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
-        case 2: sh_grad_from_views_kernel<2><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
-        case 3: sh_grad_from_views_kernel<3><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
-        case 4: sh_grad_from_views_kernel<4><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh); break;
+        case 0: sh_grad_from_views_kernel<0><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh, view_stride); break;
+        case 1: sh_grad_from_views_kernel<1><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh, view_stride); break;
+        case 2: sh_grad_from_views_kernel<2><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh, view_stride); break;
+        case 3: sh_grad_from_views_kernel<3><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh, view_stride); break;
+        case 4: sh_grad_from_views_kernel<4><<<grid, PB_THREADS, 0, s>>>(transforms, v_color_all, n, cams, out_scale, v_sh, view_stride); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

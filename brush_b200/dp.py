@@ -36,19 +36,24 @@ class FlatGradients:
 
 
 class FactoredGradients:
-    """Exchange buffers of the SH-factored scheme: `small` = v_transforms [n,10] | v_raw_opac [n] (all-reduced),
-    `v_color` [n,3] (this rank's view; all-gathered into `v_color_all` [views,n,3]), `v_sh` [n,k,3] (rebuilt
-    locally).  Per step a rank sends 44 n + 12 n bytes instead of (44 + 12 k) n."""
+    """Exchange buffers of the SH-factored scheme, two collectives per step:
+      `small`  = v_transforms [n,10] | v_raw_opac [n] | visible [n]           -> ONE all-reduce (SUM), 48 B/Gaussian
+      `record` = v_color [n,3] | v_refine [n] | max_radius [n] of this view   -> ONE all-gather, 20 B/Gaussian/view
+    v_sh [n,k,3] is rebuilt locally from the gathered colours; the refine statistics that need MAX (stats.rs:40-50)
+    are reduced locally over the gathered records.  A rank sends 68 n bytes instead of (44 + 12 k) n + 12 n."""
 
     def __init__(self, n: int, k: int, views: int, device):
         self.n, self.k, self.views = n, k, views
-        self.small = torch.empty(n * 11, dtype=torch.float32, device=device)
+        self.small = torch.zeros(n * 12, dtype=torch.float32, device=device)
         self.v_t = self.small[:n * 10].view(n, 10)
-        self.v_o = self.small[n * 10:].view(n)
-        self.v_color = torch.empty((n, 3), dtype=torch.float32, device=device)
-        self.v_color_all = torch.empty((views, n, 3), dtype=torch.float32, device=device)
+        self.v_o = self.small[n * 10:n * 11].view(n)
+        self.visible = self.small[n * 11:].view(n)
+        self.record = torch.zeros(n * 5, dtype=torch.float32, device=device)
+        self.v_color = self.record[:n * 3].view(n, 3)
+        self.v_r = self.record[n * 3:n * 4].view(n)
+        self.max_radius = self.record[n * 4:].view(n)
+        self.records_all = torch.empty((views, n * 5), dtype=torch.float32, device=device)
         self.v_sh = torch.empty((n, k, 3), dtype=torch.float32, device=device)
-        self.v_r = torch.empty(n, dtype=torch.float32, device=device)
 
     def outputs(self):
         """For render.project_bwd_factored(outputs=...)."""
@@ -59,25 +64,37 @@ class FactoredGradients:
 
 
 class ShFactoredReducer:
-    """One view per rank.  all-reduce(small) + all-gather(v_color) + local rebuild of v_sh in view order, so
-    every rank ends with bit-identical gradients (a property a ring all-reduce also has, but here it follows
-    from the fixed summation order of bg_sh_grad_from_views)."""
+    """One view per rank.  all-reduce(small) + all-gather(record) + local rebuild of v_sh in view order, so every
+    rank ends with bit-identical gradients (a property a ring all-reduce also has, but here it follows from the
+    fixed summation order of bg_sh_grad_from_views)."""
 
     def __init__(self, ctx, num_views_total: int, group=None):
         self.ctx, self.views, self.group = ctx, num_views_total, group
 
-    def reduce(self, fg: FactoredGradients, transforms: torch.Tensor, cam_positions) -> None:
+    def reduce(self, fg: FactoredGradients, transforms: torch.Tensor, cam_positions, visible: torch.Tensor = None,
+               max_radius: torch.Tensor = None) -> None:
+        """In place on fg (gradients) and, when given, on `visible` (SUM) / `max_radius` (MAX); fg.v_r gets MAX."""
         from .render import sh_grad_from_views
+        n = fg.n
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if visible is not None:
+            fg.visible.copy_(visible)
+        if max_radius is not None:
+            fg.max_radius.copy_(max_radius)
         if multi:
-            dist.all_gather_into_tensor(fg.v_color_all.view(-1), fg.v_color.view(-1), group=self.group)
+            dist.all_gather_into_tensor(fg.records_all.view(-1), fg.record, group=self.group)
             dist.all_reduce(fg.small, op=dist.ReduceOp.SUM, group=self.group)
         else:
-            fg.v_color_all[0].copy_(fg.v_color)
+            fg.records_all[0].copy_(fg.record)
         inv = 1.0 / self.views
-        sh_grad_from_views(self.ctx, transforms, fg.k, cam_positions, fg.v_color_all, inv, out=fg.v_sh)
+        sh_grad_from_views(self.ctx, transforms, fg.k, cam_positions, fg.records_all, inv, out=fg.v_sh, view_stride=5 * n)
         if self.views != 1:
-            fg.small.mul_(inv)
+            fg.small[:11 * n].mul_(inv)
+        torch.amax(fg.records_all[:, 3 * n:4 * n], dim=0, out=fg.v_r)
+        if visible is not None:
+            visible.copy_(fg.visible)
+        if max_radius is not None:
+            torch.amax(fg.records_all[:, 4 * n:], dim=0, out=max_radius)
 
 
 class ViewShardedReducer:

@@ -259,13 +259,17 @@ def project_bwd_factored(out: RenderOutput, transforms, sh_coeffs, raw_opacities
 
 
 def sh_grad_from_views(ctx: RenderContext, transforms, k: int, cam_positions, v_color_all, out_scale: float = 1.0,
-                       out=None):
+                       out=None, view_stride: int = 0):
     """bg_sh_grad_from_views: v_sh [n,k,3] = out_scale * sum_v Y(dir(mean, cam_positions[v])) x v_color_all[v].
-    cam_positions: sequence of `views` world-space camera positions; v_color_all: [views, n, 3]."""
+    cam_positions: sequence of `views` world-space camera positions; v_color_all: [views, n, 3], or with
+    view_stride > 0 a [views, view_stride] buffer whose rows START with the view's [n,3] colours."""
     lib = _lib.load()
     transforms = _f32c(transforms, "transforms")
     v_color_all = _f32c(v_color_all, "v_color_all")
-    views, n = int(v_color_all.shape[0]), int(v_color_all.shape[1])
+    views = int(v_color_all.shape[0])
+    n = int(transforms.shape[0])
+    if view_stride == 0 and (v_color_all.dim() != 3 or int(v_color_all.shape[1]) != n):
+        raise ValueError("v_color_all must be [views, n, 3]")
     pos = [float(x) for p in cam_positions for x in p]
     if len(pos) != 3 * views:
         raise ValueError("cam_positions must hold one xyz per view of v_color_all")
@@ -275,7 +279,7 @@ def sh_grad_from_views(ctx: RenderContext, transforms, k: int, cam_positions, v_
         raise ValueError("out must be a contiguous float32 [n,k,3] tensor")
     arr = (C.c_float * len(pos))(*pos)
     _lib.check(lib.bg_sh_grad_from_views(ctx.handle, _stream_ptr(ctx.device), n, k, transforms.data_ptr(), arr, views,
-                                         v_color_all.data_ptr(), float(out_scale), out.data_ptr()),
+                                         v_color_all.data_ptr(), int(view_stride), float(out_scale), out.data_ptr()),
                "bg_sh_grad_from_views")
     return out
 

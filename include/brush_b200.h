@@ -172,14 +172,16 @@ int32_t bg_fold_min_scale_backward(BgContext *ctx, void *stream, uint32_t n, con
  * it writes v_color [n,3] instead (zeros where no gradient).  Ranks all-reduce v_transforms / v_raw_opac,
  * all-gather their v_color rows (12 B instead of 12K B per Gaussian), and bg_sh_grad_from_views rebuilds
  *   v_sh[g,k,:] = out_scale * sum_v Y_k(dir(mean_g, cam_positions[v])) * v_color_all[v,g,:]
- * in view order (bit-identical on every rank).  cam_positions: host float[views*3]; views <= 16. */
+ * in view order (bit-identical on every rank).  cam_positions: host float[views*3]; views <= 16.
+ * view_stride: floats between the colour blocks of consecutive views (0 = n*3, dense); larger when each view's
+ * all-gathered record also carries other per-Gaussian values (refine weight, radius) behind its colours. */
 int32_t bg_project_backward_factored(BgContext *ctx, void *stream, const BgCamera *cam, const BgRenderState *state,
                                      const float *transforms, const float *sh, const float *raw_opac,
                                      const float *v_combined, float *v_transforms, float *v_color,
                                      float *v_raw_opac, float *v_refine);
 int32_t bg_sh_grad_from_views(BgContext *ctx, void *stream, uint32_t n, uint32_t k, const float *transforms,
                               const float *cam_positions, uint32_t views, const float *v_color_all,
-                              float out_scale, float *v_sh);
+                              uint64_t view_stride, float out_scale, float *v_sh);
 
 /* Replaces brush_sort::radix_argsort, brush-sort/src/lib.rs:16-125: stable ascending sort of
  * (key,value) pairs on the low `bits` bits.  n_dev (device, may be null) overrides n with a
