@@ -9,8 +9,9 @@ import brush_b200.render as R
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
 h = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
-cam, tr, sh, op = synthetic_scene(n, w, h)
-ctx = R.RenderContext(n, w, h, 0)
+shift = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0   # log-scale shift (config [3]: 4M Gaussians at 4K use -ln 2)
+cam, tr, sh, op = synthetic_scene(n, w, h, scale_shift=shift)
+ctx = R.RenderContext(n, w, h, int(sys.argv[5]) if len(sys.argv) > 5 else 0)
 d = ctx.device
 ttr, tsh, top = (torch.from_numpy(x).to(d) for x in (tr, sh, op))
 vout = torch.from_numpy(random_v_output(h, w)).to(d)
