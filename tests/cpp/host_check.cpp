@@ -1,0 +1,118 @@
+// Exercises the C++ host layer (include/brush_b200.hpp).  Modes:
+//   uniforms            stdin: one camera per line -> stdout: the BgCamera fields as hex floats   (no GPU needed)
+//   fov                 stdin: "focal pixels model p0..p7" -> fov and the focal it maps back to    (no GPU needed)
+//   errors              exceptions for invalid arguments                                           (no GPU needed)
+//   render IN OUT       forward + backward of a scene file written by tests/test_cpp_host.py       (GPU)
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "brush_b200.hpp"
+
+using namespace brush_b200;
+
+static Camera read_camera(std::istream &in, uint32_t &w, uint32_t &h) {
+    Camera c;
+    uint32_t model;
+    in >> c.position[0] >> c.position[1] >> c.position[2] >> c.rotation[0] >> c.rotation[1] >> c.rotation[2] >> c.rotation[3] >>
+        c.fov_x >> c.fov_y >> c.center_uv[0] >> c.center_uv[1] >> model;
+    c.model = (CameraModel)model;
+    for (int i = 0; i < 8; i++) in >> c.model_params[i];
+    in >> w >> h;
+    return c;
+}
+
+static void print_uniforms(const BgCamera &u) {
+    for (int i = 0; i < 12; i++) std::printf("%a ", u.viewmat[i]);
+    std::printf("%a %a %a %a %a %a %a %a %a %a %a %a %u", u.fx, u.fy, u.cx, u.cy, u.cam_pos[0], u.cam_pos[1], u.cam_pos[2],
+                u.lim_pos_x, u.lim_pos_y, u.lim_neg_x, u.lim_neg_y, u.half_max_render_fov, u.camera_model);
+    for (int i = 0; i < 8; i++) std::printf(" %a", u.model_params[i]);
+    std::printf("\n");
+}
+
+template <typename T>
+static std::vector<T> read_vec(std::ifstream &f, size_t n) {
+    std::vector<T> v(n);
+    f.read(reinterpret_cast<char *>(v.data()), n * sizeof(T));
+    return v;
+}
+template <typename T>
+static void write_vec(std::ofstream &f, const std::vector<T> &v) { f.write(reinterpret_cast<const char *>(v.data()), v.size() * sizeof(T)); }
+
+int main(int argc, char **argv) {
+    const std::string mode = argc > 1 ? argv[1] : "";
+    try {
+        if (mode == "uniforms") {
+            std::string line;
+            while (std::getline(std::cin, line)) {
+                if (line.empty()) continue;
+                std::istringstream ss(line);
+                uint32_t w, h;
+                Camera c = read_camera(ss, w, h);
+                print_uniforms(make_uniforms(c, w, h));
+            }
+            return 0;
+        }
+        if (mode == "fov") {
+            double focal; uint32_t px, model; float p[8];
+            while (std::cin >> focal >> px >> model) {
+                for (float &v : p) std::cin >> v;
+                double fov = focal_to_fov(focal, px, (CameraModel)model, p);
+                std::printf("%.17g %.17g\n", fov, fov_to_focal(fov, px, (CameraModel)model, p));
+            }
+            return 0;
+        }
+        if (mode == "errors") {
+            int caught = 0;
+            try { make_uniforms(Camera{}, 0, 16); } catch (const Error &e) { caught += e.status == BG_ERR_INVALID; }
+            try { Context c(0, 0, 64, 64); } catch (const Error &e) { caught += e.status == BG_ERR_INVALID; }
+            try { check(bg_ctx_destroy(nullptr), "destroy"); } catch (const Error &e) { caught += e.status == BG_ERR_NULL; }
+            std::printf("caught %d\n", caught);
+            return caught == 3 ? 0 : 1;
+        }
+        if (mode == "render" && argc == 4) {
+            std::ifstream f(argv[2], std::ios::binary);
+            uint32_t hdr[6];   // n k w h mip pass
+            f.read(reinterpret_cast<char *>(hdr), sizeof(hdr));
+            const uint32_t n = hdr[0], k = hdr[1], w = hdr[2], h = hdr[3];
+            std::string camline;
+            { uint32_t len; f.read(reinterpret_cast<char *>(&len), 4); camline.resize(len); f.read(&camline[0], len); }
+            std::istringstream ss(camline);
+            uint32_t cw, ch;
+            Camera cam = read_camera(ss, cw, ch);
+            float bg[3];
+            f.read(reinterpret_cast<char *>(bg), sizeof(bg));
+            auto tr = read_vec<float>(f, (size_t)n * 10), sh = read_vec<float>(f, (size_t)n * k * 3), op = read_vec<float>(f, n);
+            auto v_out = read_vec<float>(f, (size_t)w * h * 4);
+            Context ctx(0, n, w, h);
+            DeviceBuffer<float> d_tr(tr.size()), d_sh(sh.size()), d_op(op.size()), d_vo(v_out.size());
+            d_tr.upload(tr.data(), tr.size()); d_sh.upload(sh.data(), sh.size()); d_op.upload(op.data(), op.size());
+            d_vo.upload(v_out.data(), v_out.size());
+            RenderOutput out = render(ctx, nullptr, cam, w, h, d_tr.data(), d_sh.data(), d_op.data(), n, k,
+                                      hdr[4] ? SplatRenderMode::Mip : SplatRenderMode::Default, bg, (RasterPass)hdr[5]);
+            DeviceBuffer<float> vc = rasterize_bwd(ctx, nullptr, out, d_vo.data(), bg, hdr[5] == 2);
+            SplatGrads g = project_bwd(ctx, nullptr, out, d_tr.data(), d_sh.data(), d_op.data(), vc.data());
+            std::vector<float> img((size_t)w * h * 4), vt((size_t)n * 10), vsh((size_t)n * k * 3), vo(n), vis(n);
+            out.out_img_f32.download(img.data(), img.size());
+            g.v_transforms.download(vt.data(), vt.size());
+            g.v_coeffs.download(vsh.data(), vsh.size());
+            g.v_raw_opac.download(vo.data(), vo.size());
+            out.visible.download(vis.data(), vis.size());
+            std::ofstream o(argv[3], std::ios::binary);
+            uint32_t counts[2] = {out.num_visible(), out.num_intersections()};
+            o.write(reinterpret_cast<const char *>(counts), sizeof(counts));
+            write_vec(o, img); write_vec(o, vt); write_vec(o, vsh); write_vec(o, vo); write_vec(o, vis);
+            std::printf("V %u I %u arena %llu\n", counts[0], counts[1], (unsigned long long)ctx.arena_bytes());
+            return 0;
+        }
+    } catch (const Error &e) {
+        std::fprintf(stderr, "brush_b200::Error %d: %s\n", e.status, e.what());
+        return 2;
+    }
+    std::fprintf(stderr, "usage: host_check uniforms|fov|errors|render IN OUT\n");
+    return 64;
+}
