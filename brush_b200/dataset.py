@@ -2,12 +2,12 @@
 
   view_to_packed_data / pack_rgba <- brush-dataset/src/scene.rs:97-136 (u8 RGBA packed little endian into one int32
                                       per pixel, byte-space premultiplication for AlphaMode::Transparent)
-  load_colmap_text                <- brush-dataset/src/formats/colmap.rs:102-303 (views sorted by image name,
+  load_colmap (text or binary)    <- brush-dataset/src/formats/colmap.rs:102-303 (views sorted by image name,
                                       subsample / max frames, w2c -> c2w, fov from focal per camera model,
                                       missing images skipped with a warning, initial points from points3D.txt)
   build_camera_model              <- formats/colmap.rs:305-390 (COLMAP sensor models -> pinhole / RT8 / KB4 / TPF)
   split_eval_every                <- formats/mod.rs:135-148
-  COLMAP text grammar             <- colmap-reader (cameras.txt / images.txt / points3D.txt)
+  COLMAP text / binary grammar    <- colmap-reader/src/lib.rs (cameras / images / points3D, .txt and .bin)
 
 The step's only host->device input is the packed [H,W] int32 image; `SceneLoader` keeps two pinned staging buffers
 so the upload of view i+1 overlaps the step on view i.
@@ -119,6 +119,59 @@ def read_points3d_text(text: str):
     return np.array(xyz, np.float32).reshape(-1, 3), np.array(rgb, np.uint8).reshape(-1, 3)
 
 
+# ---- COLMAP binary model (colmap-reader/src/lib.rs:278-300, 389-470, 546-600) ---------------------------------
+_MODEL_BY_ID = {0: ("SIMPLE_PINHOLE", 3), 1: ("PINHOLE", 4), 2: ("SIMPLE_RADIAL", 4), 3: ("RADIAL", 5), 4: ("OPENCV", 8),
+                5: ("OPENCV_FISHEYE", 8), 6: ("FULL_OPENCV", 12), 7: ("FOV", 5), 8: ("SIMPLE_RADIAL_FISHEYE", 4),
+                9: ("RADIAL_FISHEYE", 5), 10: ("THIN_PRISM_FISHEYE", 12)}
+
+
+def read_cameras_binary(data: bytes) -> List[ColmapCamera]:
+    import struct
+    (num,), off, out = struct.unpack_from("<Q", data, 0), 8, []
+    for _ in range(num):
+        cid, mid, w, h = struct.unpack_from("<iiQQ", data, off)
+        off += 24
+        if mid not in _MODEL_BY_ID:
+            raise ValueError("Invalid camera model")
+        name, npar = _MODEL_BY_ID[mid]
+        params = list(struct.unpack_from(f"<{npar}d", data, off))
+        off += 8 * npar
+        out.append(ColmapCamera(cid, name, int(w), int(h), params))
+    return out
+
+
+def read_images_binary(data: bytes) -> List[ColmapImage]:
+    import struct
+    (num,), off, out = struct.unpack_from("<Q", data, 0), 8, []
+    for _ in range(num):
+        iid, qw, qx, qy, qz, tx, ty, tz, cid = struct.unpack_from("<i7di", data, off)
+        off += 4 + 56 + 4
+        end = data.find(b"\0", off)
+        if end < 0:
+            raise ValueError("image name was not null-terminated (truncated images file?)")
+        name = data[off:end].decode("utf-8")
+        off = end + 1
+        (npts,) = struct.unpack_from("<Q", data, off)
+        off += 8 + 24 * npts                                   # (x, y, point3D id) per 2D point: skipped
+        if off > len(data):
+            raise ValueError("truncated images file")
+        f32 = lambda v: float(np.float32(v))                    # the reference narrows pose values to f32 on read
+        out.append(ColmapImage(iid, (f32(qw), f32(qx), f32(qy), f32(qz)), (f32(tx), f32(ty), f32(tz)), cid, name))
+    return out
+
+
+def read_points3d_binary(data: bytes):
+    import struct
+    (num,), off = struct.unpack_from("<Q", data, 0), 8
+    xyz, rgb = np.empty((num, 3), np.float32), np.empty((num, 3), np.uint8)
+    for i in range(num):
+        _, x, y, z, r, g, b, _err, track = struct.unpack_from("<q3d3BdQ", data, off)
+        off += 8 + 24 + 3 + 8 + 8 + 8 * track
+        xyz[i] = (x, y, z)
+        rgb[i] = (r, g, b)
+    return xyz, rgb
+
+
 def build_camera_model(c: ColmapCamera):
     """formats/colmap.rs:305-390 -> (camera_model id, model_params)."""
     p, m = c.params, c.model
@@ -210,14 +263,21 @@ def _find(root: str, name: str) -> Optional[str]:
     return None
 
 
-def load_colmap_text(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
-                     eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None) -> DatasetLoadResult:
-    cam_path = _find(root, "cameras.txt")
+def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
+                eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None) -> DatasetLoadResult:
+    """Text or binary COLMAP model (cameras.{txt,bin} decides; images / points3D are taken from the same directory)."""
+    cam_path = _find(root, "cameras.bin") or _find(root, "cameras.txt")
     if cam_path is None:
-        raise FileNotFoundError("no cameras.txt under " + root)
+        raise FileNotFoundError("no cameras.txt / cameras.bin under " + root)
     sparse = os.path.dirname(cam_path)
-    cams = {c.id: c for c in read_cameras_text(open(cam_path).read())}
-    infos = sorted(read_images_text(open(os.path.join(sparse, "images.txt")).read()), key=lambda i: i.name)
+    is_binary = cam_path.endswith(".bin")
+    if is_binary:
+        cams = {c.id: c for c in read_cameras_binary(open(cam_path, "rb").read())}
+        infos = read_images_binary(open(os.path.join(sparse, "images.bin"), "rb").read())
+    else:
+        cams = {c.id: c for c in read_cameras_text(open(cam_path).read())}
+        infos = read_images_text(open(os.path.join(sparse, "images.txt")).read())
+    infos = sorted(infos, key=lambda i: i.name)
     views, warnings = [], []
     picked = infos[::max(int(subsample_frames or 1), 1)]
     if max_frames is not None:
@@ -236,15 +296,19 @@ def load_colmap_text(root: str, subsample_frames: Optional[int] = None, max_fram
         views.append(SceneView(camera, path))
     train, ev = split_eval_every(views, eval_split_every)
     init = None
-    pts = os.path.join(sparse, "points3D.txt")
-    if os.path.exists(pts):
-        xyz, rgb = read_points3d_text(open(pts).read())
+    pts_txt, pts_bin = os.path.join(sparse, "points3D.txt"), os.path.join(sparse, "points3D.bin")
+    if os.path.exists(pts_txt) or os.path.exists(pts_bin):
+        xyz, rgb = read_points3d_text(open(pts_txt).read()) if os.path.exists(pts_txt) else \
+            read_points3d_binary(open(pts_bin, "rb").read())
         step = max(int(subsample_points or 1), 1)
         xyz, rgb = xyz[::step], rgb[::step]
         if len(xyz):
             sh = ((rgb.astype(np.float32) / np.float32(255.0)) - np.float32(0.5)) / np.float32(SH_C0)   # rgb_to_sh
             init = SplatData(means=xyz, sh_coeffs=sh.reshape(-1, 1, 3))
     return DatasetLoadResult(train, ev, init, warnings)
+
+
+load_colmap_text = load_colmap   # earlier name
 
 
 class SceneLoader:

@@ -123,3 +123,42 @@ def test_scene_loader_cycles_through_views(tmp_path):
     assert len(seen) == 3
     b = loader.next_batch()
     assert tuple(b.img_packed.shape) == (3, 4) and not b.has_alpha
+
+
+def test_binary_model_equals_text_model(tmp_path):
+    """colmap-reader's binary layout (lib.rs:278-300, 389-470, 546-600): same dataset, written as .bin."""
+    import struct
+    txt_root, bin_root = tmp_path / "t", tmp_path / "b"
+    txt_root.mkdir(); bin_root.mkdir()
+    _write_dataset(str(txt_root))
+    _write_dataset(str(bin_root))
+    sparse = bin_root / "sparse" / "0"
+    for f in ("cameras.txt", "images.txt", "points3D.txt"):
+        os.remove(sparse / f)
+    (sparse / "cameras.bin").write_bytes(struct.pack("<QiiQQ4d", 1, 1, 1, IMG_W, IMG_H, FX, FY, CX, CY))
+    q, t = _img1_w2c()
+    imgs = [(1, (1.0, 0, 0, 0), (1.0, 2.0, 3.0), "img0.png", 0), (2, q, t, "img1.png", 2), (3, (1.0, 0, 0, 0), (0, 0, 0), "img2.png", 0),
+            (4, (1.0, 0, 0, 0), (5.0, 5.0, 5.0), "missing.png", 0)]
+    blob = struct.pack("<Q", len(imgs))
+    for iid, qq, tt, name, npts in imgs:
+        blob += struct.pack("<i7di", iid, *qq, *tt, 1) + name.encode() + b"\0" + struct.pack("<Q", npts)
+        blob += b"".join(struct.pack("<ddq", 10.0 * j, 20.0, -1) for j in range(npts))
+    (sparse / "images.bin").write_bytes(blob)
+    pts = [(1, (1.5, 2.5, 3.5), (255, 0, 0), 1), (2, (-1.0, 0.0, 1.0), (0, 255, 0), 2), (3, (0.0, 1.0, 0.0), (0, 0, 255), 0),
+           (4, (2.0, 2.0, 2.0), (128, 128, 128), 1)]
+    blob = struct.pack("<Q", len(pts))
+    for pid, xyz, rgb, track in pts:
+        blob += struct.pack("<q3d3BdQ", pid, *xyz, *rgb, 0.5, track) + b"".join(struct.pack("<ii", 1, j) for j in range(track))
+    (sparse / "points3D.bin").write_bytes(blob)
+    a, b = ds.load_colmap(str(txt_root)), ds.load_colmap(str(bin_root))
+    assert len(a.train) == len(b.train) == 3 and len(b.warnings) == 1
+    for va, vb in zip(a.train, b.train):
+        np.testing.assert_allclose(va.camera.position, vb.camera.position, atol=1e-6)
+        np.testing.assert_allclose(va.camera.rotation, vb.camera.rotation, atol=1e-6)
+        assert abs(va.camera.fov_x - vb.camera.fov_x) < 1e-12 and va.camera.center_uv == vb.camera.center_uv
+    np.testing.assert_array_equal(a.init_splat.means, b.init_splat.means)
+    np.testing.assert_array_equal(a.init_splat.sh_coeffs, b.init_splat.sh_coeffs)
+    with pytest.raises(ValueError):
+        ds.read_cameras_binary(struct.pack("<QiiQQ", 1, 1, 99, 4, 4))
+    with pytest.raises(ValueError):
+        ds.read_images_binary(struct.pack("<Qi7di", 1, 1, 1, 0, 0, 0, 0, 0, 0, 1) + b"unterminated")
