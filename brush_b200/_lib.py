@@ -56,6 +56,33 @@ class BgRenderState(C.Structure):
     ]
 
 
+class BgTrainStepArgs(C.Structure):
+    _fields_ = [
+        ("cam", BgCamera),
+        ("w", C.c_uint32), ("h", C.c_uint32), ("n", C.c_uint32), ("k", C.c_uint32),
+        ("mip", C.c_int32),
+        ("background", C.c_float * 3),
+        ("transforms", C.c_void_p), ("sh", C.c_void_p), ("raw_opac", C.c_void_p),
+        ("m_t", C.c_void_p), ("v_t", C.c_void_p), ("m_sh", C.c_void_p), ("v_sh", C.c_void_p), ("m_o", C.c_void_p), ("v_o", C.c_void_p),
+        ("refine_norm", C.c_void_p), ("vis_weight", C.c_void_p), ("max_screen", C.c_void_p),
+        ("gt_packed", C.c_void_p),
+        ("l1_weight", C.c_float), ("ssim_weight", C.c_float),
+        ("has_composite_bg", C.c_int32),
+        ("composite_bg", C.c_float * 3),
+        ("mask", C.c_int32), ("channels", C.c_int32),
+        ("alpha_weight", C.c_float),
+        ("lr_mean", C.c_float), ("lr_rotation", C.c_float), ("lr_scale", C.c_float), ("lr_coeffs_dc", C.c_float),
+        ("lr_coeffs_sh_scale", C.c_float), ("lr_opac", C.c_float),
+        ("noise_scale", C.c_float), ("median_scale", C.c_float),
+        ("seed", C.c_uint64),
+        ("step", C.c_int32),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_uint64),
+        ("loss_out", C.c_void_p),
+        ("state_out", BgRenderState),
+    ]
+
+
 # name -> (restype, argtypes); one entry per function declared in include/brush_b200.h
 _P, _U32, _U64, _I32, _I64, _F = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -68,6 +95,9 @@ SIGNATURES = {
                                  C.POINTER(_F), _I32, _P, _P, _P, C.POINTER(BgRenderState)]),
     "bg_rasterize_backward": (_I32, [_P, _P, C.POINTER(BgRenderState), _P, _P, C.POINTER(_F), _I32, _P, _U32]),
     "bg_project_backward": (_I32, [_P, _P, C.POINTER(BgCamera), C.POINTER(BgRenderState), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bg_normal_noise": (_I32, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "bg_train_step_workspace_bytes": (C.c_uint64, [_U32, _U32, _U32, _U32]),
+    "bg_train_step": (_I32, [_P, _P, C.POINTER(BgTrainStepArgs)]),
     "bg_compute_min_scale": (_I32, [_P, _P, _U32, _P, _P, _U32, _F, _P]),
     "bg_fold_min_scale_forward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),
     "bg_fold_min_scale_backward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),

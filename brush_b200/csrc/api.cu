@@ -42,6 +42,9 @@ cudaError_t launch_rasterize_bwd(cudaStream_t, bool, uint32_t, const uint32_t *,
 cudaError_t launch_project_bwd(cudaStream_t, bool, int, const float *, const float *, const float *,
                                const uint32_t *, const float *, uint32_t, const BgCamera &, float *, float *, float *,
                                float *, float *);
+cudaError_t launch_normal_noise(cudaStream_t, uint64_t, uint64_t, uint64_t, float *);
+cudaError_t launch_train_fill_lr(cudaStream_t, float *, float *, uint32_t, float, float, float, float);
+cudaError_t launch_loss_reduce(cudaStream_t, const float *, uint32_t, uint32_t, const float *, float *);
 cudaError_t launch_min_scale(cudaStream_t, uint32_t, const float *, const float *, uint32_t, float, float *);
 cudaError_t launch_fold_min_scale_fwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
 cudaError_t launch_fold_min_scale_bwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
@@ -536,4 +539,97 @@ extern "C" int32_t bg_fold_min_scale_backward(BgContext *c, void *stream, uint32
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(launch_fold_min_scale_bwd((cudaStream_t)stream, n, transforms, raw_opac, f, v_transforms, v_raw_opac));
     return BG_OK;
+}
+
+extern "C" int32_t bg_normal_noise(BgContext *c, void *stream, uint64_t seed, uint64_t offset, uint64_t count, float *out) {
+    if (!c) return BG_ERR_NULL;
+    if (count == 0) return BG_OK;
+    if (!out) return BG_ERR_NULL;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_normal_noise((cudaStream_t)stream, seed, offset, count, out));
+    return BG_OK;
+}
+
+// ---- bg_train_step: SplatTrainer::step (brush-train/src/train.rs:176-429) as ONE call: every launch of the step on
+// the caller's stream, nothing read back, scratch from a caller-provided workspace.
+namespace {
+struct TrainWs {
+    float *out_img, *v_output, *partials, *v_combined, *v_t, *v_sh, *v_o, *v_r, *visible, *max_radius, *noise, *t_lr, *sh_scale;
+    uint64_t bytes;
+};
+TrainWs carve_train_ws(void *base, uint32_t n, uint32_t k, uint32_t w, uint32_t h, uint32_t channels) {
+    uint64_t off = 0;
+    auto take = [&](uint64_t floats) {
+        float *p = base ? reinterpret_cast<float *>(static_cast<char *>(base) + off) : nullptr;
+        off += (floats * 4 + 255) / 256 * 256;
+        return p;
+    };
+    TrainWs ws;
+    const uint64_t px = (uint64_t)w * h;
+    ws.out_img = take(px * 4);
+    ws.v_output = take(px * 4);
+    ws.partials = take(bg_image_loss_num_partials(channels, h, w));
+    ws.v_combined = take((uint64_t)n * BG_VCOMBINED_STRIDE);
+    ws.v_t = take((uint64_t)n * 10);
+    ws.v_sh = take((uint64_t)n * k * 3);
+    ws.v_o = take(n);
+    ws.v_r = take(n);
+    ws.visible = take(n);
+    ws.max_radius = take(n);
+    ws.noise = take((uint64_t)n * 3);
+    ws.t_lr = take(16);
+    ws.sh_scale = take((uint64_t)k * 3);
+    ws.bytes = off;
+    return ws;
+}
+}  // namespace
+
+extern "C" uint64_t bg_train_step_workspace_bytes(uint32_t n, uint32_t k, uint32_t w, uint32_t h) {
+    return carve_train_ws(nullptr, n, k, w, h, 4).bytes;
+}
+
+extern "C" int32_t bg_train_step(BgContext *c, void *stream, BgTrainStepArgs *a) {
+    if (!c || !a) return BG_ERR_NULL;
+    if (!a->transforms || !a->sh || !a->raw_opac || !a->m_t || !a->v_t || !a->m_sh || !a->v_sh || !a->m_o || !a->v_o ||
+        !a->refine_norm || !a->vis_weight || !a->max_screen || !a->gt_packed || !a->workspace || !a->loss_out)
+        return BG_ERR_NULL;
+    if (a->step < 1) { set_err("bg_train_step: step is 1-based", cudaSuccess); return BG_ERR_INVALID; }
+    if (a->channels != 3 && a->channels != 4) { set_err("bg_train_step: channels must be 3 or 4", cudaSuccess); return BG_ERR_INVALID; }
+    if ((uintptr_t)a->workspace % 256) { set_err("bg_train_step: workspace must be 256-byte aligned", cudaSuccess); return BG_ERR_INVALID; }
+    const uint32_t n = a->n, k = a->k, w = a->w, h = a->h;
+    const TrainWs ws = carve_train_ws(a->workspace, n, k, w, h, a->channels);
+    if (ws.bytes > a->workspace_bytes) { set_err("bg_train_step: workspace too small (bg_train_step_workspace_bytes)", cudaSuccess); return BG_ERR_CAPACITY; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    int32_t r;
+    // render forward (train.rs:200-216)
+    r = bg_render_forward(c, stream, &a->cam, w, h, n, k, a->transforms, a->sh, a->raw_opac, a->mip, a->background, BG_PASS_BACKWARD,
+                          ws.out_img, ws.visible, ws.max_radius, &a->state_out);
+    if (r != BG_OK) return r;
+    // loss value + gradient (train.rs:220-260): mean over [h,w,3] (+ alpha mean * weight)
+    const float npx = (float)w * (float)h;
+    float chain[4] = {1.0f / (3.0f * npx), 1.0f / (3.0f * npx), 1.0f / (3.0f * npx), a->channels == 4 ? a->alpha_weight / npx : 0.0f};
+    BG_CUDA(cudaMemsetAsync(ws.v_output, 0, (size_t)w * h * 4 * sizeof(float), s));
+    r = bg_image_loss_fused(c, stream, ws.out_img, a->gt_packed, a->channels, h, w, 1, (int64_t)w * 4, 4, a->l1_weight, a->ssim_weight,
+                            a->has_composite_bg ? a->composite_bg : nullptr, a->mask, chain, ws.v_output, ws.partials);
+    if (r != BG_OK) return r;
+    BG_CUDA(launch_loss_reduce(s, ws.partials, a->channels, bg_image_loss_num_partials(a->channels, h, w) / a->channels, chain, a->loss_out));
+    // backward (bwd/burn_glue.rs:121-182)
+    r = bg_rasterize_backward(c, stream, &a->state_out, ws.out_img, ws.v_output, a->background, 0, ws.v_combined, n);
+    if (r != BG_OK) return r;
+    r = bg_project_backward(c, stream, &a->cam, &a->state_out, a->transforms, a->sh, a->raw_opac, ws.v_combined, ws.v_t, ws.v_sh, ws.v_o, ws.v_r);
+    if (r != BG_OK) return r;
+    // optimiser (train.rs:300-381): per-column LR for the transforms, DC vs higher-band LR for SH
+    BG_CUDA(launch_train_fill_lr(s, ws.t_lr, ws.sh_scale, k, a->lr_mean, a->lr_rotation, a->lr_scale, 1.0f / a->lr_coeffs_sh_scale));
+    r = bg_adam_step(c, stream, a->transforms, ws.v_t, a->m_t, a->v_t, n, 10, ws.t_lr, 1.0f, 0.9f, 0.999f, 1e-15f, a->step, 0);
+    if (r != BG_OK) return r;
+    r = bg_adam_step(c, stream, a->sh, ws.v_sh, a->m_sh, a->v_sh, n, k * 3, ws.sh_scale, a->lr_coeffs_dc, 0.9f, 0.999f, 1e-15f, a->step, 1);
+    if (r != BG_OK) return r;
+    r = bg_adam_step(c, stream, a->raw_opac, ws.v_o, a->m_o, a->v_o, n, 1, nullptr, a->lr_opac, 0.9f, 0.999f, 1e-15f, a->step, 0);
+    if (r != BG_OK) return r;
+    // refine statistics + mean noise on the updated opacities (train.rs:280-298, 389-416)
+    const bool noisy = a->noise_scale != 0.0f;
+    if (noisy) BG_CUDA(launch_normal_noise(s, a->seed, (uint64_t)(a->step - 1) * (((uint64_t)n * 3 + 3) / 4), (uint64_t)n * 3, ws.noise));
+    return bg_refine_stats_noise(c, stream, n, ws.v_r, ws.visible, ws.max_radius, a->refine_norm, a->vis_weight, a->max_screen,
+                                 a->transforms, a->raw_opac, noisy ? ws.noise : nullptr, a->noise_scale, a->median_scale);
 }

@@ -292,4 +292,82 @@ cudaError_t launch_fold_min_scale_bwd(cudaStream_t s, uint32_t n, const float *t
     return cudaGetLastError();
 }
 
+// ---- counter-based normal noise (Philox4x32-10 + Box-Muller).  The reference draws Tensor::random(Normal) from
+// burn's unseeded generator (train.rs:395-399: parity unpinned); a counter-based stream keyed by (seed, offset)
+// gives every data-parallel rank the same draw without any communication, and makes a train step replayable.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+
+__global__ void __launch_bounds__(256)
+normal_noise_kernel(uint64_t seed, uint64_t offset, uint64_t count, float *__restrict__ out) {
+    const uint64_t quads = (count + 3) / 4;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t ctr = offset + q;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float z[4];
+        const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
+        float s0, c0, s1, c1;
+        sincospif(2.0f * u01(r.y), &s0, &c0);
+        sincospif(2.0f * u01(r.w), &s1, &c1);
+        z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (q * 4 + i < count) out[q * 4 + i] = z[i];
+    }
+}
+
+// learning-rate vectors of the train step (train.rs:328-350, config.rs:17-45) and the loss scalar
+__global__ void train_fill_lr_kernel(float *t_lr /*[10]*/, float *sh_scale /*[3k]*/, uint32_t k, float lr_mean, float lr_rotation,
+                                     float lr_scale, float sh_rest_scale) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 10) t_lr[i] = i < 3 ? lr_mean : (i < 7 ? lr_rotation : lr_scale);
+    if (i < 3 * k) sh_scale[i] = (i < 3) ? 1.0f : sh_rest_scale;
+}
+__global__ void __launch_bounds__(256)
+loss_reduce_kernel(const float *__restrict__ partials, uint32_t channels, uint32_t per_channel, float c0, float c1, float c2,
+                   float c3, float *__restrict__ loss_out) {
+    __shared__ float s_red[256];
+    const float chain[4] = {c0, c1, c2, c3};
+    float acc = 0.0f;
+    for (uint32_t c = 0; c < channels; c++) {
+        float s = 0.0f;
+        for (uint32_t i = threadIdx.x; i < per_channel; i += 256) s += partials[(size_t)c * per_channel + i];
+        acc += s * chain[c];
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss_out = s_red[0];
+}
+
+cudaError_t launch_normal_noise(cudaStream_t s, uint64_t seed, uint64_t offset, uint64_t count, float *out) {
+    if (count == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((count / 4 + 255) / 256 + 1, 148ull * 16);
+    normal_noise_kernel<<<grid, 256, 0, s>>>(seed, offset, count, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_fill_lr(cudaStream_t s, float *t_lr, float *sh_scale, uint32_t k, float lr_mean, float lr_rotation,
+                                 float lr_scale, float sh_rest_scale) {
+    train_fill_lr_kernel<<<(std::max(10u, 3 * k) + 127) / 128, 128, 0, s>>>(t_lr, sh_scale, k, lr_mean, lr_rotation, lr_scale, sh_rest_scale);
+    return cudaGetLastError();
+}
+cudaError_t launch_loss_reduce(cudaStream_t s, const float *partials, uint32_t channels, uint32_t per_channel,
+                               const float *chain, float *loss_out) {
+    loss_reduce_kernel<<<1, 256, 0, s>>>(partials, channels, per_channel, chain[0], chain[1], chain[2], channels > 3 ? chain[3] : 0.0f, loss_out);
+    return cudaGetLastError();
+}
+
 }  // namespace bg

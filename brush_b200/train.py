@@ -244,6 +244,8 @@ class SplatTrainer:
         self._host_rng = np.random.default_rng(config.seed)
         self.view_cams: Optional[torch.Tensor] = None
         self._views_buf = None
+        self._fused_ws = None
+        self._fused_loss = None
 
     def set_view_cams(self, view_cams) -> None:
         """train.rs:172-174.  view_cams: sequence of ((x, y, z), focal_px) of the training views."""
@@ -321,6 +323,54 @@ class SplatTrainer:
         lr_mean = self._apply_updates(splats, v_t, v_sh, v_o, v_r, out.visible, out.max_radius, median_scale)
         return TrainStepStats(num_visible_event=out, lr_mean=lr_mean, loss=loss)
 
+
+    # ------------------------------------------------------------------------------------------------
+    def step_fused(self, batch: SceneBatch, splats: Splats) -> TrainStepStats:
+        """The same step through ONE ABI call (bg_train_step): every launch of the step is issued by the library on
+        the current stream, scratch comes from a workspace allocated once.  No min-scale floor, no gradient hook."""
+        if splats.min_scale is not None or self.grad_hook is not None:
+            raise ValueError("step_fused handles the plain single-view step; use step() with a scale floor or a gradient hook")
+        cfg = self.config
+        self._ensure_state(splats)
+        st = self._state
+        self.step_count += 1
+        img_h, img_w = batch.img_size()
+        dev = self.ctx.device
+        lib = _lib.load()
+        gt_packed = batch.img_packed.to(dev, non_blocking=True)
+        background = self.sample_background()
+        median_scale = self.bounds.median_size()
+        n, k = splats.num_splats(), splats.sh_coeffs.shape[1]
+        need = int(lib.bg_train_step_workspace_bytes(n, k, img_w, img_h))
+        if self._fused_ws is None or self._fused_ws.numel() < need:
+            self._fused_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._fused_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        from .camera import build_uniforms
+        a = _lib.BgTrainStepArgs()
+        a.cam = _lib.camera_struct(build_uniforms(batch.camera, img_w, img_h))
+        a.w, a.h, a.n, a.k, a.mip = img_w, img_h, n, k, int(cfg.render_mip)
+        for i in range(3):
+            a.background[i] = float(background[i])
+        a.transforms, a.sh, a.raw_opac = splats.transforms.data_ptr(), splats.sh_coeffs.data_ptr(), splats.raw_opacities.data_ptr()
+        a.m_t, a.v_t, a.m_sh, a.v_sh, a.m_o, a.v_o = (st[x].data_ptr() for x in ("m_t", "v_t", "m_sh", "v_sh", "m_o", "v_o"))
+        a.refine_norm, a.vis_weight, a.max_screen = (st[x].data_ptr() for x in ("refine_norm", "vis_weight", "max_screen"))
+        a.gt_packed = gt_packed.data_ptr()
+        a.l1_weight, a.ssim_weight = (1.0 - cfg.ssim_weight, -cfg.ssim_weight) if self.ssim_enabled else (1.0, 0.0)
+        do_alpha_match = batch.has_alpha and not batch.masked_alpha and cfg.match_alpha_weight > 0.0
+        comp = batch.has_alpha and any(b != 0.0 for b in background)
+        a.has_composite_bg = int(comp)
+        for i in range(3):
+            a.composite_bg[i] = float(background[i])
+        a.mask, a.channels, a.alpha_weight = int(batch.masked_alpha), (4 if do_alpha_match else 3), float(cfg.match_alpha_weight)
+        lr_mean = cfg.lr_mean * self.lr_mean_decay ** (self.step_count - 1) * float(median_scale)
+        a.lr_mean, a.lr_rotation, a.lr_scale = float(np.float32(lr_mean)), cfg.lr_rotation, cfg.lr_scale
+        a.lr_coeffs_dc, a.lr_coeffs_sh_scale, a.lr_opac = cfg.lr_coeffs_dc, cfg.lr_coeffs_sh_scale, cfg.lr_opac
+        a.noise_scale = float(np.float32(lr_mean) * np.float32(cfg.mean_noise_weight))
+        a.median_scale, a.seed, a.step = float(median_scale), int(cfg.seed), self.step_count
+        a.workspace, a.workspace_bytes = self._fused_ws.data_ptr(), need
+        a.loss_out = self._fused_loss.data_ptr()
+        _lib.check(lib.bg_train_step(self.ctx.handle, _stream_ptr(dev), C.byref(a)), "bg_train_step")
+        return TrainStepStats(num_visible_event=None, lr_mean=lr_mean, loss=self._fused_loss[0])
 
     # ------------------------------------------------------------------------------------------------
     def step_views(self, batches: Sequence[SceneBatch], splats: Splats, group=None) -> TrainStepStats:
@@ -422,8 +472,11 @@ class SplatTrainer:
         self._adam(splats.sh_coeffs, v_sh, st["m_sh"], st["v_sh"], cfg.lr_coeffs_dc, st["sh_lr_scale"], True)
         self._adam(splats.raw_opacities, v_o, st["m_o"], st["v_o"], cfg.lr_opac, None, False)
         n = splats.num_splats()
-        noise = torch.randn((n, 3), dtype=torch.float32, device=dev, generator=self._gen)
         lib = _lib.load()
+        # counter-based draw keyed by (seed, step): identical on every data-parallel rank and in bg_train_step
+        noise = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.bg_normal_noise(self.ctx.handle, _stream_ptr(dev), int(cfg.seed), (self.step_count - 1) * ((3 * n + 3) // 4),
+                                       3 * n, noise.data_ptr()), "bg_normal_noise")
         _lib.check(lib.bg_refine_stats_noise(self.ctx.handle, _stream_ptr(dev), n, v_r.data_ptr(), visible.data_ptr(),
                                              max_radius.data_ptr(), st["refine_norm"].data_ptr(),
                                              st["vis_weight"].data_ptr(), st["max_screen"].data_ptr(),

@@ -145,6 +145,44 @@ int32_t bg_project_backward(BgContext *ctx, void *stream, const BgCamera *cam, c
                             const float *v_combined, float *v_transforms, float *v_sh, float *v_raw_opac,
                             float *v_refine);
 
+/* Counter-based N(0,1) draws (Philox4x32-10 + Box-Muller): out[i], i < count, is a pure function of (seed, offset, i);
+ * the reference draws the mean noise with burn's Tensor::random(Normal) from an unseeded generator (train.rs:395-399). */
+int32_t bg_normal_noise(BgContext *ctx, void *stream, uint64_t seed, uint64_t offset, uint64_t count, float *out);
+
+/* SplatTrainer::step (brush-train/src/train.rs:176-429) as one call: render forward -> L1 + SSIM loss value and
+ * gradient -> rasterize / project backward -> AdamScaled on transforms, SH, opacity -> refine statistics -> mean noise.
+ * Every launch goes to `stream`; nothing is read back (the step can be captured in a CUDA graph).  Parameters, Adam
+ * moments and the refine record are updated in place.  Scratch comes from `workspace` (device, 256-byte aligned,
+ * bg_train_step_workspace_bytes(n, k, w, h) bytes).  Learning rates are the step's values: the caller evaluates the
+ * schedule lr_mean(n) = lr_mean * decay^(n-1) * median_scale (train.rs:328-333).  `step` is the 1-based Adam step.
+ * noise_scale = lr_mean * mean_noise_weight (0 disables the noise); the draw is bg_normal_noise(seed, step). */
+typedef struct {
+    BgCamera cam;
+    uint32_t w, h, n, k;
+    int32_t mip;
+    float background[3];
+    float *transforms, *sh, *raw_opac;              /* [n,10] [n,k,3] [n], updated in place */
+    float *m_t, *v_t, *m_sh, *v_sh, *m_o, *v_o;     /* Adam moments; v_sh is [n] (row-reduced, adam_scaled.rs:152-165) */
+    float *refine_norm, *vis_weight, *max_screen;   /* RefineRecord (stats.rs:15-50), [n] each */
+    const uint32_t *gt_packed;                      /* device [h,w] rgba8 (scene.rs:97-136) */
+    float l1_weight, ssim_weight;                   /* train.rs:228-232: 1 - w, -w */
+    int32_t has_composite_bg;
+    float composite_bg[3];
+    int32_t mask;                                   /* AlphaMode::Masked */
+    int32_t channels;                               /* 3, or 4 when the alpha channel is matched (train.rs:236-249) */
+    float alpha_weight;                             /* match_alpha_weight */
+    float lr_mean, lr_rotation, lr_scale, lr_coeffs_dc, lr_coeffs_sh_scale, lr_opac;
+    float noise_scale, median_scale;
+    uint64_t seed;
+    int32_t step;
+    void *workspace;
+    uint64_t workspace_bytes;
+    float *loss_out;                                /* device scalar */
+    BgRenderState state_out;                        /* the step's render state (counters etc.) */
+} BgTrainStepArgs;
+uint64_t bg_train_step_workspace_bytes(uint32_t n, uint32_t k, uint32_t w, uint32_t h);
+int32_t bg_train_step(BgContext *ctx, void *stream, BgTrainStepArgs *args);
+
 /* Mip-Splatting 3D smoothing filter (scale floor).
  * bg_compute_min_scale  <- compute_min_scale (brush-train/src/train.rs:102-125):
  *     f[i] = sqrt(factor) * min_v(|mean_i - cam_v| / max(focal_v, 1e-6)); view_cams: DEVICE [views,4] =
