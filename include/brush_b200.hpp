@@ -10,6 +10,7 @@
 //   radix_argsort / prefix_sum  <- brush-sort/src/lib.rs:16, brush-prefix-sum/src/lib.rs:11
 //   image_loss_forward/backward <- LossOps                     brush-loss/src/lib.rs:718-733
 //   AdamScaled                  <- brush-train/src/adam_scaled.rs:64-165
+//   TrainConfig, SplatTrainer   <- brush-train/src/config.rs, train.rs:138-429 (the per-step path, over bg_train_step)
 //
 // Errors: the reference panics on shape / device violations (render.rs:50-64); here every non-zero ABI status
 // becomes a brush_b200::Error (std::runtime_error) carrying the status and bg_last_error_string().
@@ -363,6 +364,83 @@ class AdamScaled {                           // adam_scaled.rs:64-165: one insta
     float b1_, b2_, eps_;
     int t_ = 0;
     DeviceBuffer<float> m_, v_;
+};
+
+// ---------------------------------------------------------------------------------------------- train step
+struct TrainConfig {                         // brush-train/src/config.rs:5-132 (the fields the step uses, same defaults)
+    uint32_t total_train_iters = 30000;
+    double lr_mean = 2e-5, lr_mean_end = 2e-7;
+    float mean_noise_weight = 50.0f;
+    float lr_coeffs_dc = 2e-3f, lr_coeffs_sh_scale = 10.0f, lr_opac = 0.012f, lr_scale = 5e-3f, lr_rotation = 2e-3f;
+    float ssim_weight = 0.2f, match_alpha_weight = 0.1f;
+    float background[3] = {0, 0, 0};
+    bool render_mip = false;
+    uint64_t seed = 0;
+};
+
+// SplatTrainer::step (train.rs:176-429) over bg_train_step.  Owns the Adam moments, the refine record and the step's
+// workspace; the splat parameters stay with the caller and are updated in place.
+class SplatTrainer {
+   public:
+    SplatTrainer(const TrainConfig &cfg, uint32_t n, uint32_t k, float median_scale)
+        : cfg_(cfg), n_(n), k_(k), median_scale_(median_scale),
+          m_t_((size_t)n * 10, true), v_t_((size_t)n * 10, true), m_sh_((size_t)n * k * 3, true), v_sh_(n, true), m_o_(n, true),
+          v_o_(n, true), refine_norm_(n, true), vis_weight_(n, true), max_screen_(n, true), loss_(1, true) {
+        decay_ = std::pow(cfg.lr_mean_end / cfg.lr_mean, 1.0 / (double)cfg.total_train_iters);
+    }
+    // gt_packed: device [h,w] rgba8 (view_to_packed_data, scene.rs:97-136).  Returns the device scalar holding the loss.
+    const float *step(Context &ctx, cudaStream_t stream, const Camera &camera, const uint32_t *gt_packed, uint32_t w, uint32_t h,
+                      float *transforms, float *sh_coeffs, float *raw_opacities, bool has_alpha = false, bool masked_alpha = false) {
+        step_ += 1;
+        const uint64_t need = bg_train_step_workspace_bytes(n_, k_, w, h);
+        if (ws_.size() < need) ws_ = DeviceBuffer<unsigned char>(need);
+        BgTrainStepArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.cam = make_uniforms(camera, w, h);
+        a.w = w; a.h = h; a.n = n_; a.k = k_;
+        a.mip = cfg_.render_mip;
+        for (int i = 0; i < 3; i++) { a.background[i] = cfg_.background[i]; a.composite_bg[i] = cfg_.background[i]; }
+        a.transforms = transforms; a.sh = sh_coeffs; a.raw_opac = raw_opacities;
+        a.m_t = m_t_.data(); a.v_t = v_t_.data(); a.m_sh = m_sh_.data(); a.v_sh = v_sh_.data(); a.m_o = m_o_.data(); a.v_o = v_o_.data();
+        a.refine_norm = refine_norm_.data(); a.vis_weight = vis_weight_.data(); a.max_screen = max_screen_.data();
+        a.gt_packed = gt_packed;
+        const bool ssim = cfg_.ssim_weight > 0.0f;
+        a.l1_weight = ssim ? 1.0f - cfg_.ssim_weight : 1.0f;
+        a.ssim_weight = ssim ? -cfg_.ssim_weight : 0.0f;
+        const bool bg_nonzero = cfg_.background[0] != 0.0f || cfg_.background[1] != 0.0f || cfg_.background[2] != 0.0f;
+        a.has_composite_bg = has_alpha && bg_nonzero;
+        a.mask = masked_alpha;
+        a.channels = (has_alpha && !masked_alpha && cfg_.match_alpha_weight > 0.0f) ? 4 : 3;
+        a.alpha_weight = cfg_.match_alpha_weight;
+        const double lr_mean = cfg_.lr_mean * std::pow(decay_, (double)(step_ - 1)) * (double)median_scale_;   // train.rs:328-333
+        a.lr_mean = (float)lr_mean;
+        a.lr_rotation = cfg_.lr_rotation; a.lr_scale = cfg_.lr_scale;
+        a.lr_coeffs_dc = cfg_.lr_coeffs_dc; a.lr_coeffs_sh_scale = cfg_.lr_coeffs_sh_scale; a.lr_opac = cfg_.lr_opac;
+        a.noise_scale = (float)lr_mean * cfg_.mean_noise_weight;
+        a.median_scale = median_scale_;
+        a.seed = cfg_.seed;
+        a.step = step_;
+        a.workspace = ws_.data(); a.workspace_bytes = need;
+        a.loss_out = loss_.data();
+        check(bg_train_step(ctx.handle(), stream, &a), "SplatTrainer::step");
+        last_state_ = a.state_out;
+        return loss_.data();
+    }
+    int steps() const { return step_; }
+    const BgRenderState &last_render_state() const { return last_state_; }
+    const float *refine_weight_norm() const { return refine_norm_.data(); }
+    const float *vis_weight() const { return vis_weight_.data(); }
+    const float *max_screen_size() const { return max_screen_.data(); }
+
+   private:
+    TrainConfig cfg_;
+    uint32_t n_, k_;
+    float median_scale_;
+    double decay_ = 1.0;
+    int step_ = 0;
+    DeviceBuffer<float> m_t_, v_t_, m_sh_, v_sh_, m_o_, v_o_, refine_norm_, vis_weight_, max_screen_, loss_;
+    DeviceBuffer<unsigned char> ws_;
+    BgRenderState last_state_{};
 };
 
 }  // namespace brush_b200

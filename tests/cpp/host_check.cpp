@@ -3,6 +3,7 @@
 //   fov                 stdin: "focal pixels model p0..p7" -> fov and the focal it maps back to    (no GPU needed)
 //   errors              exceptions for invalid arguments                                           (no GPU needed)
 //   render IN OUT       forward + backward of a scene file written by tests/test_cpp_host.py       (GPU)
+//   train IN STEPS      SplatTrainer::step on the same kind of file (+ packed ground truth)         (GPU)
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -107,6 +108,41 @@ int main(int argc, char **argv) {
             o.write(reinterpret_cast<const char *>(counts), sizeof(counts));
             write_vec(o, img); write_vec(o, vt); write_vec(o, vsh); write_vec(o, vo); write_vec(o, vis);
             std::printf("V %u I %u arena %llu\n", counts[0], counts[1], (unsigned long long)ctx.arena_bytes());
+            return 0;
+        }
+        if (mode == "train" && argc == 4) {   // scene file as for `render`, then the packed ground truth [h,w] u32; argv[3]: steps
+            std::ifstream f(argv[2], std::ios::binary);
+            uint32_t hdr[6];
+            f.read(reinterpret_cast<char *>(hdr), sizeof(hdr));
+            const uint32_t n = hdr[0], k = hdr[1], w = hdr[2], h = hdr[3];
+            std::string camline;
+            { uint32_t len; f.read(reinterpret_cast<char *>(&len), 4); camline.resize(len); f.read(&camline[0], len); }
+            std::istringstream ss(camline);
+            uint32_t cw, ch;
+            Camera cam = read_camera(ss, cw, ch);
+            float bg[3];
+            f.read(reinterpret_cast<char *>(bg), sizeof(bg));
+            auto tr = read_vec<float>(f, (size_t)n * 10), sh = read_vec<float>(f, (size_t)n * k * 3), op = read_vec<float>(f, n);
+            auto skip = read_vec<float>(f, (size_t)w * h * 4);
+            auto gt = read_vec<uint32_t>(f, (size_t)w * h);
+            float median_scale;
+            f.read(reinterpret_cast<char *>(&median_scale), 4);
+            Context ctx(0, n, w, h);
+            DeviceBuffer<float> d_tr(tr.size()), d_sh(sh.size()), d_op(op.size());
+            DeviceBuffer<uint32_t> d_gt(gt.size());
+            d_tr.upload(tr.data(), tr.size()); d_sh.upload(sh.data(), sh.size()); d_op.upload(op.data(), op.size());
+            d_gt.upload(gt.data(), gt.size());
+            TrainConfig cfg;
+            cfg.total_train_iters = 1000;
+            cfg.seed = 7;
+            SplatTrainer trainer(cfg, n, k, median_scale);
+            const int steps = std::atoi(argv[3]);
+            for (int i = 0; i < steps; i++) {
+                const float *loss_dev = trainer.step(ctx, nullptr, cam, d_gt.data(), w, h, d_tr.data(), d_sh.data(), d_op.data());
+                float loss;
+                check_cuda(cudaMemcpy(&loss, loss_dev, 4, cudaMemcpyDeviceToHost), "loss readback");
+                std::printf("loss %.9g\n", loss);
+            }
             return 0;
         }
     } catch (const Error &e) {

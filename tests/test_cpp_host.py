@@ -26,7 +26,7 @@ def exe():
     hdrs = [os.path.join(ROOT, "include", h) for h in ("brush_b200.hpp", "brush_b200.h")]
     if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(p) for p in [src] + hdrs):
         lib = os.path.join(ROOT, "brush_b200")
-        cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CUDA, "include"), src,
+        cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CUDA, "include"), src,
                "-o", EXE, "-L", lib, "-lbrush_b200", "-L", os.path.join(CUDA, "lib64"), "-lcudart",
                f"-Wl,-rpath,{lib}", f"-Wl,-rpath,{os.path.join(CUDA, 'lib64')}"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -138,4 +138,43 @@ def test_cpp_operators_match_python_mirror(exe, tmp_path):
     for a, b in ((vt, pvt), (vsh, pvsh), (vo, pvo)):   # f32 atomics in the blend backward: equal up to summation order
         b = b.cpu().numpy()
         assert np.linalg.norm(a.astype(np.float64) - b) <= 1e-4 * np.linalg.norm(b) + 1e-12
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_cpp_splat_trainer_matches_python_fused_step(exe, tmp_path):
+    """brush_b200::SplatTrainer (C++) and SplatTrainer.step_fused (Python) drive the same bg_train_step: same losses."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import brush_b200.render as R
+    import brush_b200.train as T
+    from scenes import synthetic_scene
+    n, w, h, k = 15_000, 192, 128, 4
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=k, seed=55)
+    ctx = R.RenderContext(n, w, h)
+    d = ctx.device
+    tgt = R.render_splats(ctx, cam, (w, h), *(torch.from_numpy(x).to(d) for x in (tr, sh, op)), rpass=0)
+    gt = (tgt.out_img | (255 << 24)).clone()
+    sh0 = (sh + np.float32(0.1)).astype(np.float32)
+    bounds = T.bounds_from_pos(0.8, tr[:, :3])
+    line = _cam_line(cam, w, h).encode()
+    scene = tmp_path / "train.bin"
+    with open(scene, "wb") as f:
+        f.write(struct.pack("<6I", n, k, w, h, 0, 1))
+        f.write(struct.pack("<I", len(line)) + line)
+        f.write(np.zeros(3, np.float32).tobytes() + tr.tobytes() + sh0.tobytes() + op.tobytes())
+        f.write(np.zeros((h, w, 4), np.float32).tobytes())
+        f.write(gt.cpu().numpy().astype(np.int32).tobytes())
+        f.write(struct.pack("<f", bounds.median_size()))
+    r = subprocess.run([exe, "train", str(scene), "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp_losses = [float(ln.split()[1]) for ln in r.stdout.strip().splitlines() if ln.startswith("loss")]
+    cfg = T.TrainConfig(total_train_iters=1000, background_noise_strength=0.0, seed=7)
+    splats = T.Splats(*(torch.from_numpy(x.copy()).to(d) for x in (tr, sh0, op)))
+    trainer = T.SplatTrainer(cfg, ctx, bounds)
+    batch = T.SceneBatch(img_packed=gt, camera=cam)
+    py_losses = [float(trainer.step_fused(batch, splats).loss.item()) for _ in range(3)]
+    assert len(cpp_losses) == 3 and all(math.isfinite(x) for x in cpp_losses)
+    np.testing.assert_allclose(cpp_losses, py_losses, rtol=1e-3)
     ctx.close()
