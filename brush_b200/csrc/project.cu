@@ -6,7 +6,8 @@
 //                                 + map_gaussians_to_intersect_kernel (kernels/map_gaussians.rs:14-80)
 //   tile_offsets_kernel        <- get_tile_offsets        (get_tile_offset.rs:10-58)
 //
-// All four are HBM-bound streaming kernels.  Design notes:
+// HBM-bound in principle; in practice project_cull is issue-bound (exact tile tests) and project_visible_emit is
+// gather-latency bound (profiles/README.md).  Design notes:
 //   * persistent CTAs pull tiles from an atomic ticket; counts that the reference reads back to
 //     the host (num_visible, num_intersections) stay on the device and downstream kernels read
 //     them from the control block;

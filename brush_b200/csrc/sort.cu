@@ -2,9 +2,10 @@
 //
 // Replaces brush_sort::radix_argsort (brush-sort/src/lib.rs:16-125; kernels.rs:28-443), which runs
 // 5 dispatches per 4-bit digit (count, reduce, scan, scan_add, scatter): 40 dispatches for the
-// 32-bit depth sort and 20 for a 13-bit tile sort.  Here: one histogram kernel for all digits,
-// then one kernel per 8-bit digit that reads every key once and writes it once (chained scan with
-// decoupled look-back): 1 + 4 launches for 32 bits, 1 + 2 for 13..16 bits.
+// 32-bit depth sort and 20 for a 13-bit tile sort.  Here: digit histograms for all passes up front (one
+// kernel for bg_radix_argsort_u32; inside a render the kernels that PRODUCE the keys count them, so no
+// histogram pass exists), then one kernel per 8-bit digit that reads every key once and writes it once
+// (chained scan with a two-level decoupled look-back): 4 launches for 32 bits, 2 for 13..16 bits.
 //
 // Result spec (the reference's tests, brush-sort/src/lib.rs:147-151): equal to a stable argsort on
 // the low `bits` bits.  Stability comes from (a) ranking keys inside a warp in lane order (peer
