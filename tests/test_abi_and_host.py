@@ -112,3 +112,32 @@ def test_synthetic_scene_is_deterministic():
     b = synthetic_scene(1000, 64, 64)
     for x, y in zip(a[1:], b[1:]):
         np.testing.assert_array_equal(x, y)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as the C compiler lays it out vs the ctypes mirrors."""
+    import subprocess
+    from brush_b200 import _lib
+    fields = {"BgCamera": ["viewmat", "fx", "cam_pos", "half_max_render_fov", "camera_model", "model_params"],
+              "BgRenderState": ["projected", "counters_host", "n", "tiles_y", "mip"],
+              "BgTrainStepArgs": ["cam", "w", "background", "transforms", "gt_packed", "l1_weight", "composite_bg", "channels",
+                                  "lr_mean", "median_scale", "seed", "step", "workspace", "loss_out", "state_out"]}
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "brush_b200.h"', 'int main(void){']
+    for st, fs in fields.items():
+        prog.append(f'printf("{st} %zu", sizeof({st}));')
+        for f in fs:
+            prog.append(f'printf(" %zu", offsetof({st}, {f}));')
+        prog.append('printf("\\n");')
+    prog.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out:
+        tok = line.split()
+        cls = getattr(_lib, tok[0])
+        assert ctypes.sizeof(cls) == int(tok[1]), tok[0]
+        for f, off in zip(fields[tok[0]], tok[2:]):
+            name = "pass_" if f == "pass" else f
+            assert getattr(cls, name).offset == int(off), (tok[0], f)
