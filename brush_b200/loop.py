@@ -72,9 +72,9 @@ def train_loop(ctx, splats, train_views: Sequence, eval_views: Sequence, config,
                 psnr.append(float(s.psnr)); ssim.append(float(s.ssim))
             evals.append({"iter": done, "psnr": float(np.mean(psnr)), "ssim": float(np.mean(ssim)), "splats": splats.num_splats()})
         if should_export(done, process.export_every, total):
-            splats.bake_min_scale(ctx)                      # export.rs:183: the floor is folded in, never stored
-            data = ply.splat_to_ply(splats.transforms.cpu().numpy(), splats.sh_coeffs.cpu().numpy(),
-                                    splats.raw_opacities.cpu().numpy(), render_mip=config.render_mip)
+            t_fold, o_fold = splats.folded(ctx)            # export.rs:183: the floor is folded into a COPY, never stored
+            data = ply.splat_to_ply(t_fold.cpu().numpy(), splats.sh_coeffs.cpu().numpy(), o_fold.cpu().numpy(),
+                                    render_mip=config.render_mip)
             os.makedirs(process.export_path, exist_ok=True)
             with open(os.path.join(process.export_path, process.export_name.replace("{iter}", str(done))), "wb") as f:
                 f.write(data)
