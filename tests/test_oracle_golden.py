@@ -38,3 +38,20 @@ def test_packed_output_matches_float(golden_dir):
     np.testing.assert_array_equal(got, exp)
     # forward pass leaves the tile ranges untrimmed
     np.testing.assert_array_equal(p.tile_offsets, p.tile_offsets_untrimmed)
+
+
+def test_oracle_matches_its_committed_camera_model_vectors():
+    """Drift pin: tests/golden/oracle_camera_models.npz was written by tests/golden/make_oracle_goldens.py after the
+    oracle's camera models passed their finite-difference checks."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_goldens", os.path.join(here, "golden", "make_oracle_goldens.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.compute()
+    want = np.load(os.path.join(here, "golden", "oracle_camera_models.npz"))
+    for name in mod.MODELS:
+        assert (got[name + "_counts"] == want[name + "_counts"]).all(), name
+        np.testing.assert_allclose(got[name + "_img"], want[name + "_img"], rtol=0, atol=2e-6, err_msg=name)
+        np.testing.assert_allclose(got[name + "_grad_sums"], want[name + "_grad_sums"], rtol=1e-5, err_msg=name)
+    assert want["kb4_counts"][0] > 500 and not np.array_equal(want["kb4_img"], want["pinhole_img"])
