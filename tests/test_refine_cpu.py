@@ -138,3 +138,20 @@ def test_opacity_decay_and_bounds_update():
     np.testing.assert_allclose(tr.bounds.extent, b.extent, rtol=1e-6)
     d = bounds_from_pos_device(0.8, sp.transforms[:, :3])
     np.testing.assert_allclose(d.center, b.center, rtol=1e-6, atol=1e-7)
+
+
+def test_bounds_from_pos_degenerate_inputs():
+    """splat_init.rs:245-295: all-NaN, empty, mixed and one-axis-NaN inputs give finite boxes (unit-box fallback)."""
+    import numpy as np
+    for fn in (bounds_from_pos, lambda p, m: bounds_from_pos_device(p, torch.from_numpy(m))):
+        for means in (np.full((10, 3), np.nan, np.float32), np.zeros((0, 3), np.float32)):
+            bb = fn(0.8, means)
+            assert np.isfinite(bb.center).all() and np.isfinite(bb.extent).all()
+            assert (bb.center == 0).all() and (bb.extent == 1).all()
+        mixed = np.full((100, 3), np.nan, np.float32)
+        mixed[1::2] = np.arange(1, 100, 2, dtype=np.float32)[:, None]
+        bb = fn(0.8, mixed)
+        assert np.isfinite(bb.center).all() and 0.0 < bb.extent[0] < 100.0
+        one_axis = np.stack([np.arange(50), np.full(50, np.nan), np.arange(50)], 1).astype(np.float32)
+        bb = fn(0.8, one_axis)
+        assert np.isfinite(bb.center).all() and np.isfinite(bb.extent).all()
