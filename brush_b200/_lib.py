@@ -94,6 +94,7 @@ SIGNATURES = {
     "bg_render_forward": (_I32, [_P, _P, C.POINTER(BgCamera), _U32, _U32, _U32, _U32, _P, _P, _P, _I32,
                                  C.POINTER(_F), _I32, _P, _P, _P, C.POINTER(BgRenderState)]),
     "bg_rasterize_backward": (_I32, [_P, _P, C.POINTER(BgRenderState), _P, _P, C.POINTER(_F), _I32, _P, _U32]),
+    "bg_debug_blend_stats": (_I32, [_P, _P, C.POINTER(BgRenderState), _P, _P, C.POINTER(_F), _P, _P]),
     "bg_project_backward": (_I32, [_P, _P, C.POINTER(BgCamera), C.POINTER(BgRenderState), _P, _P, _P, _P, _P, _P, _P, _P]),
     "bg_normal_noise": (_I32, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "bg_train_step_workspace_bytes": (C.c_uint64, [_U32, _U32, _U32, _U32]),

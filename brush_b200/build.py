@@ -30,6 +30,8 @@ SOURCES = {
     "sort.cu": [],
     "raster_fwd.cu": [],
     "raster_bwd.cu": [],
+    "blend_fwd.cu": [],
+    "blend_bwd.cu": [],
     "loss.cu": [],
     "optim.cu": [],
 }

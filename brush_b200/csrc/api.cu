@@ -39,6 +39,12 @@ cudaError_t launch_rasterize_fwd(cudaStream_t, bool, bool, uint32_t, const uint3
                                  const uint32_t *, void *, float *, uint32_t, uint32_t, uint32_t, const float *);
 cudaError_t launch_rasterize_bwd(cudaStream_t, bool, uint32_t, const uint32_t *, const uint32_t *, const float *,
                                  const float *, const float *, float *, uint32_t, uint32_t, uint32_t, const float *);
+// blend_fwd.cu / blend_bwd.cu (hard alpha cutoff: the production blend kernels)
+cudaError_t launch_blend_fwd(cudaStream_t, bool, uint32_t, const uint32_t *, uint32_t *, const float *, const uint32_t *,
+                             void *, float *, uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, const float *);
+cudaError_t launch_blend_bwd(cudaStream_t, uint32_t, const uint32_t *, const uint32_t *, const float *, const float *,
+                             const float *, const uint32_t *, const uint32_t *, float *, unsigned long long *, uint32_t,
+                             uint32_t, uint32_t, const float *);
 cudaError_t launch_project_bwd(cudaStream_t, bool, int, const float *, const float *, const float *,
                                const uint32_t *, const float *, uint32_t, const BgCamera &, float *, float *, float *,
                                float *, float *);
@@ -97,6 +103,10 @@ struct BgContext {
     uint32_t *isect_key[2] = {nullptr, nullptr};
     uint32_t *isect_val[2] = {nullptr, nullptr};
     uint32_t *tile_offsets = nullptr;
+    // forward -> backward hand-off of the blend kernels (blend_common.cuh): per (tile, batch, warp) splat sets and
+    // per (tile, warp) batch counts
+    uint32_t *live_masks = nullptr, *warp_batches = nullptr;
+    unsigned long long *blend_stats = nullptr;   // [4] development counters (bg_debug_blend_stats)
     unsigned long long *lb_scan = nullptr;  // look-back words for project/scan kernels
     unsigned long long *lb_sort = nullptr;  // look-back words for the sort passes: [tiles][256]
     uint64_t lb_scan_words = 0, lb_sort_words = 0, lb_sort_tile_words = 0;
@@ -125,7 +135,7 @@ extern "C" int32_t bg_ctx_destroy(BgContext *c) {
     cudaSetDevice(c->device);
     void *ptrs[] = {c->ctl, c->depth_key[0], c->depth_key[1], c->depth_val[0], c->depth_val[1], c->counts, c->cum,
                     c->cgid_from_gid, c->hit_masks, c->projected, c->isect_key[0], c->isect_key[1], c->isect_val[0], c->isect_val[1],
-                    c->tile_offsets, c->lb_scan, c->lb_sort, c->epoch_dev};
+                    c->tile_offsets, c->lb_scan, c->lb_sort, c->epoch_dev, c->live_masks, c->warp_batches, c->blend_stats};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->counters_host) cudaFreeHost(c->counters_host);
@@ -170,6 +180,9 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
     ok = ok && arena_alloc(c, &c->hit_masks, n) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->projected, n * BG_PROJECTED_STRIDE) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->tile_offsets, (uint64_t)c->max_tiles * 2) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->live_masks, (I / 32 + c->max_tiles + 2) * 4) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->warp_batches, (uint64_t)c->max_tiles * 4) == cudaSuccess;
+    ok = ok && arena_alloc(c, &c->blend_stats, 4) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->lb_scan, c->lb_scan_words) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->lb_sort, c->lb_sort_words) == cudaSuccess;
     ok = ok && arena_alloc(c, &c->epoch_dev, 1) == cudaSuccess;
@@ -288,8 +301,12 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
     // K4
     BG_CUDA(launch_tile_offsets(s, c->sm_count * 16, c->isect_key[iout], c->ctl, num_tiles, c->tile_offsets));
     // K5
-    BG_CUDA(launch_rasterize_fwd(s, bwd_info, pass == BG_PASS_BACKWARD_SMOOTH, num_tiles, c->isect_val[iout],
-                                 c->tile_offsets, c->projected, gid_sorted, out_img, visible, tiles_x, w, h, bg));
+    if (pass == BG_PASS_BACKWARD_SMOOTH)   // test-only smooth alpha cutoff (finite-difference suites)
+        BG_CUDA(launch_rasterize_fwd(s, true, true, num_tiles, c->isect_val[iout], c->tile_offsets, c->projected,
+                                     gid_sorted, out_img, visible, tiles_x, w, h, bg));
+    else
+        BG_CUDA(launch_blend_fwd(s, bwd_info, num_tiles, c->isect_val[iout], c->tile_offsets, c->projected, gid_sorted,
+                                 out_img, visible, c->live_masks, c->warp_batches, tiles_x, w, h, bg));
     BG_CUDA(cudaMemcpyAsync(c->counters_host, counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 
     st->projected = c->projected;
@@ -316,8 +333,34 @@ extern "C" int32_t bg_rasterize_backward(BgContext *c, void *stream, const BgRen
     const uint32_t zr = std::min(rows, std::max(st->n, 1u));
     BG_CUDA(cudaMemsetAsync(v_combined, 0, (size_t)zr * BG_VCOMBINED_STRIDE * sizeof(float), s));
     const uint32_t num_tiles = st->tiles_x * st->tiles_y;
-    BG_CUDA(launch_rasterize_bwd(s, smooth != 0, num_tiles, st->compact_gid_from_isect, st->tile_offsets, st->projected,
-                                 out_img, v_output, v_combined, st->tiles_x, st->w, st->h, bg));
+    if (st->pass == BG_PASS_BACKWARD && !smooth && st->tile_offsets == c->tile_offsets)
+        // the forward of this context left its hand-off words: replay exactly the splats it used
+        BG_CUDA(launch_blend_bwd(s, num_tiles, st->compact_gid_from_isect, st->tile_offsets, st->projected, out_img,
+                                 v_output, c->live_masks, c->warp_batches, v_combined, nullptr, st->tiles_x, st->w, st->h, bg));
+    else
+        BG_CUDA(launch_rasterize_bwd(s, smooth != 0, num_tiles, st->compact_gid_from_isect, st->tile_offsets,
+                                     st->projected, out_img, v_output, v_combined, st->tiles_x, st->w, st->h, bg));
+    return BG_OK;
+}
+
+// Development counters of the blend loop for the last Backward-pass forward of this context:
+// out[0] warp-splat iterations (64 pixel-splat pairs each), out[1] pairs that blended, out[2] pairs that stopped a
+// pixel, out[3] tile-list entries (num_intersections).  Runs the backward kernel's counting variant into a scratch
+// v_combined (caller-provided, [n,10]); synchronises the stream.
+extern "C" int32_t bg_debug_blend_stats(BgContext *c, void *stream, const BgRenderState *st, const float *out_img,
+                                        const float *v_output, const float *bg, float *v_combined_scratch,
+                                        unsigned long long *out4) {
+    if (!c || !st || !out_img || !v_output || !bg || !v_combined_scratch || !out4) return BG_ERR_NULL;
+    if (st->pass != BG_PASS_BACKWARD || st->tile_offsets != c->tile_offsets) { set_err("bg_debug_blend_stats: needs the state of this context's last Backward pass", cudaSuccess); return BG_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(cudaMemsetAsync(c->blend_stats, 0, 4 * sizeof(unsigned long long), s));
+    BG_CUDA(launch_blend_bwd(s, st->tiles_x * st->tiles_y, st->compact_gid_from_isect, st->tile_offsets, st->projected,
+                             out_img, v_output, c->live_masks, c->warp_batches, v_combined_scratch, c->blend_stats,
+                             st->tiles_x, st->w, st->h, bg));
+    BG_CUDA(cudaMemcpyAsync(out4, c->blend_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    BG_CUDA(cudaStreamSynchronize(s));
+    out4[3] = st->counters_host ? st->counters_host[1] : 0;
     return BG_OK;
 }
 

@@ -199,6 +199,23 @@ def rasterize_bwd(out: RenderOutput, v_output: torch.Tensor, smooth_cutoff: Opti
     return v_combined
 
 
+def blend_stats(out: RenderOutput, v_output: torch.Tensor) -> dict:
+    """Measurement aid (bg_debug_blend_stats): counters of the blend loop for `out` (a PASS_BACKWARD render that is
+    still this context's last forward).  Synchronises the stream."""
+    lib = _lib.load()
+    v_output = _f32c(v_output, "v_output")
+    st = out.state
+    scratch = torch.empty((max(int(st.n), 1), VCOMBINED_STRIDE), dtype=torch.float32, device=out.ctx.device)
+    scratch.zero_()
+    res = (C.c_ulonglong * 4)()
+    bg = (C.c_float * 3)(*out.background)
+    _lib.check(lib.bg_debug_blend_stats(out.ctx.handle, _stream_ptr(out.ctx.device), C.byref(st), out.out_img.data_ptr(),
+                                        v_output.data_ptr(), bg, scratch.data_ptr(), res), "bg_debug_blend_stats")
+    it, live, stop, isect = (int(x) for x in res)
+    return {"tile_list_entries": isect, "warp_splat_iterations": it, "pairs_evaluated": it * 64, "pairs_live": live,
+            "pairs_stopping": stop, "lane_utilisation": (live / (it * 64)) if it else 0.0}
+
+
 def project_bwd(out: RenderOutput, transforms, sh_coeffs, raw_opacities, v_combined, outputs=None):
     """SplatBwdOps::project_bwd (bwd/render_bwd.rs:102-171) -> (v_transforms, v_coeffs, v_raw_opac, v_refine_weight).
     `outputs`: optional preallocated (v_t [n,10], v_sh [n,k,3], v_o [n], v_r [n]) -- e.g. views of one flat

@@ -137,6 +137,14 @@ int32_t bg_rasterize_backward(BgContext *ctx, void *stream, const BgRenderState 
                               const float *v_output, const float *bg, int32_t smooth_cutoff,
                               float *v_combined, uint32_t v_combined_rows);
 
+/* Measurement aid (not a reference operator): counters of the blend loop for the state of this context's last
+ * BG_PASS_BACKWARD forward.  out4 (host): [0] warp-splat iterations of the backward walk (64 pixel-splat pairs each),
+ * [1] pixel-splat pairs that blended, [2] pairs that stopped a pixel, [3] tile-list entries (num_intersections).
+ * v_combined_scratch: device [n,10] scratch that receives the gradients of the counting run.  Synchronises `stream`. */
+int32_t bg_debug_blend_stats(BgContext *ctx, void *stream, const BgRenderState *state, const float *out_img,
+                             const float *v_output, const float *bg, float *v_combined_scratch,
+                             unsigned long long *out4);
+
 /* Replaces SplatBwdOps::project_bwd, bwd/render_bwd.rs:102-171 (kernel:
  * bwd/kernels/project_backwards.rs:99-254).  Dense outputs; every row is written (zeros for
  * Gaussians that received no gradient), so no separate zero-fill is needed. */

@@ -22,16 +22,8 @@ def step():
     return out, g
 for _ in range(3): out, g = step()
 torch.cuda.synchronize()
-import ctypes
-from brush_b200 import _lib
-_h = ctypes.CDLL(_lib.LIB_PATH)
-if hasattr(_h, "bg_debug_fwd_stats"):
-    buf = (ctypes.c_ulonglong * 4)()
-    _h.bg_debug_fwd_stats(buf, 1)
-    out = R.render_splats(ctx, cam, (w, h), ttr, tsh, top); torch.cuda.synchronize()
-    _h.bg_debug_fwd_stats(buf, 1)
-    T_ = ((w + 15) // 16) * ((h + 15) // 16)
-    print("fwd stats per frame: tested(warp-splats) %d  iterations %d  useful iterations %d  contributing pairs %d | per tile: %.0f %.0f %.0f %.0f" % (buf[0], buf[1], buf[2], buf[3], buf[0]/T_, buf[1]/T_, buf[2]/T_, buf[3]/T_))
+out = R.render_splats(ctx, cam, (w, h), ttr, tsh, top)
+print("blend stats:", R.blend_stats(out, vout))
 print("V", out.num_visible, "I", out.num_intersections, "overflow", out.intersection_overflow, "arena MB", ctx.arena_bytes() / 1e6)
 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 tf = tb = tp = 0.0
