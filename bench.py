@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (contract: task statement, section 4).
 
-Workload (BASELINE.json configs[1]): 1M synthetic Gaussians (SURVEY.md 8d generator, K=16),
-1920x1080, one "step" = render forward (RasterPass::Backward) + rasterize backward + project
-backward of one view.  metric = forward+backward Mpix/s.
+Headline workload (BASELINE.json configs[1]): 1M synthetic Gaussians (SURVEY.md 8d generator, K=16), 1920x1080,
+one "step" = render forward (RasterPass::Backward) + rasterize backward + project backward of one view.
+metric = forward+backward Mpix/s.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference
-                                                           # kernels on the host cores (the reference
-                                                           # itself needs cargo+wgpu: not buildable here)
-N > 1 (torchrun, one rank per GPU): the step is view-sharded -- every rank renders its own view of the
-replicated scene and the dense per-Gaussian gradients are summed with one NCCL all-reduce.
-Weak scaling: per-GPU work is fixed, value = N * pixels / max-over-ranks step time.
+  python bench.py --impl reference --steps K --warmup W    # CPU arm: the restatement of the reference kernels (oracle/)
+                                                           # on the host's physical cores (the reference itself needs
+                                                           # cargo + wgpu: not buildable here)
+  python bench.py --configs 1,3,4,2                        # which BASELINE configs ride in the line (default: all)
+
+N > 1 (torchrun, one rank per GPU): the step is view-sharded -- every rank renders its own view of the replicated scene
+and the ranks exchange the gradients over the library's NCCL communicator (bg_dp_exchange: all-reduce 48 N B,
+all-gather 20 N B per rank; the SH gradient stays in its per-view rank-one form, which is what the optimiser pass
+consumes).  Weak scaling: per-GPU work is fixed, value = N * pixels / max-over-ranks step time.
+
+The other configs ride in the same JSON line under "configs":
+  "3": 4M Gaussians at 3840x2160 (sort / scan / blend stress), forward+backward, N=1
+  "4": 2M Gaussians, ONE optimizer step over 8 views sharded over the N ranks (SplatTrainer.step_views)
+  "2": a short end-to-end training run on a synthetic COLMAP-format 200-view set (loader -> step -> refine -> eval),
+       N=1 (scripts/train_colmap.py holds the full-length version)
 """
 from __future__ import annotations
 
@@ -30,10 +39,21 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-N_SPLATS, IMG_W, IMG_H, SH_K = 1_000_000, 1920, 1080, 16
+SH_K = 16
+CONFIGS = {   # BASELINE.json configs by index; seeds follow tests/scenes.py (0xB2000000 + index)
+    1: dict(n=1_000_000, w=1920, h=1080, seed=0xB2000001, shift=0.0),
+    3: dict(n=4_000_000, w=3840, h=2160, seed=0xB2000003, shift=-math.log(2.0)),   # focal doubles at 4K: scales halve
+    4: dict(n=2_000_000, w=1920, h=1080, seed=0xB2000004, shift=0.0),
+}
+N_SPLATS, IMG_W, IMG_H = CONFIGS[1]["n"], CONFIGS[1]["w"], CONFIGS[1]["h"]
 WORKLOAD = "configs[1]: 1M synthetic Gaussians (K=16), 1920x1080, render fwd + rasterize bwd + project bwd, 1 view/GPU"
 METRIC, UNIT = "fwd+bwd Mpix/s @1M Gaussians 1080p", "Mpix/s"
 KERNELS_PER_STEP = 14  # fwd: epoch bump, cull, 4 sort, scan, visible+emit, 2 sort, offsets, blend = 12; bwd: blend, project = 2
+
+
+def base_config():
+    """The keys both arms print, so that the driver can tell they ran the same workload."""
+    return {"workload": WORKLOAD, "n_gaussians": N_SPLATS, "width": IMG_W, "height": IMG_H, "sh_k": SH_K}
 
 
 def measured_peak_gbs():
@@ -87,10 +107,11 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(inside)}
 
 
-def scene_np():
+def scene_np(cfg_idx=1):
     from scenes import random_v_output, synthetic_scene
-    cam, tr, sh, op = synthetic_scene(N_SPLATS, IMG_W, IMG_H, k=SH_K, seed=0xB2000001)
-    return cam, tr, sh, op, random_v_output(IMG_H, IMG_W)
+    c = CONFIGS[cfg_idx]
+    cam, tr, sh, op = synthetic_scene(c["n"], c["w"], c["h"], k=SH_K, seed=c["seed"], scale_shift=c["shift"])
+    return cam, tr, sh, op, random_v_output(c["h"], c["w"])
 
 
 def rank_camera(cam, rank):
@@ -111,15 +132,24 @@ def cpu_oracle_pass(u, tr, sh, op, v_out):
     return dt
 
 
-def _oracle_on_all_cores():
-    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs are the oracle on ALL the host's cores.  The
-    OpenMP default (one thread per core the runtime may use) is what a plain `python bench.py` gets; it is restored
-    by dropping the variable before the oracle's OpenMP runtime starts, with an explicit count as a fallback."""
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _oracle_on_physical_cores():
+    """Both CPU legs (cpu_baseline of the default run, and --impl reference) run the restatement on the host's PHYSICAL
+    cores: one OpenMP thread per core, SMT siblings left idle (they slow this code down).  torchrun exports
+    OMP_NUM_THREADS=1 to its workers, so the count is always set explicitly."""
     os.environ.pop("OMP_NUM_THREADS", None)
     from oracle import oracle as orc
-    if orc.num_threads() <= 1:
-        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        orc.set_num_threads(max(1, n // 2) if n >= 4 else n)   # physical cores: SMT siblings slow this code down
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc.set_num_threads(max(1, n // 2) if n >= 4 else n)
     return orc
 
 
@@ -128,8 +158,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     from brush_b200.camera import build_uniforms
-    orc = _oracle_on_all_cores()
-    cam, tr, sh, op, v_out = scene_np()
+    orc = _oracle_on_physical_cores()
+    cam, tr, sh, op, v_out = scene_np(1)
     u = build_uniforms(cam, IMG_W, IMG_H)
     # One "step" of this arm is one full fwd+bwd pass of the workload on the host cores (seconds each).
     # The number of timed passes is bounded so that the whole run stays within a few minutes whatever
@@ -141,12 +171,13 @@ def run_reference(args):
     val = IMG_W * IMG_H / (ms * 1e-3) / 1e6
     cores = orc.num_threads()
     sample = (f"{n_pass} full fwd+bwd passes of the same 1M-Gaussian 1080p scene timed (of {args.steps} steps requested; "
-              f"bounded to ~150 s), OpenMP, {cores} threads")
+              f"bounded to ~150 s), OpenMP, {cores} threads = physical cores of {cpu_model()}")
+    cfg = base_config()
+    cfg["note"] = ("CPU restatement of Brush's kernels (oracle/), not the Brush binary: the reference needs cargo + wgpu and "
+                   "has no CPU path (SURVEY.md F3/F4)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement of Brush's kernels (oracle/), not the Brush binary: "
-                       "the reference needs cargo + wgpu and has no CPU path (SURVEY.md F3/F4)"},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
@@ -172,6 +203,269 @@ def _emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+def log(msg):
+    sys.stderr.write(f"[bench] {msg}\n")
+    sys.stderr.flush()
+
+
+class Bench:
+    """Shared timing helpers of the GPU legs (device timing with CUDA events, max over ranks)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.sampler = ClockSampler(self.local_rank)
+        self.sampler.start()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps):
+        """Total milliseconds of `steps` calls of fn(i): barrier + synchronize on both sides, max over ranks."""
+        torch = self.torch
+        self.barrier()
+        w0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        self.sampler.mark(w0, time.time())
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def capture(self, fn, replays=3):
+        """fn as ONE CUDA graph (None if capture is not possible)."""
+        torch = self.torch
+        try:
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(replays):
+                g.replay()
+            torch.cuda.synchronize(self.dev)
+            return g
+        except Exception as e:  # capture not possible: measure the eager loop instead
+            log(f"CUDA graph capture failed ({e}); timing eager launches")
+            return None
+
+
+def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool):
+    """forward + rasterize backward + project backward of one view per rank; returns the measurements as a dict."""
+    import brush_b200.render as R
+    torch = B.torch
+    c = CONFIGS[cfg_idx]
+    n, w, h = c["n"], c["w"], c["h"]
+    world, rank, dev = B.world, B.rank, B.dev
+    cam0, tr, sh, op, v_out_np = scene_np(cfg_idx)
+    cam = rank_camera(cam0, rank)
+    ctx = R.RenderContext(n, w, h, 0, device=B.local_rank)
+    ttr, tsh, top = (torch.from_numpy(x).to(dev) for x in (tr, sh, op))
+    v_out = torch.from_numpy(v_out_np).to(dev)
+    P = w * h
+    dp = world > 1
+    comm = None
+    if dp:
+        from brush_b200.dp import DpComm
+        comm = DpComm(ctx)
+        small = torch.zeros(12 * n, dtype=torch.float32, device=dev)       # v_transforms | v_raw_opac | visible
+        record = torch.zeros(5 * n, dtype=torch.float32, device=dev)       # v_color | v_refine | max_radius
+        recv = torch.zeros(world * 5 * n, dtype=torch.float32, device=dev)
+        outs = (small[:10 * n].view(n, 10), record[:3 * n].view(n, 3), small[10 * n:11 * n], record[3 * n:4 * n])
+        dense = None
+    else:
+        dense = (torch.empty((n, 10), device=dev), torch.empty((n, SH_K, 3), device=dev), torch.empty(n, device=dev),
+                 torch.empty(n, device=dev))
+    last = [None]
+
+    def compute(vo=v_out):
+        out = R.render_splats(ctx, cam, (w, h), ttr, tsh, top)
+        last[0] = out
+        vc = R.rasterize_bwd(out, vo)
+        if dp:
+            g = R.project_bwd_factored(out, ttr, tsh, top, vc, outputs=outs)
+            small[11 * n:].copy_(out.visible)
+            record[4 * n:].copy_(out.max_radius)
+        else:
+            g = R.project_bwd(out, ttr, tsh, top, vc, outputs=dense)
+        return out, g
+
+    def exchange():
+        if dp:
+            comm.exchange(n, 1, small, record, recv, chunks=1)
+
+    def step():
+        r = compute()
+        exchange()
+        return r
+
+    for _ in range(warmup):
+        out, g = step()
+    torch.cuda.synchronize(dev)
+    V, I = out.num_visible, out.num_intersections
+    overflow = out.intersection_overflow
+    toff = out.tile_offsets().cpu().numpy().astype(np.int64)
+    per_tile = toff[..., 1] - toff[..., 0]
+    T = per_tile.size
+    stats = R.blend_stats(out, v_out)
+    # The step is ~20 short launches; replaying it as one CUDA graph removes the host launch gaps (the library keeps
+    # nothing launch-specific on the host: counters and look-back epochs live on the device).  N>1: the exchange runs on
+    # the communicator's own stream between two events, which a capture records as a fork/join.
+    graph = None if os.environ.get("BG_BENCH_NO_GRAPH") else B.capture(lambda: step())
+    launch = "one CUDA graph replay per step" + (" (exchange included)" if dp and graph is not None else "")
+    if graph is None and dp and not os.environ.get("BG_BENCH_NO_GRAPH"):
+        graph_c = B.capture(lambda: compute())
+        if graph_c is not None:
+            launch = "one CUDA graph replay per step + eager exchange"
+            run_step = lambda i: (graph_c.replay(), exchange())
+        else:
+            launch = "eager launches"
+            run_step = lambda i: step()
+    elif graph is None:
+        launch = "eager launches"
+        run_step = lambda i: step()
+    else:
+        run_step = lambda i: graph.replay()
+    ms_step = B.timed(run_step, steps) / steps
+    res = {"n": n, "w": w, "h": h, "V": V, "I": I, "T": T, "P": P, "ms_step": ms_step, "launch": launch, "overflow": overflow,
+           "per_tile_mean": float(per_tile.mean()), "per_tile_max": int(per_tile.max()), "stats": stats}
+    if dp:   # phases: this rank's kernels alone, the exchange alone
+        res["ms_compute"] = B.timed(lambda i: compute(), steps) / steps
+        res["ms_exchange"] = B.timed(lambda i: exchange(), steps) / steps
+    if headline:
+        # ---- e2e: host input, copies inside the timed region
+        v_out_host = torch.from_numpy(v_out_np).pin_memory()
+        copy_stream = torch.cuda.Stream(dev)
+        staged = [torch.empty_like(v_out), torch.empty_like(v_out)]
+        staged_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        result_host = torch.empty(8, dtype=torch.float32).pin_memory()
+
+        def stage(i):  # H2D of the step's upstream gradient image from pinned host memory
+            with torch.cuda.stream(copy_stream):
+                staged[i & 1].copy_(v_out_host, non_blocking=True)
+                staged_ev[i & 1].record(copy_stream)
+
+        def step_e2e(i, is_last):
+            torch.cuda.current_stream(dev).wait_event(staged_ev[i & 1])
+            _, g = compute(staged[i & 1])
+            if not is_last:
+                stage(i + 1)  # next step's upload overlaps this step's kernels
+            exchange()
+            res_t = torch.stack([x.sum() for x in g])
+            result_host[:4].copy_(res_t, non_blocking=True)  # D2H of the step's result
+
+        stage(0)
+        for i in range(2):
+            step_e2e(i, False)
+        torch.cuda.synchronize(dev)
+        stage(0)
+        res["ms_e2e"] = B.timed(lambda i: step_e2e(i, i == steps - 1), steps) / steps
+        _ = float(result_host[0])
+        res["h2d_bytes"] = int(v_out_host.numel() * 4)
+        # ---- dominant kernel alone (blend backward) for the roofline figure, and the forward alone
+        out = R.render_splats(ctx, cam, (w, h), ttr, tsh, top)
+        for _ in range(3):
+            R.rasterize_bwd(out, v_out)
+        res["ms_bwd_kernel"] = B.timed(lambda i: R.rasterize_bwd(out, v_out), steps) / steps
+        res["ms_forward"] = B.timed(lambda i: R.render_splats(ctx, cam, (w, h), ttr, tsh, top), steps) / steps
+        res["scene"] = (cam0, tr, sh, op, v_out_np)
+        res["ctx"], res["dev_params"] = ctx, (ttr, tsh, top)
+    if comm is not None:
+        comm.close()
+    if not headline:
+        ctx.close()
+    return res
+
+
+def train_step_leg(B: Bench, ctx, dev_params, tr_np, cam, steps):
+    """Secondary figure of the metric at N=1: SplatTrainer.step (render + L1/SSIM loss + backward + the update pass)."""
+    import brush_b200.train as T
+    torch = B.torch
+    ttr, tsh, top = dev_params
+    gt = torch.randint(0, 2 ** 31 - 1, (IMG_H, IMG_W), dtype=torch.int32, device=B.dev) | (255 << 24)
+    splats = T.Splats(ttr.clone(), tsh.clone(), top.clone())
+    trainer = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr_np[:, :3]))
+    batch = T.SceneBatch(img_packed=gt, camera=cam)
+    for _ in range(3):
+        trainer.step(batch, splats)
+    ms = B.timed(lambda i: trainer.step(batch, splats), steps) / steps
+    for _ in range(3):
+        trainer.step_fused(batch, splats)
+    ms_abi = B.timed(lambda i: trainer.step_fused(batch, splats), steps) / steps
+    return {"iters_per_s": 1e3 / min(ms, ms_abi), "ms_per_iter": min(ms, ms_abi), "ms_host_orchestrated": ms, "ms_one_abi_call": ms_abi,
+            "note": "SplatTrainer.step, 1 view/step, 1M Gaussians 1080p, GT resident on the device, refine() not included"}
+
+
+def views_leg(B: Bench, steps: int):
+    """BASELINE config [4]: ONE optimizer step over 8 views, 2M Gaussians, views sharded over the ranks."""
+    import brush_b200.render as R
+    import brush_b200.train as T
+    torch = B.torch
+    world, rank, dev = B.world, B.rank, B.dev
+    c = CONFIGS[4]
+    n, w, h = c["n"], c["w"], c["h"]
+    cam0, tr, sh, op, _ = scene_np(4)
+    ctx = R.RenderContext(n, w, h, 0, device=B.local_rank)
+    local = 8 // world
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
+    batches = []
+    for v in range(local):
+        gtv = torch.randint(0, 2 ** 31 - 1, (h, w), dtype=torch.int32, device=dev, generator=gen) | (255 << 24)
+        batches.append(T.SceneBatch(img_packed=gtv, camera=rank_camera(cam0, rank * local + v)))
+    params = [torch.from_numpy(x).to(dev) for x in (tr, sh, op)]
+    splats = T.Splats(*params)
+    trainer = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
+    for _ in range(2):
+        trainer.step_views(batches, splats)
+    k8 = max(10, steps // 5)
+    ms = B.timed(lambda i: trainer.step_views(batches, splats), k8) / k8
+    res = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "views_per_step": 8, "views_per_rank": local, "n_gaussians": n,
+           "width": w, "height": h,
+           "note": "bg_train_step_views: 8 views per optimizer step sharded over the ranks, SH-factored gradient exchange "
+                   "in slices under the update pass"}
+    if world > 1:   # phases: the same step without the exchange (local views only), unchunked exchange
+        s2 = T.Splats(*(p.clone() for p in params))
+        t2 = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
+        for _ in range(2):
+            t2.step_views(batches, s2, distributed=False)
+        res["ms_local_views_no_exchange"] = B.timed(lambda i: t2.step_views(batches, s2, distributed=False), k8) / k8
+        for _ in range(2):
+            trainer.step_views(batches, splats, chunks=1)
+        res["ms_unpipelined_exchange"] = B.timed(lambda i: trainer.step_views(batches, splats, chunks=1), k8) / k8
+    ctx.close()
+    return res
+
+
+def train_run_leg(B: Bench, iters: int):
+    """BASELINE config [2], shortened: synthetic COLMAP-format 200-view set -> loader -> step -> refine -> eval."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import train_colmap
+    return train_colmap.run(device=B.local_rank, iters=iters, views=200, width=IMG_W, height=IMG_H, init_points=500_000,
+                            max_splats=2_000_000, quiet=True)
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -179,257 +473,112 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--configs", default="1,3,4,2", help="BASELINE configs to run (1 is always run)")
+    ap.add_argument("--train-iters", type=int, default=600, help="length of the config [2] run inside the bench line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    want = {int(x) for x in args.configs.split(",") if x.strip()} | {1}
 
-    import torch
-    import torch.distributed as dist
-
-    import brush_b200.render as R
     from brush_b200.camera import build_uniforms
+    B = Bench(args)
+    world, rank = B.world, B.rank
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    cam0, tr, sh, op, v_out_np = scene_np()
-    cam = rank_camera(cam0, rank)
-    ctx = R.RenderContext(N_SPLATS, IMG_W, IMG_H, 0, device=local_rank)
-    ttr, tsh, top = (torch.from_numpy(x).to(dev) for x in (tr, sh, op))
-    v_out = torch.from_numpy(v_out_np).to(dev)
-    v_out_host = torch.from_numpy(v_out_np).pin_memory()
-    P = IMG_W * IMG_H
-
-    from brush_b200.dp import FactoredGradients, FlatGradients, ShFactoredReducer, ViewShardedReducer
-    # N>1: view-sharded DP.  Default exchange is SH-factored (all-reduce 44 N B + all-gather 12 N B per rank and a
-    # local rebuild of v_sh); BG_DP_DENSE=1 selects the plain all-reduce of the dense (44+12K) N B gradient.
-    factored = world > 1 and os.environ.get("BG_DP_DENSE") is None
-    reducer = ViewShardedReducer(num_views_total=world)
-    if factored:
-        fg = FactoredGradients(N_SPLATS, SH_K, world, dev)
-        fred = ShFactoredReducer(ctx, world)
-        cam_positions = [rank_camera(cam0, r).position for r in range(world)]
-        project_bwd = R.project_bwd_factored
-    else:
-        fg = FlatGradients(N_SPLATS, SH_K, dev)      # gradients live in one flat buffer: one collective per step
-        project_bwd = R.project_bwd
-
-    def allreduce(g):
-        if world > 1:
-            if factored:   # gradients AND refine statistics in two collectives
-                fred.reduce(fg, ttr, cam_positions, last_out[0].visible, last_out[0].max_radius)
-            else:
-                reducer.reduce_flat(fg)               # SUM over ranks, 1/views scaling
-                reducer.reduce_stats(g[3], last_out[0].visible, last_out[0].max_radius)
-
-    last_out = [None]
-
-    def step_compute():   # this rank's kernels (what the CUDA graph holds)
-        out = R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top)
-        last_out[0] = out
-        vc = R.rasterize_bwd(out, v_out)
-        g = project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
-        return out, g
-
-    def step_device():
-        out, g = step_compute()
-        allreduce(g)
-        return out, g
-
-    copy_stream = torch.cuda.Stream(dev)
-    staged = [torch.empty_like(v_out), torch.empty_like(v_out)]
-    staged_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    result_host = torch.empty(8, dtype=torch.float32).pin_memory()
-
-    def stage(i):  # H2D of the step's upstream gradient image from pinned host memory
-        with torch.cuda.stream(copy_stream):
-            staged[i & 1].copy_(v_out_host, non_blocking=True)
-            staged_ev[i & 1].record(copy_stream)
-
-    def step_e2e(i, last):
-        torch.cuda.current_stream(dev).wait_event(staged_ev[i & 1])
-        vo = staged[i & 1]
-        out = R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top)
-        if not last:
-            stage(i + 1)  # next step's upload overlaps this step's kernels
-        last_out[0] = out
-        vc = R.rasterize_bwd(out, vo)
-        g = project_bwd(out, ttr, tsh, top, vc, outputs=fg.outputs())
-        allreduce(g)
-        g = fg.gradients() if factored else g
-        res = torch.stack([g[0].sum(), g[1].sum(), g[2].sum(), g[3].sum()])
-        result_host[:4].copy_(res, non_blocking=True)  # D2H of the step's result
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps):
-        barrier()
-        w0 = time.time()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        sampler.mark(w0, time.time())
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    # ---- warm-up
-    for _ in range(args.warmup):
-        out, g = step_device()
-    torch.cuda.synchronize(dev)
-    V, I = out.num_visible, out.num_intersections
-    toff = out.tile_offsets().cpu().numpy().astype(np.int64)
-    per_tile = toff[..., 1] - toff[..., 0]
-    T = per_tile.size
-
-    # The step is ~20 short launches; replaying it as one CUDA graph removes the host launch gaps
-    # (the library keeps nothing launch-specific on the host: counters and look-back epochs live on the device).
-    # N>1: the graph holds this rank's kernels only; the NCCL collectives of the gradient exchange are issued eagerly
-    # after each replay (capturing them too hung at N=2: two collectives on NCCL's internal stream inside one capture).
-    use_graph = os.environ.get("BG_BENCH_NO_GRAPH") is None
-    graph = None
-    if use_graph:
-        try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    step_compute()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out, g = step_compute()
-            for _ in range(3):
-                graph.replay()
-                allreduce(g)
-            torch.cuda.synchronize(dev)
-            assert out.num_visible == V and out.num_intersections == I
-        except Exception as e:  # capture not possible: measure the eager loop instead
-            sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing eager launches\n")
-            graph = None
-    def step_graph(i):
-        graph.replay()
-        allreduce(g)     # no-op at N=1
-
-    ms_dev = timed(step_graph if graph is not None else (lambda i: step_device()), args.steps)
-    # ---- e2e: host input, copies inside the timed region
-    stage(0)
-    for i in range(2):
-        step_e2e(i, False)
-    torch.cuda.synchronize(dev)
-    stage(0)
-    ms_e2e = timed(lambda i: step_e2e(i, i == args.steps - 1), args.steps)
-    _ = float(result_host[0])
-    # ---- dominant kernel alone (blend backward) for the roofline figure
-    out = R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top)
-    for _ in range(3):
-        R.rasterize_bwd(out, v_out)
-    ms_bwd = timed(lambda i: R.rasterize_bwd(out, v_out), args.steps) / args.steps
-    ms_fwd_all = timed(lambda i: R.render_splats(ctx, cam, (IMG_W, IMG_H), ttr, tsh, top), args.steps) / args.steps
-
-    ms_step = ms_dev / args.steps
+    h1 = fwd_bwd_leg(B, 1, args.steps, args.warmup, headline=True)
+    V, I, T, P = h1["V"], h1["I"], h1["T"], h1["P"]
+    ms_step = h1["ms_step"]
     value = world * P / (ms_step * 1e-3) / 1e6
-    e2e_value = world * P / (ms_e2e / args.steps * 1e-3) / 1e6
+    e2e_value = world * P / (h1["ms_e2e"] * 1e-3) / 1e6
     peak, peak_src = measured_peak_gbs()
     algo_bytes = 40 * I + 32 * P + 80 * V
+    ms_bwd = h1["ms_bwd_kernel"]
     achieved = algo_bytes / (ms_bwd * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("rasterize_bwd_kernel")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic, traffic_src = tj.get("blend_bwd_kernel"), tj.get("source")
     except Exception:
         pass
-    k16 = SH_K
-    b_fwd = 52 * N_SPLATS + (200 + 12 * k16) * V + 88 * I + 8 * T + 16 * P
-    b_bwd = 40 * I + 32 * P + (168 + 12 * k16) * V + (48 + 12 * k16) * N_SPLATS
+    b_fwd = 52 * N_SPLATS + (200 + 12 * SH_K) * V + 88 * I + 8 * T + 16 * P
+    b_bwd = 40 * I + 32 * P + (168 + 12 * SH_K) * V + (48 + 12 * SH_K) * N_SPLATS
+    st = h1["stats"]
+    cfg = base_config()
+    cfg.update({
+        "num_visible": V, "num_intersections": I, "splats_per_tile_mean": h1["per_tile_mean"], "splats_per_tile_max": h1["per_tile_max"],
+        "pairs": {"tile_list_entries": st["tile_list_entries"], "evaluated": st["pairs_evaluated"], "live": st["pairs_live"],
+                  "stopping": st["pairs_stopping"], "lane_utilisation": st["lane_utilisation"],
+                  "note": "blend loop of one view: pixel-splat pairs evaluated by the backward walk (64 per warp-splat iteration) / "
+                          "pairs that blended; the forward hands the backward the exact splat sets, so untouched tile-list "
+                          "entries cost nothing in the backward"},
+        "parallelism": "single GPU" if world == 1 else
+                       f"view-sharded dp{world}: one exchange per step on the library's NCCL communicator (all-reduce 48N B + "
+                       "all-gather 20N B per rank: gradients and refine statistics; the SH gradient stays per-view rank one)",
+        "launch": h1["launch"],
+        "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 33 MB images per step vs 126 MB L2)"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_gaussians": N_SPLATS, "width": IMG_W, "height": IMG_H, "sh_k": SH_K,
-                   "num_visible": V, "num_intersections": I, "splats_per_tile_mean": float(per_tile.mean()),
-                   "splats_per_tile_max": int(per_tile.max()),
-                   "parallelism": "single GPU" if world == 1 else (f"view-sharded dp{world}, SH-factored exchange: all-reduce 48N B + all-gather 20N B/rank (gradients and refine statistics), v_sh rebuilt locally"
-                                                                           if factored else f"view-sharded dp{world}, one NCCL all-reduce of the dense gradients per step"),
-                   "launch": ("one CUDA graph replay per step" + ("" if world == 1 else " + eager NCCL exchange")) if graph is not None else "eager launches",
-                   "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 33 MB images per step vs 126 MB L2)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(v_out_host.numel() * 4), "d2h_bytes_per_step": 16 + 16,
+        "data": "synthetic", "config": cfg,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h1["h2d_bytes"], "d2h_bytes_per_step": 16 + 16,
                 "note": "upstream-gradient image uploaded from pinned host memory every step (double-buffered on a copy stream), "
                         "gradient checksums + counters read back; Gaussian parameters stay resident as in the reference trainer"},
-        "gpu_launches": (KERNELS_PER_STEP + (1 if factored else 0)) * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps,
         "clocks": None,
-        "roofline": {"bound": "hbm", "kernel": "rasterize_bwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": algo_bytes, "kernel_ms": ms_bwd,
-                     "note": "blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md H5); frac is reported on the "
-                             "mandated HBM basis", "pairs_upper_bound": int(I) * 256,
+                     "note": "the blend kernels are instruction-issue bound (FP32 + MUFU + select), not HBM bound (SURVEY.md H5): "
+                             "frac is reported on the mandated HBM basis; instructions per live pair are in profiles/",
+                     "pairs_upper_bound": int(I) * 256, "pairs_live": st["pairs_live"],
+                     "ns_per_live_pair_bwd": ms_bwd * 1e6 / max(st["pairs_live"], 1),
                      "pipeline_fwd_bwd": {"algorithmic_bytes": b_fwd + b_bwd, "achieved": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9,
-                                          "frac": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9 / peak, "forward_ms": ms_fwd_all}},
+                                          "frac": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9 / peak, "forward_ms": h1["ms_forward"]}},
     }
+    if world > 1:
+        line["phases"] = {"compute_ms": h1["ms_compute"], "exchange_ms": h1["ms_exchange"], "step_ms": ms_step}
+    cam0, tr, sh, op, v_out_np = h1["scene"]
     if world == 1 and not args.no_train:
-        # secondary figure of the metric: full train step (render + L1/SSIM loss + backward + Adam x3 + stats/noise)
-        import brush_b200.train as T
-        gt = torch.randint(0, 2 ** 31 - 1, (IMG_H, IMG_W), dtype=torch.int32, device=dev) | (255 << 24)
-        splats = T.Splats(ttr.clone(), tsh.clone(), top.clone())
-        trainer = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
-        batch = T.SceneBatch(img_packed=gt, camera=cam)
-        for _ in range(3):
-            trainer.step(batch, splats)
-        ms_train = timed(lambda i: trainer.step(batch, splats), args.steps) / args.steps
-        line["train"] = {"iters_per_s": 1e3 / ms_train, "ms_per_iter": ms_train,
-                         "note": "SplatTrainer.step, 1 view/step, GT resident on the device, refine() not included"}
-    if not args.no_train and 8 % world == 0:
-        # BASELINE config [4] shape (at this scene's 1M Gaussians): ONE optimizer step over 8 views, views sharded over
-        # the ranks, SH-factored exchange, identical Adam update on every rank (SplatTrainer.step_views)
-        import brush_b200.train as T
-        local = 8 // world
-        batches = []
-        g = torch.Generator(device=dev)
-        g.manual_seed(1234)
-        for v in range(local):
-            gtv = torch.randint(0, 2 ** 31 - 1, (IMG_H, IMG_W), dtype=torch.int32, device=dev, generator=g) | (255 << 24)
-            batches.append(T.SceneBatch(img_packed=gtv, camera=rank_camera(cam0, rank * local + v)))
-        splats8 = T.Splats(ttr.clone(), tsh.clone(), top.clone())
-        trainer8 = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
-        for _ in range(2):
-            trainer8.step_views(batches, splats8)
-        k8 = max(10, args.steps // 5)
-        ms8 = timed(lambda i: trainer8.step_views(batches, splats8), k8) / k8
-        line["train_8_views"] = {"iters_per_s": 1e3 / ms8, "ms_per_iter": ms8, "views_per_step": 8, "views_per_rank": local,
-                                 "note": "SplatTrainer.step_views: 8 views per optimizer step sharded over the ranks "
-                                         "(BASELINE config [4] at 1M Gaussians), SH-factored gradient exchange"}
+        line["train"] = train_step_leg(B, h1["ctx"], h1["dev_params"], tr, rank_camera(cam0, 0), args.steps)
+    h1["ctx"].close()
+    del h1["dev_params"]
+    B.torch.cuda.empty_cache()
+    extra = {}
+    if 3 in want and world == 1:
+        log("config [3]: 4M Gaussians at 3840x2160")
+        r3 = fwd_bwd_leg(B, 3, max(10, args.steps // 5), 3, headline=False)
+        extra["3"] = {"workload": "configs[3]: 4M synthetic Gaussians, 3840x2160, fwd+bwd, 1 view", "mpix_per_s": r3["P"] / (r3["ms_step"] * 1e-3) / 1e6,
+                      "ms_per_step": r3["ms_step"], "num_visible": r3["V"], "num_intersections": r3["I"], "overflow": r3["overflow"],
+                      "pairs_live": r3["stats"]["pairs_live"], "pairs_evaluated": r3["stats"]["pairs_evaluated"], "launch": r3["launch"]}
+        B.torch.cuda.empty_cache()
+    if 4 in want and not args.no_train and 8 % world == 0:
+        log("config [4]: 8 views per optimizer step, 2M Gaussians")
+        extra["4"] = views_leg(B, args.steps)
+        line["train_8_views"] = extra["4"]
+        B.torch.cuda.empty_cache()
+    if 2 in want and world == 1 and not args.no_train:
+        log("config [2]: end-to-end training run on a synthetic COLMAP set")
+        try:
+            extra["2"] = train_run_leg(B, args.train_iters)
+        except Exception as e:   # the headline must survive a failure of this leg
+            extra["2"] = {"error": repr(e)}
+    line["configs"] = extra
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        orc = _oracle_on_all_cores()
+        orc = _oracle_on_physical_cores()
         u = build_uniforms(cam0, IMG_W, IMG_H)
         cpu_oracle_pass(u, tr, sh, op, v_out_np)
         reps = 3
         dt = sum(cpu_oracle_pass(u, tr, sh, op, v_out_np) for _ in range(reps)) / reps
         line["cpu_baseline"] = {"value": P / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                                "sample": f"{reps} full fwd+bwd passes of the same scene on the host cores (oracle/, OpenMP)"}
-    line["clocks"] = sampler.stop()
+                                "sample": f"{reps} full fwd+bwd passes of the same scene on the host's physical cores "
+                                          f"({cpu_model()}; oracle/, OpenMP)"}
+    line["clocks"] = B.sampler.stop()
     if rank == 0:
         _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
     return 0
 
 

@@ -16,7 +16,7 @@ BG_OK, BG_ERR_NULL, BG_ERR_INVALID, BG_ERR_CUDA, BG_ERR_CAPACITY, BG_ERR_UNSUPPO
 PASS_FORWARD, PASS_BACKWARD, PASS_BACKWARD_SMOOTH = 0, 1, 2
 PROJECTED_STRIDE = 16
 VCOMBINED_STRIDE = 10
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _STATUS_NAMES = {1: "BG_ERR_NULL", 2: "BG_ERR_INVALID", 3: "BG_ERR_CUDA", 4: "BG_ERR_CAPACITY", 5: "BG_ERR_UNSUPPORTED"}
 
@@ -83,6 +83,79 @@ class BgTrainStepArgs(C.Structure):
     ]
 
 
+class BgTrainUpdateArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32), ("k", C.c_uint32),
+        ("transforms", C.c_void_p), ("sh", C.c_void_p), ("raw_opac", C.c_void_p),
+        ("m_t", C.c_void_p), ("v_t", C.c_void_p), ("m_sh", C.c_void_p), ("v_sh", C.c_void_p), ("m_o", C.c_void_p), ("v_o", C.c_void_p),
+        ("refine_norm", C.c_void_p), ("vis_weight", C.c_void_p), ("max_screen", C.c_void_p),
+        ("v_transforms", C.c_void_p), ("v_sh_grad", C.c_void_p), ("v_raw_opac", C.c_void_p),
+        ("v_refine", C.c_void_p), ("visible", C.c_void_p), ("max_radius", C.c_void_p),
+        ("lr_mean", C.c_float), ("lr_rotation", C.c_float), ("lr_scale", C.c_float), ("lr_coeffs_dc", C.c_float),
+        ("lr_coeffs_sh_scale", C.c_float), ("lr_opac", C.c_float),
+        ("noise_scale", C.c_float), ("median_scale", C.c_float),
+        ("seed", C.c_uint64),
+        ("step", C.c_int32),
+    ]
+
+
+class BgRefineStats(C.Structure):
+    _fields_ = [("num_added", C.c_uint32), ("num_split_oversized", C.c_uint32), ("num_split_high_grad", C.c_uint32),
+                ("num_pruned", C.c_uint32), ("num_pruned_non_finite", C.c_uint32), ("total_splats", C.c_uint32)]
+
+
+class BgRefineArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32), ("k", C.c_uint32), ("capacity", C.c_uint32),
+        ("transforms", C.c_void_p), ("sh", C.c_void_p), ("raw_opac", C.c_void_p),
+        ("m_t", C.c_void_p), ("v_t", C.c_void_p), ("m_sh", C.c_void_p), ("v_sh", C.c_void_p), ("m_o", C.c_void_p), ("v_o", C.c_void_p),
+        ("refine_norm", C.c_void_p), ("vis_weight", C.c_void_p), ("max_screen", C.c_void_p),
+        ("transforms_out", C.c_void_p), ("sh_out", C.c_void_p), ("raw_opac_out", C.c_void_p),
+        ("m_t_out", C.c_void_p), ("v_t_out", C.c_void_p), ("m_sh_out", C.c_void_p), ("v_sh_out", C.c_void_p), ("m_o_out", C.c_void_p),
+        ("v_o_out", C.c_void_p),
+        ("bounds_center", C.c_float * 3),
+        ("max_allowed", C.c_float),
+        ("split_at_screen_size", C.c_float), ("growth_grad_threshold", C.c_float), ("growth_select_fraction", C.c_float),
+        ("max_splats", C.c_uint32),
+        ("growth_enabled", C.c_int32),
+        ("opac_decay_minus", C.c_float),
+        ("seed", C.c_uint64),
+        ("refine_index", C.c_uint32),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_uint64),
+    ]
+
+
+class BgTrainViewsArgs(C.Structure):
+    _fields_ = [
+        ("w", C.c_uint32), ("h", C.c_uint32), ("n", C.c_uint32), ("k", C.c_uint32),
+        ("mip", C.c_int32),
+        ("background", C.c_float * 3),
+        ("local_views", C.c_uint32),
+        ("cams", C.POINTER(BgCamera)),
+        ("gt_packed", C.POINTER(C.c_void_p)),
+        ("transforms", C.c_void_p), ("sh", C.c_void_p), ("raw_opac", C.c_void_p),
+        ("m_t", C.c_void_p), ("v_t", C.c_void_p), ("m_sh", C.c_void_p), ("v_sh", C.c_void_p), ("m_o", C.c_void_p), ("v_o", C.c_void_p),
+        ("refine_norm", C.c_void_p), ("vis_weight", C.c_void_p), ("max_screen", C.c_void_p),
+        ("min_scale", C.c_void_p),
+        ("l1_weight", C.c_float), ("ssim_weight", C.c_float),
+        ("has_composite_bg", C.c_int32),
+        ("composite_bg", C.c_float * 3),
+        ("mask", C.c_int32), ("channels", C.c_int32),
+        ("alpha_weight", C.c_float),
+        ("lr_mean", C.c_float), ("lr_rotation", C.c_float), ("lr_scale", C.c_float), ("lr_coeffs_dc", C.c_float),
+        ("lr_coeffs_sh_scale", C.c_float), ("lr_opac", C.c_float),
+        ("noise_scale", C.c_float), ("median_scale", C.c_float),
+        ("seed", C.c_uint64),
+        ("step", C.c_int32),
+        ("chunks", C.c_uint32),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_uint64),
+        ("loss_out", C.c_void_p),
+        ("state_out", BgRenderState),
+    ]
+
+
 # name -> (restype, argtypes); one entry per function declared in include/brush_b200.h
 _P, _U32, _U64, _I32, _I64, _F = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -99,6 +172,18 @@ SIGNATURES = {
     "bg_normal_noise": (_I32, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "bg_train_step_workspace_bytes": (C.c_uint64, [_U32, _U32, _U32, _U32]),
     "bg_train_step": (_I32, [_P, _P, C.POINTER(BgTrainStepArgs)]),
+    "bg_train_update": (_I32, [_P, _P, C.POINTER(BgTrainUpdateArgs)]),
+    "bg_dp_unique_id": (_I32, [_P]),
+    "bg_dp_comm_create": (_I32, [_P, _P, _I32, _I32, C.POINTER(_P)]),
+    "bg_dp_comm_destroy": (_I32, [_P]),
+    "bg_dp_small_floats": (_U64, [_U32]),
+    "bg_dp_record_floats": (_U64, [_U32, _U32]),
+    "bg_dp_exchange": (_I32, [_P, _P, _P, _U32, _U32, _P, _P, _P, _U32]),
+    "bg_train_step_views_workspace_bytes": (_U64, [_U32, _U32, _U32, _U32, _U32, _U32]),
+    "bg_train_step_views": (_I32, [_P, _P, _P, C.POINTER(BgTrainViewsArgs)]),
+    "bg_refine_workspace_bytes": (_U64, [_U32]),
+    "bg_refine": (_I32, [_P, _P, C.POINTER(BgRefineArgs), C.POINTER(BgRefineStats)]),
+    "bg_bounds_percentile": (_I32, [_P, _P, _U32, _P, _F, _P, _U64, C.POINTER(_F)]),
     "bg_compute_min_scale": (_I32, [_P, _P, _U32, _P, _P, _U32, _F, _P]),
     "bg_fold_min_scale_forward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),
     "bg_fold_min_scale_backward": (_I32, [_P, _P, _U32, _P, _P, _P, _P, _P]),

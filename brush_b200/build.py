@@ -34,6 +34,9 @@ SOURCES = {
     "blend_bwd.cu": [],
     "loss.cu": [],
     "optim.cu": [],
+    "update.cu": ["-fmad=false"],
+    "dp.cu": [],
+    "refine.cu": ["-fmad=false"],
 }
 
 
@@ -80,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES.items()))
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -11,6 +11,9 @@
 
 #include "bg_common.cuh"
 #include "bg_project.cuh"
+#include "bg_dp.cuh"
+#include "bg_update.cuh"
+#include "bg_refine.cuh"
 
 namespace bg {
 // project.cu
@@ -593,6 +596,49 @@ extern "C" int32_t bg_normal_noise(BgContext *c, void *stream, uint64_t seed, ui
     return BG_OK;
 }
 
+// compiler-rt __powisf2 is defined above (powi_f32).  Fills the step-dependent constants of the update pass.
+static void fill_update_consts(UpdateParams &P, float lr_mean, float lr_rotation, float lr_scale, float lr_coeffs_dc,
+                               float lr_coeffs_sh_scale, float lr_opac, float noise_scale, float median_scale, uint64_t seed,
+                               int32_t step, uint32_t n) {
+    for (int i = 0; i < 10; i++) P.lr_t[i] = i < 3 ? lr_mean : (i < 7 ? lr_rotation : lr_scale);   // train.rs:328-350
+    P.lr_sh_dc = 1.0f * lr_coeffs_dc;                                   // lr_scale_per_col * lr, as AdamScaled forms it
+    P.lr_sh_rest = (1.0f / lr_coeffs_sh_scale) * lr_coeffs_dc;
+    P.lr_opac = lr_opac;
+    P.beta1 = 0.9f; P.beta2 = 0.999f; P.eps = 1e-15f; P.f1 = 1.0f - P.beta1; P.f2 = 1.0f - P.beta2;
+    P.bc1 = 1.0f - powi_f32(P.beta1, step); P.bc2 = 1.0f - powi_f32(P.beta2, step);
+    P.first = step == 1;
+    P.noisy = noise_scale != 0.0f;
+    P.noise_scale = noise_scale; P.median_scale = median_scale;
+    P.seed = seed;
+    P.noise_offset = (unsigned long long)(step - 1) * (((unsigned long long)n * 3 + 3) / 4);
+}
+
+extern "C" int32_t bg_train_update(BgContext *c, void *stream, const BgTrainUpdateArgs *a) {
+    if (!c || !a) return BG_ERR_NULL;
+    if (a->n == 0) return BG_OK;
+    if (!a->transforms || !a->sh || !a->raw_opac || !a->m_t || !a->v_t || !a->m_sh || !a->v_sh || !a->m_o || !a->v_o ||
+        !a->refine_norm || !a->vis_weight || !a->max_screen || !a->v_transforms || !a->v_sh_grad || !a->v_raw_opac ||
+        !a->v_refine || !a->visible || !a->max_radius)
+        return BG_ERR_NULL;
+    const int deg = sh_degree_from_k(a->k);
+    if (deg < 0) { set_err("Invalid nr. of sh bases", cudaSuccess); return BG_ERR_INVALID; }
+    if (a->step < 1) { set_err("bg_train_update: step is 1-based", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    UpdateParams P;
+    memset(&P, 0, sizeof(P));
+    P.g_begin = 0; P.count = a->n;
+    P.transforms = a->transforms; P.sh = a->sh; P.raw_opac = a->raw_opac;
+    P.m_t = a->m_t; P.v_t = a->v_t; P.m_sh = a->m_sh; P.v_sh = a->v_sh; P.m_o = a->m_o; P.v_o = a->v_o;
+    P.refine_norm = a->refine_norm; P.vis_weight = a->vis_weight; P.max_screen = a->max_screen;
+    P.g_t = a->v_transforms; P.g_o = a->v_raw_opac; P.g_sh = a->v_sh_grad;
+    P.grad_scale = 1.0f; P.sh_grad_scale = 1.0f;
+    P.v_refine = a->v_refine; P.max_radius = a->max_radius; P.visible = a->visible;
+    fill_update_consts(P, a->lr_mean, a->lr_rotation, a->lr_scale, a->lr_coeffs_dc, a->lr_coeffs_sh_scale, a->lr_opac,
+                       a->noise_scale, a->median_scale, a->seed, a->step, a->n);
+    BG_CUDA(launch_train_update((cudaStream_t)stream, deg, P, false));
+    return BG_OK;
+}
+
 // ---- bg_train_step: SplatTrainer::step (brush-train/src/train.rs:176-429) as ONE call: every launch of the step on
 // the caller's stream, nothing read back, scratch from a caller-provided workspace.
 namespace {
@@ -662,17 +708,355 @@ extern "C" int32_t bg_train_step(BgContext *c, void *stream, BgTrainStepArgs *a)
     if (r != BG_OK) return r;
     r = bg_project_backward(c, stream, &a->cam, &a->state_out, a->transforms, a->sh, a->raw_opac, ws.v_combined, ws.v_t, ws.v_sh, ws.v_o, ws.v_r);
     if (r != BG_OK) return r;
-    // optimiser (train.rs:300-381): per-column LR for the transforms, DC vs higher-band LR for SH
-    BG_CUDA(launch_train_fill_lr(s, ws.t_lr, ws.sh_scale, k, a->lr_mean, a->lr_rotation, a->lr_scale, 1.0f / a->lr_coeffs_sh_scale));
-    r = bg_adam_step(c, stream, a->transforms, ws.v_t, a->m_t, a->v_t, n, 10, ws.t_lr, 1.0f, 0.9f, 0.999f, 1e-15f, a->step, 0);
+    // optimiser, refine statistics, mean noise (train.rs:280-416): one pass over the Gaussians
+    BgTrainUpdateArgs up;
+    memset(&up, 0, sizeof(up));
+    up.n = n; up.k = k;
+    up.transforms = a->transforms; up.sh = a->sh; up.raw_opac = a->raw_opac;
+    up.m_t = a->m_t; up.v_t = a->v_t; up.m_sh = a->m_sh; up.v_sh = a->v_sh; up.m_o = a->m_o; up.v_o = a->v_o;
+    up.refine_norm = a->refine_norm; up.vis_weight = a->vis_weight; up.max_screen = a->max_screen;
+    up.v_transforms = ws.v_t; up.v_sh_grad = ws.v_sh; up.v_raw_opac = ws.v_o;
+    up.v_refine = ws.v_r; up.visible = ws.visible; up.max_radius = ws.max_radius;
+    up.lr_mean = a->lr_mean; up.lr_rotation = a->lr_rotation; up.lr_scale = a->lr_scale; up.lr_coeffs_dc = a->lr_coeffs_dc;
+    up.lr_coeffs_sh_scale = a->lr_coeffs_sh_scale; up.lr_opac = a->lr_opac;
+    up.noise_scale = a->noise_scale; up.median_scale = a->median_scale; up.seed = a->seed; up.step = a->step;
+    return bg_train_update(c, stream, &up);
+}
+
+// ---- view-sharded data parallelism (dp.cu): communicator, exchange, the multi-view step
+struct BgDpComm { DpComm *c; };
+
+static int32_t nccl_fail(const char *what, int rc) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, rc < 0 ? "NCCL is not available (libnccl.so.2) or a CUDA call failed" : dp_nccl_error(rc));
+    return rc == -1 ? BG_ERR_UNSUPPORTED : BG_ERR_CUDA;
+}
+
+extern "C" int32_t bg_dp_unique_id(uint8_t *out_id) {
+    if (!out_id) return BG_ERR_NULL;
+    NcclUniqueId id;
+    const int rc = dp_unique_id(&id);
+    if (rc != 0) return nccl_fail("bg_dp_unique_id", rc);
+    memcpy(out_id, id.internal, BG_DP_UNIQUE_ID_BYTES);
+    return BG_OK;
+}
+
+extern "C" int32_t bg_dp_comm_create(BgContext *c, const uint8_t *id_bytes, int32_t rank, int32_t world, BgDpComm **out) {
+    if (!c || !id_bytes || !out) return BG_ERR_NULL;
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) { set_err("bg_dp_comm_create: rank/world", cudaSuccess); return BG_ERR_INVALID; }
+    NcclUniqueId id;
+    memcpy(id.internal, id_bytes, BG_DP_UNIQUE_ID_BYTES);
+    int rc = 0;
+    DpComm *d = dp_comm_create(c->device, id, rank, world, &rc);
+    if (!d) return nccl_fail("bg_dp_comm_create", rc ? rc : -2);
+    BgDpComm *h = new (std::nothrow) BgDpComm();
+    if (!h) { dp_comm_destroy(d); return BG_ERR_CUDA; }
+    h->c = d;
+    *out = h;
+    return BG_OK;
+}
+
+extern "C" int32_t bg_dp_comm_destroy(BgDpComm *h) {
+    if (!h) return BG_ERR_NULL;
+    dp_comm_destroy(h->c);
+    delete h;
+    return BG_OK;
+}
+
+extern "C" uint64_t bg_dp_small_floats(uint32_t n) { return (uint64_t)12 * n; }
+extern "C" uint64_t bg_dp_record_floats(uint32_t n, uint32_t local) { return ((uint64_t)3 * local + 2) * n; }
+
+// Issues all slices of the exchange on the communicator's stream behind `s`; s waits for slice c through ev_chunk[c].
+static int32_t issue_exchange(DpComm *d, cudaStream_t s, uint32_t n, uint32_t local, uint32_t chunks, float *small,
+                              const float *record, float *recv, const float *hdr, float *hdr_all) {
+    BG_CUDA(cudaEventRecord(d->ev_ready, s));
+    BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
+    if (hdr) {
+        const int rc = dp_exchange_header(d, local, hdr, hdr_all);
+        if (rc != 0) return nccl_fail("exchange (camera positions)", rc);
+    }
+    for (uint32_t ch = 0; ch < chunks; ch++) {
+        const int rc = dp_exchange_chunk(d, n, local, chunks, ch, small, record, recv);
+        if (rc != 0) return nccl_fail("exchange", rc);
+    }
+    return BG_OK;
+}
+
+extern "C" int32_t bg_dp_exchange(BgContext *c, BgDpComm *h, void *stream, uint32_t n, uint32_t local, float *small,
+                                  const float *record, float *recv, uint32_t chunks) {
+    if (!c || !h || !small || !record || !recv) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (local == 0 || local * (uint32_t)h->c->world > DP_MAX_VIEWS || chunks == 0 || chunks > DP_MAX_CHUNKS) {
+        set_err("bg_dp_exchange: 1..16 views in total, 1..16 chunks", cudaSuccess);
+        return BG_ERR_INVALID;
+    }
+    BG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t r = issue_exchange(h->c, s, n, local, chunks, small, record, recv, nullptr, nullptr);
     if (r != BG_OK) return r;
-    r = bg_adam_step(c, stream, a->sh, ws.v_sh, a->m_sh, a->v_sh, n, k * 3, ws.sh_scale, a->lr_coeffs_dc, 0.9f, 0.999f, 1e-15f, a->step, 1);
-    if (r != BG_OK) return r;
-    r = bg_adam_step(c, stream, a->raw_opac, ws.v_o, a->m_o, a->v_o, n, 1, nullptr, a->lr_opac, 0.9f, 0.999f, 1e-15f, a->step, 0);
-    if (r != BG_OK) return r;
-    // refine statistics + mean noise on the updated opacities (train.rs:280-298, 389-416)
-    const bool noisy = a->noise_scale != 0.0f;
-    if (noisy) BG_CUDA(launch_normal_noise(s, a->seed, (uint64_t)(a->step - 1) * (((uint64_t)n * 3 + 3) / 4), (uint64_t)n * 3, ws.noise));
-    return bg_refine_stats_noise(c, stream, n, ws.v_r, ws.visible, ws.max_radius, a->refine_norm, a->vis_weight, a->max_screen,
-                                 a->transforms, a->raw_opac, noisy ? ws.noise : nullptr, a->noise_scale, a->median_scale);
+    for (uint32_t ch = 0; ch < chunks; ch++) BG_CUDA(cudaStreamWaitEvent(s, h->c->ev_chunk[ch], 0));
+    return BG_OK;
+}
+
+namespace {
+struct ViewsWs {
+    float *out_img, *v_output, *partials, *loss_terms, *v_combined, *small, *tmp_small, *record, *recv, *hdr, *hdr_all;
+    float *r_transforms, *r_opac, *vis_view, *refine_view, *radius_view;
+    uint64_t bytes;
+};
+ViewsWs carve_views_ws(void *base, uint32_t n, uint32_t k, uint32_t w, uint32_t h, uint32_t local, uint32_t world, bool fold) {
+    uint64_t off = 0;
+    auto take = [&](uint64_t floats) {
+        float *p = base ? reinterpret_cast<float *>(static_cast<char *>(base) + off) : nullptr;
+        off += (floats * 4 + 255) / 256 * 256;
+        return p;
+    };
+    (void)k;
+    ViewsWs ws;
+    const uint64_t px = (uint64_t)w * h;
+    const DpLayout L = dp_layout(n, local, world);
+    ws.out_img = take(px * 4);
+    ws.v_output = take(px * 4);
+    ws.partials = take(bg_image_loss_num_partials(4, h, w));
+    ws.loss_terms = take(DP_MAX_VIEWS);
+    ws.v_combined = take((uint64_t)n * BG_VCOMBINED_STRIDE);
+    ws.small = take(L.small_floats);
+    ws.tmp_small = take(local > 1 ? L.small_floats : 0);
+    ws.record = take(L.rec_floats);
+    ws.recv = take(world > 1 ? L.recv_floats : 0);
+    ws.hdr = take(DP_MAX_VIEWS * 4);
+    ws.hdr_all = take(DP_MAX_VIEWS * 4);
+    ws.r_transforms = take(fold ? (uint64_t)n * 10 : 0);
+    ws.r_opac = take(fold ? n : 0);
+    ws.vis_view = take(local > 1 ? n : 0);
+    ws.refine_view = take(local > 1 ? n : 0);
+    ws.radius_view = take(local > 1 ? n : 0);
+    ws.bytes = off;
+    return ws;
+}
+}  // namespace
+
+namespace bg {
+cudaError_t launch_loss_mean(cudaStream_t, const float *, uint32_t, float *);
+}
+
+extern "C" uint64_t bg_train_step_views_workspace_bytes(uint32_t n, uint32_t k, uint32_t w, uint32_t h, uint32_t local,
+                                                        uint32_t world) {
+    return carve_views_ws(nullptr, n, k, w, h, std::max(local, 1u), std::max(world, 1u), true).bytes;
+}
+
+extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, BgTrainViewsArgs *a) {
+    if (!c || !a) return BG_ERR_NULL;
+    if (!a->transforms || !a->sh || !a->raw_opac || !a->m_t || !a->v_t || !a->m_sh || !a->v_sh || !a->m_o || !a->v_o ||
+        !a->refine_norm || !a->vis_weight || !a->max_screen || !a->cams || !a->gt_packed || !a->workspace || !a->loss_out)
+        return BG_ERR_NULL;
+    const uint32_t n = a->n, k = a->k, w = a->w, hh = a->h, local = a->local_views;
+    const uint32_t world = h ? (uint32_t)h->c->world : 1u, rank = h ? (uint32_t)h->c->rank : 0u;
+    const uint32_t views = local * world;
+    if (local == 0 || views > DP_MAX_VIEWS) { set_err("bg_train_step_views: 1..16 views per step in total", cudaSuccess); return BG_ERR_INVALID; }
+    if (a->step < 1) { set_err("bg_train_step_views: step is 1-based", cudaSuccess); return BG_ERR_INVALID; }
+    if (a->channels != 3 && a->channels != 4) { set_err("bg_train_step_views: channels must be 3 or 4", cudaSuccess); return BG_ERR_INVALID; }
+    if ((uintptr_t)a->workspace % 256) { set_err("bg_train_step_views: workspace must be 256-byte aligned", cudaSuccess); return BG_ERR_INVALID; }
+    const int deg = sh_degree_from_k(k);
+    if (deg < 0) { set_err("Invalid nr. of sh bases", cudaSuccess); return BG_ERR_INVALID; }
+    for (uint32_t i = 0; i < local; i++)
+        if (!a->gt_packed[i]) return BG_ERR_NULL;
+    const bool fold = a->min_scale != nullptr;
+    const ViewsWs ws = carve_views_ws(a->workspace, n, k, w, hh, local, world, fold);
+    if (ws.bytes > a->workspace_bytes) { set_err("bg_train_step_views: workspace too small (bg_train_step_views_workspace_bytes)", cudaSuccess); return BG_ERR_CAPACITY; }
+    uint32_t chunks = a->chunks ? a->chunks : (world > 1 ? 4u : 1u);
+    if (world == 1) chunks = 1;
+    if (chunks > DP_MAX_CHUNKS) { set_err("bg_train_step_views: at most 16 chunks", cudaSuccess); return BG_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    const DpLayout L = dp_layout(n, local, world);
+    int32_t r;
+    // the 3D-filter floor folded into what the renderer sees (bwd/burn_glue.rs:260-270)
+    const float *r_t = a->transforms, *r_o = a->raw_opac;
+    if (fold) {
+        r = bg_fold_min_scale_forward(c, stream, n, a->transforms, a->raw_opac, a->min_scale, ws.r_transforms, ws.r_opac);
+        if (r != BG_OK) return r;
+        r_t = ws.r_transforms; r_o = ws.r_opac;
+    }
+    const float npx = (float)w * (float)hh;
+    float chain[4] = {1.0f / (3.0f * npx), 1.0f / (3.0f * npx), 1.0f / (3.0f * npx), a->channels == 4 ? a->alpha_weight / npx : 0.0f};
+    BG_CUDA(cudaMemsetAsync(ws.v_output, 0, (size_t)w * hh * 4 * sizeof(float), s));
+    float *small_t = ws.small, *small_o = ws.small + (size_t)n * 10, *small_vis = ws.small + (size_t)n * 11;
+    float *rec_refine = ws.record + L.rec_refine, *rec_radius = ws.record + L.rec_radius;
+    DpHeader hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    for (uint32_t i = 0; i < local; i++) {
+        const bool first = i == 0;
+        const BgCamera *cam = a->cams + i;
+        for (int q = 0; q < 3; q++) hdr.pos[i][q] = cam->cam_pos[q];
+        float *vis = first ? small_vis : ws.vis_view, *rad = first ? rec_radius : ws.radius_view;
+        r = bg_render_forward(c, stream, cam, w, hh, n, k, r_t, a->sh, r_o, a->mip, a->background, BG_PASS_BACKWARD, ws.out_img, vis, rad,
+                              &a->state_out);
+        if (r != BG_OK) return r;
+        r = bg_image_loss_fused(c, stream, ws.out_img, a->gt_packed[i], a->channels, hh, w, 1, (int64_t)w * 4, 4, a->l1_weight,
+                                a->ssim_weight, a->has_composite_bg ? a->composite_bg : nullptr, a->mask, chain, ws.v_output, ws.partials);
+        if (r != BG_OK) return r;
+        BG_CUDA(launch_loss_reduce(s, ws.partials, a->channels, bg_image_loss_num_partials(a->channels, hh, w) / a->channels, chain,
+                                   ws.loss_terms + i));
+        r = bg_rasterize_backward(c, stream, &a->state_out, ws.out_img, ws.v_output, a->background, 0, ws.v_combined, n);
+        if (r != BG_OK) return r;
+        r = bg_project_backward_factored(c, stream, cam, &a->state_out, r_t, a->sh, r_o, ws.v_combined, first ? small_t : ws.tmp_small,
+                                         ws.record + (size_t)i * n * 3, first ? small_o : ws.tmp_small + (size_t)n * 10,
+                                         first ? rec_refine : ws.refine_view);
+        if (r != BG_OK) return r;
+        if (!first)
+            BG_CUDA(launch_accumulate_view(s, n, ws.small, ws.tmp_small, ws.vis_view, rec_refine, ws.refine_view, rec_radius, ws.radius_view));
+    }
+    BG_CUDA(launch_loss_mean(s, ws.loss_terms, local, a->loss_out));
+    // ---- exchange (slices on the communicator's stream) and the update pass slice by slice under it
+    const float *colours_base = ws.record, *cam_all = ws.hdr;
+    BG_CUDA(launch_write_header(s, ws.hdr, hdr, local));
+    if (world > 1) {
+        r = issue_exchange(h->c, s, n, local, chunks, ws.small, ws.record, ws.recv, ws.hdr, ws.hdr_all);
+        if (r != BG_OK) return r;
+        colours_base = ws.recv; cam_all = ws.hdr_all;
+    }
+    (void)rank;
+    UpdateParams P;
+    memset(&P, 0, sizeof(P));
+    P.transforms = a->transforms; P.sh = a->sh; P.raw_opac = a->raw_opac;
+    P.m_t = a->m_t; P.v_t = a->v_t; P.m_sh = a->m_sh; P.v_sh = a->v_sh; P.m_o = a->m_o; P.v_o = a->v_o;
+    P.refine_norm = a->refine_norm; P.vis_weight = a->vis_weight; P.max_screen = a->max_screen;
+    P.g_t = small_t; P.g_o = small_o; P.visible = small_vis;
+    P.grad_scale = 1.0f / (float)views; P.sh_grad_scale = 1.0f / (float)views;
+    P.cam_all = cam_all; P.views = views; P.local = local; P.world = world;
+    fill_update_consts(P, a->lr_mean, a->lr_rotation, a->lr_scale, a->lr_coeffs_dc, a->lr_coeffs_sh_scale, a->lr_opac, a->noise_scale,
+                       a->median_scale, a->seed, a->step, n);
+    for (uint32_t ch = 0; ch < chunks; ch++) {
+        uint32_t g0, len;
+        dp_chunk_range(n, chunks, ch, &g0, &len);
+        if (world > 1) BG_CUDA(cudaStreamWaitEvent(s, h->c->ev_chunk[ch], 0));
+        if (len == 0) continue;
+        if (fold) {   // chain the gradients w.r.t. the folded values back to the learned ones (linear: after the sum)
+            r = bg_fold_min_scale_backward(c, stream, len, a->transforms + (size_t)g0 * 10, a->raw_opac + g0, a->min_scale + g0,
+                                           small_t + (size_t)g0 * 10, small_o + g0);
+            if (r != BG_OK) return r;
+        }
+        const float *base = colours_base + L.chunk_base(g0);
+        P.g_begin = g0; P.count = len;
+        P.colours = base + L.colour_off(len, 0);
+        P.refine_all = base + L.refine_off(len);
+        P.radius_all = base + L.radius_off(len);
+        BG_CUDA(launch_train_update(s, deg, P, true));
+    }
+    return BG_OK;
+}
+
+// ---- refine (refine.cu): every decision on the device, one readback of the counts at the end
+namespace {
+struct RefineWs {
+    uint32_t *ctl, *keep, *keep_incl, *keys, *vals, *keys_s, *vals_s, *split, *cand, *cand_incl, *split_incl;
+    float *refine_norm, *vis_weight, *max_screen, *bounds_out;
+    uint64_t bytes;
+};
+RefineWs carve_refine_ws(void *base, uint32_t n) {
+    uint64_t off = 0;
+    auto take = [&](uint64_t words) {
+        uint32_t *p = base ? reinterpret_cast<uint32_t *>(static_cast<char *>(base) + off) : nullptr;
+        off += (words * 4 + 255) / 256 * 256;
+        return p;
+    };
+    RefineWs w;
+    w.ctl = take(64);
+    w.keep = take(n); w.keep_incl = take(n); w.keys = take(n); w.vals = take(n); w.keys_s = take(n); w.vals_s = take(n);
+    w.split = take(n); w.cand = take(n); w.cand_incl = take(n); w.split_incl = take(n);
+    w.refine_norm = reinterpret_cast<float *>(take(n)); w.vis_weight = reinterpret_cast<float *>(take(n));
+    w.max_screen = reinterpret_cast<float *>(take(n));
+    w.bounds_out = reinterpret_cast<float *>(take(16));
+    w.bytes = off;
+    return w;
+}
+}  // namespace
+
+extern "C" uint64_t bg_refine_workspace_bytes(uint32_t n) { return carve_refine_ws(nullptr, std::max(n, 1u)).bytes; }
+
+extern "C" int32_t bg_refine(BgContext *c, void *stream, const BgRefineArgs *a, BgRefineStats *out) {
+    if (!c || !a || !out) return BG_ERR_NULL;
+    memset(out, 0, sizeof(*out));
+    const uint32_t n0 = a->n;
+    if (n0 == 0) return BG_OK;
+    if (!a->transforms || !a->sh || !a->raw_opac || !a->m_t || !a->v_t || !a->m_sh || !a->v_sh || !a->m_o || !a->v_o ||
+        !a->refine_norm || !a->vis_weight || !a->max_screen || !a->transforms_out || !a->sh_out || !a->raw_opac_out ||
+        !a->m_t_out || !a->v_t_out || !a->m_sh_out || !a->v_sh_out || !a->m_o_out || !a->v_o_out || !a->workspace)
+        return BG_ERR_NULL;
+    if (sh_degree_from_k(a->k) < 0) { set_err("Invalid nr. of sh bases", cudaSuccess); return BG_ERR_INVALID; }
+    if (a->capacity < n0) { set_err("bg_refine: capacity smaller than n", cudaSuccess); return BG_ERR_CAPACITY; }
+    if ((uintptr_t)a->workspace % 256) { set_err("bg_refine: workspace must be 256-byte aligned", cudaSuccess); return BG_ERR_INVALID; }
+    const RefineWs w = carve_refine_ws(a->workspace, n0);
+    if (w.bytes > a->workspace_bytes) { set_err("bg_refine: workspace too small (bg_refine_workspace_bytes)", cudaSuccess); return BG_ERR_CAPACITY; }
+    if (n0 > std::max(c->max_n, c->max_isect)) { set_err("bg_refine: n exceeds the context's sort capacity", cudaSuccess); return BG_ERR_CAPACITY; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    const uint32_t kf = a->k * 3;
+    RefinePtrs p;
+    p.transforms = a->transforms; p.sh = a->sh; p.raw_opac = a->raw_opac; p.m_t = a->m_t; p.v_t = a->v_t; p.m_sh = a->m_sh;
+    p.v_sh = a->v_sh; p.m_o = a->m_o; p.v_o = a->v_o; p.refine_norm = a->refine_norm; p.vis_weight = a->vis_weight; p.max_screen = a->max_screen;
+    p.transforms_out = a->transforms_out; p.sh_out = a->sh_out; p.raw_opac_out = a->raw_opac_out; p.m_t_out = a->m_t_out;
+    p.v_t_out = a->v_t_out; p.m_sh_out = a->m_sh_out; p.v_sh_out = a->v_sh_out; p.m_o_out = a->m_o_out; p.v_o_out = a->v_o_out;
+    p.refine_norm_tmp = w.refine_norm; p.vis_weight_tmp = w.vis_weight; p.max_screen_tmp = w.max_screen;
+    int32_t r;
+    BG_CUDA(cudaMemsetAsync(w.ctl, 0, 64 * sizeof(uint32_t), s));
+    BG_CUDA(cudaMemsetAsync(w.split, 0, (size_t)n0 * sizeof(uint32_t), s));
+    // prune mask -> flag scan -> compaction of all rows (train.rs:487-535, 848-893)
+    BG_CUDA(launch_refine_classify(s, n0, kf, a->transforms, a->sh, a->raw_opac, a->bounds_center, a->max_allowed, w.keep, w.ctl));
+    if ((r = bg_inclusive_scan_u32(c, stream, w.keep, n0, w.keep_incl)) != BG_OK) return r;
+    BG_CUDA(launch_refine_plan_prune(s, n0, w.keep_incl, w.ctl));
+    BG_CUDA(launch_refine_compact(s, n0, kf, p, w.keep, w.keep_incl, w.ctl));
+    const uint64_t stream_base = (uint64_t)a->refine_index * 2;
+    // replace the pruned splats: sample `pruned` survivors by opacity x visibility (train.rs:544-556)
+    BG_CUDA(launch_refine_keys(s, n0, 0, p, 0.0f, a->seed, stream_base, w.keys, w.vals, w.ctl));
+    if ((r = bg_radix_argsort_u32(c, stream, w.keys, w.vals, n0, w.ctl + RC_N, 32, w.keys_s, w.vals_s)) != BG_OK) return r;
+    BG_CUDA(launch_refine_mark_topk(s, n0, w.vals_s, RC_PRUNED, RC_POS0, RC_SPLIT_REPLACE, w.split, w.ctl));
+    // force-split what is too big on screen, in index order, within the max_splats budget (train.rs:562-586)
+    BG_CUDA(launch_refine_oversize_flags(s, n0, a->split_at_screen_size, p, w.split, w.cand, w.ctl));
+    if ((r = bg_inclusive_scan_u32(c, stream, w.cand, n0, w.cand_incl)) != BG_OK) return r;
+    BG_CUDA(launch_refine_oversize_mark(s, n0, a->max_splats, w.cand, w.cand_incl, w.split, w.ctl));
+    // growth: sample among the splats whose refine weight is above the threshold (train.rs:590-632)
+    BG_CUDA(launch_refine_keys(s, n0, 1, p, a->growth_grad_threshold, a->seed, stream_base + 1, w.keys, w.vals, w.ctl));
+    BG_CUDA(launch_refine_plan_growth(s, a->growth_select_fraction, a->max_splats, a->growth_enabled != 0, w.ctl));
+    if ((r = bg_radix_argsort_u32(c, stream, w.keys, w.vals, n0, w.ctl + RC_N, 32, w.keys_s, w.vals_s)) != BG_OK) return r;
+    BG_CUDA(launch_refine_mark_topk(s, n0, w.vals_s, RC_GROW, RC_POS1, RC_SPLIT_GROWTH, w.split, w.ctl));
+    // split (refine_splats, train.rs:665-821) and opacity decay (:808-816)
+    if ((r = bg_inclusive_scan_u32(c, stream, w.split, n0, w.split_incl)) != BG_OK) return r;
+    BG_CUDA(launch_refine_plan_split(s, n0, w.split_incl, a->capacity, w.ctl));
+    BG_CUDA(launch_refine_split(s, n0, kf, a->capacity, a->split_at_screen_size, p, w.split, w.split_incl, w.ctl));
+    BG_CUDA(launch_refine_decay(s, a->capacity, a->opac_decay_minus, a->raw_opac_out, w.ctl));
+    uint32_t host[RC_WORDS];
+    BG_CUDA(cudaMemcpyAsync(host, w.ctl, sizeof(host), cudaMemcpyDeviceToHost, s));
+    BG_CUDA(cudaStreamSynchronize(s));
+    out->num_added = host[RC_REFINE_COUNT];
+    out->num_split_oversized = host[RC_SPLIT_OVERSIZED];
+    out->num_split_high_grad = host[RC_SPLIT_GROWTH];
+    out->num_pruned = host[RC_PRUNED];
+    out->num_pruned_non_finite = host[RC_NON_FINITE];
+    out->total_splats = host[RC_N_NEW];
+    if (host[RC_OVERFLOW]) { set_err("bg_refine: capacity of the destination arrays exceeded", cudaSuccess); return BG_ERR_CAPACITY; }
+    return BG_OK;
+}
+
+extern "C" int32_t bg_bounds_percentile(BgContext *c, void *stream, uint32_t n, const float *transforms, float percentile,
+                                        void *workspace, uint64_t workspace_bytes, float *out6) {
+    if (!c || !out6) return BG_ERR_NULL;
+    for (int i = 0; i < 6; i++) out6[i] = 0.0f;
+    if (n == 0) return BG_OK;
+    if (!transforms || !workspace) return BG_ERR_NULL;
+    const RefineWs w = carve_refine_ws(workspace, n);
+    if (w.bytes > workspace_bytes) { set_err("bg_bounds_percentile: workspace too small (bg_refine_workspace_bytes)", cudaSuccess); return BG_ERR_CAPACITY; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(cudaMemsetAsync(w.ctl, 0, 64 * sizeof(uint32_t), s));
+    for (int axis = 0; axis < 3; axis++) {
+        BG_CUDA(launch_bounds_keys(s, n, axis, transforms, w.keys, w.vals, w.ctl + axis));
+        int32_t r = bg_radix_argsort_u32(c, stream, w.keys, w.vals, n, nullptr, 32, w.keys_s, w.vals_s);
+        if (r != BG_OK) return r;
+        BG_CUDA(launch_bounds_pick(s, w.keys_s, w.ctl + axis, percentile, w.bounds_out + 2 * axis));
+    }
+    BG_CUDA(cudaMemcpyAsync(out6, w.bounds_out, 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BG_CUDA(cudaStreamSynchronize(s));
+    return BG_OK;
 }

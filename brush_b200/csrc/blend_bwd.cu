@@ -24,7 +24,9 @@
 
 namespace bg {
 
-constexpr int BROW = 32;          // floats per staged row: 16 of the projected row (fixed up) + id + 10 factors
+constexpr int BROW = 28;          // floats per staged row: 16 of the projected row (fixed up, id in lane 12) + 10 factors.
+                                  // 112 B: consecutive rows start 28 banks apart, so the per-lane fix-up accesses
+                                  // (one row per lane, 128 bits each) are conflict free, and 7 CTAs fit one SM
 constexpr int BROW_ID = 12;       // compact Gaussian id (bits)
 constexpr int BROW_FACT = 16;     // ten post-reduction factors
 
@@ -39,7 +41,7 @@ blend_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *_
                  const float4 *__restrict__ v_output, const uint32_t *__restrict__ live_masks,
                  const uint32_t *__restrict__ warp_batches, float *__restrict__ v_combined,
                  unsigned long long *__restrict__ stats, BlendUniforms u) {
-    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * BROW];  // per warp, double buffered: 32 KB
+    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * BROW];  // per warp, double buffered: 28 KB
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;

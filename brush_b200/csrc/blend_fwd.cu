@@ -21,7 +21,10 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
                  const float *__restrict__ projected, const uint32_t *__restrict__ gid_from_cgid,
                  float4 *__restrict__ out_f32, uint32_t *__restrict__ out_packed, float *__restrict__ visible,
                  uint32_t *__restrict__ live_masks, uint32_t *__restrict__ warp_batches, BlendUniforms u) {
-    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * ROW];  // per warp, double buffered
+    // staged rows are 80 bytes apart (the 64-byte projected row + 16 bytes of padding): one row per lane at 128 bits
+    // each is then free of bank conflicts in the per-lane phase (block test + colour clamp)
+    constexpr int SROW = ROW + 4;
+    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * SROW];  // per warp, double buffered
     __shared__ uint32_t s_max_useful;
 
     const uint32_t tile = blockIdx.x;
@@ -56,7 +59,7 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
             uint32_t id = __ldg(cgid_from_isect + idx);
             next_id = id;
             const float *src = projected + (size_t)id * ROW;
-            float *dst = &s_rows[wid][b & 1u][lane * ROW];
+            float *dst = &s_rows[wid][b & 1u][lane * SROW];
             cp_async16(dst, src);
             cp_async16(dst + 4, src + 4);
             cp_async16(dst + 8, src + 8);
@@ -81,7 +84,7 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
             const float *rows = s_rows[wid][b & 1u];
             bool hit = false;
             if (lane < count) {
-                float *mine = s_rows[wid][b & 1u] + lane * ROW;
+                float *mine = s_rows[wid][b & 1u] + lane * SROW;
                 const float4 A = *reinterpret_cast<const float4 *>(mine);
                 const float4 B = *reinterpret_cast<const float4 *>(mine + 4);
                 const float bcol = mine[8], pt = mine[ROW_PT];
@@ -95,7 +98,7 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
             while (bits) {
                 const uint32_t s = (uint32_t)__ffs(bits) - 1u;
                 bits &= bits - 1u;
-                const float *row = rows + s * ROW;
+                const float *row = rows + s * SROW;
                 const float4 A = *reinterpret_cast<const float4 *>(row);       // mx my a b
                 const float4 B = *reinterpret_cast<const float4 *>(row + 4);   // c opac r g
                 const float4 C = *reinterpret_cast<const float4 *>(row + 8);   // b_col, then log2(e)-scaled c/2, a/2, b

@@ -1,0 +1,196 @@
+// dp.cu -- view-sharded data parallelism behind the C ABI (the reference is single-device).
+//
+// Parameters are replicated, every rank renders its own views of the step's batch, and ONE exchange per step makes
+// the gradient of the mean-over-views loss available on every rank:
+//   small  = v_transforms [n,10] | v_raw_opac [n] | visible [n]   summed over the rank's views  -> all-reduce (SUM)
+//   record = v_color [local,n,3] | v_refine [n] | max_radius [n]  (the MAX statistics over the rank's views)
+//                                                                                               -> all-gather
+// The SH gradient of one view is rank one per Gaussian (update.cu), so the views' colour gradients (12 B per
+// Gaussian and view) replace the dense [n,K,3] gradient (192 B at K=16) on the wire; the optimiser pass rebuilds it in
+// registers in global view order (view = rank * local + i), which makes the update bit-identical on every rank.
+//
+// Overlap: the exchange is issued on the communicator's own stream in `chunks` slices of the Gaussian range, each
+// slice's collectives in one NCCL group; the optimiser pass of slice c runs on the caller's stream as soon as slice c
+// has arrived, under the transfer of slice c+1.  The receive buffer is laid out per slice
+//   [local][world][len,3] colours | [world][len] refine | [world][len] radius
+// so that every all-gather lands contiguously.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy already loaded by the host process -- torch's in the
+// Python mirror -- or the system one), so the library itself links against nothing but the CUDA runtime.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "bg_common.cuh"
+#include "bg_dp.cuh"
+
+namespace bg {
+
+// ---- minimal NCCL surface (stable since NCCL 2.x)
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;
+
+static NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);   // the copy the process already holds
+        if (api.handle) break;
+    }
+    if (!api.handle)
+        for (const char *nm : names) {
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+    if (!api.handle) return api;
+#define BG_SYM(field, name) *(void **)(&api.field) = dlsym(api.handle, name)
+    BG_SYM(GetUniqueId, "ncclGetUniqueId");
+    BG_SYM(CommInitRank, "ncclCommInitRank");
+    BG_SYM(CommDestroy, "ncclCommDestroy");
+    BG_SYM(AllReduce, "ncclAllReduce");
+    BG_SYM(AllGather, "ncclAllGather");
+    BG_SYM(GroupStart, "ncclGroupStart");
+    BG_SYM(GroupEnd, "ncclGroupEnd");
+    BG_SYM(GetErrorString, "ncclGetErrorString");
+#undef BG_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GroupStart &&
+             api.GroupEnd && api.GetErrorString;
+    return api;
+}
+
+const char *dp_nccl_error(int code) {
+    NcclApi &a = nccl();
+    return a.ok ? a.GetErrorString(code) : "NCCL is not loaded";
+}
+
+int dp_unique_id(NcclUniqueId *out) {
+    NcclApi &a = nccl();
+    if (!a.ok) return -1;
+    return a.GetUniqueId(out);
+}
+
+DpComm *dp_comm_create(int device, const NcclUniqueId &id, int rank, int world, int *nccl_rc) {
+    *nccl_rc = 0;
+    NcclApi &a = nccl();
+    if (!a.ok) { *nccl_rc = -1; return nullptr; }
+    DpComm *c = new (std::nothrow) DpComm();
+    if (!c) return nullptr;
+    c->device = device; c->rank = rank; c->world = world;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return nullptr; }
+    int rc = a.CommInitRank(&c->comm, world, id, rank);
+    if (rc != 0) { *nccl_rc = rc; delete c; return nullptr; }
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < DP_MAX_CHUNKS && ok; i++) ok = cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { dp_comm_destroy(c); return nullptr; }
+    return c;
+}
+
+void dp_comm_destroy(DpComm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    NcclApi &a = nccl();
+    if (c->comm && a.ok) a.CommDestroy(c->comm);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    for (int i = 0; i < DP_MAX_CHUNKS; i++)
+        if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// Gaussian range of slice c of `chunks` (multiples of 64 rows so that every slice pointer stays 256-byte aligned).
+void dp_chunk_range(uint32_t n, uint32_t chunks, uint32_t c, uint32_t *g0, uint32_t *len) {
+    const uint64_t per = (((uint64_t)n + chunks - 1) / chunks + 63) / 64 * 64;
+    const uint64_t a = std::min<uint64_t>(per * c, n), b = std::min<uint64_t>(per * (c + 1), n);
+    *g0 = (uint32_t)a;
+    *len = (uint32_t)(b - a);
+}
+
+// Enqueues slice `c` of the exchange on the communicator's stream (which must already wait on the producer of
+// `small` / `record`) and records ev_chunk[c] behind it.  Returns 0 or the failing NCCL / CUDA code (negative = CUDA).
+int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, uint32_t c, float *small,
+                      const float *record, float *recv) {
+    NcclApi &a = nccl();
+    uint32_t g0, len;
+    dp_chunk_range(n, chunks, c, &g0, &len);
+    const DpLayout L = dp_layout(n, local, (uint32_t)cm->world);
+    int rc = 0;
+    if (len > 0) {
+        float *base = recv + L.chunk_base(g0);
+        if ((rc = a.GroupStart()) != 0) return rc;
+        for (uint32_t li = 0; li < local && rc == 0; li++)
+            rc = a.AllGather(record + ((size_t)li * n + g0) * 3, base + L.colour_off(len, li), (size_t)len * 3, NCCL_FLOAT32,
+                             cm->comm, cm->stream);
+        if (rc == 0) rc = a.AllGather(record + L.rec_refine + g0, base + L.refine_off(len), len, NCCL_FLOAT32, cm->comm, cm->stream);
+        if (rc == 0) rc = a.AllGather(record + L.rec_radius + g0, base + L.radius_off(len), len, NCCL_FLOAT32, cm->comm, cm->stream);
+        if (rc == 0) rc = a.AllReduce(small + (size_t)g0 * 10, small + (size_t)g0 * 10, (size_t)len * 10, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+        if (rc == 0) rc = a.AllReduce(small + (size_t)n * 10 + g0, small + (size_t)n * 10 + g0, len, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+        if (rc == 0) rc = a.AllReduce(small + (size_t)n * 11 + g0, small + (size_t)n * 11 + g0, len, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+        const int rc_end = a.GroupEnd();
+        if (rc == 0) rc = rc_end;
+        if (rc != 0) return rc;
+    }
+    if (cudaEventRecord(cm->ev_chunk[c], cm->stream) != cudaSuccess) return -1;
+    return 0;
+}
+
+// The views' camera positions ([local][4] floats per rank) travel once per step, ahead of the slices.
+int dp_exchange_header(DpComm *cm, uint32_t local, const float *hdr, float *hdr_all) {
+    NcclApi &a = nccl();
+    return a.AllGather(hdr, hdr_all, (size_t)local * 4, NCCL_FLOAT32, cm->comm, cm->stream);
+}
+
+// ---- small device helpers of the multi-view step
+__global__ void write_header_kernel(float *hdr, DpHeader h, uint32_t local) {
+    const uint32_t i = threadIdx.x;
+    if (i < local * 4) hdr[i] = (i & 3u) < 3u ? h.pos[i >> 2][i & 3u] : 0.0f;
+}
+
+// accumulate one more local view: small += tmp (v_transforms, v_raw_opac), visible += view's flags,
+// refine / radius = max (stats.rs:40-50 over the rank's views)
+__global__ void __launch_bounds__(256)
+accumulate_view_kernel(uint32_t n, float *__restrict__ small, const float *__restrict__ tmp, const float *__restrict__ vis_view,
+                       float *__restrict__ refine, const float *__restrict__ refine_view, float *__restrict__ radius,
+                       const float *__restrict__ radius_view) {
+    const size_t total = (size_t)n * 11;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        small[i] += tmp[i];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        small[(size_t)n * 11 + i] += vis_view[i];
+        refine[i] = fmaxf(refine[i], refine_view[i]);
+        radius[i] = fmaxf(radius[i], radius_view[i]);
+    }
+}
+
+cudaError_t launch_write_header(cudaStream_t s, float *hdr, const DpHeader &h, uint32_t local) {
+    write_header_kernel<<<1, 64, 0, s>>>(hdr, h, local);
+    return cudaGetLastError();
+}
+cudaError_t launch_accumulate_view(cudaStream_t s, uint32_t n, float *small, const float *tmp, const float *vis_view,
+                                   float *refine, const float *refine_view, float *radius, const float *radius_view) {
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n * 11 + 255) / 256, 148ull * 16);
+    accumulate_view_kernel<<<grid, 256, 0, s>>>(n, small, tmp, vis_view, refine, refine_view, radius, radius_view);
+    return cudaGetLastError();
+}
+
+}  // namespace bg

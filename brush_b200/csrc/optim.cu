@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "bg_common.cuh"
+#include "bg_rng.cuh"
 
 namespace bg {
 
@@ -295,31 +296,12 @@ cudaError_t launch_fold_min_scale_bwd(cudaStream_t s, uint32_t n, const float *t
 // ---- counter-based normal noise (Philox4x32-10 + Box-Muller).  The reference draws Tensor::random(Normal) from
 // burn's unseeded generator (train.rs:395-399: parity unpinned); a counter-based stream keyed by (seed, offset)
 // gives every data-parallel rank the same draw without any communication, and makes a train step replayable.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
-
 __global__ void __launch_bounds__(256)
 normal_noise_kernel(uint64_t seed, uint64_t offset, uint64_t count, float *__restrict__ out) {
     const uint64_t quads = (count + 3) / 4;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t ctr = offset + q;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
         float z[4];
-        const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
-        float s0, c0, s1, c1;
-        sincospif(2.0f * u01(r.y), &s0, &c0);
-        sincospif(2.0f * u01(r.w), &s1, &c1);
-        z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+        normal_quad(seed, offset + q, z);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (q * 4 + i < count) out[q * 4 + i] = z[i];
@@ -351,6 +333,16 @@ loss_reduce_kernel(const float *__restrict__ partials, uint32_t channels, uint32
         __syncthreads();
     }
     if (threadIdx.x == 0) *loss_out = s_red[0];
+}
+
+__global__ void loss_mean_kernel(const float *__restrict__ terms, uint32_t count, float *__restrict__ out) {
+    float s = 0.0f;
+    for (uint32_t i = 0; i < count; i++) s += terms[i];
+    *out = s * (1.0f / (float)count);
+}
+cudaError_t launch_loss_mean(cudaStream_t s, const float *terms, uint32_t count, float *out) {
+    loss_mean_kernel<<<1, 1, 0, s>>>(terms, count, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_normal_noise(cudaStream_t s, uint64_t seed, uint64_t offset, uint64_t count, float *out) {

@@ -312,31 +312,90 @@ load_colmap_text = load_colmap   # earlier name
 
 
 class SceneLoader:
-    """Double-buffered pinned staging of the packed views: `next_batch()` returns a SceneBatch whose image is a
-    pinned host tensor (uploaded by SplatTrainer.step with a non-blocking copy) while the following view is decoded."""
+    """Threaded prefetch + packed-batch cache (brush-dataset/src/scene_loader.rs:13-170).
 
-    def __init__(self, views: Sequence[SceneView], alpha_mode: str = ALPHA_MASKED, seed: int = 0):
+    `threads` loader threads, each walking its own shuffled order of the views (seed + task index, like the reference's
+    loader tasks), decode -> premultiply -> pack into the [H,W] u32 layout the loss kernel reads and push SceneBatches
+    into a bounded queue (4 batches ahead of the trainer, scene_loader.rs:69-72).  A packed batch is cached the first
+    time it is produced while the cache stays under `cache_bytes` (BatchCache, :13-58): a hit hands out the same
+    immutable pinned tensor again, so nothing a pending host->device copy reads is ever overwritten; batches that do
+    not fit the cache are fresh allocations.  `next_batch()` blocks on the queue only."""
+
+    def __init__(self, views: Sequence[SceneView], alpha_mode: str = ALPHA_MASKED, seed: int = 0,
+                 cache_bytes: int = 6 << 30, threads: Optional[int] = None, prefetch: int = 4):
+        import queue
+        import threading
         self.views, self.alpha_mode = list(views), alpha_mode
-        self._rng = np.random.default_rng(seed)
-        self._order: List[int] = []
-        self._buf = [None, None]
-        self._i = 0
+        if not self.views:
+            raise ValueError("SceneLoader needs at least one view")
+        self._cache = [None] * len(self.views)
+        self._cache_used, self._cache_budget = 0, int(cache_bytes)
+        self._lock = threading.Lock()
+        self._q = queue.Queue(maxsize=max(int(prefetch), 1))
+        self._stop = threading.Event()
+        n_threads = threads if threads is not None else max(1, min(8, (os.cpu_count() or 2) // 2))
+        self._threads = [threading.Thread(target=self._run, args=(seed + i,), daemon=True, name=f"dataloader-{i}")
+                         for i in range(n_threads)]
+        for t in self._threads:
+            t.start()
 
-    def next_batch(self):
+    def _make_batch(self, index: int):
         import torch
         from .train import SceneBatch
-        if not self._order:
-            self._order = list(self._rng.permutation(len(self.views)))
-        v = self.views[self._order.pop()]
+        with self._lock:
+            hit = self._cache[index]
+        if hit is not None:
+            return hit
+        v = self.views[index]
         packed, has_alpha = v.load_packed(self.alpha_mode)
-        slot = self._i & 1
-        self._i += 1
-        t = self._buf[slot]
-        if t is None or tuple(t.shape) != packed.shape:
-            t = torch.empty(packed.shape, dtype=torch.int32)
-            if torch.cuda.is_available():
-                t = t.pin_memory()
-            self._buf[slot] = t
-        t.copy_(torch.from_numpy(packed))
-        return SceneBatch(img_packed=t, camera=v.camera, has_alpha=has_alpha,
-                          masked_alpha=has_alpha and self.alpha_mode == ALPHA_MASKED)
+        t = torch.from_numpy(np.ascontiguousarray(packed).view(np.int32))
+        nbytes = t.numel() * 4
+        with self._lock:
+            admit = self._cache[index] is None and self._cache_used + nbytes < self._cache_budget
+        if admit and torch.cuda.is_available():
+            t = t.pin_memory()      # cached batches are uploaded many times: pin them once
+        batch = SceneBatch(img_packed=t, camera=v.camera, has_alpha=has_alpha,
+                           masked_alpha=has_alpha and self.alpha_mode == ALPHA_MASKED)
+        if admit:
+            with self._lock:
+                if self._cache[index] is not None:          # another loader task produced it meanwhile: one buffer per view
+                    return self._cache[index]
+                if self._cache_used + nbytes < self._cache_budget:
+                    self._cache[index] = batch
+                    self._cache_used += nbytes
+        return batch
+
+    def _run(self, seed: int):
+        import queue
+        rng = np.random.default_rng(seed)
+        order: List[int] = []
+        while not self._stop.is_set():
+            if not order:
+                order = list(rng.permutation(len(self.views)))
+            try:
+                batch = self._make_batch(int(order.pop()))
+            except Exception as e:   # surface loader failures to the trainer instead of hanging it
+                batch = e
+            while not self._stop.is_set():
+                try:
+                    self._q.put(batch, timeout=0.1)
+                    break
+                except queue.Full:
+                    continue
+
+    def next_batch(self):
+        b = self._q.get()
+        if isinstance(b, Exception):
+            raise b
+        return b
+
+    def close(self):
+        self._stop.set()
+        for t in self._threads:
+            t.join(timeout=2.0)
+
+    def __del__(self):
+        try:
+            self._stop.set()
+        except Exception:
+            pass

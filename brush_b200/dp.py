@@ -16,6 +16,50 @@ import torch
 import torch.distributed as dist
 
 
+class DpComm:
+    """One NCCL rank of the library's own communicator (bg_dp_comm_create), bound to the render context's device.
+    The 128-byte NCCL id is made by rank 0 and broadcast through torch.distributed (whatever backend it runs on);
+    everything after that -- the gradient exchange of bg_train_step_views / bg_dp_exchange -- happens inside
+    libbrush_b200.so on its own stream.  A Rust host would pass the id through its own rendezvous."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        from . import _lib
+        if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            raise RuntimeError("DpComm needs an initialised torch.distributed group with more than one rank")
+        lib = _lib.load()
+        self.rank, self.world, self.ctx = dist.get_rank(group), dist.get_world_size(group), ctx
+        ident = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            _lib.check(lib.bg_dp_unique_id(ident), "bg_dp_unique_id")
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=ctx.device if on_gpu else "cpu")
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        _lib.check(lib.bg_dp_comm_create(ctx.handle, ident, self.rank, self.world, C.byref(h)), "bg_dp_comm_create")
+        self.handle = h
+
+    def exchange(self, n: int, local_views: int, small: torch.Tensor, record: torch.Tensor, recv: torch.Tensor, chunks: int = 1):
+        """bg_dp_exchange: all-reduce `small` in place, all-gather `record` into `recv` (layout: csrc/bg_dp.cuh)."""
+        from . import _lib
+        from .render import _stream_ptr
+        _lib.check(_lib.load().bg_dp_exchange(self.ctx.handle, self.handle, _stream_ptr(self.ctx.device), n, local_views,
+                                              small.data_ptr(), record.data_ptr(), recv.data_ptr(), chunks), "bg_dp_exchange")
+
+    def close(self):
+        if self.handle:
+            from . import _lib
+            _lib.load().bg_dp_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FlatGradients:
     """One allocation holding v_transforms [n,10] | v_sh [n,k,3] | v_raw_opac [n]: project_bwd writes
     straight into the views, the all-reduce runs once over `flat` with no packing copies."""

@@ -22,14 +22,18 @@ class EvalSample:
     render_aux: RenderOutput
 
 
-def eval_stats(ctx: RenderContext, splats, camera, gt_image: np.ndarray, alpha_mode: str = ALPHA_MASKED) -> EvalSample:
-    """splats: train.Splats (a min-scale floor is folded in, as in render_splats, gaussian_splats.rs:379-384)."""
+def eval_stats(ctx: RenderContext, splats, camera, gt_image: np.ndarray, alpha_mode: str = ALPHA_MASKED,
+               render_mip: bool = False) -> EvalSample:
+    """splats: train.Splats (a min-scale floor is folded in, as in render_splats, gaussian_splats.rs:379-384).
+    render_mip: the splats' render mode -- evaluation renders with the filter the model is trained with
+    (gaussian_splats.rs:395: `splats.render_mip`).  gt_image: [H,W,3] or [H,W,4] u8; an alpha channel goes through
+    view_to_packed_data(alpha_mode) like a training view (eval.rs:31)."""
     h, w = gt_image.shape[0], gt_image.shape[1]
     packed, _ = view_to_packed_data(gt_image, alpha_mode)
     gt = torch.from_numpy(packed).to(ctx.device)
     transforms, raw_opac = splats.folded(ctx)
-    out = render_splats(ctx, camera, (w, h), transforms, splats.sh_coeffs, raw_opac, background=(0.0, 0.0, 0.0),
-                        rpass=PASS_BACKWARD)
+    out = render_splats(ctx, camera, (w, h), transforms, splats.sh_coeffs, raw_opac, mip=render_mip,
+                        background=(0.0, 0.0, 0.0), rpass=PASS_BACKWARD)
     rgb = torch.round(out.out_img[..., 0:3] * 255.0) / 255.0            # eval.rs:41-42
     rgb = rgb.contiguous()
     l1 = image_loss_forward(ctx, rgb, gt, 3, ImageLossConfig(1.0, 0.0, None, False))

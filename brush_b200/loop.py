@@ -49,26 +49,52 @@ def train_loop(ctx, splats, train_views: Sequence, eval_views: Sequence, config,
     from .eval import eval_stats
     from .train import BOUND_PERCENTILE, SplatTrainer, bounds_from_pos_device
     process = process or ProcessConfig()
+    from PIL import Image
     loader = SceneLoader(train_views, alpha_mode, seed=process.seed)
-    trainer = SplatTrainer(config, ctx, bounds_from_pos_device(BOUND_PERCENTILE, splats.transforms[:, 0:3]))
+    trainer = SplatTrainer(config, ctx, bounds_from_pos_device(ctx, BOUND_PERCENTILE, splats.transforms))
+    # refine grows the model up to config.max_splats: the context must have been created for it (the reference sizes
+    # its buffers per render; here capacity is fixed at bg_ctx_create)
+    cap = min(int(config.max_splats), max(int(ctx.max_splats), 0))
+    if ctx.max_splats < min(config.max_splats, splats.num_splats()):
+        raise ValueError(f"render context holds {ctx.max_splats} splats, the model already has {splats.num_splats()}")
+    if cap < config.max_splats:
+        import dataclasses
+        config = dataclasses.replace(config, max_splats=cap)     # never grow past what the context can render
+        trainer.config = config
     view_cams = []
     for v in train_views:                                   # (position, focal in px at native resolution): the 3D filter
-        packed, _ = v.load_packed(alpha_mode)
-        view_cams.append((v.camera.position, float(v.camera.focal(packed.shape[1], packed.shape[0])[0])))
+        with Image.open(v.image_path) as im:                # header only: no decode
+            iw, ih = im.size
+        view_cams.append((v.camera.position, float(v.camera.focal(iw, ih)[0])))
     trainer.set_view_cams(view_cams)
     total = config.total_train_iters
     evals: List[dict] = []
+    last_out = None
+
+    def check_overflow():
+        # a view whose tile list exceeds the arena is rendered with the overflowing intersections dropped: never silently
+        if last_out is not None and last_out.intersection_overflow:
+            raise RuntimeError("intersection arena overflow: create the RenderContext with a larger max_intersections "
+                               f"(num_intersections {last_out.num_intersections})")
+
     for it in range(process.start_iter, total):
         stats = trainer.step(loader.next_batch(), splats)
-        refine = trainer.refine(it, splats) if should_refine(it, config.refine_every, total) else None
+        if stats.num_visible_event is not None:
+            last_out = stats.num_visible_event
+        refine = None
+        if should_refine(it, config.refine_every, total):
+            check_overflow()                                # refine synchronises anyway
+            refine = trainer.refine(it, splats)
         done = it + 1
         if on_step is not None:
             on_step(done, stats, refine)
         if eval_views and should_eval(done, process.eval_every, total):
-            from PIL import Image
+            check_overflow()
             psnr, ssim = [], []
             for v in eval_views:
-                s = eval_stats(ctx, splats, v.camera, np.asarray(Image.open(v.image_path).convert("RGB"), np.uint8), alpha_mode)
+                with Image.open(v.image_path) as im:
+                    gt = np.asarray(im.convert("RGBA" if "A" in im.getbands() else "RGB"), np.uint8)
+                s = eval_stats(ctx, splats, v.camera, gt, alpha_mode, render_mip=config.render_mip)
                 psnr.append(float(s.psnr)); ssim.append(float(s.ssim))
             evals.append({"iter": done, "psnr": float(np.mean(psnr)), "ssim": float(np.mean(ssim)), "splats": splats.num_splats()})
         if should_export(done, process.export_every, total):
@@ -79,4 +105,6 @@ def train_loop(ctx, splats, train_views: Sequence, eval_views: Sequence, config,
             with open(os.path.join(process.export_path, process.export_name.replace("{iter}", str(done))), "wb") as f:
                 f.write(data)
     torch.cuda.synchronize(ctx.device)
+    check_overflow()
+    loader.close()
     return evals

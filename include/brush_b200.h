@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 3u
+#define BG_ABI_VERSION 4u
 
 /* f32 lanes per projected splat: a 64-byte row, four aligned 128-bit loads.  Lanes 0..8 are the reference
  * layout (kernels/helpers.rs:49-53: xy_x, xy_y, conic_x, conic_y, conic_z, color_a, color_r, color_g, color_b).
@@ -191,6 +191,66 @@ typedef struct {
 uint64_t bg_train_step_workspace_bytes(uint32_t n, uint32_t k, uint32_t w, uint32_t h);
 int32_t bg_train_step(BgContext *ctx, void *stream, BgTrainStepArgs *args);
 
+/* The parameter update of one step as ONE pass over the Gaussians (update.cu): AdamScaled::step on the three parameter
+ * tensors (brush-train/src/adam_scaled.rs:75-165, train.rs:328-381), RefineRecord::gather_stats (stats.rs:40-50) and the
+ * mean noise (train.rs:389-416; the draw is bg_normal_noise(seed, (step-1)*ceil(3n/4) ..)).  Gradients are the dense
+ * outputs of bg_project_backward; v_refine / visible / max_radius are the step's statistics.  bg_train_step and
+ * bg_train_step_views end with this pass; it is exported for hosts that drive the operators themselves. */
+typedef struct {
+    uint32_t n, k;
+    float *transforms, *sh, *raw_opac;              /* [n,10] [n,k,3] [n], updated in place */
+    float *m_t, *v_t, *m_sh, *v_sh, *m_o, *v_o;     /* Adam moments; v_sh is [n] */
+    float *refine_norm, *vis_weight, *max_screen;   /* RefineRecord, [n] each */
+    const float *v_transforms, *v_sh_grad, *v_raw_opac;   /* gradients [n,10] [n,k,3] [n] */
+    const float *v_refine, *visible, *max_radius;   /* [n] each */
+    float lr_mean, lr_rotation, lr_scale, lr_coeffs_dc, lr_coeffs_sh_scale, lr_opac;
+    float noise_scale, median_scale;
+    uint64_t seed;
+    int32_t step;                                   /* 1-based Adam step; step == 1 initialises the moments */
+} BgTrainUpdateArgs;
+int32_t bg_train_update(BgContext *ctx, void *stream, const BgTrainUpdateArgs *args);
+
+/* SplatTrainer::refine (brush-train/src/train.rs:431-893) on the device: prune (opacity < 1/255, scale or position
+ * beyond max_allowed, non-finite) -> replace the pruned splats by splitting survivors sampled by opacity x visibility
+ * -> force-split splats larger than split_at_screen_size on screen -> sample growth_select_fraction of the splats whose
+ * refine weight exceeds growth_grad_threshold -> split (refine_splats, :665-821: child opacity 1-(1-o)^(1/sqrt2),
+ * per-axis shrink, +-offset along the rotated scale, zero Adam moments on both halves) -> opacity decay.
+ * Weighted sampling without replacement (multinomial.rs:1-26) is Efraimidis-Spirakis on the device: keys
+ * log(u_i)/w_i from the counter-based stream (seed, refine_index), the context's radix sort, the k best taken.
+ * Sources are [n,...]; destinations have `capacity` rows (capacity >= min(2n, max(n, max_splats)) always suffices).
+ * The call synchronises `stream` once, at its end, to return the counts; BG_ERR_CAPACITY if capacity was too small.
+ * The refine record (refine_norm, vis_weight, max_screen) restarts at zero after a refine (train.rs:442-445): the
+ * caller allocates it for stats_out->total_splats. */
+typedef struct {
+    uint32_t num_added, num_split_oversized, num_split_high_grad, num_pruned, num_pruned_non_finite, total_splats;
+} BgRefineStats;
+typedef struct {
+    uint32_t n, k, capacity;
+    const float *transforms, *sh, *raw_opac;                /* [n,10] [n,k,3] [n] */
+    const float *m_t, *v_t, *m_sh, *v_sh, *m_o, *v_o;       /* Adam moments (v_sh: [n]) */
+    const float *refine_norm, *vis_weight, *max_screen;     /* RefineRecord since the last refine */
+    float *transforms_out, *sh_out, *raw_opac_out;          /* [capacity,...] */
+    float *m_t_out, *v_t_out, *m_sh_out, *v_sh_out, *m_o_out, *v_o_out;
+    float bounds_center[3];                                 /* self.bounds.center */
+    float max_allowed;                                      /* self.bounds.extent.max_element() * 100 */
+    float split_at_screen_size, growth_grad_threshold, growth_select_fraction;
+    uint32_t max_splats;
+    int32_t growth_enabled;                                 /* iter < growth_stop_iter */
+    float opac_decay_minus;                                 /* opac_decay * (1 - clamp(iter / total_iters, 0, 1)) */
+    uint64_t seed;
+    uint32_t refine_index;                                  /* selects the random stream (the iteration number) */
+    void *workspace;
+    uint64_t workspace_bytes;                               /* >= bg_refine_workspace_bytes(n) */
+} BgRefineArgs;
+uint64_t bg_refine_workspace_bytes(uint32_t n);
+int32_t bg_refine(BgContext *ctx, void *stream, const BgRefineArgs *args, BgRefineStats *stats_out /* host */);
+
+/* bounds_from_pos (brush-train/src/splat_init.rs:130-160): per axis the ((1-p)/2, (1+p)/2) order statistics of the
+ * finite means, through three radix sorts.  out6 (host): (lo, hi) for x, y, z; NaN when no finite value exists.
+ * workspace: bg_refine_workspace_bytes(n).  Synchronises `stream`. */
+int32_t bg_bounds_percentile(BgContext *ctx, void *stream, uint32_t n, const float *transforms, float percentile,
+                             void *workspace, uint64_t workspace_bytes, float *out6);
+
 /* Mip-Splatting 3D smoothing filter (scale floor).
  * bg_compute_min_scale  <- compute_min_scale (brush-train/src/train.rs:102-125):
  *     f[i] = sqrt(factor) * min_v(|mean_i - cam_v| / max(focal_v, 1e-6)); view_cams: DEVICE [views,4] =
@@ -212,7 +272,70 @@ int32_t bg_fold_min_scale_backward(BgContext *ctx, void *stream, uint32_t n, con
                                    const float *raw_opac, const float *f, float *v_transforms,
                                    float *v_raw_opac);
 
-/* View-sharded data parallelism (the reference is single-device).  The SH part of the
+/* ---- View-sharded data parallelism behind the boundary (the reference is single-device).
+ * A communicator is one NCCL rank bound to the context's device.  Rank 0 calls bg_dp_unique_id and ships the 128 bytes
+ * to the other ranks by any side channel (the Python mirror uses torch.distributed's store; a Rust host would use
+ * its own rendezvous); every rank then calls bg_dp_comm_create (collective).  NCCL is bound at run time
+ * (libnccl.so.2); without it these calls return BG_ERR_UNSUPPORTED and everything else works. */
+typedef struct BgDpComm BgDpComm;
+#define BG_DP_UNIQUE_ID_BYTES 128
+int32_t bg_dp_unique_id(uint8_t *out_id /* host [128] */);
+int32_t bg_dp_comm_create(BgContext *ctx, const uint8_t *id /* host [128] */, int32_t rank, int32_t world,
+                          BgDpComm **out_comm);
+int32_t bg_dp_comm_destroy(BgDpComm *comm);
+
+/* Float counts of the exchange buffers for n Gaussians and `local_views` views per rank:
+ *   small  [12 n]                 v_transforms [n,10] | v_raw_opac [n] | visible [n], summed over the rank's views
+ *   record [(3 local + 2) n]      v_color [local,n,3] | v_refine [n] | max_radius [n]  (MAX over the rank's views)
+ *   recv   [world * record]       the gathered records, laid out per slice (csrc/bg_dp.cuh) */
+uint64_t bg_dp_small_floats(uint32_t n);
+uint64_t bg_dp_record_floats(uint32_t n, uint32_t local_views);
+
+/* The gradient exchange of one step on its own: all-gather of the records, all-reduce (SUM) of `small` in place, both
+ * on the communicator's stream behind everything already enqueued on `stream`; `stream` waits for the result.
+ * chunks (1..16) slices the Gaussian range for the pipelined variant used by bg_train_step_views. */
+int32_t bg_dp_exchange(BgContext *ctx, BgDpComm *comm, void *stream, uint32_t n, uint32_t local_views,
+                       float *small, const float *record, float *recv, uint32_t chunks);
+
+/* One optimizer step over views_total = world * local_views views (BASELINE config [4]): the loss is the mean of the
+ * per-view losses (train.rs:254-260 per view), i.e. the step equals accumulating the views' gradients on one GPU.
+ * Per rank: for each local view render -> L1+SSIM loss -> rasterize / project backward (SH gradient kept in its
+ * rank-one form); ONE exchange (bg_dp_exchange); the update pass (bg_train_update's kernel in its factored form)
+ * slice by slice under the exchange.  comm == NULL runs the same step on one device.  Every rank must pass the same
+ * n, local_views, learning rates, seed and step; cams / gt_packed are this rank's views, global view index =
+ * rank * local_views + i.  min_scale (optional, [n]): the Mip-Splatting scale floor folded in for the renders and
+ * chained out of the gradients (gaussian_splats.rs:86-111).  loss_out: mean loss of this rank's views. */
+typedef struct {
+    uint32_t w, h, n, k;
+    int32_t mip;
+    float background[3];
+    uint32_t local_views;
+    const BgCamera *cams;                           /* host [local_views] */
+    const uint32_t *const *gt_packed;               /* host [local_views] device pointers, each [h,w] rgba8 */
+    float *transforms, *sh, *raw_opac;
+    float *m_t, *v_t, *m_sh, *v_sh, *m_o, *v_o;
+    float *refine_norm, *vis_weight, *max_screen;
+    const float *min_scale;                         /* device [n] or NULL */
+    float l1_weight, ssim_weight;
+    int32_t has_composite_bg;
+    float composite_bg[3];
+    int32_t mask, channels;
+    float alpha_weight;
+    float lr_mean, lr_rotation, lr_scale, lr_coeffs_dc, lr_coeffs_sh_scale, lr_opac;
+    float noise_scale, median_scale;
+    uint64_t seed;
+    int32_t step;
+    uint32_t chunks;                                /* slices of the exchange/update pipeline; 0 = default */
+    void *workspace;
+    uint64_t workspace_bytes;
+    float *loss_out;
+    BgRenderState state_out;                        /* render state of the last local view */
+} BgTrainViewsArgs;
+uint64_t bg_train_step_views_workspace_bytes(uint32_t n, uint32_t k, uint32_t w, uint32_t h, uint32_t local_views,
+                                             uint32_t world);
+int32_t bg_train_step_views(BgContext *ctx, BgDpComm *comm, void *stream, BgTrainViewsArgs *args);
+
+/* Building blocks of the exchange for hosts that drive the operators themselves.  The SH part of the
  * gradient of ONE view is rank one per Gaussian: v_sh[g,k,:] = Y_k(dir(mean_g, camera)) * v_color[g,:]
  * (kernels/sh.rs:265-355).  bg_project_backward_factored is bg_project_backward without the dense v_sh:
  * it writes v_color [n,3] instead (zeros where no gradient).  Ranks all-reduce v_transforms / v_raw_opac,

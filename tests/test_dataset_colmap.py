@@ -118,11 +118,34 @@ def test_view_to_packed_data_and_premultiplication():
 def test_scene_loader_cycles_through_views(tmp_path):
     _write_dataset(str(tmp_path))
     r = ds.load_colmap_text(str(tmp_path))
-    loader = ds.SceneLoader(r.train, seed=1)
+    loader = ds.SceneLoader(r.train, seed=1, threads=1)     # one loader task: every view once per epoch
     seen = {loader.next_batch().camera.position for _ in range(3)}
     assert len(seen) == 3
     b = loader.next_batch()
     assert tuple(b.img_packed.shape) == (3, 4) and not b.has_alpha
+    loader.close()
+
+
+def test_scene_loader_threads_and_cache(tmp_path):
+    """scene_loader.rs:13-58,67-110: several loader tasks feed one bounded queue; a packed batch that fits the cache
+    budget is handed out again as the SAME buffer (never rewritten), one that does not fit is re-made every time."""
+    _write_dataset(str(tmp_path))
+    r = ds.load_colmap_text(str(tmp_path))
+    loader = ds.SceneLoader(r.train, seed=3, threads=3)
+    got = [loader.next_batch() for _ in range(40)]
+    assert {b.camera.position for b in got} == {v.camera.position for v in r.train}
+    by_view = {}
+    for b in got:
+        by_view.setdefault(b.camera.position, []).append(b.img_packed)
+    for tensors in by_view.values():
+        assert len({t.data_ptr() for t in tensors}) == 1          # cached: one buffer per view
+    loader.close()
+    tiny = ds.SceneLoader(r.train, seed=3, threads=2, cache_bytes=0)   # nothing fits: fresh buffers, same contents
+    a = [tiny.next_batch() for _ in range(12)]
+    ref = {v.camera.position: v.load_packed()[0] for v in r.train}
+    for b in a:
+        np.testing.assert_array_equal(b.img_packed.numpy().view(np.uint32), ref[b.camera.position].view(np.uint32))
+    tiny.close()
 
 
 def test_binary_model_equals_text_model(tmp_path):

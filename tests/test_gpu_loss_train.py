@@ -308,34 +308,61 @@ def test_step_views_equals_sequential_accumulation(rt):
     for cam in (cam0, cam1):
         tgt = rt.R.render_splats(rt.ctx, cam, (w, h), *dev_params(), rpass=0)
         batches.append(rt.T.SceneBatch(img_packed=(tgt.out_img | (255 << 24)).clone(), camera=cam))
-    cfg = rt.T.TrainConfig(total_train_iters=1000, background_noise_strength=0.0, mean_noise_weight=0.0)
+    cfg = rt.T.TrainConfig(total_train_iters=1000, background_noise_strength=0.0, mean_noise_weight=50.0, seed=11)
     captured = {}
 
     class Capture(rt.T.SplatTrainer):
         def _apply_updates(self, splats, v_t, v_sh, v_o, v_r, visible, max_radius, median_scale):
             captured.update(v_t=v_t.clone(), v_sh=v_sh.clone(), v_o=v_o.clone(), v_r=v_r.clone(), vis=visible.clone(),
                             rad=max_radius.clone())
-            return super()._apply_updates(splats, v_t, v_sh, v_o, v_r, visible, max_radius, median_scale)
+            return 0.0   # gradients only: the parameters stay untouched
 
     bounds = rt.T.bounds_from_pos(0.8, tr[:, :3])
     p = dev_params()
     sh_start = p[1] + 0.1
-    multi = rt.T.Splats(p[0].clone(), sh_start.clone(), p[2].clone())
-    st = Capture(cfg, rt.ctx, bounds).step_views(batches, multi)
-    got = dict(captured)
+    fresh = lambda: rt.T.Splats(p[0].clone(), sh_start.clone(), p[2].clone())
+    # the step under test: ONE ABI call (bg_train_step_views), SH gradient kept factored, fused update pass
+    multi = fresh()
+    t_multi = rt.T.SplatTrainer(cfg, rt.ctx, bounds)
+    st = t_multi.step_views(batches, multi)
+    # the definition: per-view dense gradients through the per-operator entry points, averaged, MAX / SUM statistics,
+    # then the same update pass on the dense gradient
     per_view = []
     for b in batches:
-        s1 = rt.T.Splats(p[0].clone(), sh_start.clone(), p[2].clone())
-        Capture(cfg, rt.ctx, bounds).step(b, s1)
+        Capture(cfg, rt.ctx, bounds).step(b, fresh())
         per_view.append(dict(captured))
-    for key in ("v_t", "v_sh", "v_o"):
-        want = (per_view[0][key].double() + per_view[1][key].double()) / 2.0
-        rel = (got[key].double() - want).norm() / want.norm()
-        assert rel < 1e-5, (key, rel)
-    # the refine weight comes out of f32 atomics in the blend backward: equal up to summation order
-    torch.testing.assert_close(got["v_r"], torch.maximum(per_view[0]["v_r"], per_view[1]["v_r"]), rtol=1e-4, atol=1e-7)
-    assert torch.equal(got["vis"], per_view[0]["vis"] + per_view[1]["vis"])
-    assert torch.equal(got["rad"], torch.maximum(per_view[0]["rad"], per_view[1]["rad"]))
+    avg = {k: ((per_view[0][k].double() + per_view[1][k].double()) / 2.0).float() for k in ("v_t", "v_sh", "v_o")}
+    ref = fresh()
+    t_ref = rt.T.SplatTrainer(cfg, rt.ctx, bounds)
+    t_ref._ensure_state(ref)
+    t_ref.step_count = 1
+    t_ref._apply_updates(ref, avg["v_t"], avg["v_sh"], avg["v_o"], torch.maximum(per_view[0]["v_r"], per_view[1]["v_r"]),
+                         per_view[0]["vis"] + per_view[1]["vis"], torch.maximum(per_view[0]["rad"], per_view[1]["rad"]),
+                         bounds.median_size())
+    torch.cuda.synchronize()
+    for name in ("transforms", "sh_coeffs", "raw_opacities"):
+        a, b = getattr(ref, name).double(), getattr(multi, name).double()
+        assert torch.isfinite(b).all()
+        # Adam's first step moves every entry by ~lr * sign(g): entries whose tiny gradient changes sign with the
+        # summation order differ by 2 lr; everything else agrees closely
+        close = (a - b).abs() <= 1e-6 + 1e-4 * a.abs()
+        assert close.double().mean() > 0.995, (name, float(close.double().mean()))
+    for key in ("m_t", "m_sh", "m_o", "v_sh"):   # the moments are linear / quadratic in the gradient: direct comparison
+        a, b = t_ref._state[key].double(), t_multi._state[key].double()
+        assert (a - b).norm() / a.norm() < 1e-4, key
+    assert torch.equal(t_multi._state["vis_weight"], per_view[0]["vis"] + per_view[1]["vis"])
+    assert torch.equal(t_multi._state["max_screen"], torch.maximum(per_view[0]["rad"], per_view[1]["rad"]))
+    torch.testing.assert_close(t_multi._state["refine_norm"], torch.maximum(per_view[0]["v_r"], per_view[1]["v_r"]), rtol=1e-4, atol=1e-7)
+    assert np.isfinite(float(st.loss.item()))
+    # a second and third step keep working on the moments (t > 1 path) and the chunked update equals the unchunked one
+    multi_c = fresh()
+    t_c = rt.T.SplatTrainer(cfg, rt.ctx, bounds)
+    t_c.step_views(batches, multi_c, chunks=3)   # chunks only matter with a communicator; must be accepted and ignored
+    for name in ("transforms", "sh_coeffs", "raw_opacities"):   # (two runs differ by the order of the blend's f32 atomics)
+        a, b = getattr(multi_c, name).double(), getattr(multi, name).double()
+        assert ((a - b).abs() <= 1e-6 + 1e-4 * a.abs()).double().mean() > 0.995, name
+    for _ in range(2):
+        st = t_multi.step_views(batches, multi)
     assert np.isfinite(float(st.loss.item()))
     assert all(torch.isfinite(x).all() for x in (multi.transforms, multi.sh_coeffs, multi.raw_opacities))
 

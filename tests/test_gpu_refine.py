@@ -1,0 +1,247 @@
+"""bg_refine (csrc/refine.cu) against restatements of SplatTrainer::refine (brush-train/src/train.rs:431-893):
+  * the decisions (prune set, both weighted samples, force-split, counts) against an exact numpy restatement that
+    draws the same counter-based uniforms (Philox4x32-10) and forms the same keys log(u)/w with the oracle's
+    deterministic log -- the selections must agree exactly;
+  * the split / decay arithmetic against the torch restatement tests/refine_ref.py (tolerance: different exp/log)."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+M32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over the counter words (uint64 arrays holding 32-bit values)."""
+    c = [np.asarray(x, np.uint64) & M32 for x in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & M32, p1 >> np.uint64(32), p1 & M32
+        c = [(hi1 ^ c[1] ^ k0) & M32, lo1, (hi0 ^ c[3] ^ k1) & M32, lo0]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M32, (k1 + np.uint64(0xBB67AE85)) & M32
+    return c
+
+
+def uniform01(seed, stream, idx):
+    ctr = (np.uint64(stream) << np.uint64(40)) + (idx.astype(np.uint64) >> np.uint64(2))
+    r = philox4x32_10(ctr & M32, ctr >> np.uint64(32), np.full(idx.shape, 0x52464E45, np.uint64), np.zeros(idx.shape, np.uint64),
+                      seed & 0xFFFFFFFF, seed >> 32)
+    w = np.choose(idx & 3, r).astype(np.uint64)
+    return ((w >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+
+
+@pytest.fixture(scope="module")
+def rt():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import brush_b200.render as R
+    import brush_b200.train as T
+    from oracle import oracle as orc
+    ctx = R.RenderContext(50_000, 64, 64, 1 << 20, device=0)
+    from types import SimpleNamespace
+    yield SimpleNamespace(torch=torch, R=R, T=T, orc=orc, ctx=ctx)
+    ctx.close()
+
+
+def _scene(rt, n, k, seed):
+    torch, T = rt.torch, rt.T
+    g = np.random.default_rng(seed)
+    means = g.uniform(-2, 2, (n, 3)).astype(np.float32)
+    quats = g.normal(size=(n, 4)).astype(np.float32)
+    ls = np.log(g.uniform(0.01, 0.06, (n, 3))).astype(np.float32)
+    tr = np.concatenate([means, quats, ls], 1)
+    sh = (g.normal(size=(n, k, 3)) * 0.2).astype(np.float32)
+    op = g.uniform(-1, 3, n).astype(np.float32)
+    op[:40] = -8.0                       # dead: sigmoid < 1/255
+    tr[40:45, 7] = 9.0                   # scale far beyond the bounds
+    tr[45:50, 0] = 1e6                   # out of bounds
+    tr[50, 1] = np.nan; sh[51, 0, 0] = np.inf; op[52] = np.nan
+    d = rt.ctx.device
+    splats = T.Splats(*(torch.from_numpy(x.copy()).to(d) for x in (tr, sh, op)))
+    return tr, sh, op, splats
+
+
+def test_refine_decisions_match_exact_restatement(rt):
+    torch, T, orc = rt.torch, rt.T, rt.orc
+    n, k, seed, it = 3000, 4, 9, 400
+    tr, sh, op, splats = _scene(rt, n, k, 3)
+    cfg = T.TrainConfig(total_train_iters=1000, max_splats=3600, growth_stop_iter=800, seed=seed)
+    bounds = T.bounds_from_pos(0.8, tr[50:, :3][np.isfinite(tr[50:, :3]).all(1)])
+    trainer = T.SplatTrainer(cfg, rt.ctx, bounds)
+    trainer._ensure_state(splats)
+    st = trainer._state
+    g = np.random.default_rng(5)
+    rec = {"refine_norm": g.uniform(0, 0.006, n).astype(np.float32), "vis_weight": (g.uniform(size=n) > 0.2).astype(np.float32) * 3,
+           "max_screen": g.uniform(0, 0.6, n).astype(np.float32)}
+    for key, v in rec.items():
+        st[key] = torch.from_numpy(v).to(rt.ctx.device)
+    for key in ("m_t", "v_t", "m_sh", "v_sh", "m_o", "v_o"):
+        st[key] += 1.0
+    trainer.step_count = it
+    before = {x: getattr(splats, x).clone() for x in ("transforms", "sh_coeffs", "raw_opacities")}
+    stats = trainer.refine(it, splats)
+    torch.cuda.synchronize()
+
+    # ---------------- exact restatement of the decisions
+    sig = np.vectorize(lambda x: np.float32(1.0) / (np.float32(1.0) + np.float32(orc.expf_det(float(-x)))), otypes=[np.float32])
+    logd = np.vectorize(lambda x: np.float32(orc.logf_det(float(x))), otypes=[np.float32])
+    expd = np.vectorize(lambda x: np.float32(orc.expf_det(float(x))), otypes=[np.float32])
+    max_allowed = np.float32(np.max(bounds.extent)) * np.float32(100.0)
+    with np.errstate(invalid="ignore", over="ignore"):
+        nonfin = ~np.isfinite(tr).all(1) | ~np.isfinite(sh.reshape(n, -1)).all(1) | ~np.isfinite(op)
+        prune = (sig(op) < np.float32(1 / 255)) | (expd(tr[:, 7:10]) > max_allowed).any(1) | \
+                (np.abs(tr[:, :3] - bounds.center.astype(np.float32)) > max_allowed).any(1) | nonfin
+    keep = np.nonzero(~prune)[0]
+    pruned = n - keep.size
+    assert stats.num_pruned == pruned == 53 and stats.num_pruned_non_finite == int(nonfin.sum()) == 3
+    m = keep.size
+    rn, vw, ms, opk = rec["refine_norm"][keep], rec["vis_weight"][keep], rec["max_screen"][keep], op[keep]
+    idx = np.arange(m, dtype=np.uint32)
+
+    def sample(weights, count, stream):
+        w = np.where(np.isfinite(weights) & (weights > 0), weights, 0).astype(np.float32)
+        pos = w > 0
+        keyv = np.full(m, -np.inf, np.float32)
+        with np.errstate(divide="ignore"):
+            keyv[pos] = logd(uniform01(seed, stream, idx[pos])) / w[pos]
+        order = np.argsort(-keyv.astype(np.float64), kind="stable")
+        return order[:min(count, int(pos.sum()))]
+
+    split = np.zeros(m, bool)
+    split[sample(sig(opk) * (vw > 0), pruned, 2 * it)] = True
+    pre = int(split.sum())
+    cand = np.nonzero((ms > np.float32(cfg.split_at_screen_size)) & (vw > 0) & ~split)[0]
+    budget = max(0, cfg.max_splats - (m + pre))
+    split[cand[:budget]] = True
+    n_over = int(split.sum()) - pre
+    above = (rn > np.float32(cfg.growth_grad_threshold)) & (vw > 0)
+    grow = max(0, int(np.floor(np.float32(above.sum()) * np.float32(cfg.growth_select_fraction) + np.float32(0.5))) - pruned)
+    grow = min(grow, max(0, cfg.max_splats - (m + int(split.sum()))))
+    pre_g = int(split.sum())
+    split[sample(np.where(above, rn, 0), grow, 2 * it + 1)] = True
+    n_grow = int(split.sum()) - pre_g
+    assert (stats.num_split_oversized, stats.num_split_high_grad, stats.num_added) == (n_over, n_grow, int(split.sum()))
+    assert stats.total_splats == m + int(split.sum()) == splats.num_splats() <= cfg.max_splats + pruned
+    assert n_over > 0 and n_grow > 0 and pre == pruned
+    # the device split exactly the expected parents: both halves restart with zero moments, the others keep theirs
+    m_t = st["m_t"].cpu().numpy()
+    got_split = (m_t[:m] == 0).all(1)
+    assert np.array_equal(got_split, split)
+    assert (m_t[m:] == 0).all() and (st["v_sh"].cpu().numpy()[m:] == 0).all()
+    assert (st["m_o"].cpu().numpy()[:m][~split] == 1).all() and (st["m_sh"].cpu().numpy()[:m][~split] == 1).all()
+
+    # ---------------- split / decay arithmetic against the torch restatement, on the same parents
+    import refine_ref
+    inds = torch.from_numpy(np.nonzero(split)[0]).to(rt.ctx.device)
+    keep_t = torch.from_numpy(keep).to(rt.ctx.device)
+    cur = before["transforms"].index_select(0, keep_t)
+    cur_op = before["raw_opacities"].index_select(0, keep_t)
+    sel = cur.index_select(0, inds)
+    rots = sel[:, 3:7] / sel[:, 3:7].pow(2).sum(1, keepdim=True).sqrt().clamp_min(1e-32)
+    scales = sel[:, 7:10].exp()
+    new_opac = (1.0 - (1.0 - torch.sigmoid(cur_op.index_select(0, inds))).pow(T.FRAC_1_SQRT_2)).clamp(T.MIN_OPACITY, 1 - T.MIN_OPACITY)
+    sq = scales.pow(2)
+    ratio = sq / sq.max(1, keepdim=True).values.clamp_min(1e-30)
+    k_max = (torch.from_numpy(ms).to(rt.ctx.device).index_select(0, inds).unsqueeze(1).clamp_min(1e-6).reciprocal()
+             * cfg.split_at_screen_size).clamp_max(T.FRAC_1_SQRT_2)
+    k_axis = -(ratio * (1.0 - k_max)) + 1.0
+    samples = refine_ref.quaternion_vec_multiply(rots, (1.0 - k_axis.pow(2)).clamp_min(0).sqrt() * scales)
+    nls = sel[:, 7:10] + k_axis.log()
+    out_t = splats.transforms
+    torch.testing.assert_close(out_t[m:, 0:3], sel[:, 0:3] + samples, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out_t.index_select(0, inds)[:, 0:3], sel[:, 0:3] - samples, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out_t[m:, 3:7], rots, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out_t[m:, 7:10], nls, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out_t.index_select(0, inds)[:, 7:10], nls, rtol=1e-5, atol=1e-5)
+    assert torch.equal(out_t.index_select(0, inds)[:, 3:7], sel[:, 3:7])            # the parent keeps its raw rotation
+    assert torch.equal(splats.sh_coeffs[m:], before["sh_coeffs"].index_select(0, keep_t).index_select(0, inds))
+    # opacity: split where selected, then the decay on everything
+    raw = cur_op.clone()
+    raw[inds] = torch.log(new_opac / (1 - new_opac))
+    raw = torch.cat([raw, torch.log(new_opac / (1 - new_opac))])
+    minus = cfg.opac_decay * (1.0 - it / cfg.total_train_iters)
+    o = (torch.sigmoid(raw) - minus).clamp(1e-12, 1 - 1e-12)
+    torch.testing.assert_close(splats.raw_opacities, torch.log(o / (1 - o)), rtol=2e-5, atol=2e-5)
+    # untouched rows are copied bit for bit
+    untouched = torch.from_numpy(np.nonzero(~split)[0]).to(rt.ctx.device)
+    assert torch.equal(out_t.index_select(0, untouched), cur.index_select(0, untouched))
+    # record restarted, bounds recomputed from the new means (splat_init.rs:130-160)
+    assert all(float(st[x].abs().sum()) == 0 and st[x].numel() == stats.total_splats for x in ("refine_norm", "vis_weight", "max_screen"))
+    want = T.bounds_from_pos(0.8, out_t[:, :3].cpu().numpy())
+    np.testing.assert_array_equal(trainer.bounds.center, want.center)
+    np.testing.assert_array_equal(trainer.bounds.extent, want.extent)
+
+
+def test_refine_sampling_is_proportional_and_without_replacement(rt):
+    """multinomial.rs:28-85 properties on the device sampler: no duplicates, only positive weights, count capped by
+    the positives, frequencies proportional to the weights."""
+    torch, T = rt.torch, rt.T
+    n, k = 64, 1
+    hits = np.zeros(n)
+    w = np.linspace(0.05, 0.95, n).astype(np.float32)            # opacities = the replacement weights
+    raw = np.log(w / (1 - w)).astype(np.float32)
+    runs = 300
+    for it in range(runs):
+        tr = np.zeros((n + 8, 10), np.float32); tr[:, 3] = 1.0; tr[:, 7:10] = -3.0
+        tr[:, 0] = np.linspace(-1, 1, n + 8)
+        op = np.concatenate([raw, np.full(8, -9.0, np.float32)])   # 8 dead splats at the end -> 8 replacements
+        d = rt.ctx.device
+        splats = T.Splats(torch.from_numpy(tr).to(d), torch.zeros((n + 8, k, 3), device=d), torch.from_numpy(op).to(d))
+        cfg = T.TrainConfig(total_train_iters=10_000, max_splats=10_000, split_at_screen_size=0.0, growth_stop_iter=0, opac_decay=0.0, seed=77)
+        trainer = T.SplatTrainer(cfg, rt.ctx, T.BoundingBox(np.zeros(3, np.float32), np.ones(3, np.float32)))
+        trainer._ensure_state(splats)
+        trainer._state["vis_weight"] += 1.0
+        for key in ("m_t",):
+            trainer._state[key] += 1.0
+        stats = trainer.refine(it, splats)
+        assert (stats.num_pruned, stats.num_added, stats.total_splats) == (8, 8, n + 8)
+        picked = (trainer._state["m_t"][:n] == 0).all(1).cpu().numpy()
+        assert picked.sum() == 8
+        hits += picked
+    # inclusion frequency grows with the weight (without replacement it saturates, so compare halves)
+    lo, hi = hits[: n // 2].sum(), hits[n // 2:].sum()
+    assert hi > 1.5 * lo and hits[-8:].mean() > 3 * max(hits[:8].mean(), 1e-9) * 0.5
+    # nothing to sample from: every survivor invisible -> no replacement splits
+    trainer2 = T.SplatTrainer(cfg, rt.ctx, T.BoundingBox(np.zeros(3, np.float32), np.ones(3, np.float32)))
+    splats2 = T.Splats(torch.from_numpy(tr).to(d), torch.zeros((n + 8, k, 3), device=d), torch.from_numpy(op).to(d))
+    trainer2._ensure_state(splats2)
+    s2 = trainer2.refine(3, splats2)
+    assert (s2.num_pruned, s2.num_added, s2.total_splats) == (8, 0, n)
+
+
+def test_refine_edge_cases(rt):
+    torch, T = rt.torch, rt.T
+    d = rt.ctx.device
+    cfg = T.TrainConfig(total_train_iters=1000, max_splats=100, seed=1)
+    box = T.BoundingBox(np.zeros(3, np.float32), np.ones(3, np.float32))
+
+    def mk(n, raw):
+        tr = np.zeros((n, 10), np.float32); tr[:, 3] = 1.0; tr[:, 7:10] = -3.0
+        s = T.Splats(torch.from_numpy(tr).to(d), torch.zeros((n, 1, 3), device=d), torch.full((n,), raw, device=d))
+        t = T.SplatTrainer(cfg, rt.ctx, box)
+        t._ensure_state(s)
+        return t, s
+    # every splat matches the prune mask: prune_points keeps them all (train.rs:866-869 "Trying to create empty splat")
+    t, s = mk(10, -9.0)
+    st = t.refine(10, s)
+    assert (st.num_pruned, st.total_splats) == (0, 10)
+    # nothing to prune, nothing visible: only the opacity decay acts
+    t, s = mk(10, 1.0)
+    st = t.refine(10, s)
+    assert (st.num_pruned, st.num_added, st.total_splats) == (0, 0, 10)
+    assert float(s.raw_opacities.max()) < 1.0 and torch.isfinite(s.raw_opacities).all()
+    # the max_splats budget caps force-splits: 90 oversized visible splats, room for 10
+    t, s = mk(90, 1.0)
+    t._state["vis_weight"] += 1.0
+    t._state["max_screen"] += 0.9
+    st = t.refine(900, s)     # past growth_stop_iter? no: growth gated by refine weight = 0 anyway
+    assert (st.num_split_oversized, st.total_splats) == (10, 100)
+    assert (t._state["m_t"].shape[0], s.transforms.shape[0]) == (100, 100)

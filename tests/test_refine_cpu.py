@@ -1,5 +1,5 @@
-"""refine() host logic (brush-train/src/train.rs:431-893, multinomial.rs, quat_vec.rs) on CPU tensors: it is
-built from generic tensor ops exactly like the reference, so it needs no GPU.  The reference pins none of
+"""refine() semantics (brush-train/src/train.rs:431-893, multinomial.rs, quat_vec.rs) on CPU tensors, through the test-side
+torch restatement tests/refine_ref.py (the product path is bg_refine, compared against it in tests/test_gpu_refine.py).  The reference pins none of
 this numerically (unseeded RNG); the tests check its own unit tests' properties (multinomial.rs tests,
 quat_vec.rs tests) and the invariants stated in the code/comments."""
 import math
@@ -8,8 +8,9 @@ import numpy as np
 import pytest
 import torch
 
-from brush_b200.train import (BoundingBox, RefineStats, SplatTrainer, Splats, TrainConfig, bounds_from_pos,
-                              bounds_from_pos_device, multinomial_sample, quaternion_vec_multiply)
+from brush_b200.train import BoundingBox, RefineStats, SplatTrainer, Splats, TrainConfig, bounds_from_pos
+from refine_ref import bounds_from_pos_torch as bounds_from_pos_device
+from refine_ref import multinomial_sample, quaternion_vec_multiply, refine_reference
 
 
 def test_multinomial_sampling_properties():
@@ -61,7 +62,7 @@ def test_refine_prunes_dead_and_nonfinite_and_reuses_the_budget():
     sp.transforms[50:55, 0] = float("nan")
     sp.transforms[55:60, 7] = 20.0          # scale far above 100 * extent
     n0 = sp.num_splats()
-    stats = tr.refine(200, sp)
+    stats = refine_reference(tr, 200, sp)
     assert isinstance(stats, RefineStats)
     assert stats.num_pruned == 60 and stats.num_pruned_non_finite == 5
     assert stats.num_added >= 60            # pruned budget is re-used by splitting survivors
@@ -80,7 +81,7 @@ def test_split_geometry_opacity_and_moments():
     tr._state["refine_norm"][10] = 1.0      # one splat above the growth threshold
     tr._state["max_screen"][:] = 0.01
     before = Splats(sp.transforms.clone(), sp.sh_coeffs.clone(), sp.raw_opacities.clone())
-    stats = tr.refine(100, sp)
+    stats = refine_reference(tr, 100, sp)
     # growth = round(0.25 * 1) - 0 = 0 -> nothing split; raise the fraction to force the split
     assert stats.num_added == 0
     tr, sp = _trainer(200, opac_decay=0.0, growth_select_fraction=1.0)
@@ -88,7 +89,7 @@ def test_split_geometry_opacity_and_moments():
     tr._state["refine_norm"][10] = 1.0
     tr._state["max_screen"][:] = 0.01
     before = Splats(sp.transforms.clone(), sp.sh_coeffs.clone(), sp.raw_opacities.clone())
-    stats = tr.refine(100, sp)
+    stats = refine_reference(tr, 100, sp)
     assert stats.num_added == 1 and stats.num_split_high_grad == 1 and sp.num_splats() == 201
     parent, child, old = sp.transforms[10], sp.transforms[200], before.transforms[10]
     # centroid preserved, children symmetric about the old mean
@@ -115,13 +116,13 @@ def test_oversized_force_split_and_growth_stop():
     tr, sp = _trainer(300, growth_stop_iter=100)
     tr._state["max_screen"][:5] = 0.9
     tr._state["refine_norm"][:] = 1.0        # would all grow, but iteration >= growth_stop_iter
-    stats = tr.refine(150, sp)
+    stats = refine_reference(tr, 150, sp)
     assert stats.num_split_oversized == 5 and stats.num_split_high_grad == 0 and stats.num_added == 5
     # max_splats caps the force split
     tr, sp = _trainer(300, max_splats=302)
     tr._state["max_screen"][:5] = 0.9
     tr._state["refine_norm"][:] = 0.0
-    stats = tr.refine(10, sp)
+    stats = refine_reference(tr, 10, sp)
     assert stats.num_split_oversized == 2 and sp.num_splats() == 302
 
 
@@ -131,7 +132,7 @@ def test_opacity_decay_and_bounds_update():
     tr._state["max_screen"][:] = 0.0
     o0 = torch.sigmoid(sp.raw_opacities).clone()
     keep = o0 >= 1 / 255
-    tr.refine(250, sp)
+    refine_reference(tr, 250, sp)
     o1 = torch.sigmoid(sp.raw_opacities)
     assert torch.allclose(o1, (o0[keep] - 0.004 * 0.75).clamp(1e-12, 1 - 1e-12), atol=1e-6)
     b = bounds_from_pos(0.8, sp.transforms[:, :3].numpy())
