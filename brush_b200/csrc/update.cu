@@ -5,8 +5,8 @@
 //   RefineRecord::gather_stats (MAX refine weight, SUM visible, MAX radius)            (stats.rs:40-50)
 //   the mean noise  means += clamp(N(0,1) (1-sigmoid(opac'))^150 vis lr 50, +-median)    (train.rs:389-416)
 // The reference issues ~80 generic tensor ops for this; round 1 used five kernels (3 Adam, noise draw, stats+noise).
-// One thread owns one Gaussian: every row is read and written once with 128/256-bit accesses (consecutive threads own
-// consecutive rows, so a warp's accesses cover one contiguous span and every fetched sector is used), the normal
+// A warp owns 32 consecutive Gaussians: the short rows (transforms, opacity, statistics) one lane each, the SH rows as
+// one contiguous span read and written with coalesced 128-bit accesses; the normal
 // draws are evaluated in registers (counter-based Philox, bg_rng.cuh; only Gaussians whose noise weight is non-zero
 // draw at all), nothing but the parameters, moments and the refine record touches HBM:
 //   (316 + 48 K + g) N bytes, g = 44 + 12 K (dense gradient) or 48 + 12 views (factored).
@@ -35,192 +35,236 @@ __device__ __forceinline__ float adam_p(float p, float m, float v, float step, c
     return p - (m_hat / (sqrtf(v_hat) + P.eps)) * step;
 }
 
-__device__ __forceinline__ void ld256(const float *p, float *o) {   // plain (read-write data) 256-bit load
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
-                 : "l"(p) : "memory");
-}
+constexpr int UP_THREADS = 128;   // 4 warps; a warp owns 32 consecutive Gaussians and never waits for another warp
 
-constexpr int UP_THREADS = 128;
-
+// One lane owns one Gaussian for everything that is a row of <= 10 floats (transforms, opacity, statistics, noise).
+// The SH rows (3K floats) are handled by the whole warp: the 32 rows of a warp are one contiguous span of every SH array,
+// which the lanes read and write as consecutive float4 (a fully coalesced 512-byte access per instruction, 12 of them in
+// flight per lane at K = 16); the gradient rows pass through shared memory once so that lane r can form row r's mean of
+// g^2 (the row-reduced second moment) in column order.
 template <int DEG, bool FACTORED>
 __global__ void __launch_bounds__(UP_THREADS)
 train_update_kernel(const UpdateParams P) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int KF = K * 3;
-    const uint32_t j = blockIdx.x * UP_THREADS + threadIdx.x;   // index inside this launch's slice
-    if (j >= P.count) return;
-    const uint32_t i = P.g_begin + j;
+    constexpr int SROW = KF | 1;   // odd row stride: lane r walking row r is bank-conflict free
+    constexpr uint32_t NF_FULL = 8u * KF;            // float4 in the span of a full warp (32 rows)
+    constexpr int NF_LANE = (NF_FULL + 31) / 32;     // ... per lane
+    __shared__ float s_g[UP_THREADS / 32][32 * SROW];
+    __shared__ float s_v[UP_THREADS / 32][32];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t j0 = (blockIdx.x * (UP_THREADS / 32) + wid) * 32u;   // first row of this warp inside the launch's slice
+    if (j0 >= P.count) return;
+    const uint32_t rows = min(32u, P.count - j0);
+    const uint32_t j = j0 + lane;             // this lane's row inside the slice
+    const uint32_t i = P.g_begin + j;         // ... and its Gaussian
+    const bool valid = lane < rows;
+    float *sg = s_g[wid];
 
-    // ---- transforms row: Adam with per-column learning rates (train.rs:328-350)
-    float p[10], old_mean[3];
-    {
-        float g[10], m[10], v[10];
-        const float2 *p2 = reinterpret_cast<const float2 *>(P.transforms + (size_t)i * 10);
-        const float2 *g2 = reinterpret_cast<const float2 *>(P.g_t + (size_t)i * 10);
-        float2 *m2 = reinterpret_cast<float2 *>(P.m_t + (size_t)i * 10);
-        float2 *v2 = reinterpret_cast<float2 *>(P.v_t + (size_t)i * 10);
+    float old_mean[3] = {0.0f, 0.0f, 0.0f};
+    if (valid) {
+        // ---- transforms row: Adam with per-column learning rates (train.rs:328-350)
+        float p[10];
+        {
+            float g[10], m[10], v[10];
+            const float2 *p2 = reinterpret_cast<const float2 *>(P.transforms + (size_t)i * 10);
+            const float2 *g2 = reinterpret_cast<const float2 *>(P.g_t + (size_t)i * 10);
+            float2 *m2 = reinterpret_cast<float2 *>(P.m_t + (size_t)i * 10);
+            float2 *v2 = reinterpret_cast<float2 *>(P.v_t + (size_t)i * 10);
 #pragma unroll
-        for (int q = 0; q < 5; q++) {
-            const float2 a = p2[q], b = __ldg(g2 + q);
-            p[2 * q] = a.x; p[2 * q + 1] = a.y; g[2 * q] = b.x; g[2 * q + 1] = b.y;
-            if (!P.first) { const float2 c = m2[q], d = v2[q]; m[2 * q] = c.x; m[2 * q + 1] = c.y; v[2 * q] = d.x; v[2 * q + 1] = d.y; }
-            else { m[2 * q] = m[2 * q + 1] = v[2 * q] = v[2 * q + 1] = 0.0f; }
-        }
-        old_mean[0] = p[0]; old_mean[1] = p[1]; old_mean[2] = p[2];
-#pragma unroll
-        for (int c = 0; c < 10; c++) {
-            const float gg = P.grad_scale == 1.0f ? g[c] : g[c] * P.grad_scale;
-            m[c] = adam_m(m[c], gg, P);
-            v[c] = adam_v(v[c], gg * gg, P);
-            p[c] = adam_p(p[c], m[c], v[c], P.lr_t[c], P);
-        }
-#pragma unroll
-        for (int q = 0; q < 5; q++) { m2[q] = make_float2(m[2 * q], m[2 * q + 1]); v2[q] = make_float2(v[2 * q], v[2 * q + 1]); }
-    }
-    // ---- raw opacity
-    float raw;
-    {
-        const float g0 = __ldg(P.g_o + i);
-        const float gg = P.grad_scale == 1.0f ? g0 : g0 * P.grad_scale;
-        const float mm = adam_m(P.first ? 0.0f : P.m_o[i], gg, P);
-        const float vv = adam_v(P.first ? 0.0f : P.v_o[i], gg * gg, P);
-        raw = adam_p(P.raw_opac[i], mm, vv, P.lr_opac, P);
-        P.m_o[i] = mm; P.v_o[i] = vv; P.raw_opac[i] = raw;
-    }
-    // ---- refine statistics of the step (stats.rs:40-50): MAX over the views, SUM of the visibility counts
-    const float vis = __ldg(P.visible + i);
-    {
-        float vr, rad;
-        if (FACTORED) {
-            vr = __ldg(P.refine_all + j); rad = __ldg(P.radius_all + j);
-            for (uint32_t r = 1; r < P.world; r++) {
-                vr = fmaxf(vr, __ldg(P.refine_all + (size_t)r * P.count + j));
-                rad = fmaxf(rad, __ldg(P.radius_all + (size_t)r * P.count + j));
+            for (int q = 0; q < 5; q++) {
+                const float2 a = p2[q], b = __ldg(g2 + q);
+                p[2 * q] = a.x; p[2 * q + 1] = a.y; g[2 * q] = b.x; g[2 * q + 1] = b.y;
+                if (!P.first) { const float2 c = m2[q], d = v2[q]; m[2 * q] = c.x; m[2 * q + 1] = c.y; v[2 * q] = d.x; v[2 * q + 1] = d.y; }
+                else { m[2 * q] = m[2 * q + 1] = v[2 * q] = v[2 * q + 1] = 0.0f; }
             }
-        } else {
-            vr = __ldg(P.v_refine + i); rad = __ldg(P.max_radius + i);
-        }
-        P.refine_norm[i] = fmaxf(vr, P.refine_norm[i]);
-        P.vis_weight[i] = P.vis_weight[i] + vis;
-        P.max_screen[i] = fmaxf(rad, P.max_screen[i]);
-    }
-    // ---- mean noise on the updated means, gated by the updated opacity (train.rs:389-416)
-    if (P.noisy) {
-        const float opac = 1.0f / (1.0f + expf(-raw));
-        const float wgt = fminf(fmaxf(powf(1.0f - opac, 150.0f), 0.0f), 1.0f) * (vis > 0.0f ? 1.0f : 0.0f);
-        const float wm = wgt * P.noise_scale;
-        if (wm != 0.0f) {
-            const unsigned long long e0 = 3ull * i;
-            const uint32_t off = (uint32_t)(e0 & 3ull);   // elements 3i..3i+2 of the stream: quad e0/4, spilling into the next
-            float z[8];
-            normal_quad(P.seed, P.noise_offset + e0 / 4, z);
-            if (off > 1u) normal_quad(P.seed, P.noise_offset + e0 / 4 + 1, z + 4);
-            else z[4] = z[5] = z[6] = z[7] = 0.0f;
+            old_mean[0] = p[0]; old_mean[1] = p[1]; old_mean[2] = p[2];
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float zc = off == 0u ? z[c] : (off == 1u ? z[c + 1] : (off == 2u ? z[c + 2] : z[c + 3]));
-                p[c] += fminf(fmaxf(zc * wm, -P.median_scale), P.median_scale);
+            for (int c = 0; c < 10; c++) {
+                const float gg = P.grad_scale == 1.0f ? g[c] : g[c] * P.grad_scale;
+                m[c] = adam_m(m[c], gg, P);
+                v[c] = adam_v(v[c], gg * gg, P);
+                p[c] = adam_p(p[c], m[c], v[c], P.lr_t[c], P);
+            }
+#pragma unroll
+            for (int q = 0; q < 5; q++) { m2[q] = make_float2(m[2 * q], m[2 * q + 1]); v2[q] = make_float2(v[2 * q], v[2 * q + 1]); }
+        }
+        // ---- raw opacity
+        float raw;
+        {
+            const float g0 = __ldg(P.g_o + i);
+            const float gg = P.grad_scale == 1.0f ? g0 : g0 * P.grad_scale;
+            const float mm = adam_m(P.first ? 0.0f : P.m_o[i], gg, P);
+            const float vv = adam_v(P.first ? 0.0f : P.v_o[i], gg * gg, P);
+            raw = adam_p(P.raw_opac[i], mm, vv, P.lr_opac, P);
+            P.m_o[i] = mm; P.v_o[i] = vv; P.raw_opac[i] = raw;
+        }
+        // ---- refine statistics of the step (stats.rs:40-50): MAX over the views, SUM of the visibility counts
+        const float vis = __ldg(P.visible + i);
+        {
+            float vr, rad;
+            if (FACTORED) {
+                vr = __ldg(P.refine_all + j); rad = __ldg(P.radius_all + j);
+                for (uint32_t r = 1; r < P.world; r++) {
+                    vr = fmaxf(vr, __ldg(P.refine_all + (size_t)r * P.count + j));
+                    rad = fmaxf(rad, __ldg(P.radius_all + (size_t)r * P.count + j));
+                }
+            } else {
+                vr = __ldg(P.v_refine + i); rad = __ldg(P.max_radius + i);
+            }
+            P.refine_norm[i] = fmaxf(vr, P.refine_norm[i]);
+            P.vis_weight[i] = P.vis_weight[i] + vis;
+            P.max_screen[i] = fmaxf(rad, P.max_screen[i]);
+        }
+        // ---- mean noise on the updated means, gated by the updated opacity (train.rs:389-416)
+        if (P.noisy) {
+            const float opac = 1.0f / (1.0f + expf(-raw));
+            const float wgt = fminf(fmaxf(powf(1.0f - opac, 150.0f), 0.0f), 1.0f) * (vis > 0.0f ? 1.0f : 0.0f);
+            const float wm = wgt * P.noise_scale;
+            if (wm != 0.0f) {
+                const unsigned long long e0 = 3ull * i;
+                const uint32_t off = (uint32_t)(e0 & 3ull);   // elements 3i..3i+2 of the stream: quad e0/4, spilling into the next
+                float z[8];
+                normal_quad(P.seed, P.noise_offset + e0 / 4, z);
+                if (off > 1u) normal_quad(P.seed, P.noise_offset + e0 / 4 + 1, z + 4);
+                else z[4] = z[5] = z[6] = z[7] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float zc = off == 0u ? z[c] : (off == 1u ? z[c + 1] : (off == 2u ? z[c + 2] : z[c + 3]));
+                    p[c] += fminf(fmaxf(zc * wm, -P.median_scale), P.median_scale);
+                }
             }
         }
-    }
-    {
         float2 *p2 = reinterpret_cast<float2 *>(P.transforms + (size_t)i * 10);
 #pragma unroll
         for (int q = 0; q < 5; q++) p2[q] = make_float2(p[2 * q], p[2 * q + 1]);
     }
 
-    // ---- SH coefficients: gradient row (dense, or rebuilt from the views), row-mean second moment, per-band LR
-    float g[KF];
+    // ---- SH gradient rows of the warp's 32 Gaussians -> shared memory
+    const size_t span0 = (size_t)P.g_begin * KF + (size_t)j0 * KF;   // first float of the warp's span in the SH arrays
+    const uint32_t total = rows * KF;                                // floats in the span
+    const bool vec = (total & 3u) == 0;                              // (always true for full warps)
     if (FACTORED) {
+        if (valid) {
+            float g[KF];
 #pragma unroll
-        for (int c = 0; c < KF; c++) g[c] = 0.0f;
-        for (uint32_t v = 0; v < P.views; v++) {
-            const uint32_t r = v / P.local, li = v - r * P.local;
-            const float *vc = P.colours + (((size_t)li * P.world + r) * P.count + j) * 3;
-            const float cr = __ldg(vc), cg = __ldg(vc + 1), cb = __ldg(vc + 2);
-            if (cr == 0.0f && cg == 0.0f && cb == 0.0f) continue;
-            const float4 cp = __ldg(reinterpret_cast<const float4 *>(P.cam_all) + v);
-            const V3 u_world = sub(mk3(old_mean[0], old_mean[1], old_mean[2]), mk3(cp.x, cp.y, cp.z));
-            const V3 vdir = scale(u_world, 1.0f / length(u_world));
-            float Y[K];
-            sh_basis<DEG>(vdir, Y);
+            for (int c = 0; c < KF; c++) g[c] = 0.0f;
+            for (uint32_t v = 0; v < P.views; v++) {
+                const uint32_t r = v / P.local, li = v - r * P.local;
+                const float *vc = P.colours + (((size_t)li * P.world + r) * P.count + j) * 3;
+                const float cr = __ldg(vc), cg = __ldg(vc + 1), cb = __ldg(vc + 2);
+                if (cr == 0.0f && cg == 0.0f && cb == 0.0f) continue;
+                const float4 cp = __ldg(reinterpret_cast<const float4 *>(P.cam_all) + v);
+                const V3 u_world = sub(mk3(old_mean[0], old_mean[1], old_mean[2]), mk3(cp.x, cp.y, cp.z));
+                const V3 vdir = scale(u_world, 1.0f / length(u_world));
+                float Y[K];
+                sh_basis<DEG>(vdir, Y);
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                g[3 * k] += cr * Y[k];
-                g[3 * k + 1] += cg * Y[k];
-                g[3 * k + 2] += cb * Y[k];
+                for (int k = 0; k < K; k++) {
+                    g[3 * k] += cr * Y[k];
+                    g[3 * k + 1] += cg * Y[k];
+                    g[3 * k + 2] += cb * Y[k];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < KF; c++) sg[lane * SROW + c] = g[c] * P.sh_grad_scale;
+        }
+    } else if (rows == 32u) {   // full warp: a compile-time number of float4 per lane, all loads in flight before the first use
+        const float4 *g4 = reinterpret_cast<const float4 *>(P.g_sh + span0);
+        float4 t[NF_LANE];
+#pragma unroll
+        for (int q = 0; q < NF_LANE; q++) { const uint32_t f = lane + 32u * q; if (f < NF_FULL) t[q] = __ldg(g4 + f); }
+#pragma unroll
+        for (int q = 0; q < NF_LANE; q++) {
+            const uint32_t f = lane + 32u * q;
+            if (f < NF_FULL) {
+                const uint32_t e = f * 4;
+                const float tv[4] = {t[q].x, t[q].y, t[q].z, t[q].w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) sg[((e + c) / KF) * SROW + (e + c) % KF] = tv[c];
             }
         }
+    } else if (vec) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(P.g_sh + span0);
+        for (uint32_t f = lane; f < (total >> 2); f += 32) {
+            const float4 t = __ldg(g4 + f);
+            const uint32_t e = f * 4;
+            const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int c = 0; c < KF; c++) g[c] = g[c] * P.sh_grad_scale;
+            for (int q = 0; q < 4; q++) sg[((e + q) / KF) * SROW + (e + q) % KF] = tv[q];
+        }
     } else {
-        const float *src = P.g_sh + (size_t)i * KF;
-        if ((KF % 8) == 0 && (reinterpret_cast<uintptr_t>(P.g_sh) & 31u) == 0) {
-#pragma unroll
-            for (int q = 0; q < KF / 8; q++) ldg256(src + 8 * q, g + 8 * q);
-        } else if ((KF % 4) == 0) {
-#pragma unroll
-            for (int q = 0; q < KF / 4; q++) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(src) + q);
-                g[4 * q] = t.x; g[4 * q + 1] = t.y; g[4 * q + 2] = t.z; g[4 * q + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < KF; c++) g[c] = __ldg(src + c);
-        }
+        for (uint32_t e = lane; e < total; e += 32) sg[(e / KF) * SROW + e % KF] = __ldg(P.g_sh + span0 + e);
     }
-    float s = 0.0f;
+    __syncwarp();
+    // ---- row-mean second moment (adam_scaled.rs:152-165), in column order
+    if (valid) {
+        float s = 0.0f;
 #pragma unroll
-    for (int c = 0; c < KF; c++) s += g[c] * g[c];
-    const float mean_sq = s / (float)KF;
-    const float vv = adam_v(P.first ? 0.0f : P.v_sh[i], mean_sq, P);
-    P.v_sh[i] = vv;
-    float *ps = P.sh + (size_t)i * KF, *ms = P.m_sh + (size_t)i * KF;
-    const bool a32 = ((reinterpret_cast<uintptr_t>(P.sh) | reinterpret_cast<uintptr_t>(P.m_sh)) & 31u) == 0;
-    if ((KF % 8) == 0 && a32) {
+        for (int c = 0; c < KF; c++) { const float gv = sg[lane * SROW + c]; s += gv * gv; }
+        const float vv = adam_v(P.first ? 0.0f : P.v_sh[i], s / (float)KF, P);
+        P.v_sh[i] = vv;
+        s_v[wid][lane] = vv;
+    }
+    __syncwarp();
+    // ---- element-wise update of the warp's span, coalesced
+    float *ps = P.sh + span0, *ms = P.m_sh + span0;
+    auto update4 = [&](float4 &pp, float4 &mm, uint32_t f) {
+        float *pe = &pp.x, *me = &mm.x;
+        const uint32_t e = f * 4;
 #pragma unroll
-        for (int q = 0; q < KF / 8; q++) {
-            float pp[8], mm[8];
-            ld256(ps + 8 * q, pp);
-            if (!P.first) ld256(ms + 8 * q, mm);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int c = 8 * q + e;
-                mm[e] = adam_m(P.first ? 0.0f : mm[e], g[c], P);
-                pp[e] = adam_p(pp[e], mm[e], vv, c < 3 ? P.lr_sh_dc : P.lr_sh_rest, P);
-            }
-            stg256(ms + 8 * q, mm);
-            stg256(ps + 8 * q, pp);
+        for (int q = 0; q < 4; q++) {
+            const uint32_t r = (e + q) / KF, c = (e + q) % KF;
+            me[q] = adam_m(me[q], sg[r * SROW + c], P);
+            pe[q] = adam_p(pe[q], me[q], s_v[wid][r], c < 3 ? P.lr_sh_dc : P.lr_sh_rest, P);
         }
-    } else if ((KF % 4) == 0) {
+    };
+    if (rows == 32u) {
+        float4 *p4 = reinterpret_cast<float4 *>(ps), *m4 = reinterpret_cast<float4 *>(ms);
+        constexpr int GROUP = 4;   // float4 pairs in flight per lane
 #pragma unroll
-        for (int q = 0; q < KF / 4; q++) {
-            float4 p4 = reinterpret_cast<float4 *>(ps)[q];
-            float4 m4 = P.first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4 *>(ms)[q];
-            float *pp = &p4.x, *mm = &m4.x;
+        for (int q0 = 0; q0 < NF_LANE; q0 += GROUP) {
+            float4 pp[GROUP], mm[GROUP];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int c = 4 * q + e;
-                mm[e] = adam_m(mm[e], g[c], P);
-                pp[e] = adam_p(pp[e], mm[e], vv, c < 3 ? P.lr_sh_dc : P.lr_sh_rest, P);
+            for (int q = 0; q < GROUP; q++) {
+                const uint32_t f = lane + 32u * (q0 + q);
+                if (q0 + q < NF_LANE && f < NF_FULL) {
+                    pp[q] = p4[f];
+                    mm[q] = P.first ? make_float4(0.f, 0.f, 0.f, 0.f) : m4[f];
+                }
             }
-            reinterpret_cast<float4 *>(ms)[q] = m4;
-            reinterpret_cast<float4 *>(ps)[q] = p4;
+#pragma unroll
+            for (int q = 0; q < GROUP; q++) {
+                const uint32_t f = lane + 32u * (q0 + q);
+                if (q0 + q < NF_LANE && f < NF_FULL) {
+                    update4(pp[q], mm[q], f);
+                    m4[f] = mm[q];
+                    p4[f] = pp[q];
+                }
+            }
+        }
+    } else if (vec) {
+        float4 *p4 = reinterpret_cast<float4 *>(ps), *m4 = reinterpret_cast<float4 *>(ms);
+        for (uint32_t f = lane; f < (total >> 2); f += 32) {
+            float4 pp = p4[f];
+            float4 mm = P.first ? make_float4(0.f, 0.f, 0.f, 0.f) : m4[f];
+            update4(pp, mm, f);
+            m4[f] = mm;
+            p4[f] = pp;
         }
     } else {
-#pragma unroll
-        for (int c = 0; c < KF; c++) {
-            const float mm = adam_m(P.first ? 0.0f : ms[c], g[c], P);
-            ms[c] = mm;
-            ps[c] = adam_p(ps[c], mm, vv, c < 3 ? P.lr_sh_dc : P.lr_sh_rest, P);
+        for (uint32_t e = lane; e < total; e += 32) {
+            const uint32_t r = e / KF, c = e % KF;
+            const float mm = adam_m(P.first ? 0.0f : ms[e], sg[r * SROW + c], P);
+            ms[e] = mm;
+            ps[e] = adam_p(ps[e], mm, s_v[wid][r], c < 3 ? P.lr_sh_dc : P.lr_sh_rest, P);
         }
     }
 }
 
 template <int DEG>
 static cudaError_t launch_deg(cudaStream_t s, const UpdateParams &P, bool factored) {
-    const unsigned grid = (P.count + UP_THREADS - 1) / UP_THREADS;
+    const unsigned grid = (P.count + UP_THREADS - 1) / UP_THREADS;   // 32 rows per warp
     if (factored) train_update_kernel<DEG, true><<<grid, UP_THREADS, 0, s>>>(P);
     else train_update_kernel<DEG, false><<<grid, UP_THREADS, 0, s>>>(P);
     return cudaGetLastError();

@@ -351,14 +351,16 @@ class SceneLoader:
         t = torch.from_numpy(np.ascontiguousarray(packed).view(np.int32))
         nbytes = t.numel() * 4
         with self._lock:
-            admit = self._cache[index] is None and self._cache_used + nbytes < self._cache_budget
+            if self._cache[index] is not None:              # another loader task produced it meanwhile: one buffer per view
+                return self._cache[index]
+            admit = self._cache_used + nbytes < self._cache_budget
         if admit and torch.cuda.is_available():
             t = t.pin_memory()      # cached batches are uploaded many times: pin them once
         batch = SceneBatch(img_packed=t, camera=v.camera, has_alpha=has_alpha,
                            masked_alpha=has_alpha and self.alpha_mode == ALPHA_MASKED)
         if admit:
             with self._lock:
-                if self._cache[index] is not None:          # another loader task produced it meanwhile: one buffer per view
+                if self._cache[index] is not None:
                     return self._cache[index]
                 if self._cache_used + nbytes < self._cache_budget:
                     self._cache[index] = batch

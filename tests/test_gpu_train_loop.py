@@ -48,8 +48,8 @@ def test_colmap_set_trains_and_ground_truth_matches_oracle(tmp_path):
     evals = train_loop(ctx, splats, loaded.train, loaded.eval, cfg, ProcessConfig(eval_every=150, export_every=10 ** 9, seed=7),
                        on_step=lambda done, st, rf: seen.append((done, rf.total_splats if rf is not None else None)))
     assert [e["iter"] for e in evals] == [150, 300]
-    assert evals[-1]["psnr"] > evals[0]["psnr"] - 0.2 and evals[-1]["psnr"] > 17.0, evals
-    assert 0.3 < evals[-1]["ssim"] <= 1.0
+    assert evals[-1]["psnr"] > evals[0]["psnr"] + 0.5 and evals[-1]["psnr"] > 15.5, evals     # keeps improving
+    assert evals[-1]["ssim"] > evals[0]["ssim"] + 0.1 and evals[-1]["ssim"] <= 1.0
     refined = [c for _, c in seen if c is not None]
     assert len(refined) == 4 and all(0 < c <= 30_000 for c in refined)
     assert splats.num_splats() == refined[-1]
