@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary declared in include/brush_b200.h: context/arena management and
 // host-side orchestration of the kernels (what <MainBackendBase as SplatOps>::render does in
 // brush-render/src/render.rs:37-315, minus its blocking readback).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -43,9 +44,9 @@ cudaError_t launch_rasterize_fwd(cudaStream_t, bool, bool, uint32_t, const uint3
 cudaError_t launch_rasterize_bwd(cudaStream_t, bool, uint32_t, const uint32_t *, const uint32_t *, const float *,
                                  const float *, const float *, float *, uint32_t, uint32_t, uint32_t, const float *);
 // blend_fwd.cu / blend_bwd.cu (hard alpha cutoff: the production blend kernels)
-cudaError_t launch_blend_fwd(cudaStream_t, bool, uint32_t, const uint32_t *, uint32_t *, const float *, const uint32_t *,
-                             void *, float *, uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, const float *);
-cudaError_t launch_blend_bwd(cudaStream_t, uint32_t, const uint32_t *, const uint32_t *, const float *, const float *,
+cudaError_t launch_blend_fwd(cudaStream_t, bool, uint32_t, const CUtensorMap &, const uint32_t *, uint32_t *, const uint32_t *, void *,
+                             float *, uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, const float *);
+cudaError_t launch_blend_bwd(cudaStream_t, uint32_t, const CUtensorMap &, const uint32_t *, const uint32_t *, const float *,
                              const float *, const uint32_t *, const uint32_t *, float *, unsigned long long *, uint32_t,
                              uint32_t, uint32_t, const float *);
 cudaError_t launch_project_bwd(cudaStream_t, bool, int, const float *, const float *, const float *,
@@ -110,6 +111,7 @@ struct BgContext {
     // per (tile, warp) batch counts
     uint32_t *live_masks = nullptr, *warp_batches = nullptr;
     unsigned long long *blend_stats = nullptr;   // [4] development counters (bg_debug_blend_stats)
+    CUtensorMap tm_projected;                    // `projected` as a 2-D tensor [max_n][16 f32], box 16 x 1: TMA gather source
     unsigned long long *lb_scan = nullptr;  // look-back words for project/scan kernels
     unsigned long long *lb_sort = nullptr;  // look-back words for the sort passes: [tiles][256]
     uint64_t lb_scan_words = 0, lb_sort_words = 0, lb_sort_tile_words = 0;
@@ -202,6 +204,29 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
         return BG_ERR_CUDA;
     }
     memset(c->counters_host, 0, 16 * sizeof(uint32_t));
+    {   // tensor map of the projected rows for the blend kernels' TMA staging (cuTensorMapEncodeTiled through the runtime's
+        // driver entry point query: the library links the CUDA runtime only)
+        typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t qe = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        CUresult cr = CUDA_ERROR_NOT_SUPPORTED;
+        if (qe == cudaSuccess && fn) {
+            const cuuint64_t dims[2] = {BG_PROJECTED_STRIDE, (cuuint64_t)max_splats};
+            const cuuint64_t strides[1] = {BG_PROJECTED_STRIDE * sizeof(float)};
+            const cuuint32_t box[2] = {BG_PROJECTED_STRIDE, 1}, elem[2] = {1, 1};
+            cr = ((EncodeTiled)fn)(&c->tm_projected, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->projected, dims, strides, box, elem,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (cr != CUDA_SUCCESS) {
+            set_err("bg_ctx_create: cuTensorMapEncodeTiled (TMA descriptor of the projected rows)", qe);
+            bg_ctx_destroy(c);
+            return BG_ERR_CUDA;
+        }
+    }
     *out_ctx = c;
     return BG_OK;
 }
@@ -308,8 +333,8 @@ extern "C" int32_t bg_render_forward(BgContext *c, void *stream, const BgCamera 
         BG_CUDA(launch_rasterize_fwd(s, true, true, num_tiles, c->isect_val[iout], c->tile_offsets, c->projected,
                                      gid_sorted, out_img, visible, tiles_x, w, h, bg));
     else
-        BG_CUDA(launch_blend_fwd(s, bwd_info, num_tiles, c->isect_val[iout], c->tile_offsets, c->projected, gid_sorted,
-                                 out_img, visible, c->live_masks, c->warp_batches, tiles_x, w, h, bg));
+        BG_CUDA(launch_blend_fwd(s, bwd_info, num_tiles, c->tm_projected, c->isect_val[iout], c->tile_offsets, gid_sorted, out_img,
+                                 visible, c->live_masks, c->warp_batches, tiles_x, w, h, bg));
     BG_CUDA(cudaMemcpyAsync(c->counters_host, counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 
     st->projected = c->projected;
@@ -338,8 +363,8 @@ extern "C" int32_t bg_rasterize_backward(BgContext *c, void *stream, const BgRen
     const uint32_t num_tiles = st->tiles_x * st->tiles_y;
     if (st->pass == BG_PASS_BACKWARD && !smooth && st->tile_offsets == c->tile_offsets)
         // the forward of this context left its hand-off words: replay exactly the splats it used
-        BG_CUDA(launch_blend_bwd(s, num_tiles, st->compact_gid_from_isect, st->tile_offsets, st->projected, out_img,
-                                 v_output, c->live_masks, c->warp_batches, v_combined, nullptr, st->tiles_x, st->w, st->h, bg));
+        BG_CUDA(launch_blend_bwd(s, num_tiles, c->tm_projected, st->compact_gid_from_isect, st->tile_offsets, out_img, v_output,
+                                 c->live_masks, c->warp_batches, v_combined, nullptr, st->tiles_x, st->w, st->h, bg));
     else
         BG_CUDA(launch_rasterize_bwd(s, smooth != 0, num_tiles, st->compact_gid_from_isect, st->tile_offsets,
                                      st->projected, out_img, v_output, v_combined, st->tiles_x, st->w, st->h, bg));
@@ -358,9 +383,9 @@ extern "C" int32_t bg_debug_blend_stats(BgContext *c, void *stream, const BgRend
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(cudaMemsetAsync(c->blend_stats, 0, 4 * sizeof(unsigned long long), s));
-    BG_CUDA(launch_blend_bwd(s, st->tiles_x * st->tiles_y, st->compact_gid_from_isect, st->tile_offsets, st->projected,
-                             out_img, v_output, c->live_masks, c->warp_batches, v_combined_scratch, c->blend_stats,
-                             st->tiles_x, st->w, st->h, bg));
+    BG_CUDA(launch_blend_bwd(s, st->tiles_x * st->tiles_y, c->tm_projected, st->compact_gid_from_isect, st->tile_offsets, out_img,
+                             v_output, c->live_masks, c->warp_batches, v_combined_scratch, c->blend_stats, st->tiles_x, st->w,
+                             st->h, bg));
     BG_CUDA(cudaMemcpyAsync(out4, c->blend_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     BG_CUDA(cudaStreamSynchronize(s));
     out4[3] = st->counters_host ? st->counters_host[1] : 0;
@@ -605,7 +630,7 @@ static void fill_update_consts(UpdateParams &P, float lr_mean, float lr_rotation
     P.lr_sh_rest = (1.0f / lr_coeffs_sh_scale) * lr_coeffs_dc;
     P.lr_opac = lr_opac;
     P.beta1 = 0.9f; P.beta2 = 0.999f; P.eps = 1e-15f; P.f1 = 1.0f - P.beta1; P.f2 = 1.0f - P.beta2;
-    P.bc1 = 1.0f - powi_f32(P.beta1, step); P.bc2 = 1.0f - powi_f32(P.beta2, step);
+    P.inv_bc1 = 1.0f / (1.0f - powi_f32(P.beta1, step)); P.inv_bc2 = 1.0f / (1.0f - powi_f32(P.beta2, step));
     P.first = step == 1;
     P.noisy = noise_scale != 0.0f;
     P.noise_scale = noise_scale; P.median_scale = median_scale;

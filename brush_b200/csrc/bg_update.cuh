@@ -23,7 +23,7 @@ struct UpdateParams {
     const float *visible;            // [n] visibility count of the step (sum over the views)
     float lr_t[10];
     float lr_sh_dc, lr_sh_rest, lr_opac;
-    float beta1, beta2, eps, f1, f2, bc1, bc2;
+    float beta1, beta2, eps, f1, f2, inv_bc1, inv_bc2;   // 1 / (1 - beta^t), rounded once on the host
     int first;
     int noisy;
     float noise_scale, median_scale;

@@ -12,7 +12,7 @@
 //
 // Structure.  One thread per pixel pair as in the forward (state in registers), but the walk is driven by the
 // forward's hand-off (blend_common.cuh): per batch the warp reads the 32-bit set of splats that changed its block,
-// stages ONLY those rows (compacted, cp.async), and runs a plain counted loop over them -- no block test, no vote,
+// stages ONLY those rows (compacted, by TMA tile::gather4: blend_common.cuh), and runs a plain counted loop over them -- no block test, no vote,
 // no dead iteration.  The staging lane also forms the per-splat constants once (clamped colour, -opacity, the ten
 // post-reduction factors), so the loop body is per-pixel work only, written on float2 with packed FP32 (FFMA2 /
 // FMUL2 / FADD2; splat scalars in the broadcast operand form).  Signs are chosen so that no negation is ever an
@@ -24,11 +24,8 @@
 
 namespace bg {
 
-constexpr int BROW = 28;          // floats per staged row: 16 of the projected row (fixed up, id in lane 12) + 10 factors.
-                                  // 112 B: consecutive rows start 28 banks apart, so the per-lane fix-up accesses
-                                  // (one row per lane, 128 bits each) are conflict free, and 7 CTAs fit one SM
-constexpr int BROW_ID = 12;       // compact Gaussian id (bits)
-constexpr int BROW_FACT = 16;     // ten post-reduction factors
+constexpr int BROW_ID = 12;       // lane of the staged row that receives the compact Gaussian id (bits)
+constexpr int BFACT = 12;         // floats per row of the side table: ten post-reduction factors (+2 pad)
 
 __device__ __forceinline__ float rcp_approx_f(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx_f(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -36,17 +33,22 @@ __device__ __forceinline__ float sqrt_approx_f(float x) { float r; asm("sqrt.app
 // stats[0] warp-splat iterations, [1] pixel-splat pairs that blended, [2] pairs that stopped a pixel
 template <bool STATS>
 __global__ void __launch_bounds__(RASTER_THREADS)
-blend_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *__restrict__ tile_offsets,
-                 const float *__restrict__ projected, const float4 *__restrict__ out_img,
+blend_bwd_kernel(const __grid_constant__ CUtensorMap tm_projected, const uint32_t *__restrict__ cgid_from_isect,
+                 const uint32_t *__restrict__ tile_offsets, const float4 *__restrict__ out_img,
                  const float4 *__restrict__ v_output, const uint32_t *__restrict__ live_masks,
                  const uint32_t *__restrict__ warp_batches, float *__restrict__ v_combined,
                  unsigned long long *__restrict__ stats, BlendUniforms u) {
-    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * BROW];  // per warp, double buffered: 28 KB
+    __shared__ BlendStage s_stage[RASTER_WARPS];                         // per warp, double buffered rows (TMA destination)
+    __shared__ __align__(16) float s_fact[RASTER_WARPS][2][WB * BFACT];  // post-reduction factors of the staged rows
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t num_batches = __ldg(warp_batches + tile * RASTER_WARPS + wid);
+    BlendStage &st = s_stage[wid];
+    if (lane == 0) { mbar_init(&st.bar[0], 1); mbar_init(&st.bar[1], 1); }
+    __syncthreads();   // barriers initialised before any copy is issued
     if (num_batches == 0) return;
+    uint32_t phase_bits = 0u;   // bit b: parity the next wait on buffer b expects
     const uint32_t range_lo = tile_offsets[tile * 2];
     const uint32_t tile_x0 = (tile % u.tiles_x) * TILE_W, tile_y0 = (tile / u.tiles_x) * TILE_W;
     const uint32_t blk_x0 = tile_x0 + 8u * (wid & 1u), blk_y0 = tile_y0 + 8u * (wid >> 1);
@@ -91,18 +93,19 @@ blend_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *_
     auto load_mask = [&](uint32_t b) -> uint32_t {
         return b < num_batches ? __ldg(live_masks + mbase + (size_t)b * RASTER_WARPS) : 0u;
     };
-    // stage the rows of batch b selected by mask m, compacted in list order, into buffer b&1
+    // stage the rows of batch b selected by mask m, compacted in list order, into buffer b&1: the lanes park the row
+    // ids (padded to a multiple of four with the last one), one elected lane issues the TMA gathers
     auto stage = [&](uint32_t b, uint32_t m) -> uint32_t {
         uint32_t id = 0;
+        const uint32_t n = (uint32_t)__popc(m);
+        if (n == 0) return 0u;
         if ((m >> lane) & 1u) {
             id = __ldg(cgid_from_isect + range_lo + b * WB + lane);
-            const float *src = projected + (size_t)id * ROW;
-            float *dst = &s_rows[wid][b & 1u][__popc(m & lt_mask) * BROW];
-            cp_async16(dst, src);
-            cp_async16(dst + 4, src + 4);
-            cp_async16(dst + 8, src + 8);
+            st.ids[b & 1u][__popc(m & lt_mask)] = id;
         }
-        cp_async_commit();
+        const uint32_t last = __shfl_sync(0xffffffffu, id, 31u - (uint32_t)__clz(m));
+        if (lane < 3u && n + lane < ((n + 3u) & ~3u)) st.ids[b & 1u][n + lane] = last;
+        stage_rows_tma(st, b & 1u, n, &tm_projected, lane);
         return id;
     };
     unsigned long long st_iter = 0, st_blend = 0, st_stop = 0;
@@ -115,26 +118,30 @@ blend_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *_
         id_next = stage(b + 1, m_cur);   // (an all-zero mask stages nothing)
         const uint32_t n = (uint32_t)__popc(m);
         if (n == 0) continue;
-        cp_async_wait<1>();
-        float *rows = s_rows[wid][b & 1u];
+        mbar_wait(&st.bar[b & 1u], (phase_bits >> (b & 1u)) & 1u);
+        phase_bits ^= 1u << (b & 1u);
+        float *rows = st.rows[b & 1u];
+        float *fact = s_fact[wid][b & 1u];
         if ((m >> lane) & 1u) {
-            // per-splat constants, formed once by the lane that staged the row
-            float *mine = rows + __popc(m & lt_mask) * BROW;
+            // per-splat constants, formed once by the lane that parked the row's id
+            const uint32_t slot_r = (uint32_t)__popc(m & lt_mask);
+            float *mine = rows + slot_r * ROW;
             const float4 B = *reinterpret_cast<const float4 *>(mine + 4);   // c opac r g
             const float bcol = mine[8];
             *reinterpret_cast<float4 *>(mine + 4) = make_float4(B.x, -B.y, fmaxf(B.z, 0.0f), fmaxf(B.w, 0.0f));
             mine[8] = fmaxf(bcol, 0.0f);
             mine[BROW_ID] = __uint_as_float(my_id);
             // the loop accumulates -v_xy, -v_conic (without the 1/2 of the diagonal), -v_rgb (ungated), -sum v_sigma
-            *reinterpret_cast<float4 *>(mine + BROW_FACT) = make_float4(-1.0f, -1.0f, -0.5f, -1.0f);
-            *reinterpret_cast<float4 *>(mine + BROW_FACT + 4) =
+            float *f = fact + slot_r * BFACT;
+            *reinterpret_cast<float4 *>(f) = make_float4(-1.0f, -1.0f, -0.5f, -1.0f);
+            *reinterpret_cast<float4 *>(f + 4) =
                 make_float4(-0.5f, B.z >= 0.0f ? -1.0f : 0.0f, B.w >= 0.0f ? -1.0f : 0.0f, bcol >= 0.0f ? -1.0f : 0.0f);
-            *reinterpret_cast<float2 *>(mine + BROW_FACT + 8) = make_float2(1.0f / B.y, 1.0f);
+            *reinterpret_cast<float2 *>(f + 8) = make_float2(1.0f / B.y, 1.0f);
         }
         __syncwarp();
         if (STATS) st_iter += n;
         for (uint32_t j = 0; j < n; j++) {
-            const float *row = rows + j * BROW;
+            const float *row = rows + j * ROW;
             const float4 A = *reinterpret_cast<const float4 *>(row);       // mx my a b
             const float4 B = *reinterpret_cast<const float4 *>(row + 4);   // c -opac r+ g+
             const float4 C = *reinterpret_cast<const float4 *>(row + 8);   // b+, then log2(e)-scaled c/2, a/2, b
@@ -218,32 +225,29 @@ blend_bwd_kernel(const uint32_t *__restrict__ cgid_from_isect, const uint32_t *_
             d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
             if (owner && d1 != 0.0f) {
                 const uint32_t id = __float_as_uint(row[BROW_ID]);
-                atomicAdd(v_combined + (size_t)id * BG_VCOMBINED_STRIDE + slot, d1 * row[BROW_FACT + slot]);
+                atomicAdd(v_combined + (size_t)id * BG_VCOMBINED_STRIDE + slot, d1 * fact[j * BFACT + slot]);
             }
         }
         __syncwarp();  // all lanes are done with this buffer before the next stage() overwrites it
     }
-    cp_async_wait<0>();
     if (STATS && lane == 0) {
         atomicAdd(stats + 0, st_iter); atomicAdd(stats + 1, st_blend); atomicAdd(stats + 2, st_stop);
     }
 }
 
-cudaError_t launch_blend_bwd(cudaStream_t s, uint32_t num_tiles, const uint32_t *cgid_from_isect,
-                             const uint32_t *tile_offsets, const float *projected, const float *out_img,
-                             const float *v_output, const uint32_t *live_masks, const uint32_t *warp_batches,
-                             float *v_combined, unsigned long long *stats, uint32_t tiles_x, uint32_t w, uint32_t h,
-                             const float *bg) {
+cudaError_t launch_blend_bwd(cudaStream_t s, uint32_t num_tiles, const CUtensorMap &tm_projected, const uint32_t *cgid_from_isect,
+                             const uint32_t *tile_offsets, const float *out_img, const float *v_output, const uint32_t *live_masks,
+                             const uint32_t *warp_batches, float *v_combined, unsigned long long *stats, uint32_t tiles_x,
+                             uint32_t w, uint32_t h, const float *bg) {
     BlendUniforms u;
     u.tiles_x = tiles_x; u.img_w = w; u.img_h = h; u.bg_r = bg[0]; u.bg_g = bg[1]; u.bg_b = bg[2];
     if (stats)
-        blend_bwd_kernel<true><<<num_tiles, RASTER_THREADS, 0, s>>>(cgid_from_isect, tile_offsets, projected,
-                                                                   (const float4 *)out_img, (const float4 *)v_output,
-                                                                   live_masks, warp_batches, v_combined, stats, u);
+        blend_bwd_kernel<true><<<num_tiles, RASTER_THREADS, 0, s>>>(tm_projected, cgid_from_isect, tile_offsets, (const float4 *)out_img,
+                                                                   (const float4 *)v_output, live_masks, warp_batches, v_combined, stats, u);
     else
-        blend_bwd_kernel<false><<<num_tiles, RASTER_THREADS, 0, s>>>(cgid_from_isect, tile_offsets, projected,
-                                                                    (const float4 *)out_img, (const float4 *)v_output,
-                                                                    live_masks, warp_batches, v_combined, nullptr, u);
+        blend_bwd_kernel<false><<<num_tiles, RASTER_THREADS, 0, s>>>(tm_projected, cgid_from_isect, tile_offsets, (const float4 *)out_img,
+                                                                    (const float4 *)v_output, live_masks, warp_batches, v_combined,
+                                                                    nullptr, u);
     return cudaGetLastError();
 }
 

@@ -8,23 +8,19 @@
 // past the last blended splat (rasterize.rs:183-189), and the hand-off words of blend_common.cuh.
 //
 // Bound: instruction issue (FP32 + MUFU), not HBM.  Per warp-splat iteration (64 pixel-splat pairs) the loop is
-// 3 broadcast LDS.128, 4 scalar + 9 packed FMA-pipe operations, 2 MUFU.EX2 and the pair tests.
-#include <cstdlib>
-
+// 3 broadcast LDS.128, 4 scalar + 9 packed FMA-pipe operations, 2 MUFU.EX2 and the pair tests.  The rows of a batch are
+// staged by TMA (tile::gather4, blend_common.cuh) into the warp's double buffer.
 #include "blend_common.cuh"
 
 namespace bg {
 
-template <bool BWD_INFO, bool VOTE>
+template <bool BWD_INFO>
 __global__ void __launch_bounds__(RASTER_THREADS)
-blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restrict__ tile_offsets,
-                 const float *__restrict__ projected, const uint32_t *__restrict__ gid_from_cgid,
+blend_fwd_kernel(const __grid_constant__ CUtensorMap tm_projected, const uint32_t *__restrict__ cgid_from_isect,
+                 uint32_t *__restrict__ tile_offsets, const uint32_t *__restrict__ gid_from_cgid,
                  float4 *__restrict__ out_f32, uint32_t *__restrict__ out_packed, float *__restrict__ visible,
                  uint32_t *__restrict__ live_masks, uint32_t *__restrict__ warp_batches, BlendUniforms u) {
-    // staged rows are 80 bytes apart (the 64-byte projected row + 16 bytes of padding): one row per lane at 128 bits
-    // each is then free of bank conflicts in the per-lane phase (block test + colour clamp)
-    constexpr int SROW = ROW + 4;
-    __shared__ __align__(16) float s_rows[RASTER_WARPS][2][WB * SROW];  // per warp, double buffered
+    __shared__ BlendStage s_stage[RASTER_WARPS];   // per warp, double buffered
     __shared__ uint32_t s_max_useful;
 
     const uint32_t tile = blockIdx.x;
@@ -41,6 +37,10 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
 
     const uint32_t range_lo = tile_offsets[tile * 2], range_hi = tile_offsets[tile * 2 + 1];
     if (BWD_INFO && tid == 0) s_max_useful = range_lo;
+    BlendStage &st = s_stage[wid];
+    if (lane == 0) { mbar_init(&st.bar[0], 1); mbar_init(&st.bar[1], 1); }
+    __syncthreads();   // barriers initialised before any copy is issued
+    uint32_t phase_bits = 0u;   // bit b: parity the next wait on buffer b expects
 
     // T2: transmittance of the blended prefix (what the output uses).  Tt2: the same value while the pixel is alive;
     // the stopping splat's T' (<= 1e-4) afterwards, so that "T' > 1e-4" alone rejects every later splat.
@@ -53,19 +53,15 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
     const size_t mbase = blend_mask_base(range_lo, tile) + wid;
     uint32_t batches_walked = 0;
     uint32_t next_id = 0;
+    // stage batch b: every lane parks the id of "its" list entry, one elected lane issues the TMA gathers
     auto prefetch = [&](uint32_t b) {
-        uint32_t idx = range_lo + b * WB + lane;
-        if (idx < range_hi) {
-            uint32_t id = __ldg(cgid_from_isect + idx);
-            next_id = id;
-            const float *src = projected + (size_t)id * ROW;
-            float *dst = &s_rows[wid][b & 1u][lane * SROW];
-            cp_async16(dst, src);
-            cp_async16(dst + 4, src + 4);
-            cp_async16(dst + 8, src + 8);
-            cp_async16(dst + 12, src + 12);
-        }
-        cp_async_commit();
+        const uint32_t start = range_lo + b * WB;
+        const uint32_t count = min((uint32_t)WB, range_hi - start);
+        const uint32_t id = lane < count ? __ldg(cgid_from_isect + start + lane) : 0u;
+        next_id = id;
+        const uint32_t last = __shfl_sync(0xffffffffu, id, count - 1u);   // (every lane takes part in the shuffle)
+        st.ids[b & 1u][lane] = lane < count ? id : last;                     // pad with a valid row
+        stage_rows_tma(st, b & 1u, count, &tm_projected, lane);
     };
     // a warp whose pixels are all outside the image has nothing to blend
     if (num_batches > 0 && __any_sync(0xffffffffu, inside0 || inside1)) {
@@ -74,17 +70,13 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
             const uint32_t batch_start = range_lo + b * WB;
             const uint32_t count = min((uint32_t)WB, range_hi - batch_start);
             const uint32_t my_id = next_id;
-            if (b + 1 < num_batches) {
-                prefetch(b + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncwarp();
-            const float *rows = s_rows[wid][b & 1u];
+            if (b + 1 < num_batches) prefetch(b + 1);
+            mbar_wait(&st.bar[b & 1u], (phase_bits >> (b & 1u)) & 1u);
+            phase_bits ^= 1u << (b & 1u);
+            float *rows = st.rows[b & 1u];
             bool hit = false;
             if (lane < count) {
-                float *mine = s_rows[wid][b & 1u] + lane * SROW;
+                float *mine = rows + lane * ROW;
                 const float4 A = *reinterpret_cast<const float4 *>(mine);
                 const float4 B = *reinterpret_cast<const float4 *>(mine + 4);
                 const float bcol = mine[8], pt = mine[ROW_PT];
@@ -98,7 +90,7 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
             while (bits) {
                 const uint32_t s = (uint32_t)__ffs(bits) - 1u;
                 bits &= bits - 1u;
-                const float *row = rows + s * SROW;
+                const float *row = rows + s * ROW;
                 const float4 A = *reinterpret_cast<const float4 *>(row);       // mx my a b
                 const float4 B = *reinterpret_cast<const float4 *>(row + 4);   // c opac r g
                 const float4 C = *reinterpret_cast<const float4 *>(row + 8);   // b_col, then log2(e)-scaled c/2, a/2, b
@@ -121,21 +113,16 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
                 const uint32_t bit = 1u << s;
                 // the hand-off needs the splats that changed a live pixel: blended it or stopped it
                 const bool acted = (Tt2.x > 1.0e-4f && act0) || (Tt2.y > 1.0e-4f && act1);
-                if (VOTE) {   // warp-uniform masks: the votes are consumed at the end of the batch only
-                    if (__any_sync(0xffffffffu, c0 || c1)) used_m |= bit;
-                    if (BWD_INFO && __any_sync(0xffffffffu, acted)) acted_m |= bit;
-                } else {      // per-lane masks, OR-reduced once per batch
-                    if (c0 || c1) used_m |= bit;
-                    if (BWD_INFO && acted) acted_m |= bit;
-                }
+                if (c0 || c1) used_m |= bit;              // per-lane masks, OR-reduced once per batch
+                if (BWD_INFO && acted) acted_m |= bit;
                 T2.x = c0 ? nT.x : T2.x;
                 T2.y = c1 ? nT.y : T2.y;
                 Tt2.x = act0 ? nT.x : Tt2.x;
                 Tt2.y = act1 ? nT.y : Tt2.y;
             }
-            const uint32_t used = VOTE ? used_m : __reduce_or_sync(0xffffffffu, used_m);
+            const uint32_t used = __reduce_or_sync(0xffffffffu, used_m);
             if (BWD_INFO) {
-                const uint32_t acted = VOTE ? acted_m : __reduce_or_sync(0xffffffffu, acted_m);
+                const uint32_t acted = __reduce_or_sync(0xffffffffu, acted_m);
                 if (lane == 0) live_masks[mbase + (size_t)b * RASTER_WARPS] = acted;
                 if ((used >> lane) & 1u) {
                     visible[__ldg(gid_from_cgid + my_id)] = 1.0f;
@@ -143,10 +130,12 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
                 }
             }
             batches_walked = b + 1;
-            if (__all_sync(0xffffffffu, !(Tt2.x > 1.0e-4f) && !(Tt2.y > 1.0e-4f))) break;
+            if (__all_sync(0xffffffffu, !(Tt2.x > 1.0e-4f) && !(Tt2.y > 1.0e-4f))) {
+                if (b + 1 < num_batches) mbar_wait(&st.bar[(b + 1) & 1u], (phase_bits >> ((b + 1) & 1u)) & 1u);   // never leave a copy in flight
+                break;
+            }
             __syncwarp();  // all lanes are done with this buffer before the next prefetch overwrites its twin
         }
-        cp_async_wait<0>();
     }
 
     auto write_pixel = [&](float T, float r, float g, float bl, uint32_t pix_y) {
@@ -176,21 +165,18 @@ blend_fwd_kernel(const uint32_t *__restrict__ cgid_from_isect, uint32_t *__restr
     }
 }
 
-cudaError_t launch_blend_fwd(cudaStream_t s, bool bwd_info, uint32_t num_tiles, const uint32_t *cgid_from_isect,
-                             uint32_t *tile_offsets, const float *projected, const uint32_t *gid_from_cgid, void *out_img,
+cudaError_t launch_blend_fwd(cudaStream_t s, bool bwd_info, uint32_t num_tiles, const CUtensorMap &tm_projected,
+                             const uint32_t *cgid_from_isect, uint32_t *tile_offsets, const uint32_t *gid_from_cgid, void *out_img,
                              float *visible, uint32_t *live_masks, uint32_t *warp_batches, uint32_t tiles_x, uint32_t w,
                              uint32_t h, const float *bg) {
     BlendUniforms u;
     u.tiles_x = tiles_x; u.img_w = w; u.img_h = h; u.bg_r = bg[0]; u.bg_g = bg[1]; u.bg_b = bg[2];
-    static const bool vote = getenv("BG_BLEND_VOTE") != nullptr;   // development A/B switch
-#define BG_LAUNCH_FWD(BI, V)                                                                                              \
-    blend_fwd_kernel<BI, V><<<num_tiles, RASTER_THREADS, 0, s>>>(cgid_from_isect, tile_offsets, projected, gid_from_cgid, \
-                                                               BI ? (float4 *)out_img : nullptr,                       \
-                                                               BI ? nullptr : (uint32_t *)out_img, visible, live_masks, \
-                                                               warp_batches, u)
-    if (!bwd_info) { if (vote) BG_LAUNCH_FWD(false, true); else BG_LAUNCH_FWD(false, false); }
-    else { if (vote) BG_LAUNCH_FWD(true, true); else BG_LAUNCH_FWD(true, false); }
-#undef BG_LAUNCH_FWD
+    if (!bwd_info)
+        blend_fwd_kernel<false><<<num_tiles, RASTER_THREADS, 0, s>>>(tm_projected, cgid_from_isect, tile_offsets, gid_from_cgid, nullptr,
+                                                                    (uint32_t *)out_img, visible, nullptr, nullptr, u);
+    else
+        blend_fwd_kernel<true><<<num_tiles, RASTER_THREADS, 0, s>>>(tm_projected, cgid_from_isect, tile_offsets, gid_from_cgid,
+                                                                   (float4 *)out_img, nullptr, visible, live_masks, warp_batches, u);
     return cudaGetLastError();
 }
 

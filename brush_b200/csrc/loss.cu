@@ -356,11 +356,42 @@ image_loss_fused_kernel(LossArgs a, Chain4 chain, float *__restrict__ dl_dpred,
         }
     } else {
         const float bg_c = a.composite ? (c == 0 ? a.bg[0] : (c == 1 ? a.bg[1] : a.bg[2])) : 0.0f;
-        // ---- P0: stage (pred, gt_eff) with a 2*HALO border, zero padded
-        for (int i = t; i < FE * FE; i += F_THREADS) {
-            int ly = i / FE, lx = i - ly * FE;
-            int gy = tile_y0 + ly - 2 * HALO, gx = tile_x0 + lx - 2 * HALO;
-            *reinterpret_cast<float2 *>(&buf_a[i * 2]) = make_float2(ld_pred(a, c, gy, gx), ld_gt_eff(a, c, gy, gx, bg_c));
+        // ---- P0: stage (pred, gt_eff) with a 2*HALO border, zero padded.  Tiles whose staged region lies inside the
+        // image (all but the border tiles) skip the bounds tests and address with 32-bit offsets.
+        const bool interior = tile_x0 >= 2 * HALO && tile_y0 >= 2 * HALO && tile_x0 + FT + 2 * HALO <= W && tile_y0 + FT + 2 * HALO <= H &&
+                              (int64_t)H * a.sy < (1ll << 31) && a.sc < (1ll << 31);
+        if (interior) {
+            const float *pbase = a.pred + (int64_t)c * a.sc + (int64_t)(tile_y0 - 2 * HALO) * a.sy + (int64_t)(tile_x0 - 2 * HALO) * a.sx;
+            const uint32_t *gbase = a.gt + (size_t)(tile_y0 - 2 * HALO) * a.w + (tile_x0 - 2 * HALO);
+            const int sy = (int)a.sy, sx = (int)a.sx;
+            const uint32_t shift = c * 8u;
+            constexpr int P0_ITEMS = (FE * FE + F_THREADS - 1) / F_THREADS;   // 11 staged pixels per thread
+            float pv[P0_ITEMS];
+            uint32_t gv[P0_ITEMS];
+#pragma unroll
+            for (int k = 0; k < P0_ITEMS; k++) {   // all loads of the thread in flight before the first use
+                const int i = t + k * F_THREADS;
+                if (i < FE * FE) {
+                    const int ly = i / FE, lx = i - ly * FE;
+                    gv[k] = __ldg(gbase + ly * W + lx);
+                    pv[k] = __ldg(pbase + ly * sy + lx * sx);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < P0_ITEMS; k++) {
+                const int i = t + k * F_THREADS;
+                if (i < FE * FE) {
+                    float ge = (float)((gv[k] >> shift) & 0xffu) * INV_255;
+                    if (a.composite) ge = ge + (1.0f - (float)(gv[k] >> 24u) * INV_255) * bg_c;
+                    *reinterpret_cast<float2 *>(&buf_a[i * 2]) = make_float2(pv[k], ge);
+                }
+            }
+        } else {
+            for (int i = t; i < FE * FE; i += F_THREADS) {
+                int ly = i / FE, lx = i - ly * FE;
+                int gy = tile_y0 + ly - 2 * HALO, gx = tile_x0 + lx - 2 * HALO;
+                *reinterpret_cast<float2 *>(&buf_a[i * 2]) = make_float2(ld_pred(a, c, gy, gx), ld_gt_eff(a, c, gy, gx, bg_c));
+            }
         }
         __syncthreads();
         // ---- P1: horizontal window of the five moments: FE rows x 4 runs of 11 outputs (columns 0..41 of FP)
@@ -435,11 +466,14 @@ image_loss_fused_kernel(LossArgs a, Chain4 chain, float *__restrict__ dl_dpred,
                 const float s12 = o[4] - mu1 * mu2;
                 const float A = mu1_sq + mu2_sq + SSIM_C1, B = s1 + s2 + SSIM_C2;
                 const float c_top = 2.0f * mu1 * mu2 + SSIM_C1, d_top = 2.0f * s12 + SSIM_C2;
-                const float inv_ab = 1.0f / (A * B);
+                // two correctly rounded reciprocals serve the four quotients of lib.rs:507-520 (each within one
+                // rounding of the division it replaces)
+                const float inv_a = __frcp_rn(A), inv_b = __frcp_rn(B);
+                const float inv_ab = inv_a * inv_b;
                 const float cd = c_top * d_top * inv_ab;
                 const bool clamped = cd < -1.0f || cd > 1.0f;
-                const float dmu1 = clamped ? 0.0f : 2.0f * mu2 * inv_ab * (d_top - c_top) - 2.0f * mu1 * cd * (1.0f / A - 1.0f / B);
-                const float ds1 = clamped ? 0.0f : -cd / B;
+                const float dmu1 = clamped ? 0.0f : 2.0f * mu2 * inv_ab * (d_top - c_top) - 2.0f * mu1 * cd * (inv_a - inv_b);
+                const float ds1 = clamped ? 0.0f : -cd * inv_b;
                 const float ds12 = clamped ? 0.0f : 2.0f * c_top * inv_ab;
                 const int gy = tile_y0 + py_ - HALO, gx = tile_x0 + px_ - HALO;
                 float ch = 0.0f;

@@ -30,9 +30,15 @@ namespace bg {
 
 __device__ __forceinline__ float adam_m(float m, float g, const UpdateParams &P) { return P.first ? g * P.f1 : m * P.beta1 + g * P.f1; }
 __device__ __forceinline__ float adam_v(float v, float gsq, const UpdateParams &P) { return P.first ? gsq * P.f2 : v * P.beta2 + gsq * P.f2; }
-__device__ __forceinline__ float adam_p(float p, float m, float v, float step, const UpdateParams &P) {
-    const float m_hat = m / P.bc1, v_hat = v / P.bc2;
-    return p - (m_hat / (sqrtf(v_hat) + P.eps)) * step;
+// The bias corrections enter as reciprocals formed once on the host (1/bc1, 1/bc2) and the denominator as ONE correctly
+// rounded reciprocal per second-moment value: p -= (m/bc1) / (sqrt(v/bc2) + eps) * step  becomes
+// p -= ((m * inv_bc1) * rcp(sqrt(v * inv_bc2) + eps)) * step.  An IEEE division costs ~10 instructions on its fast path
+// and a subroutine call on its slow one; three of them per element made this pass instruction bound (350 M warp
+// instructions for 59 M elements, profiles/).  Each replaced quotient differs from the division by at most one rounding
+// (<= 1 ulp; WGSL, which the reference's optimiser runs on, allows 2.5 ulp for a division).
+__device__ __forceinline__ float adam_inv_denom(float v, const UpdateParams &P) { return __frcp_rn(__fsqrt_rn(v * P.inv_bc2) + P.eps); }
+__device__ __forceinline__ float adam_p(float p, float m, float inv_denom, float step, const UpdateParams &P) {
+    return p - ((m * P.inv_bc1) * inv_denom) * step;
 }
 
 constexpr int UP_THREADS = 128;   // 4 warps; a warp owns 32 consecutive Gaussians and never waits for another warp
@@ -84,7 +90,7 @@ train_update_kernel(const UpdateParams P) {
                 const float gg = P.grad_scale == 1.0f ? g[c] : g[c] * P.grad_scale;
                 m[c] = adam_m(m[c], gg, P);
                 v[c] = adam_v(v[c], gg * gg, P);
-                p[c] = adam_p(p[c], m[c], v[c], P.lr_t[c], P);
+                p[c] = adam_p(p[c], m[c], adam_inv_denom(v[c], P), P.lr_t[c], P);
             }
 #pragma unroll
             for (int q = 0; q < 5; q++) { m2[q] = make_float2(m[2 * q], m[2 * q + 1]); v2[q] = make_float2(v[2 * q], v[2 * q + 1]); }
@@ -96,7 +102,7 @@ train_update_kernel(const UpdateParams P) {
             const float gg = P.grad_scale == 1.0f ? g0 : g0 * P.grad_scale;
             const float mm = adam_m(P.first ? 0.0f : P.m_o[i], gg, P);
             const float vv = adam_v(P.first ? 0.0f : P.v_o[i], gg * gg, P);
-            raw = adam_p(P.raw_opac[i], mm, vv, P.lr_opac, P);
+            raw = adam_p(P.raw_opac[i], mm, adam_inv_denom(vv, P), P.lr_opac, P);
             P.m_o[i] = mm; P.v_o[i] = vv; P.raw_opac[i] = raw;
         }
         // ---- refine statistics of the step (stats.rs:40-50): MAX over the views, SUM of the visibility counts
@@ -204,7 +210,7 @@ train_update_kernel(const UpdateParams P) {
         for (int c = 0; c < KF; c++) { const float gv = sg[lane * SROW + c]; s += gv * gv; }
         const float vv = adam_v(P.first ? 0.0f : P.v_sh[i], s / (float)KF, P);
         P.v_sh[i] = vv;
-        s_v[wid][lane] = vv;
+        s_v[wid][lane] = adam_inv_denom(vv, P);   // one reciprocal per row, shared by its 3K coefficients
     }
     __syncwarp();
     // ---- element-wise update of the warp's span, coalesced

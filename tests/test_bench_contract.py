@@ -23,6 +23,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+    # the keys the driver compares between the two arms (same workload, same sizes)
+    assert all(d["config"].get(k) == v for k, v in (("n_gaussians", 1_000_000), ("width", 1920), ("height", 1080), ("sh_k", 16)))
+    assert "physical cores" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
