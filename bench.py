@@ -13,7 +13,7 @@ metric = forward+backward Mpix/s.
 
 N > 1 (torchrun, one rank per GPU): the step is view-sharded -- every rank renders its own view of the replicated scene
 and the ranks exchange the gradients over the library's NCCL communicator (bg_dp_exchange: all-reduce 48 N B,
-all-gather 20 N B per rank; the SH gradient stays in its per-view rank-one form, which is what the optimiser pass
+all-gather 20 N B per rank of interleaved per-Gaussian rows; the SH gradient stays in its per-view rank-one form, which is what the optimiser pass
 consumes).  Weak scaling: per-GPU work is fixed, value = N * pixels / max-over-ranks step time.
 
 The other configs ride in the same JSON line under "configs":
@@ -289,10 +289,10 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
     if dp:
         from brush_b200.dp import DpComm
         comm = DpComm(ctx)
-        small = torch.zeros(12 * n, dtype=torch.float32, device=dev)       # v_transforms | v_raw_opac | visible
-        record = torch.zeros(5 * n, dtype=torch.float32, device=dev)       # v_color | v_refine | max_radius
+        small = torch.zeros(12 * n, dtype=torch.float32, device=dev)       # rows: v_transforms | v_raw_opac | visible
+        record = torch.zeros(5 * n, dtype=torch.float32, device=dev)       # rows: v_color | v_refine | max_radius
         recv = torch.zeros(world * 5 * n, dtype=torch.float32, device=dev)
-        outs = (small[:10 * n].view(n, 10), record[:3 * n].view(n, 3), small[10 * n:11 * n], record[3 * n:4 * n])
+        outs = (torch.empty((n, 10), device=dev), torch.empty((n, 3), device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))
         dense = None
     else:
         dense = (torch.empty((n, 10), device=dev), torch.empty((n, SH_K, 3), device=dev), torch.empty(n, device=dev),
@@ -305,8 +305,7 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
         vc = R.rasterize_bwd(out, vo)
         if dp:
             g = R.project_bwd_factored(out, ttr, tsh, top, vc, outputs=outs)
-            small[11 * n:].copy_(out.visible)
-            record[4 * n:].copy_(out.max_radius)
+            comm.pack_view(n, 1, 0, True, outs[0], outs[2], outs[1], outs[3], out.visible, out.max_radius, small, record)
         else:
             g = R.project_bwd(out, ttr, tsh, top, vc, outputs=dense)
         return out, g
@@ -330,28 +329,25 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
     T = per_tile.size
     stats = R.blend_stats(out, v_out)
     # The step is ~20 short launches; replaying it as one CUDA graph removes the host launch gaps (the library keeps
-    # nothing launch-specific on the host: counters and look-back epochs live on the device).  N>1: the exchange runs on
-    # the communicator's own stream between two events, which a capture records as a fork/join.
-    graph = None if os.environ.get("BG_BENCH_NO_GRAPH") else B.capture(lambda: step())
-    launch = "one CUDA graph replay per step" + (" (exchange included)" if dp and graph is not None else "")
-    if graph is None and dp and not os.environ.get("BG_BENCH_NO_GRAPH"):
-        graph_c = B.capture(lambda: compute())
-        if graph_c is not None:
-            launch = "one CUDA graph replay per step + eager exchange"
-            run_step = lambda i: (graph_c.replay(), exchange())
-        else:
-            launch = "eager launches"
-            run_step = lambda i: step()
-    elif graph is None:
+    # nothing launch-specific on the host: counters and look-back epochs live on the device).  N>1: the graph holds this
+    # rank's kernels; the exchange (NCCL on the communicator's own stream) is issued eagerly behind each replay.
+    log(f"config [{cfg_idx}]: warm-up done (V={V}, I={I}); capturing the step")
+    graph = None if os.environ.get("BG_BENCH_NO_GRAPH") else B.capture(lambda: compute())
+    if graph is not None:
+        launch = "one CUDA graph replay per step" + (" + eager exchange" if dp else "")
+        run_step = (lambda i: (graph.replay(), exchange())) if dp else (lambda i: graph.replay())
+    else:
         launch = "eager launches"
         run_step = lambda i: step()
-    else:
-        run_step = lambda i: graph.replay()
+    for _ in range(3):
+        run_step(0)
+    torch.cuda.synchronize(dev)
+    log(f"config [{cfg_idx}]: timing {steps} steps ({launch})")
     ms_step = B.timed(run_step, steps) / steps
     res = {"n": n, "w": w, "h": h, "V": V, "I": I, "T": T, "P": P, "ms_step": ms_step, "launch": launch, "overflow": overflow,
            "per_tile_mean": float(per_tile.mean()), "per_tile_max": int(per_tile.max()), "stats": stats}
-    if dp:   # phases: this rank's kernels alone, the exchange alone
-        res["ms_compute"] = B.timed(lambda i: compute(), steps) / steps
+    if dp:   # phases: this rank's kernels alone (the same graph), the exchange alone
+        res["ms_compute"] = B.timed((lambda i: graph.replay()) if graph is not None else (lambda i: compute()), steps) / steps
         res["ms_exchange"] = B.timed(lambda i: exchange(), steps) / steps
     if headline:
         # ---- e2e: host input, copies inside the timed region
@@ -437,8 +433,11 @@ def views_leg(B: Bench, steps: int):
     params = [torch.from_numpy(x).to(dev) for x in (tr, sh, op)]
     splats = T.Splats(*params)
     trainer = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
+    log(f"config [4]: warm-up ({local} views per rank)")
     for _ in range(2):
         trainer.step_views(batches, splats)
+    torch.cuda.synchronize(dev)
+    log("config [4]: timing")
     k8 = max(10, steps // 5)
     ms = B.timed(lambda i: trainer.step_views(batches, splats), k8) / k8
     res = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "views_per_step": 8, "views_per_rank": local, "n_gaussians": n,
@@ -487,7 +486,9 @@ def main():
     B = Bench(args)
     world, rank = B.world, B.rank
 
+    log(f"rank {rank}/{world}: config [1]")
     h1 = fwd_bwd_leg(B, 1, args.steps, args.warmup, headline=True)
+    log("config [1] done")
     V, I, T, P = h1["V"], h1["I"], h1["T"], h1["P"]
     ms_step = h1["ms_step"]
     value = world * P / (ms_step * 1e-3) / 1e6

@@ -178,6 +178,7 @@ SIGNATURES = {
     "bg_dp_comm_destroy": (_I32, [_P]),
     "bg_dp_small_floats": (_U64, [_U32]),
     "bg_dp_record_floats": (_U64, [_U32, _U32]),
+    "bg_dp_pack_view": (_I32, [_P, _P, _U32, _U32, _U32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bg_dp_exchange": (_I32, [_P, _P, _P, _U32, _U32, _P, _P, _P, _U32]),
     "bg_train_step_views_workspace_bytes": (_U64, [_U32, _U32, _U32, _U32, _U32, _U32]),
     "bg_train_step_views": (_I32, [_P, _P, _P, C.POINTER(BgTrainViewsArgs)]),

@@ -58,6 +58,8 @@ cudaError_t launch_loss_reduce(cudaStream_t, const float *, uint32_t, uint32_t, 
 cudaError_t launch_min_scale(cudaStream_t, uint32_t, const float *, const float *, uint32_t, float, float *);
 cudaError_t launch_fold_min_scale_fwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
 cudaError_t launch_fold_min_scale_bwd(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *);
+cudaError_t launch_fold_min_scale_bwd_strided(cudaStream_t, uint32_t, const float *, const float *, const float *, float *, float *,
+                                              uint32_t, uint32_t);
 cudaError_t launch_sh_grad_from_views(cudaStream_t, int, const float *, const float *, uint32_t, const float *, uint32_t,
                                       float, float *, size_t);
 // loss.cu / optim.cu
@@ -788,8 +790,20 @@ extern "C" int32_t bg_dp_comm_destroy(BgDpComm *h) {
     return BG_OK;
 }
 
-extern "C" uint64_t bg_dp_small_floats(uint32_t n) { return (uint64_t)12 * n; }
+extern "C" uint64_t bg_dp_small_floats(uint32_t n) { return (uint64_t)DP_SMALL_ROW * n; }
 extern "C" uint64_t bg_dp_record_floats(uint32_t n, uint32_t local) { return ((uint64_t)3 * local + 2) * n; }
+
+extern "C" int32_t bg_dp_pack_view(BgContext *c, void *stream, uint32_t n, uint32_t local, uint32_t view, int32_t first, const float *v_t,
+                                   const float *v_o, const float *v_color, const float *v_refine, const float *visible,
+                                   const float *max_radius, float *small, float *record) {
+    if (!c) return BG_ERR_NULL;
+    if (n == 0) return BG_OK;
+    if (!v_t || !v_o || !v_color || !v_refine || !visible || !max_radius || !small || !record) return BG_ERR_NULL;
+    if (local == 0 || local > DP_MAX_VIEWS || view >= local) { set_err("bg_dp_pack_view: view index / views per rank", cudaSuccess); return BG_ERR_INVALID; }
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_CUDA(launch_pack_view((cudaStream_t)stream, n, local, view, first != 0, v_t, v_o, v_color, v_refine, visible, max_radius, small, record));
+    return BG_OK;
+}
 
 // Issues all slices of the exchange on the communicator's stream behind `s`; s waits for slice c through ev_chunk[c].
 static int32_t issue_exchange(DpComm *d, cudaStream_t s, uint32_t n, uint32_t local, uint32_t chunks, float *small,
@@ -825,8 +839,8 @@ extern "C" int32_t bg_dp_exchange(BgContext *c, BgDpComm *h, void *stream, uint3
 
 namespace {
 struct ViewsWs {
-    float *out_img, *v_output, *partials, *loss_terms, *v_combined, *small, *tmp_small, *record, *recv, *hdr, *hdr_all;
-    float *r_transforms, *r_opac, *vis_view, *refine_view, *radius_view;
+    float *out_img, *v_output, *partials, *loss_terms, *v_combined, *small, *record, *recv, *hdr, *hdr_all;
+    float *r_transforms, *r_opac, *v_t, *v_o, *v_color, *v_refine, *visible, *max_radius;
     uint64_t bytes;
 };
 ViewsWs carve_views_ws(void *base, uint32_t n, uint32_t k, uint32_t w, uint32_t h, uint32_t local, uint32_t world, bool fold) {
@@ -846,16 +860,15 @@ ViewsWs carve_views_ws(void *base, uint32_t n, uint32_t k, uint32_t w, uint32_t 
     ws.loss_terms = take(DP_MAX_VIEWS);
     ws.v_combined = take((uint64_t)n * BG_VCOMBINED_STRIDE);
     ws.small = take(L.small_floats);
-    ws.tmp_small = take(local > 1 ? L.small_floats : 0);
     ws.record = take(L.rec_floats);
     ws.recv = take(world > 1 ? L.recv_floats : 0);
     ws.hdr = take(DP_MAX_VIEWS * 4);
     ws.hdr_all = take(DP_MAX_VIEWS * 4);
     ws.r_transforms = take(fold ? (uint64_t)n * 10 : 0);
     ws.r_opac = take(fold ? n : 0);
-    ws.vis_view = take(local > 1 ? n : 0);
-    ws.refine_view = take(local > 1 ? n : 0);
-    ws.radius_view = take(local > 1 ? n : 0);
+    // one view's gradients, as the operators write them, before they are folded into the exchange rows
+    ws.v_t = take((uint64_t)n * 10); ws.v_o = take(n); ws.v_color = take((uint64_t)n * 3); ws.v_refine = take(n);
+    ws.visible = take(n); ws.max_radius = take(n);
     ws.bytes = off;
     return ws;
 }
@@ -906,17 +919,13 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     const float npx = (float)w * (float)hh;
     float chain[4] = {1.0f / (3.0f * npx), 1.0f / (3.0f * npx), 1.0f / (3.0f * npx), a->channels == 4 ? a->alpha_weight / npx : 0.0f};
     BG_CUDA(cudaMemsetAsync(ws.v_output, 0, (size_t)w * hh * 4 * sizeof(float), s));
-    float *small_t = ws.small, *small_o = ws.small + (size_t)n * 10, *small_vis = ws.small + (size_t)n * 11;
-    float *rec_refine = ws.record + L.rec_refine, *rec_radius = ws.record + L.rec_radius;
     DpHeader hdr;
     memset(&hdr, 0, sizeof(hdr));
     for (uint32_t i = 0; i < local; i++) {
-        const bool first = i == 0;
         const BgCamera *cam = a->cams + i;
         for (int q = 0; q < 3; q++) hdr.pos[i][q] = cam->cam_pos[q];
-        float *vis = first ? small_vis : ws.vis_view, *rad = first ? rec_radius : ws.radius_view;
-        r = bg_render_forward(c, stream, cam, w, hh, n, k, r_t, a->sh, r_o, a->mip, a->background, BG_PASS_BACKWARD, ws.out_img, vis, rad,
-                              &a->state_out);
+        r = bg_render_forward(c, stream, cam, w, hh, n, k, r_t, a->sh, r_o, a->mip, a->background, BG_PASS_BACKWARD, ws.out_img, ws.visible,
+                              ws.max_radius, &a->state_out);
         if (r != BG_OK) return r;
         r = bg_image_loss_fused(c, stream, ws.out_img, a->gt_packed[i], a->channels, hh, w, 1, (int64_t)w * 4, 4, a->l1_weight,
                                 a->ssim_weight, a->has_composite_bg ? a->composite_bg : nullptr, a->mask, chain, ws.v_output, ws.partials);
@@ -925,21 +934,19 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
                                    ws.loss_terms + i));
         r = bg_rasterize_backward(c, stream, &a->state_out, ws.out_img, ws.v_output, a->background, 0, ws.v_combined, n);
         if (r != BG_OK) return r;
-        r = bg_project_backward_factored(c, stream, cam, &a->state_out, r_t, a->sh, r_o, ws.v_combined, first ? small_t : ws.tmp_small,
-                                         ws.record + (size_t)i * n * 3, first ? small_o : ws.tmp_small + (size_t)n * 10,
-                                         first ? rec_refine : ws.refine_view);
+        r = bg_project_backward_factored(c, stream, cam, &a->state_out, r_t, a->sh, r_o, ws.v_combined, ws.v_t, ws.v_color, ws.v_o, ws.v_refine);
         if (r != BG_OK) return r;
-        if (!first)
-            BG_CUDA(launch_accumulate_view(s, n, ws.small, ws.tmp_small, ws.vis_view, rec_refine, ws.refine_view, rec_radius, ws.radius_view));
+        // fold the view into the exchange rows (sum of the small gradients, the view's colour gradient, MAX statistics)
+        BG_CUDA(launch_pack_view(s, n, local, i, i == 0, ws.v_t, ws.v_o, ws.v_color, ws.v_refine, ws.visible, ws.max_radius, ws.small, ws.record));
     }
     BG_CUDA(launch_loss_mean(s, ws.loss_terms, local, a->loss_out));
     // ---- exchange (slices on the communicator's stream) and the update pass slice by slice under it
-    const float *colours_base = ws.record, *cam_all = ws.hdr;
+    const float *records_base = ws.record, *cam_all = ws.hdr;
     BG_CUDA(launch_write_header(s, ws.hdr, hdr, local));
     if (world > 1) {
         r = issue_exchange(h->c, s, n, local, chunks, ws.small, ws.record, ws.recv, ws.hdr, ws.hdr_all);
         if (r != BG_OK) return r;
-        colours_base = ws.recv; cam_all = ws.hdr_all;
+        records_base = ws.recv; cam_all = ws.hdr_all;
     }
     (void)rank;
     UpdateParams P;
@@ -947,7 +954,7 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     P.transforms = a->transforms; P.sh = a->sh; P.raw_opac = a->raw_opac;
     P.m_t = a->m_t; P.v_t = a->v_t; P.m_sh = a->m_sh; P.v_sh = a->v_sh; P.m_o = a->m_o; P.v_o = a->v_o;
     P.refine_norm = a->refine_norm; P.vis_weight = a->vis_weight; P.max_screen = a->max_screen;
-    P.g_t = small_t; P.g_o = small_o; P.visible = small_vis;
+    P.small = ws.small;
     P.grad_scale = 1.0f / (float)views; P.sh_grad_scale = 1.0f / (float)views;
     P.cam_all = cam_all; P.views = views; P.local = local; P.world = world;
     fill_update_consts(P, a->lr_mean, a->lr_rotation, a->lr_scale, a->lr_coeffs_dc, a->lr_coeffs_sh_scale, a->lr_opac, a->noise_scale,
@@ -957,16 +964,12 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
         dp_chunk_range(n, chunks, ch, &g0, &len);
         if (world > 1) BG_CUDA(cudaStreamWaitEvent(s, h->c->ev_chunk[ch], 0));
         if (len == 0) continue;
-        if (fold) {   // chain the gradients w.r.t. the folded values back to the learned ones (linear: after the sum)
-            r = bg_fold_min_scale_backward(c, stream, len, a->transforms + (size_t)g0 * 10, a->raw_opac + g0, a->min_scale + g0,
-                                           small_t + (size_t)g0 * 10, small_o + g0);
-            if (r != BG_OK) return r;
-        }
-        const float *base = colours_base + L.chunk_base(g0);
+        if (fold)   // chain the gradients w.r.t. the folded values back to the learned ones (linear: after the sum), in the rows
+            BG_CUDA(launch_fold_min_scale_bwd_strided(s, len, a->transforms + (size_t)g0 * 10, a->raw_opac + g0, a->min_scale + g0,
+                                                      ws.small + (size_t)g0 * DP_SMALL_ROW, ws.small + (size_t)g0 * DP_SMALL_ROW + 10,
+                                                      DP_SMALL_ROW, DP_SMALL_ROW));
         P.g_begin = g0; P.count = len;
-        P.colours = base + L.colour_off(len, 0);
-        P.refine_all = base + L.refine_off(len);
-        P.radius_all = base + L.radius_off(len);
+        P.records = records_base + L.chunk_base(g0);
         BG_CUDA(launch_train_update(s, deg, P, true));
     }
     return BG_OK;

@@ -20,24 +20,23 @@ struct DpComm {
 
 struct DpHeader { float pos[DP_MAX_VIEWS][3]; };
 
-// Float offsets of the exchange buffers (see dp.cu).
+// Exchange buffers (see dp.cu), interleaved per Gaussian so that a slice of the Gaussian range is ONE contiguous piece
+// of each buffer (one all-reduce and one all-gather per slice):
+//   small  [n][12]        v_transforms (10) | v_raw_opac | visible, summed over the rank's views
+//   record [n][3 local+2] v_color of each local view (3 each) | v_refine | max_radius (MAX over the rank's views)
+//   recv   per slice (g0, len): [world][len][3 local + 2] at float offset (3 local + 2) * world * g0
+constexpr uint32_t DP_SMALL_ROW = 12;
 struct DpLayout {
-    uint32_t n, local, world;
-    size_t rec_refine, rec_radius, rec_floats;   // record: colours [local][n][3] | refine [n] | radius [n]
-    size_t small_floats;                          // v_transforms [n][10] | v_raw_opac [n] | visible [n]
-    size_t recv_floats;                           // world * rec_floats, laid out per slice
-    __host__ __device__ size_t chunk_base(uint32_t g0) const { return (size_t)(3 * local + 2) * world * g0; }
-    __host__ __device__ size_t colour_off(uint32_t len, uint32_t li) const { return (size_t)li * world * len * 3; }
-    __host__ __device__ size_t refine_off(uint32_t len) const { return (size_t)3 * local * world * len; }
-    __host__ __device__ size_t radius_off(uint32_t len) const { return (size_t)(3 * local + 1) * world * len; }
+    uint32_t n, local, world, rec_row;
+    size_t rec_floats, small_floats, recv_floats;
+    __host__ __device__ size_t chunk_base(uint32_t g0) const { return (size_t)rec_row * world * g0; }
 };
 inline DpLayout dp_layout(uint32_t n, uint32_t local, uint32_t world) {
     DpLayout L;
     L.n = n; L.local = local; L.world = world;
-    L.rec_refine = (size_t)3 * local * n;
-    L.rec_radius = L.rec_refine + n;
-    L.rec_floats = L.rec_radius + n;
-    L.small_floats = (size_t)12 * n;
+    L.rec_row = 3 * local + 2;
+    L.rec_floats = (size_t)L.rec_row * n;
+    L.small_floats = (size_t)DP_SMALL_ROW * n;
     L.recv_floats = L.rec_floats * world;
     return L;
 }
@@ -51,7 +50,8 @@ int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, u
                       float *recv);
 int dp_exchange_header(DpComm *cm, uint32_t local, const float *hdr, float *hdr_all);
 cudaError_t launch_write_header(cudaStream_t s, float *hdr, const DpHeader &h, uint32_t local);
-cudaError_t launch_accumulate_view(cudaStream_t s, uint32_t n, float *small, const float *tmp, const float *vis_view,
-                                   float *refine, const float *refine_view, float *radius, const float *radius_view);
+cudaError_t launch_pack_view(cudaStream_t s, uint32_t n, uint32_t local, uint32_t li, bool first, const float *v_t, const float *v_o,
+                             const float *v_color, const float *v_refine, const float *visible, const float *max_radius, float *small,
+                             float *record);
 
 }  // namespace bg

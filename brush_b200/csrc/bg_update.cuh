@@ -10,17 +10,18 @@ struct UpdateParams {
     float *transforms, *sh, *raw_opac;
     float *m_t, *v_t, *m_sh, *v_sh, *m_o, *v_o;
     float *refine_norm, *vis_weight, *max_screen;
-    const float *g_t, *g_o;          // [n,10], [n] (summed over the views when grad_scale != 1)
+    const float *g_t, *g_o;          // dense: [n,10], [n].  Factored: unused (the gradients are rows of `small`)
     const float *g_sh;               // dense [n,K,3] gradient; unused when factored
-    float grad_scale;                // applied to g_t and g_o (1/views)
-    // factored SH gradient + MAX statistics: the slice of the gathered records that holds [g_begin, g_begin+count)
-    // (bg_dp.cuh DpLayout): colours [local][world][count][3], refine [world][count], radius [world][count]
-    const float *colours, *refine_all, *radius_all;
+    float grad_scale;                // applied to the transforms / opacity gradients (1/views)
+    // factored form (multi-view steps, bg_dp.cuh): `small` [n][12] = v_transforms | v_raw_opac | visible summed over all
+    // views; `records` = the slice [g_begin, g_begin+count) of the gathered records, [world][count][3 local + 2] =
+    // v_color of each of the rank's views | v_refine | max_radius
+    const float *small, *records;
     const float *cam_all;            // device [views][4]: camera positions in global view order
     uint32_t views, local, world;
     float sh_grad_scale;             // 1/views
     const float *v_refine, *max_radius;   // [n] statistics of the step when not factored
-    const float *visible;            // [n] visibility count of the step (sum over the views)
+    const float *visible;            // [n] visibility of the step when not factored
     float lr_t[10];
     float lr_sh_dc, lr_sh_rest, lr_opac;
     float beta1, beta2, eps, f1, f2, inv_bc1, inv_bc2;   // 1 / (1 - beta^t), rounded once on the host

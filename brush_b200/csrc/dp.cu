@@ -2,18 +2,17 @@
 //
 // Parameters are replicated, every rank renders its own views of the step's batch, and ONE exchange per step makes
 // the gradient of the mean-over-views loss available on every rank:
-//   small  = v_transforms [n,10] | v_raw_opac [n] | visible [n]   summed over the rank's views  -> all-reduce (SUM)
-//   record = v_color [local,n,3] | v_refine [n] | max_radius [n]  (the MAX statistics over the rank's views)
-//                                                                                               -> all-gather
+//   small  [n][12]          = v_transforms (10) | v_raw_opac | visible, summed over the rank's views   -> all-reduce (SUM)
+//   record [n][3 local + 2] = v_color of each local view | v_refine | max_radius (MAX over them)         -> all-gather
+// (interleaved per Gaussian: a slice of the Gaussian range is one contiguous piece of each buffer)
 // The SH gradient of one view is rank one per Gaussian (update.cu), so the views' colour gradients (12 B per
 // Gaussian and view) replace the dense [n,K,3] gradient (192 B at K=16) on the wire; the optimiser pass rebuilds it in
 // registers in global view order (view = rank * local + i), which makes the update bit-identical on every rank.
 //
 // Overlap: the exchange is issued on the communicator's own stream in `chunks` slices of the Gaussian range, each
 // slice's collectives in one NCCL group; the optimiser pass of slice c runs on the caller's stream as soon as slice c
-// has arrived, under the transfer of slice c+1.  The receive buffer is laid out per slice
-//   [local][world][len,3] colours | [world][len] refine | [world][len] radius
-// so that every all-gather lands contiguously.
+// has arrived, under the transfer of slice c+1: two collectives per slice, in one NCCL group.  The receive buffer is laid
+// out per slice ([world][len][3 local + 2]) so that every all-gather lands contiguously.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy already loaded by the host process -- torch's in the
 // Python mirror -- or the system one), so the library itself links against nothing but the CUDA runtime.
@@ -136,16 +135,11 @@ int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, u
     const DpLayout L = dp_layout(n, local, (uint32_t)cm->world);
     int rc = 0;
     if (len > 0) {
-        float *base = recv + L.chunk_base(g0);
         if ((rc = a.GroupStart()) != 0) return rc;
-        for (uint32_t li = 0; li < local && rc == 0; li++)
-            rc = a.AllGather(record + ((size_t)li * n + g0) * 3, base + L.colour_off(len, li), (size_t)len * 3, NCCL_FLOAT32,
-                             cm->comm, cm->stream);
-        if (rc == 0) rc = a.AllGather(record + L.rec_refine + g0, base + L.refine_off(len), len, NCCL_FLOAT32, cm->comm, cm->stream);
-        if (rc == 0) rc = a.AllGather(record + L.rec_radius + g0, base + L.radius_off(len), len, NCCL_FLOAT32, cm->comm, cm->stream);
-        if (rc == 0) rc = a.AllReduce(small + (size_t)g0 * 10, small + (size_t)g0 * 10, (size_t)len * 10, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
-        if (rc == 0) rc = a.AllReduce(small + (size_t)n * 10 + g0, small + (size_t)n * 10 + g0, len, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
-        if (rc == 0) rc = a.AllReduce(small + (size_t)n * 11 + g0, small + (size_t)n * 11 + g0, len, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+        rc = a.AllGather(record + (size_t)g0 * L.rec_row, recv + L.chunk_base(g0), (size_t)len * L.rec_row, NCCL_FLOAT32, cm->comm, cm->stream);
+        if (rc == 0)
+            rc = a.AllReduce(small + (size_t)g0 * DP_SMALL_ROW, small + (size_t)g0 * DP_SMALL_ROW, (size_t)len * DP_SMALL_ROW, NCCL_FLOAT32,
+                             NCCL_SUM, cm->comm, cm->stream);
         const int rc_end = a.GroupEnd();
         if (rc == 0) rc = rc_end;
         if (rc != 0) return rc;
@@ -166,30 +160,45 @@ __global__ void write_header_kernel(float *hdr, DpHeader h, uint32_t local) {
     if (i < local * 4) hdr[i] = (i & 3u) < 3u ? h.pos[i >> 2][i & 3u] : 0.0f;
 }
 
-// accumulate one more local view: small += tmp (v_transforms, v_raw_opac), visible += view's flags,
-// refine / radius = max (stats.rs:40-50 over the rank's views)
+// Folds one local view's gradients into the exchange buffers: small row (+)= (v_transforms, v_raw_opac, visible),
+// record row gets the view's colour gradient and the running MAX of the refine weight / radius (stats.rs:40-50 over the
+// rank's views).  The first view assigns, the others accumulate.
 __global__ void __launch_bounds__(256)
-accumulate_view_kernel(uint32_t n, float *__restrict__ small, const float *__restrict__ tmp, const float *__restrict__ vis_view,
-                       float *__restrict__ refine, const float *__restrict__ refine_view, float *__restrict__ radius,
-                       const float *__restrict__ radius_view) {
-    const size_t total = (size_t)n * 11;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
-        small[i] += tmp[i];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        small[(size_t)n * 11 + i] += vis_view[i];
-        refine[i] = fmaxf(refine[i], refine_view[i]);
-        radius[i] = fmaxf(radius[i], radius_view[i]);
+pack_view_kernel(uint32_t n, uint32_t rec_row, uint32_t li, int first, const float *__restrict__ v_t, const float *__restrict__ v_o,
+                 const float *__restrict__ v_color, const float *__restrict__ v_refine, const float *__restrict__ visible,
+                 const float *__restrict__ max_radius, float *__restrict__ small, float *__restrict__ record) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float row[DP_SMALL_ROW];
+    const float2 *t2 = reinterpret_cast<const float2 *>(v_t + (size_t)i * 10);
+#pragma unroll
+    for (int q = 0; q < 5; q++) { const float2 a = __ldg(t2 + q); row[2 * q] = a.x; row[2 * q + 1] = a.y; }
+    row[10] = __ldg(v_o + i);
+    row[11] = __ldg(visible + i);
+    float4 *dst = reinterpret_cast<float4 *>(small + (size_t)i * DP_SMALL_ROW);
+    if (!first) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) { const float4 o = dst[q]; row[4 * q] += o.x; row[4 * q + 1] += o.y; row[4 * q + 2] += o.z; row[4 * q + 3] += o.w; }
     }
+#pragma unroll
+    for (int q = 0; q < 3; q++) dst[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
+    float *rec = record + (size_t)i * rec_row;
+    rec[3 * li] = __ldg(v_color + (size_t)i * 3); rec[3 * li + 1] = __ldg(v_color + (size_t)i * 3 + 1); rec[3 * li + 2] = __ldg(v_color + (size_t)i * 3 + 2);
+    const float vr = __ldg(v_refine + i), rad = __ldg(max_radius + i);
+    rec[rec_row - 2] = first ? vr : fmaxf(rec[rec_row - 2], vr);
+    rec[rec_row - 1] = first ? rad : fmaxf(rec[rec_row - 1], rad);
 }
 
 cudaError_t launch_write_header(cudaStream_t s, float *hdr, const DpHeader &h, uint32_t local) {
     write_header_kernel<<<1, 64, 0, s>>>(hdr, h, local);
     return cudaGetLastError();
 }
-cudaError_t launch_accumulate_view(cudaStream_t s, uint32_t n, float *small, const float *tmp, const float *vis_view,
-                                   float *refine, const float *refine_view, float *radius, const float *radius_view) {
-    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n * 11 + 255) / 256, 148ull * 16);
-    accumulate_view_kernel<<<grid, 256, 0, s>>>(n, small, tmp, vis_view, refine, refine_view, radius, radius_view);
+cudaError_t launch_pack_view(cudaStream_t s, uint32_t n, uint32_t local, uint32_t li, bool first, const float *v_t, const float *v_o,
+                             const float *v_color, const float *v_refine, const float *visible, const float *max_radius, float *small,
+                             float *record) {
+    if (n == 0) return cudaSuccess;
+    pack_view_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, 3 * local + 2, li, first ? 1 : 0, v_t, v_o, v_color, v_refine, visible, max_radius,
+                                                     small, record);
     return cudaGetLastError();
 }
 

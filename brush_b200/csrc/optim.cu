@@ -255,22 +255,23 @@ fold_min_scale_fwd_kernel(uint32_t n, const float *transforms, const float *raw_
 //   v_coef  = v_opac * sig
 __global__ void __launch_bounds__(256)
 fold_min_scale_bwd_kernel(uint32_t n, const float *__restrict__ transforms, const float *__restrict__ raw_opac,
-                          const float *__restrict__ f, float *__restrict__ v_transforms, float *__restrict__ v_raw_opac) {
+                          const float *__restrict__ f, float *v_transforms, float *v_raw_opac, uint32_t vt_stride,
+                          uint32_t vo_stride) {   // gradient rows may be interleaved (the exchange buffer: 12-float rows)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float ls[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) ls[a] = __ldg(transforms + (size_t)i * 10 + 7 + a);
         const float fi = __ldg(f + i);
         const FoldTerms t = fold_terms(ls, __ldg(raw_opac + i), fi);
-        const float v_rawf = v_raw_opac[i];
+        const float v_rawf = v_raw_opac[(size_t)i * vo_stride];
         const float v_opac = t.in_range ? v_rawf / (t.opac * (1.0f - t.opac)) : 0.0f;
         const float v_coef = v_opac * t.sig;
-        v_raw_opac[i] = v_opac * t.coef * (t.sig * (1.0f - t.sig));
+        v_raw_opac[(size_t)i * vo_stride] = v_opac * t.coef * (t.sig * (1.0f - t.sig));
         const float f2 = fi * fi;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const float g = v_transforms[(size_t)i * 10 + 7 + a];
-            v_transforms[(size_t)i * 10 + 7 + a] = g * (t.s2[a] / t.s2f[a]) + v_coef * t.coef * (f2 / t.s2f[a]);
+            const float g = v_transforms[(size_t)i * vt_stride + 7 + a];
+            v_transforms[(size_t)i * vt_stride + 7 + a] = g * (t.s2[a] / t.s2f[a]) + v_coef * t.coef * (f2 / t.s2f[a]);
         }
     }
 }
@@ -289,7 +290,13 @@ cudaError_t launch_fold_min_scale_fwd(cudaStream_t s, uint32_t n, const float *t
 }
 cudaError_t launch_fold_min_scale_bwd(cudaStream_t s, uint32_t n, const float *transforms, const float *raw_opac,
                                       const float *f, float *v_transforms, float *v_raw_opac) {
-    fold_min_scale_bwd_kernel<<<grid_for(n), 256, 0, s>>>(n, transforms, raw_opac, f, v_transforms, v_raw_opac);
+    fold_min_scale_bwd_kernel<<<grid_for(n), 256, 0, s>>>(n, transforms, raw_opac, f, v_transforms, v_raw_opac, 10, 1);
+    return cudaGetLastError();
+}
+cudaError_t launch_fold_min_scale_bwd_strided(cudaStream_t s, uint32_t n, const float *transforms, const float *raw_opac,
+                                              const float *f, float *v_transforms, float *v_raw_opac, uint32_t vt_stride,
+                                              uint32_t vo_stride) {
+    fold_min_scale_bwd_kernel<<<grid_for(n), 256, 0, s>>>(n, transforms, raw_opac, f, v_transforms, v_raw_opac, vt_stride, vo_stride);
     return cudaGetLastError();
 }
 

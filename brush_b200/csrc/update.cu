@@ -70,17 +70,27 @@ train_update_kernel(const UpdateParams P) {
     float old_mean[3] = {0.0f, 0.0f, 0.0f};
     if (valid) {
         // ---- transforms row: Adam with per-column learning rates (train.rs:328-350)
-        float p[10];
+        float p[10], g_opac, vis;
         {
             float g[10], m[10], v[10];
             const float2 *p2 = reinterpret_cast<const float2 *>(P.transforms + (size_t)i * 10);
-            const float2 *g2 = reinterpret_cast<const float2 *>(P.g_t + (size_t)i * 10);
             float2 *m2 = reinterpret_cast<float2 *>(P.m_t + (size_t)i * 10);
             float2 *v2 = reinterpret_cast<float2 *>(P.v_t + (size_t)i * 10);
+            if (FACTORED) {   // one 48-byte row of `small`: the ten transform gradients, the opacity gradient, the visibility
+                const float4 *r4 = reinterpret_cast<const float4 *>(P.small + (size_t)i * 12);
+                const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), r2 = __ldg(r4 + 2);
+                g[0] = r0.x; g[1] = r0.y; g[2] = r0.z; g[3] = r0.w; g[4] = r1.x; g[5] = r1.y; g[6] = r1.z; g[7] = r1.w; g[8] = r2.x; g[9] = r2.y;
+                g_opac = r2.z; vis = r2.w;
+            } else {
+                const float2 *g2 = reinterpret_cast<const float2 *>(P.g_t + (size_t)i * 10);
+#pragma unroll
+                for (int q = 0; q < 5; q++) { const float2 b = __ldg(g2 + q); g[2 * q] = b.x; g[2 * q + 1] = b.y; }
+                g_opac = __ldg(P.g_o + i); vis = __ldg(P.visible + i);
+            }
 #pragma unroll
             for (int q = 0; q < 5; q++) {
-                const float2 a = p2[q], b = __ldg(g2 + q);
-                p[2 * q] = a.x; p[2 * q + 1] = a.y; g[2 * q] = b.x; g[2 * q + 1] = b.y;
+                const float2 a = p2[q];
+                p[2 * q] = a.x; p[2 * q + 1] = a.y;
                 if (!P.first) { const float2 c = m2[q], d = v2[q]; m[2 * q] = c.x; m[2 * q + 1] = c.y; v[2 * q] = d.x; v[2 * q + 1] = d.y; }
                 else { m[2 * q] = m[2 * q + 1] = v[2 * q] = v[2 * q + 1] = 0.0f; }
             }
@@ -98,22 +108,22 @@ train_update_kernel(const UpdateParams P) {
         // ---- raw opacity
         float raw;
         {
-            const float g0 = __ldg(P.g_o + i);
-            const float gg = P.grad_scale == 1.0f ? g0 : g0 * P.grad_scale;
+            const float gg = P.grad_scale == 1.0f ? g_opac : g_opac * P.grad_scale;
             const float mm = adam_m(P.first ? 0.0f : P.m_o[i], gg, P);
             const float vv = adam_v(P.first ? 0.0f : P.v_o[i], gg * gg, P);
             raw = adam_p(P.raw_opac[i], mm, adam_inv_denom(vv, P), P.lr_opac, P);
             P.m_o[i] = mm; P.v_o[i] = vv; P.raw_opac[i] = raw;
         }
         // ---- refine statistics of the step (stats.rs:40-50): MAX over the views, SUM of the visibility counts
-        const float vis = __ldg(P.visible + i);
         {
             float vr, rad;
             if (FACTORED) {
-                vr = __ldg(P.refine_all + j); rad = __ldg(P.radius_all + j);
+                const uint32_t R = 3u * P.local + 2u;
+                const float *rec = P.records + (size_t)j * R + (R - 2u);
+                vr = __ldg(rec); rad = __ldg(rec + 1);
                 for (uint32_t r = 1; r < P.world; r++) {
-                    vr = fmaxf(vr, __ldg(P.refine_all + (size_t)r * P.count + j));
-                    rad = fmaxf(rad, __ldg(P.radius_all + (size_t)r * P.count + j));
+                    vr = fmaxf(vr, __ldg(rec + (size_t)r * P.count * R));
+                    rad = fmaxf(rad, __ldg(rec + (size_t)r * P.count * R + 1));
                 }
             } else {
                 vr = __ldg(P.v_refine + i); rad = __ldg(P.max_radius + i);
@@ -157,7 +167,7 @@ train_update_kernel(const UpdateParams P) {
             for (int c = 0; c < KF; c++) g[c] = 0.0f;
             for (uint32_t v = 0; v < P.views; v++) {
                 const uint32_t r = v / P.local, li = v - r * P.local;
-                const float *vc = P.colours + (((size_t)li * P.world + r) * P.count + j) * 3;
+                const float *vc = P.records + ((size_t)r * P.count + j) * (3u * P.local + 2u) + 3u * li;
                 const float cr = __ldg(vc), cg = __ldg(vc + 1), cb = __ldg(vc + 2);
                 if (cr == 0.0f && cg == 0.0f && cb == 0.0f) continue;
                 const float4 cp = __ldg(reinterpret_cast<const float4 *>(P.cam_all) + v);

@@ -40,6 +40,16 @@ class DpComm:
         _lib.check(lib.bg_dp_comm_create(ctx.handle, ident, self.rank, self.world, C.byref(h)), "bg_dp_comm_create")
         self.handle = h
 
+    def pack_view(self, n: int, local_views: int, view: int, first: bool, v_t, v_o, v_color, v_refine, visible, max_radius,
+                  small: torch.Tensor, record: torch.Tensor):
+        """bg_dp_pack_view: fold one view's operator outputs into the interleaved exchange rows (csrc/bg_dp.cuh)."""
+        from . import _lib
+        from .render import _stream_ptr
+        _lib.check(_lib.load().bg_dp_pack_view(self.ctx.handle, _stream_ptr(self.ctx.device), n, local_views, view, int(first),
+                                               v_t.data_ptr(), v_o.data_ptr(), v_color.data_ptr(), v_refine.data_ptr(),
+                                               visible.data_ptr(), max_radius.data_ptr(), small.data_ptr(), record.data_ptr()),
+                   "bg_dp_pack_view")
+
     def exchange(self, n: int, local_views: int, small: torch.Tensor, record: torch.Tensor, recv: torch.Tensor, chunks: int = 1):
         """bg_dp_exchange: all-reduce `small` in place, all-gather `record` into `recv` (layout: csrc/bg_dp.cuh)."""
         from . import _lib

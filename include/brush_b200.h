@@ -284,12 +284,18 @@ int32_t bg_dp_comm_create(BgContext *ctx, const uint8_t *id /* host [128] */, in
                           BgDpComm **out_comm);
 int32_t bg_dp_comm_destroy(BgDpComm *comm);
 
-/* Float counts of the exchange buffers for n Gaussians and `local_views` views per rank:
- *   small  [12 n]                 v_transforms [n,10] | v_raw_opac [n] | visible [n], summed over the rank's views
- *   record [(3 local + 2) n]      v_color [local,n,3] | v_refine [n] | max_radius [n]  (MAX over the rank's views)
- *   recv   [world * record]       the gathered records, laid out per slice (csrc/bg_dp.cuh) */
+/* Exchange buffers for n Gaussians and `local_views` views per rank, interleaved per Gaussian (so that a slice of the
+ * Gaussian range is one contiguous piece of each):
+ *   small  [n][12]                   v_transforms (10) | v_raw_opac | visible, summed over the rank's views
+ *   record [n][3 local_views + 2]    v_color of each local view (3 each) | v_refine | max_radius (MAX over the views)
+ *   recv   world * record floats     the gathered records, per slice [world][len][3 local_views + 2]
+ * bg_dp_pack_view folds one view's operator outputs (bg_project_backward_factored, the forward's visible / max_radius)
+ * into `small` / `record`: the first view of a step assigns, the others accumulate. */
 uint64_t bg_dp_small_floats(uint32_t n);
 uint64_t bg_dp_record_floats(uint32_t n, uint32_t local_views);
+int32_t bg_dp_pack_view(BgContext *ctx, void *stream, uint32_t n, uint32_t local_views, uint32_t view, int32_t first,
+                        const float *v_transforms, const float *v_raw_opac, const float *v_color, const float *v_refine,
+                        const float *visible, const float *max_radius, float *small, float *record);
 
 /* The gradient exchange of one step on its own: all-gather of the records, all-reduce (SUM) of `small` in place, both
  * on the communicator's stream behind everything already enqueued on `stream`; `stream` waits for the result.

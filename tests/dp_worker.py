@@ -92,24 +92,40 @@ def main():
     for key in ("m_t", "m_sh", "m_o"):
         a, b = t_one._state[key].double(), t_dp._state[key].double()
         assert (a - b).norm() / a.norm() < 1e-3, (key, float((a - b).norm() / a.norm()))
-    assert torch.equal(t_one._state["vis_weight"], t_dp._state["vis_weight"])
-    assert torch.equal(t_one._state["max_screen"], t_dp._state["max_screen"])
+    # after three steps the two runs' parameters differ by rounding, so their statistics agree closely, not bitwise
+    for key in ("vis_weight", "max_screen"):
+        a, b = t_one._state[key].double(), t_dp._state[key].double()
+        assert ((a - b).abs() <= 1e-6 + 1e-3 * a.abs()).double().mean() > 0.999, key
     # the loss each rank reports is the mean over ITS views; the mean over ranks is the one-device loss
     lt = torch.tensor(l_dp, device=dev, dtype=torch.float64)
     dist.all_reduce(lt)
     np.testing.assert_allclose((lt / world).cpu().numpy(), np.array(l_one), rtol=1e-4)
-    # 4. bg_dp_exchange on its own
+    # 4. bg_dp_exchange on its own: the all-reduce sums in place, the all-gather lands rank r's rows in block r of each slice
     comm = DpComm(ctx)
-    small = torch.full((12 * n,), float(rank + 1), device=dev)
-    record = torch.arange((3 * local + 2) * n, device=dev, dtype=torch.float32) + 1000.0 * rank
-    recv = torch.zeros(world * record.numel(), device=dev)
-    comm.exchange(n, local, small, record, recv, chunks=1)
+    R_ = 3 * local + 2
+    for chunks in (1, 3):
+        small = torch.full((12 * n,), float(rank + 1), device=dev)
+        record = torch.arange(R_ * n, device=dev, dtype=torch.float32) + 1.0e7 * rank
+        recv = torch.zeros(world * record.numel(), device=dev)
+        comm.exchange(n, local, small, record, recv, chunks=chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(small, torch.full_like(small, float(sum(range(1, world + 1)))))
+        per = ((n + chunks - 1) // chunks + 63) // 64 * 64
+        for c in range(chunks):
+            g0, g1 = min(per * c, n), min(per * (c + 1), n)
+            blk = recv[R_ * world * g0: R_ * world * g1].view(world, -1)
+            for r in range(world):
+                assert torch.equal(blk[r], record[R_ * g0: R_ * g1] - 1.0e7 * rank + 1.0e7 * r), (chunks, c, r)
+    # bg_dp_pack_view: assign on the first view, accumulate / MAX on the next
+    vt, vo, vc = torch.rand(n, 10, device=dev), torch.rand(n, device=dev), torch.rand(n, 3, device=dev)
+    vr, vis, rad = torch.rand(n, device=dev), (torch.rand(n, device=dev) > 0.5).float(), torch.rand(n, device=dev)
+    small, record = torch.full((12 * n,), 7.0, device=dev), torch.full((R_ * n,), 7.0, device=dev)
+    comm.pack_view(n, local, 0, True, vt, vo, vc, vr, vis, rad, small, record)
+    comm.pack_view(n, local, 1, False, 2 * vt, 2 * vo, 3 * vc, vr * 0.5, vis, rad * 2, small, record)
     torch.cuda.synchronize()
-    assert torch.equal(small, torch.full_like(small, float(sum(range(1, world + 1)))))
-    rv = recv.view(3 * local + 2, world, -1)   # one slice: [segment][rank][n * width]
-    for r in range(world):
-        for li in range(local):
-            assert torch.equal(rv.view(-1)[(li * world + r) * n * 3:(li * world + r + 1) * n * 3], record[li * n * 3:(li + 1) * n * 3] - 1000.0 * rank + 1000.0 * r)
+    sm, rc = small.view(n, 12), record.view(n, R_)
+    assert torch.equal(sm[:, :10], vt + 2 * vt) and torch.equal(sm[:, 10], vo + 2 * vo) and torch.equal(sm[:, 11], vis + vis)
+    assert torch.equal(rc[:, 0:3], vc) and torch.equal(rc[:, 3:6], 3 * vc) and torch.equal(rc[:, -2], vr) and torch.equal(rc[:, -1], rad * 2)
     comm.close()
     ctx.close()
     dist.barrier()
