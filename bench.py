@@ -298,26 +298,31 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
         dense = (torch.empty((n, 10), device=dev), torch.empty((n, SH_K, 3), device=dev), torch.empty(n, device=dev),
                  torch.empty(n, device=dev))
     last = [None]
+    staged = [v_out, v_out.clone()]     # upstream-gradient inputs of the backward: two static buffers (e2e double-buffers them)
 
-    def compute(vo=v_out):
-        out = R.render_splats(ctx, cam, (w, h), ttr, tsh, top)
-        last[0] = out
+    def compute_fwd():
+        last[0] = R.render_splats(ctx, cam, (w, h), ttr, tsh, top)
+        return last[0]
+
+    def compute_bwd(vo):
+        out = last[0]
         vc = R.rasterize_bwd(out, vo)
         if dp:
             g = R.project_bwd_factored(out, ttr, tsh, top, vc, outputs=outs)
             comm.pack_view(n, 1, 0, True, outs[0], outs[2], outs[1], outs[3], out.visible, out.max_radius, small, record)
         else:
             g = R.project_bwd(out, ttr, tsh, top, vc, outputs=dense)
-        return out, g
+        return g
 
     def exchange():
         if dp:
             comm.exchange(n, 1, small, record, recv, chunks=1)
 
     def step():
-        r = compute()
+        out = compute_fwd()
+        g = compute_bwd(staged[0])
         exchange()
-        return r
+        return out, g
 
     for _ in range(warmup):
         out, g = step()
@@ -328,45 +333,68 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
     per_tile = toff[..., 1] - toff[..., 0]
     T = per_tile.size
     stats = R.blend_stats(out, v_out)
-    # The step is ~20 short launches; replaying it as one CUDA graph removes the host launch gaps (the library keeps
-    # nothing launch-specific on the host: counters and look-back epochs live on the device).  N>1: the graph holds this
-    # rank's kernels; the exchange (NCCL on the communicator's own stream) is issued eagerly behind each replay.
+    # The step is ~20 short launches; replaying it from CUDA graphs removes the host launch gaps (the library keeps
+    # nothing launch-specific on the host: counters and look-back epochs live on the device).  Two graphs -- the forward,
+    # and the backward once per input buffer -- so that the e2e leg can upload the next step's input under the forward.
+    # N>1: the graphs hold this rank's kernels; the exchange (NCCL on the communicator's own stream) is issued eagerly.
     log(f"config [{cfg_idx}]: warm-up done (V={V}, I={I}); capturing the step")
-    graph = None if os.environ.get("BG_BENCH_NO_GRAPH") else B.capture(lambda: compute())
-    if graph is not None:
-        launch = "one CUDA graph replay per step" + (" + eager exchange" if dp else "")
-        run_step = (lambda i: (graph.replay(), exchange())) if dp else (lambda i: graph.replay())
+    g_fwd = g_bwd = None
+    if not os.environ.get("BG_BENCH_NO_GRAPH"):
+        g_fwd = B.capture(compute_fwd)
+        if g_fwd is not None:
+            g_bwd = [B.capture(lambda b=b: compute_bwd(staged[b])) for b in range(2 if headline else 1)]
+            if any(x is None for x in g_bwd):
+                g_fwd = g_bwd = None
+    if g_fwd is not None:
+        launch = "two CUDA graph replays per step (forward, backward)" + (" + eager exchange" if dp else "")
+        run_compute = lambda: (g_fwd.replay(), g_bwd[0].replay())
     else:
         launch = "eager launches"
-        run_step = lambda i: step()
+        run_compute = lambda: (compute_fwd(), compute_bwd(staged[0]))
+    run_step = lambda i: (run_compute(), exchange())
     for _ in range(3):
         run_step(0)
     torch.cuda.synchronize(dev)
+    assert last[0].num_visible == V and last[0].num_intersections == I
     log(f"config [{cfg_idx}]: timing {steps} steps ({launch})")
     ms_step = B.timed(run_step, steps) / steps
     res = {"n": n, "w": w, "h": h, "V": V, "I": I, "T": T, "P": P, "ms_step": ms_step, "launch": launch, "overflow": overflow,
            "per_tile_mean": float(per_tile.mean()), "per_tile_max": int(per_tile.max()), "stats": stats}
-    if dp:   # phases: this rank's kernels alone (the same graph), the exchange alone
-        res["ms_compute"] = B.timed((lambda i: graph.replay()) if graph is not None else (lambda i: compute()), steps) / steps
+    if dp:   # phases: this rank's kernels alone (the same graphs), the exchange alone
+        res["ms_compute"] = B.timed(lambda i: run_compute(), steps) / steps
         res["ms_exchange"] = B.timed(lambda i: exchange(), steps) / steps
     if headline:
-        # ---- e2e: host input, copies inside the timed region
+        # ---- e2e: host input, copies inside the timed region.  Step i: the forward runs while the copy stream uploads
+        # the step's upstream-gradient image from pinned host memory into input buffer i&1; the backward waits for it.
         v_out_host = torch.from_numpy(v_out_np).pin_memory()
         copy_stream = torch.cuda.Stream(dev)
-        staged = [torch.empty_like(v_out), torch.empty_like(v_out)]
         staged_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        bwd_done = [torch.cuda.Event(), torch.cuda.Event()]
         result_host = torch.empty(8, dtype=torch.float32).pin_memory()
+        for e in bwd_done:
+            e.record()
 
-        def stage(i):  # H2D of the step's upstream gradient image from pinned host memory
+        def stage(i):  # H2D of step i's input; must not overwrite the buffer before the backward of step i-2 has read it
             with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(bwd_done[i & 1])
                 staged[i & 1].copy_(v_out_host, non_blocking=True)
                 staged_ev[i & 1].record(copy_stream)
 
         def step_e2e(i, is_last):
-            torch.cuda.current_stream(dev).wait_event(staged_ev[i & 1])
-            _, g = compute(staged[i & 1])
+            cur = torch.cuda.current_stream(dev)
             if not is_last:
                 stage(i + 1)  # next step's upload overlaps this step's kernels
+            if g_fwd is not None:
+                g_fwd.replay()
+            else:
+                compute_fwd()
+            cur.wait_event(staged_ev[i & 1])
+            if g_fwd is not None:
+                g_bwd[i & 1].replay()
+                g = outs if dp else dense
+            else:
+                g = compute_bwd(staged[i & 1])
+            bwd_done[i & 1].record(cur)
             exchange()
             res_t = torch.stack([x.sum() for x in g])
             result_host[:4].copy_(res_t, non_blocking=True)  # D2H of the step's result
@@ -442,17 +470,14 @@ def views_leg(B: Bench, steps: int):
     ms = B.timed(lambda i: trainer.step_views(batches, splats), k8) / k8
     res = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "views_per_step": 8, "views_per_rank": local, "n_gaussians": n,
            "width": w, "height": h,
-           "note": "bg_train_step_views: 8 views per optimizer step sharded over the ranks, SH-factored gradient exchange "
-                   "in slices under the update pass"}
-    if world > 1:   # phases: the same step without the exchange (local views only), unchunked exchange
+           "note": "bg_train_step_views: 8 views per optimizer step sharded over the ranks, SH-factored gradient exchange, "
+                   "SH part of the update pass under the all-reduce"}
+    if world > 1:   # phase: the same step without the exchange (this rank's views only)
         s2 = T.Splats(*(p.clone() for p in params))
         t2 = T.SplatTrainer(T.TrainConfig(), ctx, T.bounds_from_pos(0.8, tr[:, :3]))
         for _ in range(2):
             t2.step_views(batches, s2, distributed=False)
         res["ms_local_views_no_exchange"] = B.timed(lambda i: t2.step_views(batches, s2, distributed=False), k8) / k8
-        for _ in range(2):
-            trainer.step_views(batches, splats, chunks=1)
-        res["ms_unpipelined_exchange"] = B.timed(lambda i: trainer.step_views(batches, splats, chunks=1), k8) / k8
     ctx.close()
     return res
 

@@ -902,9 +902,7 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     const bool fold = a->min_scale != nullptr;
     const ViewsWs ws = carve_views_ws(a->workspace, n, k, w, hh, local, world, fold);
     if (ws.bytes > a->workspace_bytes) { set_err("bg_train_step_views: workspace too small (bg_train_step_views_workspace_bytes)", cudaSuccess); return BG_ERR_CAPACITY; }
-    uint32_t chunks = a->chunks ? a->chunks : (world > 1 ? 4u : 1u);
-    if (world == 1) chunks = 1;
-    if (chunks > DP_MAX_CHUNKS) { set_err("bg_train_step_views: at most 16 chunks", cudaSuccess); return BG_ERR_INVALID; }
+    if (a->chunks > DP_MAX_CHUNKS) { set_err("bg_train_step_views: at most 16 chunks", cudaSuccess); return BG_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     BG_CUDA(cudaSetDevice(c->device));
     const DpLayout L = dp_layout(n, local, world);
@@ -941,14 +939,10 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     }
     BG_CUDA(launch_loss_mean(s, ws.loss_terms, local, a->loss_out));
     // ---- exchange (slices on the communicator's stream) and the update pass slice by slice under it
-    const float *records_base = ws.record, *cam_all = ws.hdr;
+    // ---- exchange and update.  One device: one pass.  Several: the all-gather of the records and the all-reduce of
+    // `small` run back to back on the communicator's stream; the SH part of the update (70 % of its traffic) needs the
+    // records only and runs UNDER the all-reduce, the rest follows the all-reduce.
     BG_CUDA(launch_write_header(s, ws.hdr, hdr, local));
-    if (world > 1) {
-        r = issue_exchange(h->c, s, n, local, chunks, ws.small, ws.record, ws.recv, ws.hdr, ws.hdr_all);
-        if (r != BG_OK) return r;
-        records_base = ws.recv; cam_all = ws.hdr_all;
-    }
-    (void)rank;
     UpdateParams P;
     memset(&P, 0, sizeof(P));
     P.transforms = a->transforms; P.sh = a->sh; P.raw_opac = a->raw_opac;
@@ -956,22 +950,34 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     P.refine_norm = a->refine_norm; P.vis_weight = a->vis_weight; P.max_screen = a->max_screen;
     P.small = ws.small;
     P.grad_scale = 1.0f / (float)views; P.sh_grad_scale = 1.0f / (float)views;
-    P.cam_all = cam_all; P.views = views; P.local = local; P.world = world;
+    P.views = views; P.local = local; P.world = world;
+    P.g_begin = 0; P.count = n;
     fill_update_consts(P, a->lr_mean, a->lr_rotation, a->lr_scale, a->lr_coeffs_dc, a->lr_coeffs_sh_scale, a->lr_opac, a->noise_scale,
                        a->median_scale, a->seed, a->step, n);
-    for (uint32_t ch = 0; ch < chunks; ch++) {
-        uint32_t g0, len;
-        dp_chunk_range(n, chunks, ch, &g0, &len);
-        if (world > 1) BG_CUDA(cudaStreamWaitEvent(s, h->c->ev_chunk[ch], 0));
-        if (len == 0) continue;
-        if (fold)   // chain the gradients w.r.t. the folded values back to the learned ones (linear: after the sum), in the rows
-            BG_CUDA(launch_fold_min_scale_bwd_strided(s, len, a->transforms + (size_t)g0 * 10, a->raw_opac + g0, a->min_scale + g0,
-                                                      ws.small + (size_t)g0 * DP_SMALL_ROW, ws.small + (size_t)g0 * DP_SMALL_ROW + 10,
-                                                      DP_SMALL_ROW, DP_SMALL_ROW));
-        P.g_begin = g0; P.count = len;
-        P.records = records_base + L.chunk_base(g0);
-        BG_CUDA(launch_train_update(s, deg, P, true));
+    auto fold_back = [&]() -> int32_t {   // chain the gradients w.r.t. the folded values back to the learned ones (linear: after the sum)
+        if (fold)
+            BG_CUDA(launch_fold_min_scale_bwd_strided(s, n, a->transforms, a->raw_opac, a->min_scale, ws.small, ws.small + 10, DP_SMALL_ROW,
+                                                      DP_SMALL_ROW));
+        return BG_OK;
+    };
+    if (world == 1) {
+        P.records = ws.record; P.cam_all = ws.hdr;
+        if ((r = fold_back()) != BG_OK) return r;
+        BG_CUDA(launch_train_update(s, deg, P, true, 0));
+        return BG_OK;
     }
+    DpComm *d = h->c;
+    BG_CUDA(cudaEventRecord(d->ev_ready, s));
+    BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
+    int rc = dp_exchange_header(d, local, ws.hdr, ws.hdr_all);
+    if (rc == 0) rc = dp_exchange_two_phase(d, n, local, ws.small, ws.record, ws.recv);
+    if (rc != 0) return nccl_fail("bg_train_step_views: exchange", rc);
+    P.records = ws.recv; P.cam_all = ws.hdr_all;
+    BG_CUDA(cudaStreamWaitEvent(s, d->ev_chunk[0], 0));
+    BG_CUDA(launch_train_update(s, deg, P, true, 1));          // SH coefficients: records only
+    BG_CUDA(cudaStreamWaitEvent(s, d->ev_chunk[1], 0));
+    if ((r = fold_back()) != BG_OK) return r;
+    BG_CUDA(launch_train_update(s, deg, P, true, 2));          // transforms, opacity, statistics, noise
     return BG_OK;
 }
 

@@ -48,6 +48,7 @@ void dp_comm_destroy(DpComm *c);
 void dp_chunk_range(uint32_t n, uint32_t chunks, uint32_t c, uint32_t *g0, uint32_t *len);
 int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, uint32_t c, float *small, const float *record,
                       float *recv);
+int dp_exchange_two_phase(DpComm *cm, uint32_t n, uint32_t local, float *small, const float *record, float *recv);
 int dp_exchange_header(DpComm *cm, uint32_t local, const float *hdr, float *hdr_all);
 cudaError_t launch_write_header(cudaStream_t s, float *hdr, const DpHeader &h, uint32_t local);
 cudaError_t launch_pack_view(cudaStream_t s, uint32_t n, uint32_t local, uint32_t li, bool first, const float *v_t, const float *v_o,

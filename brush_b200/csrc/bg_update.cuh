@@ -31,6 +31,6 @@ struct UpdateParams {
     unsigned long long seed, noise_offset;
 };
 
-cudaError_t launch_train_update(cudaStream_t s, int deg, const UpdateParams &P, bool factored);
+cudaError_t launch_train_update(cudaStream_t s, int deg, const UpdateParams &P, bool factored, int part = 0);
 
 }  // namespace bg

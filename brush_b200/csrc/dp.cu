@@ -9,10 +9,12 @@
 // Gaussian and view) replace the dense [n,K,3] gradient (192 B at K=16) on the wire; the optimiser pass rebuilds it in
 // registers in global view order (view = rank * local + i), which makes the update bit-identical on every rank.
 //
-// Overlap: the exchange is issued on the communicator's own stream in `chunks` slices of the Gaussian range, each
-// slice's collectives in one NCCL group; the optimiser pass of slice c runs on the caller's stream as soon as slice c
-// has arrived, under the transfer of slice c+1: two collectives per slice, in one NCCL group.  The receive buffer is laid
-// out per slice ([world][len][3 local + 2]) so that every all-gather lands contiguously.
+// Overlap (bg_train_step_views): the all-gather of the records and the all-reduce of `small` run back to back on the
+// communicator's own stream.  The SH part of the update pass -- 70 % of its HBM traffic -- needs the gathered records only
+// and runs on the caller's stream UNDER the all-reduce; the transforms / opacity / statistics part follows the all-reduce.
+// (Slicing the Gaussian range into pipelined pieces was measured first: the per-collective latency ate what the overlap
+// gave.)  bg_dp_exchange is the exchange on its own, optionally in slices of the Gaussian range; the receive buffer is
+// laid out per slice ([world][len][3 local + 2]) so that every all-gather lands contiguously.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy already loaded by the host process -- torch's in the
 // Python mirror -- or the system one), so the library itself links against nothing but the CUDA runtime.
@@ -145,6 +147,20 @@ int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, u
         if (rc != 0) return rc;
     }
     if (cudaEventRecord(cm->ev_chunk[c], cm->stream) != cudaSuccess) return -1;
+    return 0;
+}
+
+// The two halves of the exchange as separate collectives with an event behind each (the multi-view step runs the SH part of
+// the update behind the all-gather, under the all-reduce): ev_chunk[0] = records gathered, ev_chunk[1] = small reduced.
+int dp_exchange_two_phase(DpComm *cm, uint32_t n, uint32_t local, float *small, const float *record, float *recv) {
+    NcclApi &a = nccl();
+    const DpLayout L = dp_layout(n, local, (uint32_t)cm->world);
+    int rc = a.AllGather(record, recv, L.rec_floats, NCCL_FLOAT32, cm->comm, cm->stream);
+    if (rc != 0) return rc;
+    if (cudaEventRecord(cm->ev_chunk[0], cm->stream) != cudaSuccess) return -1;
+    rc = a.AllReduce(small, small, L.small_floats, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+    if (rc != 0) return rc;
+    if (cudaEventRecord(cm->ev_chunk[1], cm->stream) != cudaSuccess) return -1;
     return 0;
 }
 

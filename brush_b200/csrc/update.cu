@@ -48,7 +48,9 @@ constexpr int UP_THREADS = 128;   // 4 warps; a warp owns 32 consecutive Gaussia
 // which the lanes read and write as consecutive float4 (a fully coalesced 512-byte access per instruction, 12 of them in
 // flight per lane at K = 16); the gradient rows pass through shared memory once so that lane r can form row r's mean of
 // g^2 (the row-reduced second moment) in column order.
-template <int DEG, bool FACTORED>
+// PART: 0 = the whole update; 1 = SH coefficients only; 2 = everything but the SH coefficients.  The multi-device step runs
+// part 1 as soon as the gathered records are there (it needs nothing from the all-reduce) and part 2 behind the all-reduce.
+template <int DEG, bool FACTORED, int PART>
 __global__ void __launch_bounds__(UP_THREADS)
 train_update_kernel(const UpdateParams P) {
     constexpr int K = (DEG + 1) * (DEG + 1);
@@ -68,7 +70,10 @@ train_update_kernel(const UpdateParams P) {
     float *sg = s_g[wid];
 
     float old_mean[3] = {0.0f, 0.0f, 0.0f};
-    if (valid) {
+    if (PART == 1 && valid) {   // the SH rebuild needs the (not yet updated) means only
+        old_mean[0] = P.transforms[(size_t)i * 10]; old_mean[1] = P.transforms[(size_t)i * 10 + 1]; old_mean[2] = P.transforms[(size_t)i * 10 + 2];
+    }
+    if (PART != 1 && valid) {
         // ---- transforms row: Adam with per-column learning rates (train.rs:328-350)
         float p[10], g_opac, vis;
         {
@@ -156,6 +161,7 @@ train_update_kernel(const UpdateParams P) {
         for (int q = 0; q < 5; q++) p2[q] = make_float2(p[2 * q], p[2 * q + 1]);
     }
 
+    if (PART == 2) return;
     // ---- SH gradient rows of the warp's 32 Gaussians -> shared memory
     const size_t span0 = (size_t)P.g_begin * KF + (size_t)j0 * KF;   // first float of the warp's span in the SH arrays
     const uint32_t total = rows * KF;                                // floats in the span
@@ -279,21 +285,23 @@ train_update_kernel(const UpdateParams P) {
 }
 
 template <int DEG>
-static cudaError_t launch_deg(cudaStream_t s, const UpdateParams &P, bool factored) {
+static cudaError_t launch_deg(cudaStream_t s, const UpdateParams &P, bool factored, int part) {
     const unsigned grid = (P.count + UP_THREADS - 1) / UP_THREADS;   // 32 rows per warp
-    if (factored) train_update_kernel<DEG, true><<<grid, UP_THREADS, 0, s>>>(P);
-    else train_update_kernel<DEG, false><<<grid, UP_THREADS, 0, s>>>(P);
+    if (!factored) train_update_kernel<DEG, false, 0><<<grid, UP_THREADS, 0, s>>>(P);
+    else if (part == 1) train_update_kernel<DEG, true, 1><<<grid, UP_THREADS, 0, s>>>(P);
+    else if (part == 2) train_update_kernel<DEG, true, 2><<<grid, UP_THREADS, 0, s>>>(P);
+    else train_update_kernel<DEG, true, 0><<<grid, UP_THREADS, 0, s>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_train_update(cudaStream_t s, int deg, const UpdateParams &P, bool factored) {
+cudaError_t launch_train_update(cudaStream_t s, int deg, const UpdateParams &P, bool factored, int part) {
     if (P.count == 0) return cudaSuccess;
     switch (deg) {
-        case 0: return launch_deg<0>(s, P, factored);
-        case 1: return launch_deg<1>(s, P, factored);
-        case 2: return launch_deg<2>(s, P, factored);
-        case 3: return launch_deg<3>(s, P, factored);
-        case 4: return launch_deg<4>(s, P, factored);
+        case 0: return launch_deg<0>(s, P, factored, part);
+        case 1: return launch_deg<1>(s, P, factored, part);
+        case 2: return launch_deg<2>(s, P, factored, part);
+        case 3: return launch_deg<3>(s, P, factored, part);
+        case 4: return launch_deg<4>(s, P, factored, part);
     }
     return cudaErrorInvalidValue;
 }

@@ -306,8 +306,9 @@ int32_t bg_dp_exchange(BgContext *ctx, BgDpComm *comm, void *stream, uint32_t n,
 /* One optimizer step over views_total = world * local_views views (BASELINE config [4]): the loss is the mean of the
  * per-view losses (train.rs:254-260 per view), i.e. the step equals accumulating the views' gradients on one GPU.
  * Per rank: for each local view render -> L1+SSIM loss -> rasterize / project backward (SH gradient kept in its
- * rank-one form); ONE exchange (bg_dp_exchange); the update pass (bg_train_update's kernel in its factored form)
- * slice by slice under the exchange.  comm == NULL runs the same step on one device.  Every rank must pass the same
+ * rank-one form); ONE exchange (all-gather of the records, then all-reduce of `small`, on the communicator's stream); the
+ * SH part of the update pass (bg_train_update's kernel in its factored form: it needs the records only) runs UNDER the
+ * all-reduce, the rest of the update behind it.  comm == NULL runs the same step on one device.  Every rank must pass the same
  * n, local_views, learning rates, seed and step; cams / gt_packed are this rank's views, global view index =
  * rank * local_views + i.  min_scale (optional, [n]): the Mip-Splatting scale floor folded in for the renders and
  * chained out of the gradients (gaussian_splats.rs:86-111).  loss_out: mean loss of this rank's views. */
@@ -331,7 +332,7 @@ typedef struct {
     float noise_scale, median_scale;
     uint64_t seed;
     int32_t step;
-    uint32_t chunks;                                /* slices of the exchange/update pipeline; 0 = default */
+    uint32_t chunks;                                /* reserved, pass 0 (<= 16) */
     void *workspace;
     uint64_t workspace_bytes;
     float *loss_out;
