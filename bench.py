@@ -290,8 +290,9 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
         from brush_b200.dp import DpComm
         comm = DpComm(ctx)
         small = torch.zeros(12 * n, dtype=torch.float32, device=dev)       # rows: v_transforms | v_raw_opac | visible
-        record = torch.zeros(5 * n, dtype=torch.float32, device=dev)       # rows: v_color | v_refine | max_radius
-        recv = torch.zeros(world * 5 * n, dtype=torch.float32, device=dev)
+        stat = torch.zeros(2 * n, dtype=torch.float32, device=dev)         # rows: v_refine | max_radius (MAX)
+        record = torch.zeros(3 * n, dtype=torch.float32, device=dev)       # rows: v_color of the rank's view
+        recv = torch.zeros(world * 3 * n, dtype=torch.float32, device=dev)
         outs = (torch.empty((n, 10), device=dev), torch.empty((n, 3), device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))
         dense = None
     else:
@@ -309,14 +310,14 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
         vc = R.rasterize_bwd(out, vo)
         if dp:
             g = R.project_bwd_factored(out, ttr, tsh, top, vc, outputs=outs)
-            comm.pack_view(n, 1, 0, True, outs[0], outs[2], outs[1], outs[3], out.visible, out.max_radius, small, record)
+            comm.pack_view(n, 1, 0, True, outs[0], outs[2], outs[1], outs[3], out.visible, out.max_radius, small, stat, record)
         else:
             g = R.project_bwd(out, ttr, tsh, top, vc, outputs=dense)
         return g
 
     def exchange():
         if dp:
-            comm.exchange(n, 1, small, record, recv, chunks=1)
+            comm.exchange(n, 1, small, stat, record, recv, chunks=1)
 
     def step():
         out = compute_fwd()

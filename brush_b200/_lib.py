@@ -177,9 +177,10 @@ SIGNATURES = {
     "bg_dp_comm_create": (_I32, [_P, _P, _I32, _I32, C.POINTER(_P)]),
     "bg_dp_comm_destroy": (_I32, [_P]),
     "bg_dp_small_floats": (_U64, [_U32]),
+    "bg_dp_stat_floats": (_U64, [_U32]),
     "bg_dp_record_floats": (_U64, [_U32, _U32]),
-    "bg_dp_pack_view": (_I32, [_P, _P, _U32, _U32, _U32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "bg_dp_exchange": (_I32, [_P, _P, _P, _U32, _U32, _P, _P, _P, _U32]),
+    "bg_dp_pack_view": (_I32, [_P, _P, _U32, _U32, _U32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bg_dp_exchange": (_I32, [_P, _P, _P, _U32, _U32, _P, _P, _P, _P, _U32]),
     "bg_train_step_views_workspace_bytes": (_U64, [_U32, _U32, _U32, _U32, _U32, _U32]),
     "bg_train_step_views": (_I32, [_P, _P, _P, C.POINTER(BgTrainViewsArgs)]),
     "bg_refine_workspace_bytes": (_U64, [_U32]),

@@ -791,22 +791,23 @@ extern "C" int32_t bg_dp_comm_destroy(BgDpComm *h) {
 }
 
 extern "C" uint64_t bg_dp_small_floats(uint32_t n) { return (uint64_t)DP_SMALL_ROW * n; }
-extern "C" uint64_t bg_dp_record_floats(uint32_t n, uint32_t local) { return ((uint64_t)3 * local + 2) * n; }
+extern "C" uint64_t bg_dp_stat_floats(uint32_t n) { return (uint64_t)DP_STAT_ROW * n; }
+extern "C" uint64_t bg_dp_record_floats(uint32_t n, uint32_t local) { return (uint64_t)3 * local * n; }
 
 extern "C" int32_t bg_dp_pack_view(BgContext *c, void *stream, uint32_t n, uint32_t local, uint32_t view, int32_t first, const float *v_t,
                                    const float *v_o, const float *v_color, const float *v_refine, const float *visible,
-                                   const float *max_radius, float *small, float *record) {
+                                   const float *max_radius, float *small, float *stat, float *record) {
     if (!c) return BG_ERR_NULL;
     if (n == 0) return BG_OK;
-    if (!v_t || !v_o || !v_color || !v_refine || !visible || !max_radius || !small || !record) return BG_ERR_NULL;
+    if (!v_t || !v_o || !v_color || !v_refine || !visible || !max_radius || !small || !stat || !record) return BG_ERR_NULL;
     if (local == 0 || local > DP_MAX_VIEWS || view >= local) { set_err("bg_dp_pack_view: view index / views per rank", cudaSuccess); return BG_ERR_INVALID; }
     BG_CUDA(cudaSetDevice(c->device));
-    BG_CUDA(launch_pack_view((cudaStream_t)stream, n, local, view, first != 0, v_t, v_o, v_color, v_refine, visible, max_radius, small, record));
+    BG_CUDA(launch_pack_view((cudaStream_t)stream, n, local, view, first != 0, v_t, v_o, v_color, v_refine, visible, max_radius, small, stat, record));
     return BG_OK;
 }
 
 // Issues all slices of the exchange on the communicator's stream behind `s`; s waits for slice c through ev_chunk[c].
-static int32_t issue_exchange(DpComm *d, cudaStream_t s, uint32_t n, uint32_t local, uint32_t chunks, float *small,
+static int32_t issue_exchange(DpComm *d, cudaStream_t s, uint32_t n, uint32_t local, uint32_t chunks, float *small, float *stat,
                               const float *record, float *recv, const float *hdr, float *hdr_all) {
     BG_CUDA(cudaEventRecord(d->ev_ready, s));
     BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
@@ -815,15 +816,15 @@ static int32_t issue_exchange(DpComm *d, cudaStream_t s, uint32_t n, uint32_t lo
         if (rc != 0) return nccl_fail("exchange (camera positions)", rc);
     }
     for (uint32_t ch = 0; ch < chunks; ch++) {
-        const int rc = dp_exchange_chunk(d, n, local, chunks, ch, small, record, recv);
+        const int rc = dp_exchange_chunk(d, n, local, chunks, ch, small, stat, record, recv);
         if (rc != 0) return nccl_fail("exchange", rc);
     }
     return BG_OK;
 }
 
-extern "C" int32_t bg_dp_exchange(BgContext *c, BgDpComm *h, void *stream, uint32_t n, uint32_t local, float *small,
+extern "C" int32_t bg_dp_exchange(BgContext *c, BgDpComm *h, void *stream, uint32_t n, uint32_t local, float *small, float *stat,
                                   const float *record, float *recv, uint32_t chunks) {
-    if (!c || !h || !small || !record || !recv) return BG_ERR_NULL;
+    if (!c || !h || !small || !stat || !record || !recv) return BG_ERR_NULL;
     if (n == 0) return BG_OK;
     if (local == 0 || local * (uint32_t)h->c->world > DP_MAX_VIEWS || chunks == 0 || chunks > DP_MAX_CHUNKS) {
         set_err("bg_dp_exchange: 1..16 views in total, 1..16 chunks", cudaSuccess);
@@ -831,7 +832,7 @@ extern "C" int32_t bg_dp_exchange(BgContext *c, BgDpComm *h, void *stream, uint3
     }
     BG_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
-    int32_t r = issue_exchange(h->c, s, n, local, chunks, small, record, recv, nullptr, nullptr);
+    int32_t r = issue_exchange(h->c, s, n, local, chunks, small, stat, record, recv, nullptr, nullptr);
     if (r != BG_OK) return r;
     for (uint32_t ch = 0; ch < chunks; ch++) BG_CUDA(cudaStreamWaitEvent(s, h->c->ev_chunk[ch], 0));
     return BG_OK;
@@ -839,7 +840,7 @@ extern "C" int32_t bg_dp_exchange(BgContext *c, BgDpComm *h, void *stream, uint3
 
 namespace {
 struct ViewsWs {
-    float *out_img, *v_output, *partials, *loss_terms, *v_combined, *small, *record, *recv, *hdr, *hdr_all;
+    float *out_img, *v_output, *partials, *loss_terms, *v_combined, *small, *stat, *record, *recv, *hdr, *hdr_all;
     float *r_transforms, *r_opac, *v_t, *v_o, *v_color, *v_refine, *visible, *max_radius;
     uint64_t bytes;
 };
@@ -860,6 +861,7 @@ ViewsWs carve_views_ws(void *base, uint32_t n, uint32_t k, uint32_t w, uint32_t 
     ws.loss_terms = take(DP_MAX_VIEWS);
     ws.v_combined = take((uint64_t)n * BG_VCOMBINED_STRIDE);
     ws.small = take(L.small_floats);
+    ws.stat = take(L.stat_floats);
     ws.record = take(L.rec_floats);
     ws.recv = take(world > 1 ? L.recv_floats : 0);
     ws.hdr = take(DP_MAX_VIEWS * 4);
@@ -919,9 +921,16 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     BG_CUDA(cudaMemsetAsync(ws.v_output, 0, (size_t)w * hh * 4 * sizeof(float), s));
     DpHeader hdr;
     memset(&hdr, 0, sizeof(hdr));
+    for (uint32_t i = 0; i < local; i++)
+        for (int q = 0; q < 3; q++) hdr.pos[i][q] = a->cams[i].cam_pos[q];
+    BG_CUDA(launch_write_header(s, ws.hdr, hdr, local));
+    DpComm *d = world > 1 ? h->c : nullptr;
+    // The exchange of a step has two parts.  The colour records (all-gather) depend on the blend backward only, so they
+    // leave as soon as the last local view's blend backward is done and travel UNDER its projection backward; the summed
+    // small rows and the MAX statistics (all-reduces) follow once that is done.  The update pass is split the same way:
+    // the SH part (70 % of its traffic) needs the records only and runs under the all-reduces, the rest follows them.
     for (uint32_t i = 0; i < local; i++) {
         const BgCamera *cam = a->cams + i;
-        for (int q = 0; q < 3; q++) hdr.pos[i][q] = cam->cam_pos[q];
         r = bg_render_forward(c, stream, cam, w, hh, n, k, r_t, a->sh, r_o, a->mip, a->background, BG_PASS_BACKWARD, ws.out_img, ws.visible,
                               ws.max_radius, &a->state_out);
         if (r != BG_OK) return r;
@@ -932,23 +941,27 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
                                    ws.loss_terms + i));
         r = bg_rasterize_backward(c, stream, &a->state_out, ws.out_img, ws.v_output, a->background, 0, ws.v_combined, n);
         if (r != BG_OK) return r;
+        BG_CUDA(launch_pack_color(s, n, local, i, a->state_out.compact_from_global_gid, ws.v_combined, ws.record));
+        if (d && i + 1 == local) {
+            BG_CUDA(cudaEventRecord(d->ev_ready, s));
+            BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
+            int rc = dp_exchange_header(d, local, ws.hdr, ws.hdr_all);
+            if (rc == 0) rc = dp_exchange_gather(d, n, local, ws.record, ws.recv);
+            if (rc != 0) return nccl_fail("bg_train_step_views: exchange (records)", rc);
+        }
         r = bg_project_backward_factored(c, stream, cam, &a->state_out, r_t, a->sh, r_o, ws.v_combined, ws.v_t, ws.v_color, ws.v_o, ws.v_refine);
         if (r != BG_OK) return r;
-        // fold the view into the exchange rows (sum of the small gradients, the view's colour gradient, MAX statistics)
-        BG_CUDA(launch_pack_view(s, n, local, i, i == 0, ws.v_t, ws.v_o, ws.v_color, ws.v_refine, ws.visible, ws.max_radius, ws.small, ws.record));
+        // fold the view into the exchange rows (sum of the small gradients, MAX statistics)
+        BG_CUDA(launch_pack_view(s, n, local, i, i == 0, ws.v_t, ws.v_o, nullptr, ws.v_refine, ws.visible, ws.max_radius, ws.small, ws.stat,
+                                 ws.record));
     }
     BG_CUDA(launch_loss_mean(s, ws.loss_terms, local, a->loss_out));
-    // ---- exchange (slices on the communicator's stream) and the update pass slice by slice under it
-    // ---- exchange and update.  One device: one pass.  Several: the all-gather of the records and the all-reduce of
-    // `small` run back to back on the communicator's stream; the SH part of the update (70 % of its traffic) needs the
-    // records only and runs UNDER the all-reduce, the rest follows the all-reduce.
-    BG_CUDA(launch_write_header(s, ws.hdr, hdr, local));
     UpdateParams P;
     memset(&P, 0, sizeof(P));
     P.transforms = a->transforms; P.sh = a->sh; P.raw_opac = a->raw_opac;
     P.m_t = a->m_t; P.v_t = a->v_t; P.m_sh = a->m_sh; P.v_sh = a->v_sh; P.m_o = a->m_o; P.v_o = a->v_o;
     P.refine_norm = a->refine_norm; P.vis_weight = a->vis_weight; P.max_screen = a->max_screen;
-    P.small = ws.small;
+    P.small = ws.small; P.stat = ws.stat;
     P.grad_scale = 1.0f / (float)views; P.sh_grad_scale = 1.0f / (float)views;
     P.views = views; P.local = local; P.world = world;
     P.g_begin = 0; P.count = n;
@@ -966,12 +979,10 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
         BG_CUDA(launch_train_update(s, deg, P, true, 0));
         return BG_OK;
     }
-    DpComm *d = h->c;
-    BG_CUDA(cudaEventRecord(d->ev_ready, s));
-    BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
-    int rc = dp_exchange_header(d, local, ws.hdr, ws.hdr_all);
-    if (rc == 0) rc = dp_exchange_two_phase(d, n, local, ws.small, ws.record, ws.recv);
-    if (rc != 0) return nccl_fail("bg_train_step_views: exchange", rc);
+    BG_CUDA(cudaEventRecord(d->ev_ready2, s));
+    BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready2, 0));
+    const int rc = dp_exchange_reduce(d, n, ws.small, ws.stat);
+    if (rc != 0) return nccl_fail("bg_train_step_views: exchange (sums)", rc);
     P.records = ws.recv; P.cam_all = ws.hdr_all;
     BG_CUDA(cudaStreamWaitEvent(s, d->ev_chunk[0], 0));
     BG_CUDA(launch_train_update(s, deg, P, true, 1));          // SH coefficients: records only

@@ -14,9 +14,9 @@ struct UpdateParams {
     const float *g_sh;               // dense [n,K,3] gradient; unused when factored
     float grad_scale;                // applied to the transforms / opacity gradients (1/views)
     // factored form (multi-view steps, bg_dp.cuh): `small` [n][12] = v_transforms | v_raw_opac | visible summed over all
-    // views; `records` = the slice [g_begin, g_begin+count) of the gathered records, [world][count][3 local + 2] =
-    // v_color of each of the rank's views | v_refine | max_radius
-    const float *small, *records;
+    // views; `stat` [n][2] = v_refine | max_radius, MAX over all views; `records` = the slice [g_begin, g_begin+count) of the
+    // gathered colour gradients, [world][count][3 local]
+    const float *small, *stat, *records;
     const float *cam_all;            // device [views][4]: camera positions in global view order
     uint32_t views, local, world;
     float sh_grad_scale;             // 1/views

@@ -2,8 +2,9 @@
 //
 // Parameters are replicated, every rank renders its own views of the step's batch, and ONE exchange per step makes
 // the gradient of the mean-over-views loss available on every rank:
-//   small  [n][12]          = v_transforms (10) | v_raw_opac | visible, summed over the rank's views   -> all-reduce (SUM)
-//   record [n][3 local + 2] = v_color of each local view | v_refine | max_radius (MAX over them)         -> all-gather
+//   small  [n][12]      = v_transforms (10) | v_raw_opac | visible, summed over the rank's views   -> all-reduce (SUM)
+//   stat   [n][2]       = v_refine | max_radius, MAX over the rank's views (stats.rs:40-50)        -> all-reduce (MAX)
+//   record [n][3 local] = v_color of each local view                                               -> all-gather
 // (interleaved per Gaussian: a slice of the Gaussian range is one contiguous piece of each buffer)
 // The SH gradient of one view is rank one per Gaussian (update.cu), so the views' colour gradients (12 B per
 // Gaussian and view) replace the dense [n,K,3] gradient (192 B at K=16) on the wire; the optimiser pass rebuilds it in
@@ -14,7 +15,7 @@
 // and runs on the caller's stream UNDER the all-reduce; the transforms / opacity / statistics part follows the all-reduce.
 // (Slicing the Gaussian range into pipelined pieces was measured first: the per-collective latency ate what the overlap
 // gave.)  bg_dp_exchange is the exchange on its own, optionally in slices of the Gaussian range; the receive buffer is
-// laid out per slice ([world][len][3 local + 2]) so that every all-gather lands contiguously.
+// laid out per slice ([world][len][3 local]) so that every all-gather lands contiguously.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy already loaded by the host process -- torch's in the
 // Python mirror -- or the system one), so the library itself links against nothing but the CUDA runtime.
@@ -45,7 +46,7 @@ struct NcclApi {
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
-constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0, NCCL_MAX = 2;
 
 static NcclApi &nccl() {
     static NcclApi api;
@@ -101,6 +102,7 @@ DpComm *dp_comm_create(int device, const NcclUniqueId &id, int rank, int world, 
     if (rc != 0) { *nccl_rc = rc; delete c; return nullptr; }
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_ready2, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < DP_MAX_CHUNKS && ok; i++) ok = cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { dp_comm_destroy(c); return nullptr; }
     return c;
@@ -113,6 +115,7 @@ void dp_comm_destroy(DpComm *c) {
     NcclApi &a = nccl();
     if (c->comm && a.ok) a.CommDestroy(c->comm);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_ready2) cudaEventDestroy(c->ev_ready2);
     for (int i = 0; i < DP_MAX_CHUNKS; i++)
         if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -129,7 +132,7 @@ void dp_chunk_range(uint32_t n, uint32_t chunks, uint32_t c, uint32_t *g0, uint3
 
 // Enqueues slice `c` of the exchange on the communicator's stream (which must already wait on the producer of
 // `small` / `record`) and records ev_chunk[c] behind it.  Returns 0 or the failing NCCL / CUDA code (negative = CUDA).
-int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, uint32_t c, float *small,
+int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, uint32_t c, float *small, float *stat,
                       const float *record, float *recv) {
     NcclApi &a = nccl();
     uint32_t g0, len;
@@ -142,6 +145,9 @@ int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, u
         if (rc == 0)
             rc = a.AllReduce(small + (size_t)g0 * DP_SMALL_ROW, small + (size_t)g0 * DP_SMALL_ROW, (size_t)len * DP_SMALL_ROW, NCCL_FLOAT32,
                              NCCL_SUM, cm->comm, cm->stream);
+        if (rc == 0)
+            rc = a.AllReduce(stat + (size_t)g0 * DP_STAT_ROW, stat + (size_t)g0 * DP_STAT_ROW, (size_t)len * DP_STAT_ROW, NCCL_FLOAT32,
+                             NCCL_MAX, cm->comm, cm->stream);
         const int rc_end = a.GroupEnd();
         if (rc == 0) rc = rc_end;
         if (rc != 0) return rc;
@@ -151,17 +157,24 @@ int dp_exchange_chunk(DpComm *cm, uint32_t n, uint32_t local, uint32_t chunks, u
 }
 
 // The two halves of the exchange as separate collectives with an event behind each (the multi-view step runs the SH part of
-// the update behind the all-gather, under the all-reduce): ev_chunk[0] = records gathered, ev_chunk[1] = small reduced.
-int dp_exchange_two_phase(DpComm *cm, uint32_t n, uint32_t local, float *small, const float *record, float *recv) {
+// the update behind the all-gather, under the all-reduces): ev_chunk[0] = records gathered, ev_chunk[1] = small / stat reduced.
+int dp_exchange_gather(DpComm *cm, uint32_t n, uint32_t local, const float *record, float *recv) {
     NcclApi &a = nccl();
     const DpLayout L = dp_layout(n, local, (uint32_t)cm->world);
-    int rc = a.AllGather(record, recv, L.rec_floats, NCCL_FLOAT32, cm->comm, cm->stream);
+    const int rc = a.AllGather(record, recv, L.rec_floats, NCCL_FLOAT32, cm->comm, cm->stream);
     if (rc != 0) return rc;
-    if (cudaEventRecord(cm->ev_chunk[0], cm->stream) != cudaSuccess) return -1;
-    rc = a.AllReduce(small, small, L.small_floats, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+    return cudaEventRecord(cm->ev_chunk[0], cm->stream) == cudaSuccess ? 0 : -1;
+}
+int dp_exchange_reduce(DpComm *cm, uint32_t n, float *small, float *stat) {
+    NcclApi &a = nccl();
+    int rc = a.GroupStart();
     if (rc != 0) return rc;
-    if (cudaEventRecord(cm->ev_chunk[1], cm->stream) != cudaSuccess) return -1;
-    return 0;
+    rc = a.AllReduce(small, small, (size_t)DP_SMALL_ROW * n, NCCL_FLOAT32, NCCL_SUM, cm->comm, cm->stream);
+    if (rc == 0) rc = a.AllReduce(stat, stat, (size_t)DP_STAT_ROW * n, NCCL_FLOAT32, NCCL_MAX, cm->comm, cm->stream);
+    const int rc_end = a.GroupEnd();
+    if (rc == 0) rc = rc_end;
+    if (rc != 0) return rc;
+    return cudaEventRecord(cm->ev_chunk[1], cm->stream) == cudaSuccess ? 0 : -1;
 }
 
 // The views' camera positions ([local][4] floats per rank) travel once per step, ahead of the slices.
@@ -176,13 +189,13 @@ __global__ void write_header_kernel(float *hdr, DpHeader h, uint32_t local) {
     if (i < local * 4) hdr[i] = (i & 3u) < 3u ? h.pos[i >> 2][i & 3u] : 0.0f;
 }
 
-// Folds one local view's gradients into the exchange buffers: small row (+)= (v_transforms, v_raw_opac, visible),
-// record row gets the view's colour gradient and the running MAX of the refine weight / radius (stats.rs:40-50 over the
-// rank's views).  The first view assigns, the others accumulate.
+// Folds one local view's gradients into the exchange buffers: small row (+)= (v_transforms, v_raw_opac, visible), the stat
+// row keeps the running MAX of the refine weight / radius (stats.rs:40-50 over the rank's views), the record row gets the
+// view's colour gradient.  The first view assigns, the others accumulate.
 __global__ void __launch_bounds__(256)
 pack_view_kernel(uint32_t n, uint32_t rec_row, uint32_t li, int first, const float *__restrict__ v_t, const float *__restrict__ v_o,
                  const float *__restrict__ v_color, const float *__restrict__ v_refine, const float *__restrict__ visible,
-                 const float *__restrict__ max_radius, float *__restrict__ small, float *__restrict__ record) {
+                 const float *__restrict__ max_radius, float *__restrict__ small, float *__restrict__ stat, float *__restrict__ record) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float row[DP_SMALL_ROW];
@@ -192,17 +205,50 @@ pack_view_kernel(uint32_t n, uint32_t rec_row, uint32_t li, int first, const flo
     row[10] = __ldg(v_o + i);
     row[11] = __ldg(visible + i);
     float4 *dst = reinterpret_cast<float4 *>(small + (size_t)i * DP_SMALL_ROW);
+    float2 *sd = reinterpret_cast<float2 *>(stat + (size_t)i * DP_STAT_ROW);
+    float2 st = make_float2(__ldg(v_refine + i), __ldg(max_radius + i));
     if (!first) {
 #pragma unroll
         for (int q = 0; q < 3; q++) { const float4 o = dst[q]; row[4 * q] += o.x; row[4 * q + 1] += o.y; row[4 * q + 2] += o.z; row[4 * q + 3] += o.w; }
+        const float2 o = *sd;
+        st.x = fmaxf(st.x, o.x); st.y = fmaxf(st.y, o.y);
     }
 #pragma unroll
     for (int q = 0; q < 3; q++) dst[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
-    float *rec = record + (size_t)i * rec_row;
-    rec[3 * li] = __ldg(v_color + (size_t)i * 3); rec[3 * li + 1] = __ldg(v_color + (size_t)i * 3 + 1); rec[3 * li + 2] = __ldg(v_color + (size_t)i * 3 + 2);
-    const float vr = __ldg(v_refine + i), rad = __ldg(max_radius + i);
-    rec[rec_row - 2] = first ? vr : fmaxf(rec[rec_row - 2], vr);
-    rec[rec_row - 1] = first ? rad : fmaxf(rec[rec_row - 1], rad);
+    *sd = st;
+    if (v_color) {
+        float *rec = record + (size_t)i * rec_row + 3 * li;
+        rec[0] = __ldg(v_color + (size_t)i * 3); rec[1] = __ldg(v_color + (size_t)i * 3 + 1); rec[2] = __ldg(v_color + (size_t)i * 3 + 2);
+    }
+}
+
+// The colour record of one view straight from the rasterizer's gradient rows (what project_bwd_kernel's factored mode
+// writes as v_color: lanes 5..7 of the visible Gaussian's row, zero for culled ones and for all-zero rows).  It depends on
+// the blend backward only, so the all-gather can start while the projection backward still runs.
+__global__ void __launch_bounds__(256)
+pack_color_kernel(uint32_t n, uint32_t rec_row, uint32_t li, const uint32_t *__restrict__ cgid_from_gid, const float *__restrict__ v_combined,
+                  float *__restrict__ record) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cg = __ldg(cgid_from_gid + i);
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    if (cg != 0xFFFFFFFFu) {
+        const float2 *p = reinterpret_cast<const float2 *>(v_combined + (size_t)cg * BG_VCOMBINED_STRIDE);
+        float2 t[5];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 5; q++) { t[q] = __ldg(p + q); any = any || t[q].x != 0.0f || t[q].y != 0.0f; }
+        if (any) { r = t[2].y; g = t[3].x; b = t[3].y; }
+    }
+    float *rec = record + (size_t)i * rec_row + 3 * li;
+    rec[0] = r; rec[1] = g; rec[2] = b;
+}
+
+cudaError_t launch_pack_color(cudaStream_t s, uint32_t n, uint32_t local, uint32_t li, const uint32_t *cgid_from_gid,
+                              const float *v_combined, float *record) {
+    if (n == 0) return cudaSuccess;
+    pack_color_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, 3 * local, li, cgid_from_gid, v_combined, record);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_write_header(cudaStream_t s, float *hdr, const DpHeader &h, uint32_t local) {
@@ -211,10 +257,10 @@ cudaError_t launch_write_header(cudaStream_t s, float *hdr, const DpHeader &h, u
 }
 cudaError_t launch_pack_view(cudaStream_t s, uint32_t n, uint32_t local, uint32_t li, bool first, const float *v_t, const float *v_o,
                              const float *v_color, const float *v_refine, const float *visible, const float *max_radius, float *small,
-                             float *record) {
+                             float *stat, float *record) {
     if (n == 0) return cudaSuccess;
-    pack_view_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, 3 * local + 2, li, first ? 1 : 0, v_t, v_o, v_color, v_refine, visible, max_radius,
-                                                     small, record);
+    pack_view_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, 3 * local, li, first ? 1 : 0, v_t, v_o, v_color, v_refine, visible, max_radius,
+                                                     small, stat, record);
     return cudaGetLastError();
 }
 

@@ -123,13 +123,8 @@ train_update_kernel(const UpdateParams P) {
         {
             float vr, rad;
             if (FACTORED) {
-                const uint32_t R = 3u * P.local + 2u;
-                const float *rec = P.records + (size_t)j * R + (R - 2u);
-                vr = __ldg(rec); rad = __ldg(rec + 1);
-                for (uint32_t r = 1; r < P.world; r++) {
-                    vr = fmaxf(vr, __ldg(rec + (size_t)r * P.count * R));
-                    rad = fmaxf(rad, __ldg(rec + (size_t)r * P.count * R + 1));
-                }
+                const float2 st = __ldg(reinterpret_cast<const float2 *>(P.stat) + i);
+                vr = st.x; rad = st.y;
             } else {
                 vr = __ldg(P.v_refine + i); rad = __ldg(P.max_radius + i);
             }
@@ -173,7 +168,7 @@ train_update_kernel(const UpdateParams P) {
             for (int c = 0; c < KF; c++) g[c] = 0.0f;
             for (uint32_t v = 0; v < P.views; v++) {
                 const uint32_t r = v / P.local, li = v - r * P.local;
-                const float *vc = P.records + ((size_t)r * P.count + j) * (3u * P.local + 2u) + 3u * li;
+                const float *vc = P.records + ((size_t)r * P.count + j) * (3u * P.local) + 3u * li;
                 const float cr = __ldg(vc), cg = __ldg(vc + 1), cb = __ldg(vc + 2);
                 if (cr == 0.0f && cg == 0.0f && cb == 0.0f) continue;
                 const float4 cp = __ldg(reinterpret_cast<const float4 *>(P.cam_all) + v);

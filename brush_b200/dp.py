@@ -41,21 +41,24 @@ class DpComm:
         self.handle = h
 
     def pack_view(self, n: int, local_views: int, view: int, first: bool, v_t, v_o, v_color, v_refine, visible, max_radius,
-                  small: torch.Tensor, record: torch.Tensor):
+                  small: torch.Tensor, stat: torch.Tensor, record: torch.Tensor):
         """bg_dp_pack_view: fold one view's operator outputs into the interleaved exchange rows (csrc/bg_dp.cuh)."""
         from . import _lib
         from .render import _stream_ptr
         _lib.check(_lib.load().bg_dp_pack_view(self.ctx.handle, _stream_ptr(self.ctx.device), n, local_views, view, int(first),
                                                v_t.data_ptr(), v_o.data_ptr(), v_color.data_ptr(), v_refine.data_ptr(),
-                                               visible.data_ptr(), max_radius.data_ptr(), small.data_ptr(), record.data_ptr()),
+                                               visible.data_ptr(), max_radius.data_ptr(), small.data_ptr(), stat.data_ptr(),
+                                               record.data_ptr()),
                    "bg_dp_pack_view")
 
-    def exchange(self, n: int, local_views: int, small: torch.Tensor, record: torch.Tensor, recv: torch.Tensor, chunks: int = 1):
-        """bg_dp_exchange: all-reduce `small` in place, all-gather `record` into `recv` (layout: csrc/bg_dp.cuh)."""
+    def exchange(self, n: int, local_views: int, small: torch.Tensor, stat: torch.Tensor, record: torch.Tensor, recv: torch.Tensor,
+                 chunks: int = 1):
+        """bg_dp_exchange: all-reduce `small` (SUM) and `stat` (MAX) in place, all-gather `record` into `recv` (csrc/bg_dp.cuh)."""
         from . import _lib
         from .render import _stream_ptr
         _lib.check(_lib.load().bg_dp_exchange(self.ctx.handle, self.handle, _stream_ptr(self.ctx.device), n, local_views,
-                                              small.data_ptr(), record.data_ptr(), recv.data_ptr(), chunks), "bg_dp_exchange")
+                                              small.data_ptr(), stat.data_ptr(), record.data_ptr(), recv.data_ptr(), chunks),
+                   "bg_dp_exchange")
 
     def close(self):
         if self.handle:

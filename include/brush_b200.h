@@ -286,29 +286,32 @@ int32_t bg_dp_comm_destroy(BgDpComm *comm);
 
 /* Exchange buffers for n Gaussians and `local_views` views per rank, interleaved per Gaussian (so that a slice of the
  * Gaussian range is one contiguous piece of each):
- *   small  [n][12]                   v_transforms (10) | v_raw_opac | visible, summed over the rank's views
- *   record [n][3 local_views + 2]    v_color of each local view (3 each) | v_refine | max_radius (MAX over the views)
- *   recv   world * record floats     the gathered records, per slice [world][len][3 local_views + 2]
+ *   small  [n][12]               v_transforms (10) | v_raw_opac | visible, summed over the rank's views  (all-reduce SUM)
+ *   stat   [n][2]                v_refine | max_radius, MAX over the rank's views                       (all-reduce MAX)
+ *   record [n][3 local_views]    v_color of each local view                                             (all-gather)
+ *   recv   world * record floats the gathered records, per slice [world][len][3 local_views]
  * bg_dp_pack_view folds one view's operator outputs (bg_project_backward_factored, the forward's visible / max_radius)
- * into `small` / `record`: the first view of a step assigns, the others accumulate. */
+ * into `small` / `stat` / `record`: the first view of a step assigns, the others accumulate. */
 uint64_t bg_dp_small_floats(uint32_t n);
+uint64_t bg_dp_stat_floats(uint32_t n);
 uint64_t bg_dp_record_floats(uint32_t n, uint32_t local_views);
 int32_t bg_dp_pack_view(BgContext *ctx, void *stream, uint32_t n, uint32_t local_views, uint32_t view, int32_t first,
                         const float *v_transforms, const float *v_raw_opac, const float *v_color, const float *v_refine,
-                        const float *visible, const float *max_radius, float *small, float *record);
+                        const float *visible, const float *max_radius, float *small, float *stat, float *record);
 
-/* The gradient exchange of one step on its own: all-gather of the records, all-reduce (SUM) of `small` in place, both
- * on the communicator's stream behind everything already enqueued on `stream`; `stream` waits for the result.
- * chunks (1..16) slices the Gaussian range for the pipelined variant used by bg_train_step_views. */
+/* The gradient exchange of one step on its own: all-gather of the records, all-reduce of `small` (SUM) and `stat` (MAX)
+ * in place, all on the communicator's stream behind everything already enqueued on `stream`; `stream` waits for the
+ * result.  chunks (1..16) slices the Gaussian range (one group of collectives per slice). */
 int32_t bg_dp_exchange(BgContext *ctx, BgDpComm *comm, void *stream, uint32_t n, uint32_t local_views,
-                       float *small, const float *record, float *recv, uint32_t chunks);
+                       float *small, float *stat, const float *record, float *recv, uint32_t chunks);
 
 /* One optimizer step over views_total = world * local_views views (BASELINE config [4]): the loss is the mean of the
  * per-view losses (train.rs:254-260 per view), i.e. the step equals accumulating the views' gradients on one GPU.
  * Per rank: for each local view render -> L1+SSIM loss -> rasterize / project backward (SH gradient kept in its
- * rank-one form); ONE exchange (all-gather of the records, then all-reduce of `small`, on the communicator's stream); the
- * SH part of the update pass (bg_train_update's kernel in its factored form: it needs the records only) runs UNDER the
- * all-reduce, the rest of the update behind it.  comm == NULL runs the same step on one device.  Every rank must pass the same
+ * rank-one form).  The exchange runs on the communicator's stream in two parts: the all-gather of the colour records
+ * starts right behind the last view's rasterize backward and travels UNDER its projection backward; the all-reduces of
+ * `small` / `stat` follow.  The SH part of the update pass (bg_train_update's kernel in its factored form: it needs the
+ * records only) runs UNDER the all-reduces, the rest of the update behind them.  comm == NULL runs the same step on one device.  Every rank must pass the same
  * n, local_views, learning rates, seed and step; cams / gt_packed are this rank's views, global view index =
  * rank * local_views + i.  min_scale (optional, [n]): the Mip-Splatting scale floor folded in for the renders and
  * chained out of the gradients (gaussian_splats.rs:86-111).  loss_out: mean loss of this rank's views. */

@@ -102,14 +102,17 @@ def main():
     np.testing.assert_allclose((lt / world).cpu().numpy(), np.array(l_one), rtol=1e-4)
     # 4. bg_dp_exchange on its own: the all-reduce sums in place, the all-gather lands rank r's rows in block r of each slice
     comm = DpComm(ctx)
-    R_ = 3 * local + 2
+    R_ = 3 * local
     for chunks in (1, 3):
         small = torch.full((12 * n,), float(rank + 1), device=dev)
+        stat = torch.arange(2 * n, device=dev, dtype=torch.float32) * (1.0 if rank == world - 1 else 0.5)
+        stat_max = torch.arange(2 * n, device=dev, dtype=torch.float32)
         record = torch.arange(R_ * n, device=dev, dtype=torch.float32) + 1.0e7 * rank
         recv = torch.zeros(world * record.numel(), device=dev)
-        comm.exchange(n, local, small, record, recv, chunks=chunks)
+        comm.exchange(n, local, small, stat, record, recv, chunks=chunks)
         torch.cuda.synchronize()
         assert torch.equal(small, torch.full_like(small, float(sum(range(1, world + 1)))))
+        assert torch.equal(stat, stat_max)
         per = ((n + chunks - 1) // chunks + 63) // 64 * 64
         for c in range(chunks):
             g0, g1 = min(per * c, n), min(per * (c + 1), n)
@@ -120,12 +123,13 @@ def main():
     vt, vo, vc = torch.rand(n, 10, device=dev), torch.rand(n, device=dev), torch.rand(n, 3, device=dev)
     vr, vis, rad = torch.rand(n, device=dev), (torch.rand(n, device=dev) > 0.5).float(), torch.rand(n, device=dev)
     small, record = torch.full((12 * n,), 7.0, device=dev), torch.full((R_ * n,), 7.0, device=dev)
-    comm.pack_view(n, local, 0, True, vt, vo, vc, vr, vis, rad, small, record)
-    comm.pack_view(n, local, 1, False, 2 * vt, 2 * vo, 3 * vc, vr * 0.5, vis, rad * 2, small, record)
+    stat = torch.full((2 * n,), 7.0, device=dev)
+    comm.pack_view(n, local, 0, True, vt, vo, vc, vr, vis, rad, small, stat, record)
+    comm.pack_view(n, local, 1, False, 2 * vt, 2 * vo, 3 * vc, vr * 0.5, vis, rad * 2, small, stat, record)
     torch.cuda.synchronize()
-    sm, rc = small.view(n, 12), record.view(n, R_)
+    sm, rc, stt = small.view(n, 12), record.view(n, R_), stat.view(n, 2)
     assert torch.equal(sm[:, :10], vt + 2 * vt) and torch.equal(sm[:, 10], vo + 2 * vo) and torch.equal(sm[:, 11], vis + vis)
-    assert torch.equal(rc[:, 0:3], vc) and torch.equal(rc[:, 3:6], 3 * vc) and torch.equal(rc[:, -2], vr) and torch.equal(rc[:, -1], rad * 2)
+    assert torch.equal(rc[:, 0:3], vc) and torch.equal(rc[:, 3:6], 3 * vc) and torch.equal(stt[:, 0], vr) and torch.equal(stt[:, 1], rad * 2)
     comm.close()
     ctx.close()
     dist.barrier()
