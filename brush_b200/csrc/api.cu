@@ -37,7 +37,7 @@ cudaError_t launch_onesweep_pass(cudaStream_t, int, const uint32_t *, const uint
                                  uint32_t, const uint32_t *, uint32_t, uint32_t, const uint32_t *, uint32_t *,
                                  unsigned long long *, unsigned long long *, const uint32_t *, uint32_t);
 cudaError_t launch_bump_epoch(cudaStream_t, uint32_t *);
-uint32_t sort_tile_size();
+uint64_t sort_max_tiles(uint64_t n);
 // raster_fwd.cu / raster_bwd.cu / project_bwd.cu
 cudaError_t launch_rasterize_fwd(cudaStream_t, bool, bool, uint32_t, const uint32_t *, uint32_t *, const float *,
                                  const uint32_t *, void *, float *, uint32_t, uint32_t, uint32_t, const float *);
@@ -169,7 +169,7 @@ extern "C" int32_t bg_ctx_create(int32_t device, uint32_t max_splats, uint32_t m
     if (e != cudaSuccess) { set_err("cudaGetDeviceProperties", e); delete c; return BG_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
     const uint64_t n = max_splats, I = c->max_isect;
-    const uint64_t sort_tiles = (std::max<uint64_t>(n, I) + sort_tile_size() - 1) / sort_tile_size() + 1;
+    const uint64_t sort_tiles = sort_max_tiles(std::max<uint64_t>(n, I));
     c->lb_sort_tile_words = sort_tiles * 256;
     c->lb_sort_words = c->lb_sort_tile_words + (sort_tiles / 16 + 2) * 256;   // tile counts + group totals
     c->lb_scan_words = (n + 255) / 256 + 64;

@@ -20,6 +20,10 @@ namespace bg {
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
+// Small sorts (the depth sort of ~1M visible Gaussians) run with half-size tiles: 4096-key tiles give such a sort fewer
+// CTAs than the GPU holds (1.5 per SM at 1M keys), and a pass is then one latency-bound wave.
+constexpr int SORT_ITEMS_SMALL = 8;
+constexpr uint32_t SORT_SMALL_MAX_KEYS = 3u << 20;
 constexpr int RADIX = 256;
 
 // hist[p*256 + d] += #keys whose p-th digit is d, for p < passes.
@@ -58,6 +62,7 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n_host, const uint
 }
 
 // One digit pass.  lb_state: [num_tiles][256] tile counts, lb_group: [ceil(num_tiles/16)][256] group totals.
+template <int SORT_ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
@@ -68,6 +73,7 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     // look-back epoch = (per-context call counter kept ON THE DEVICE) * 32 + launch index inside the call: nothing
     // about it is baked into the launch, so the whole forward can be captured in a CUDA graph and replayed.
     const uint32_t epoch = ((*epoch_base) * 32u + epoch_off) & 0x3FFFFFFFu;
+    constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_ITEMS;
     __shared__ uint32_t s_keys[SORT_TILE];
     __shared__ uint32_t s_vals[SORT_TILE];
     __shared__ uint32_t s_warp_hist[(SORT_THREADS / 32) * RADIX];
@@ -240,12 +246,22 @@ cudaError_t launch_onesweep_pass(cudaStream_t s, int grid, const uint32_t *keys_
                                  uint32_t shift, uint32_t width, const uint32_t *hist, uint32_t *ticket,
                                  unsigned long long *lb, unsigned long long *lb_group, const uint32_t *epoch_base,
                                  uint32_t epoch_off) {
-    onesweep_pass_kernel<<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift, width,
-                                                       hist, ticket, lb, lb_group, epoch_base, epoch_off);
+    if (n_host <= SORT_SMALL_MAX_KEYS)
+        onesweep_pass_kernel<SORT_ITEMS_SMALL><<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift,
+                                                                             width, hist, ticket, lb, lb_group, epoch_base, epoch_off);
+    else
+        onesweep_pass_kernel<SORT_ITEMS><<<grid, SORT_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, shift, width,
+                                                                       hist, ticket, lb, lb_group, epoch_base, epoch_off);
     return cudaGetLastError();
 }
 
-uint32_t sort_tile_size() { return SORT_TILE; }
+// number of look-back tile slots a sort of up to n keys can use (api.cu sizes the look-back words with it)
+uint64_t sort_max_tiles(uint64_t n) {
+    const uint64_t big = (n + SORT_TILE - 1) / SORT_TILE;
+    const uint64_t small_n = n < SORT_SMALL_MAX_KEYS ? n : SORT_SMALL_MAX_KEYS;
+    const uint64_t small = (small_n + SORT_THREADS * SORT_ITEMS_SMALL - 1) / (SORT_THREADS * SORT_ITEMS_SMALL);
+    return (big > small ? big : small) + 1;
+}
 
 }  // namespace bg
 

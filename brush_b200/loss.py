@@ -73,10 +73,12 @@ def image_loss_backward(ctx: RenderContext, pred_hwc: torch.Tensor, gt_packed: t
 
 
 def image_loss_fused(ctx: RenderContext, pred_hwc: torch.Tensor, gt_packed: torch.Tensor, channels: int,
-                     cfg: ImageLossConfig, chain_per_channel, out_hwc: Optional[torch.Tensor] = None):
+                     cfg: ImageLossConfig, chain_per_channel, out_hwc: Optional[torch.Tensor] = None,
+                     weights: Optional[torch.Tensor] = None):
     """Train-path fusion (bg_image_loss_fused): for a loss that is a weighted mean of the map
     (train.rs:254-260) returns (dL/dpred [h,w,c'], loss scalar tensor) in one kernel pass.
-    chain_per_channel[c] = dL/dmap of channel c; loss = sum_c chain[c] * sum(map[c])."""
+    chain_per_channel[c] = dL/dmap of channel c; loss = sum_c chain[c] * sum(map[c]).
+    weights: chain_per_channel as a device tensor, for callers that capture the call in a CUDA graph (no host copy inside)."""
     lib = _lib.load()
     h, w = pred_hwc.shape[0], pred_hwc.shape[1]
     if gt_packed.shape != (h, w):
@@ -91,7 +93,8 @@ def image_loss_fused(ctx: RenderContext, pred_hwc: torch.Tensor, gt_packed: torc
                                        channels, h, w, sc, sy, sx, cfg.l1_weight, cfg.ssim_weight, _bg_ptr(cfg),
                                        int(cfg.mask), chain, out_hwc.data_ptr(), partials.data_ptr()),
                "bg_image_loss_fused")
-    weights = torch.tensor([float(x) for x in chain_per_channel], dtype=torch.float32, device=pred_hwc.device)
+    if weights is None:
+        weights = torch.tensor([float(x) for x in chain_per_channel], dtype=torch.float32, device=pred_hwc.device)
     loss = (partials.sum(dim=1) * weights).sum()
     return out_hwc, loss
 
