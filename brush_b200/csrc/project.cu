@@ -215,27 +215,15 @@ project_cull_kernel(const float *__restrict__ transforms, const float *__restric
             }
         }
         __syncthreads();
-        const uint32_t dk = __float_as_uint(r.depth);  // z >= 0.01: float order == uint order
         if (r.visible) {
             uint32_t slot = s_prefix + local;
+            const uint32_t dk = __float_as_uint(r.depth);  // z >= 0.01: float order == uint order
             depth_keys[slot] = dk;
 #pragma unroll
-            for (int p = 0; p < 3; p++) atomicAdd(&s_dhist[p * 256 + ((dk >> (8 * p)) & 255u)], 1u);
+            for (int p = 0; p < 4; p++) atomicAdd(&s_dhist[p * 256 + ((dk >> (8 * p)) & 255u)], 1u);
             gids[slot] = gid;
             counts_by_gid[gid] = r.tiles;
             hit_masks[gid] = r.mask;
-        }
-        {   // the top digit is the float exponent: a handful of values for a whole scene, so a per-lane shared atomic would
-            // serialise the warp on one address; one lane per distinct value counts its peers instead
-            const uint32_t top = dk >> 24;
-            uint32_t todo = __ballot_sync(0xffffffffu, r.visible);
-            while (todo) {
-                const uint32_t leader = (uint32_t)__ffs(todo) - 1u;
-                const uint32_t hh = __shfl_sync(0xffffffffu, top, leader);
-                const uint32_t same = __ballot_sync(0xffffffffu, r.visible && top == hh) & todo;
-                if ((threadIdx.x & 31u) == leader) atomicAdd(&s_dhist[3 * 256 + hh], (uint32_t)__popc(same));
-                todo &= ~same;
-            }
         }
         tile = s_tile_next;
         buf ^= 1u;
@@ -521,30 +509,13 @@ project_visible_emit_kernel(const float *__restrict__ transforms, const float *_
         }
         __syncwarp();
         if (staged) {
-            // 32 consecutive slots hold runs of consecutive tile ids: their low digits differ, their high digits are
-            // nearly all equal -- a plain shared atomic on the high digit would serialise the whole warp on one
-            // address, so equal high digits are counted by one lane per distinct value (ballot of the leader's digit).
-            for (uint32_t j0 = 0; j0 < warp_total; j0 += 32) {
-                const uint32_t j = j0 + lane;
+            for (uint32_t j = lane; j < warp_total; j += 32) {
                 const uint32_t o = warp_base + j;
-                const bool ok = j < warp_total && o < isect_capacity;
-                uint32_t key = 0;
-                if (ok) {
-                    key = wkeys[j];
+                if (o < isect_capacity) {
+                    const uint32_t key = wkeys[j];
                     tile_keys[o] = key;
                     isect_vals[o] = ticket * 32u + wown[j];
-                    if (hist_passes > 0) atomicAdd(&s_thist[key & lo_mask], 1u);
-                }
-                if (hist_passes > 1) {
-                    const uint32_t hi = (key >> 8) & hi_mask;
-                    uint32_t todo = __ballot_sync(0xffffffffu, ok);
-                    while (todo) {
-                        const uint32_t leader = (uint32_t)__ffs(todo) - 1u;
-                        const uint32_t h = __shfl_sync(0xffffffffu, hi, leader);
-                        const uint32_t same = __ballot_sync(0xffffffffu, ok && hi == h) & todo;
-                        if (lane == leader) atomicAdd(&s_thist[256 + h], (uint32_t)__popc(same));
-                        todo &= ~same;
-                    }
+                    count_key(key);
                 }
             }
         }
