@@ -880,6 +880,36 @@ namespace bg {
 cudaError_t launch_loss_mean(cudaStream_t, const float *, uint32_t, float *);
 }
 
+// BG_DP_TRACE=1: device timeline of the multi-device step (stderr, rank 0 only; synchronises -- a debugging aid)
+namespace {
+struct DpTrace {
+    bool on = false;
+    cudaEvent_t e[12] = {};
+    DpTrace() {
+        const char *v = getenv("BG_DP_TRACE");
+        on = v && v[0] == '1';
+    }
+    void mark(int i, cudaStream_t st) {
+        if (!on) return;
+        if (!e[i]) cudaEventCreate(&e[i]);
+        cudaEventRecord(e[i], st);
+    }
+    void report(cudaStream_t s, cudaStream_t cs, int rank) {
+        if (!on) return;
+        cudaStreamSynchronize(s); cudaStreamSynchronize(cs);
+        if (rank != 0) return;
+        static const char *names[12] = {"step start", "blend bwd + colour pack done", "project bwd + row pack done", "records arrived (s)",
+                                        "update part 1 done", "sums arrived (s)", "update part 2 done", "all-gather start (comm)",
+                                        "all-gather end (comm)", "all-reduce start (comm)", "all-reduce end (comm)", ""};
+        for (int i = 1; i < 11; i++) {
+            float ms = 0.0f;
+            if (e[i] && cudaEventElapsedTime(&ms, e[0], e[i]) == cudaSuccess) fprintf(stderr, "[bg dp trace] %-32s %8.3f ms\n", names[i], ms);
+        }
+    }
+};
+DpTrace g_dp_trace;
+}  // namespace
+
 extern "C" uint64_t bg_train_step_views_workspace_bytes(uint32_t n, uint32_t k, uint32_t w, uint32_t h, uint32_t local,
                                                         uint32_t world) {
     return carve_views_ws(nullptr, n, k, w, h, std::max(local, 1u), std::max(world, 1u), true).bytes;
@@ -925,6 +955,8 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
         for (int q = 0; q < 3; q++) hdr.pos[i][q] = a->cams[i].cam_pos[q];
     BG_CUDA(launch_write_header(s, ws.hdr, hdr, local));
     DpComm *d = world > 1 ? h->c : nullptr;
+    DpTrace &tr = g_dp_trace;
+    if (d) tr.mark(0, s);
     // The exchange of a step has two parts.  The colour records (all-gather) depend on the blend backward only, so they
     // leave as soon as the last local view's blend backward is done and travel UNDER its projection backward; the summed
     // small rows and the MAX statistics (all-reduces) follow once that is done.  The update pass is split the same way:
@@ -945,9 +977,11 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
         if (d && i + 1 == local) {
             BG_CUDA(cudaEventRecord(d->ev_ready, s));
             BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
+            tr.mark(1, s); tr.mark(7, d->stream);
             int rc = dp_exchange_header(d, local, ws.hdr, ws.hdr_all);
             if (rc == 0) rc = dp_exchange_gather(d, n, local, ws.record, ws.recv);
             if (rc != 0) return nccl_fail("bg_train_step_views: exchange (records)", rc);
+            tr.mark(8, d->stream);
         }
         r = bg_project_backward_factored(c, stream, cam, &a->state_out, r_t, a->sh, r_o, ws.v_combined, ws.v_t, ws.v_color, ws.v_o, ws.v_refine);
         if (r != BG_OK) return r;
@@ -981,14 +1015,21 @@ extern "C" int32_t bg_train_step_views(BgContext *c, BgDpComm *h, void *stream, 
     }
     BG_CUDA(cudaEventRecord(d->ev_ready2, s));
     BG_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready2, 0));
+    tr.mark(2, s); tr.mark(9, d->stream);
     const int rc = dp_exchange_reduce(d, n, ws.small, ws.stat);
     if (rc != 0) return nccl_fail("bg_train_step_views: exchange (sums)", rc);
+    tr.mark(10, d->stream);
     P.records = ws.recv; P.cam_all = ws.hdr_all;
     BG_CUDA(cudaStreamWaitEvent(s, d->ev_chunk[0], 0));
+    tr.mark(3, s);
     BG_CUDA(launch_train_update(s, deg, P, true, 1));          // SH coefficients: records only
+    tr.mark(4, s);
     BG_CUDA(cudaStreamWaitEvent(s, d->ev_chunk[1], 0));
+    tr.mark(5, s);
     if ((r = fold_back()) != BG_OK) return r;
     BG_CUDA(launch_train_update(s, deg, P, true, 2));          // transforms, opacity, statistics, noise
+    tr.mark(6, s);
+    tr.report(s, d->stream, d->rank);
     return BG_OK;
 }
 

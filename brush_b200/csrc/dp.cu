@@ -100,7 +100,10 @@ DpComm *dp_comm_create(int device, const NcclUniqueId &id, int rank, int world, 
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return nullptr; }
     int rc = a.CommInitRank(&c->comm, world, id, rank);
     if (rc != 0) { *nccl_rc = rc; delete c; return nullptr; }
-    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // highest priority: the collectives' few CTAs must be dispatched ahead of the queued CTAs of the compute grids they overlap
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_ready2, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < DP_MAX_CHUNKS && ok; i++) ok = cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
