@@ -32,6 +32,35 @@ def test_library_exports_every_declared_symbol():
     assert lib.bg_abi_version() == _lib.ABI_VERSION
 
 
+def test_integration_doc_binds_every_declared_symbol():
+    """INTEGRATION.md is the reference-side binding a maintainer would add: every entry point of the header appears in its
+    `extern "C"` block with the same number of parameters as the C declaration."""
+    hdr = open(os.path.join(ROOT, "include", "brush_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    doc_nc = re.sub(r"/\*.*?\*/", "", re.sub(r"//[^\n]*", "", doc), flags=re.S)
+
+    def n_params(text, name, opener):
+        m = re.search(opener % re.escape(name), text)
+        assert m, f"{name} not found"
+        depth, i, args = 1, m.end(), ""
+        while depth:
+            c = text[i]
+            depth += c == "("
+            depth -= c == ")"
+            if depth:
+                args += c
+            i += 1
+        args = args.strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    for name in _declared_functions():
+        assert f"fn {name}(" in doc_nc, f"{name} is declared in brush_b200.h but INTEGRATION.md does not bind it"
+        c_n = n_params(hdr, name, r"\b%s\s*\(")
+        r_n = n_params(doc_nc, name, r"fn %s\(")
+        assert c_n == r_n, f"{name}: {c_n} parameters in the header, {r_n} in INTEGRATION.md"
+
+
 def test_null_and_invalid_arguments_return_status_codes():
     """apps/brush-c/src/lib.rs:119-121 style: null -> error code, never a crash (no GPU needed)."""
     from brush_b200 import _lib
