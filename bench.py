@@ -12,9 +12,9 @@ metric = forward+backward Mpix/s.
   python bench.py --configs 1,3,4,2                        # which BASELINE configs ride in the line (default: all)
 
 N > 1 (torchrun, one rank per GPU): the step is view-sharded -- every rank renders its own view of the replicated scene
-and the ranks exchange the gradients over the library's NCCL communicator (bg_dp_exchange: all-reduce 48 N B,
-all-gather 20 N B per rank of interleaved per-Gaussian rows; the SH gradient stays in its per-view rank-one form, which is what the optimiser pass
-consumes).  Weak scaling: per-GPU work is fixed, value = N * pixels / max-over-ranks step time.
+and the ranks exchange the gradients over the library's NCCL communicator (bg_dp_exchange: all-reduce SUM 48 N B,
+all-reduce MAX 8 N B, all-gather 12 N B per rank, interleaved per-Gaussian rows; the SH gradient stays in its per-view
+rank-one form, which is what the optimiser pass consumes).  Weak scaling: per-GPU work is fixed, value = N * pixels / max-over-ranks step time.
 
 The other configs ride in the same JSON line under "configs":
   "3": 4M Gaussians at 3840x2160 (sort / scan / blend stress), forward+backward, N=1
@@ -565,8 +565,9 @@ def main():
                           "pairs that blended; the forward hands the backward the exact splat sets, so untouched tile-list "
                           "entries cost nothing in the backward"},
         "parallelism": "single GPU" if world == 1 else
-                       f"view-sharded dp{world}: one exchange per step on the library's NCCL communicator (all-reduce 48N B + "
-                       "all-gather 20N B per rank: gradients and refine statistics; the SH gradient stays per-view rank one)",
+                       f"view-sharded dp{world}: one exchange per step on the library's NCCL communicator (all-reduce SUM 48N B + "
+                       "all-reduce MAX 8N B + all-gather 12N B per rank: gradients and refine statistics; the SH gradient "
+                       "stays per-view rank one)",
         "launch": h1["launch"],
         "l2": "inputs larger than L2 (236 MB of Gaussian parameters + 33 MB images per step vs 126 MB L2)"})
     line = {
