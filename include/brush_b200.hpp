@@ -10,7 +10,11 @@
 //   radix_argsort / prefix_sum  <- brush-sort/src/lib.rs:16, brush-prefix-sum/src/lib.rs:11
 //   image_loss_forward/backward <- LossOps                     brush-loss/src/lib.rs:718-733
 //   AdamScaled                  <- brush-train/src/adam_scaled.rs:64-165
-//   TrainConfig, SplatTrainer   <- brush-train/src/config.rs, train.rs:138-429 (the per-step path, over bg_train_step)
+//   TrainConfig, SplatTrainer   <- brush-train/src/config.rs, train.rs:138-893: step (bg_train_step), step_views
+//                                  (bg_train_step_views: several views per step, one or several devices), refine (bg_refine)
+//   BoundingBox, bounds_from_pos <- brush-render/src/bounding_box.rs, brush-train/src/splat_init.rs:130-160
+//   Splats                      <- brush-render/src/gaussian_splats.rs:57-74 (owns the three parameter tensors)
+//   DpComm                      <- no reference counterpart: one NCCL rank per context, behind the ABI
 //
 // Errors: the reference panics on shape / device violations (render.rs:50-64); here every non-zero ABI status
 // becomes a brush_b200::Error (std::runtime_error) carrying the status and bg_last_error_string().
@@ -19,12 +23,14 @@
 #pragma once
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "brush_b200.h"
 
@@ -376,7 +382,98 @@ struct TrainConfig {                         // brush-train/src/config.rs:5-132 
     float background[3] = {0, 0, 0};
     bool render_mip = false;
     uint64_t seed = 0;
+    // refine (config.rs:47-92)
+    float opac_decay = 0.004f;
+    uint32_t max_splats = 10000000;
+    uint32_t refine_every = 200;
+    float growth_grad_threshold = 0.0025f, growth_select_fraction = 0.25f;
+    uint32_t growth_stop_iter = 15000;
+    float split_at_screen_size = 0.5f;
 };
+
+// brush-render/src/bounding_box.rs:5-31
+struct BoundingBox {
+    float center[3] = {0, 0, 0};
+    float extent[3] = {1, 1, 1};
+    float median_size() const {   // bounding_box.rs:23-29: twice the middle extent, ordered by f32::total_cmp (NaN-safe)
+        auto key = [](float f) {  // the total order of IEEE 754 (what total_cmp implements): sign-magnitude bits -> two's complement
+            int32_t b;
+            std::memcpy(&b, &f, 4);
+            return b ^ (int32_t)((uint32_t)(b >> 31) >> 1);
+        };
+        float e[3] = {extent[0], extent[1], extent[2]};
+        if (key(e[0]) > key(e[1])) std::swap(e[0], e[1]);
+        if (key(e[1]) > key(e[2])) std::swap(e[1], e[2]);
+        if (key(e[0]) > key(e[1])) std::swap(e[0], e[1]);
+        return e[1] * 2.0f;
+    }
+    float max_extent() const { return std::fmax(extent[0], std::fmax(extent[1], extent[2])); }
+};
+
+// bounds_from_pos (splat_init.rs:130-160) on the device: per axis the ((1-p)/2, (1+p)/2) order statistics of the finite
+// means.  No finite mean at all -> the unit box at the origin (splat_init.rs:141-143).  Synchronises `stream`.
+inline BoundingBox bounds_from_pos(Context &ctx, cudaStream_t stream, float percentile, const float *transforms, uint32_t n) {
+    BoundingBox b;
+    if (n == 0) return b;
+    const uint64_t need = bg_refine_workspace_bytes(n);
+    DeviceBuffer<unsigned char> ws(need);
+    float mm[6];
+    check(bg_bounds_percentile(ctx.handle(), stream, n, transforms, percentile, ws.data(), need, mm), "bounds_from_pos");
+    for (float v : mm)
+        if (!std::isfinite(v)) return b;
+    for (int a = 0; a < 3; a++) {
+        b.center[a] = (mm[2 * a + 1] + mm[2 * a]) / 2.0f;
+        b.extent[a] = (mm[2 * a + 1] - mm[2 * a]) / 2.0f;
+    }
+    return b;
+}
+
+// Splats (gaussian_splats.rs:57-74): owns the parameter tensors; refine replaces them (the count changes).
+struct Splats {
+    DeviceBuffer<float> transforms;      // [rows >= n, 10]  means 3, quaternion wxyz 4, log-scales 3
+    DeviceBuffer<float> sh_coeffs;       // [rows >= n, k, 3]
+    DeviceBuffer<float> raw_opacities;   // [rows >= n]
+    uint32_t n = 0, k = 1;
+    Splats() = default;
+    Splats(const float *host_transforms, const float *host_sh, const float *host_raw_opac, uint32_t n_, uint32_t k_, cudaStream_t s = nullptr)
+        : transforms((size_t)n_ * 10), sh_coeffs((size_t)n_ * k_ * 3), raw_opacities(n_), n(n_), k(k_) {
+        transforms.upload(host_transforms, (size_t)n_ * 10, s);
+        sh_coeffs.upload(host_sh, (size_t)n_ * k_ * 3, s);
+        raw_opacities.upload(host_raw_opac, n_, s);
+    }
+    uint32_t num_splats() const { return n; }
+};
+
+struct RefineStats {   // brush-train/src/msg.rs RefineStats
+    uint32_t num_added = 0, num_split_oversized = 0, num_split_high_grad = 0, num_pruned = 0, num_pruned_non_finite = 0, total_splats = 0;
+};
+
+// One NCCL rank bound to a context's device (bg_dp_comm_create).  Rank 0 obtains the 128-byte id with unique_id() and
+// ships it to the other ranks over the host's own rendezvous; construction is collective.
+class DpComm {
+   public:
+    static std::vector<uint8_t> unique_id() {
+        std::vector<uint8_t> id(128);
+        check(bg_dp_unique_id(id.data()), "bg_dp_unique_id");
+        return id;
+    }
+    DpComm(Context &ctx, const std::vector<uint8_t> &id, int rank, int world) : rank_(rank), world_(world) {
+        if (id.size() != 128) throw Error(BG_ERR_INVALID, "DpComm: the NCCL id is 128 bytes");
+        check(bg_dp_comm_create(ctx.handle(), id.data(), rank, world, &h_), "bg_dp_comm_create");
+    }
+    DpComm(const DpComm &) = delete;
+    DpComm &operator=(const DpComm &) = delete;
+    ~DpComm() { if (h_) bg_dp_comm_destroy(h_); }
+    BgDpComm *handle() const { return h_; }
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+
+   private:
+    BgDpComm *h_ = nullptr;
+    int rank_ = 0, world_ = 1;
+};
+
+constexpr float BOUND_PERCENTILE = 0.8f;   // train.rs:30: the bounds that drive the learning-rate scale and the prune radius
 
 // SplatTrainer::step (train.rs:176-429) over bg_train_step.  Owns the Adam moments, the refine record and the step's
 // workspace; the splat parameters stay with the caller and are updated in place.
@@ -387,6 +484,11 @@ class SplatTrainer {
           m_t_((size_t)n * 10, true), v_t_((size_t)n * 10, true), m_sh_((size_t)n * k * 3, true), v_sh_(n, true), m_o_(n, true),
           v_o_(n, true), refine_norm_(n, true), vis_weight_(n, true), max_screen_(n, true), loss_(1, true) {
         decay_ = std::pow(cfg.lr_mean_end / cfg.lr_mean, 1.0 / (double)cfg.total_train_iters);
+    }
+    // SplatTrainer::new (train.rs:138-166) with the scene bounds: needed by refine (prune radius) and kept current by it
+    SplatTrainer(const TrainConfig &cfg, uint32_t n, uint32_t k, const BoundingBox &bounds) : SplatTrainer(cfg, n, k, bounds.median_size()) {
+        bounds_ = bounds;
+        has_bounds_ = true;
     }
     // gt_packed: device [h,w] rgba8 (view_to_packed_data, scene.rs:97-136).  Returns the device scalar holding the loss.
     const float *step(Context &ctx, cudaStream_t stream, const Camera &camera, const uint32_t *gt_packed, uint32_t w, uint32_t h,
@@ -426,6 +528,116 @@ class SplatTrainer {
         last_state_ = a.state_out;
         return loss_.data();
     }
+    // One optimizer step over several views (BASELINE config [4]) through bg_train_step_views: the loss is the
+    // mean of the per-view losses.  `comm` == nullptr: all views on this device.  With a communicator every rank passes ITS
+    // views (the same count on every rank; global view index = rank * local + i) and all ranks end with bit-identical
+    // parameters.  gt_packed[i]: device [h,w] rgba8 of view i.  min_scale: optional device [n] Mip-Splatting scale floor.
+    const float *step_views(Context &ctx, DpComm *comm, cudaStream_t stream, const std::vector<Camera> &cameras,
+                            const std::vector<const uint32_t *> &gt_packed, uint32_t w, uint32_t h, Splats &splats,
+                            const float *min_scale = nullptr, bool has_alpha = false, bool masked_alpha = false) {
+        const uint32_t local = (uint32_t)cameras.size(), world = comm ? (uint32_t)comm->world() : 1u;
+        if (local == 0 || gt_packed.size() != cameras.size() || local * world > 16)
+            throw Error(BG_ERR_INVALID, "SplatTrainer::step_views: 1..16 views per step in total, one image per camera");
+        if (splats.n != n_ || splats.k != k_) throw Error(BG_ERR_INVALID, "SplatTrainer::step_views: splat count differs from the optimizer state");
+        step_ += 1;
+        const uint64_t need = bg_train_step_views_workspace_bytes(n_, k_, w, h, local, world);
+        if (views_ws_.size() < need) views_ws_ = DeviceBuffer<unsigned char>(need);
+        std::vector<BgCamera> cams(local);
+        for (uint32_t i = 0; i < local; i++) cams[i] = make_uniforms(cameras[i], w, h);
+        BgTrainViewsArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.w = w; a.h = h; a.n = n_; a.k = k_;
+        a.mip = cfg_.render_mip;
+        for (int i = 0; i < 3; i++) { a.background[i] = cfg_.background[i]; a.composite_bg[i] = cfg_.background[i]; }
+        a.local_views = local;
+        a.cams = cams.data();
+        a.gt_packed = gt_packed.data();
+        a.transforms = splats.transforms.data(); a.sh = splats.sh_coeffs.data(); a.raw_opac = splats.raw_opacities.data();
+        a.m_t = m_t_.data(); a.v_t = v_t_.data(); a.m_sh = m_sh_.data(); a.v_sh = v_sh_.data(); a.m_o = m_o_.data(); a.v_o = v_o_.data();
+        a.refine_norm = refine_norm_.data(); a.vis_weight = vis_weight_.data(); a.max_screen = max_screen_.data();
+        a.min_scale = min_scale;
+        const bool ssim = cfg_.ssim_weight > 0.0f;
+        a.l1_weight = ssim ? 1.0f - cfg_.ssim_weight : 1.0f;
+        a.ssim_weight = ssim ? -cfg_.ssim_weight : 0.0f;
+        const bool bg_nonzero = cfg_.background[0] != 0.0f || cfg_.background[1] != 0.0f || cfg_.background[2] != 0.0f;
+        a.has_composite_bg = has_alpha && bg_nonzero;
+        a.mask = masked_alpha;
+        a.channels = (has_alpha && !masked_alpha && cfg_.match_alpha_weight > 0.0f) ? 4 : 3;
+        a.alpha_weight = cfg_.match_alpha_weight;
+        const double lr_mean = cfg_.lr_mean * std::pow(decay_, (double)(step_ - 1)) * (double)median_scale_;   // train.rs:328-333
+        a.lr_mean = (float)lr_mean;
+        a.lr_rotation = cfg_.lr_rotation; a.lr_scale = cfg_.lr_scale;
+        a.lr_coeffs_dc = cfg_.lr_coeffs_dc; a.lr_coeffs_sh_scale = cfg_.lr_coeffs_sh_scale; a.lr_opac = cfg_.lr_opac;
+        a.noise_scale = (float)lr_mean * cfg_.mean_noise_weight;
+        a.median_scale = median_scale_;
+        a.seed = cfg_.seed;
+        a.step = step_;
+        a.chunks = 0;
+        a.workspace = views_ws_.data(); a.workspace_bytes = need;
+        a.loss_out = loss_.data();
+        check(bg_train_step_views(ctx.handle(), comm ? comm->handle() : nullptr, stream, &a), "SplatTrainer::step_views");
+        last_state_ = a.state_out;
+        return loss_.data();
+    }
+
+    // SplatTrainer::refine + refine_splats + prune_points (train.rs:431-893) through bg_refine: every decision on the
+    // device, one readback of the counts.  Replaces the tensors of `splats` and the optimizer state (the count changes),
+    // restarts the refine record (train.rs:442-445) and recomputes the bounds (train.rs:634).  `iteration` selects the
+    // random stream and the schedules (growth stop, opacity decay).  A scale floor, if the host keeps one, must be baked
+    // into the splats before the call and recomputed after it (train.rs:432-437, 641-647).
+    RefineStats refine(Context &ctx, cudaStream_t stream, uint32_t iteration, Splats &splats) {
+        if (!has_bounds_) throw Error(BG_ERR_INVALID, "SplatTrainer::refine: construct the trainer with the scene's BoundingBox");
+        if (step_ == 0) throw Error(BG_ERR_INVALID, "Can only refine after optimizer is initialized");   // train.rs:490-492
+        if (splats.n != n_ || splats.k != k_) throw Error(BG_ERR_INVALID, "SplatTrainer::refine: splat count differs from the optimizer state");
+        const uint32_t n0 = n_;
+        const uint64_t cap64 = std::max<uint64_t>(n0, std::min<uint64_t>(2ull * n0, std::max<uint64_t>(n0, cfg_.max_splats)));
+        const uint32_t cap = (uint32_t)cap64;
+        DeviceBuffer<float> t_out((size_t)cap * 10), sh_out((size_t)cap * k_ * 3), o_out(cap);
+        DeviceBuffer<float> m_t((size_t)cap * 10), v_t((size_t)cap * 10), m_sh((size_t)cap * k_ * 3), v_sh(cap), m_o(cap), v_o(cap);
+        const uint64_t need = bg_refine_workspace_bytes(n0);
+        DeviceBuffer<unsigned char> ws(need);
+        BgRefineArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.n = n0; a.k = k_; a.capacity = cap;
+        a.transforms = splats.transforms.data(); a.sh = splats.sh_coeffs.data(); a.raw_opac = splats.raw_opacities.data();
+        a.m_t = m_t_.data(); a.v_t = v_t_.data(); a.m_sh = m_sh_.data(); a.v_sh = v_sh_.data(); a.m_o = m_o_.data(); a.v_o = v_o_.data();
+        a.refine_norm = refine_norm_.data(); a.vis_weight = vis_weight_.data(); a.max_screen = max_screen_.data();
+        a.transforms_out = t_out.data(); a.sh_out = sh_out.data(); a.raw_opac_out = o_out.data();
+        a.m_t_out = m_t.data(); a.v_t_out = v_t.data(); a.m_sh_out = m_sh.data(); a.v_sh_out = v_sh.data(); a.m_o_out = m_o.data(); a.v_o_out = v_o.data();
+        for (int i = 0; i < 3; i++) a.bounds_center[i] = bounds_.center[i];
+        a.max_allowed = bounds_.max_extent() * 100.0f;                                   // train.rs:485
+        a.split_at_screen_size = cfg_.split_at_screen_size;
+        a.growth_grad_threshold = cfg_.growth_grad_threshold;
+        a.growth_select_fraction = cfg_.growth_select_fraction;
+        a.max_splats = cfg_.max_splats;
+        a.growth_enabled = iteration < cfg_.growth_stop_iter;
+        const float train_t = std::fmin(std::fmax((float)iteration / (float)cfg_.total_train_iters, 0.0f), 1.0f);   // train.rs:809-811, in f32
+        a.opac_decay_minus = cfg_.opac_decay * (1.0f - train_t);
+        a.seed = cfg_.seed;
+        a.refine_index = iteration;
+        a.workspace = ws.data(); a.workspace_bytes = need;
+        BgRefineStats rs;
+        check(bg_refine(ctx.handle(), stream, &a, &rs), "SplatTrainer::refine");   // synchronises the stream once
+        const uint32_t n_new = rs.total_splats;
+        splats.transforms = std::move(t_out); splats.sh_coeffs = std::move(sh_out); splats.raw_opacities = std::move(o_out);
+        splats.n = n_new;
+        m_t_ = std::move(m_t); v_t_ = std::move(v_t); m_sh_ = std::move(m_sh); v_sh_ = std::move(v_sh); m_o_ = std::move(m_o); v_o_ = std::move(v_o);
+        refine_norm_ = DeviceBuffer<float>(n_new, true); vis_weight_ = DeviceBuffer<float>(n_new, true); max_screen_ = DeviceBuffer<float>(n_new, true);
+        n_ = n_new;
+        bounds_ = bounds_from_pos(ctx, stream, BOUND_PERCENTILE, splats.transforms.data(), n_new);
+        median_scale_ = bounds_.median_size();
+        RefineStats out;
+        out.num_added = rs.num_added; out.num_split_oversized = rs.num_split_oversized; out.num_split_high_grad = rs.num_split_high_grad;
+        out.num_pruned = rs.num_pruned; out.num_pruned_non_finite = rs.num_pruned_non_finite; out.total_splats = n_new;
+        return out;
+    }
+    // train_stream.rs:318-326: refine after the step with 0-based index `iter`?
+    bool should_refine(uint32_t iter) const {
+        const double progress = std::fmin(std::fmax((double)iter / (double)std::max(cfg_.total_train_iters, 1u), 0.0), 1.0);
+        return iter > 0 && iter % cfg_.refine_every == 0 && progress <= 0.95;
+    }
+    uint32_t num_splats() const { return n_; }
+    const BoundingBox &bounds() const { return bounds_; }
     int steps() const { return step_; }
     const BgRenderState &last_render_state() const { return last_state_; }
     const float *refine_weight_norm() const { return refine_norm_.data(); }
@@ -439,8 +651,10 @@ class SplatTrainer {
     double decay_ = 1.0;
     int step_ = 0;
     DeviceBuffer<float> m_t_, v_t_, m_sh_, v_sh_, m_o_, v_o_, refine_norm_, vis_weight_, max_screen_, loss_;
-    DeviceBuffer<unsigned char> ws_;
+    DeviceBuffer<unsigned char> ws_, views_ws_;
     BgRenderState last_state_{};
+    BoundingBox bounds_;
+    bool has_bounds_ = false;
 };
 
 }  // namespace brush_b200

@@ -4,6 +4,9 @@
 //   errors              exceptions for invalid arguments                                           (no GPU needed)
 //   render IN OUT       forward + backward of a scene file written by tests/test_cpp_host.py       (GPU)
 //   train IN STEPS      SplatTrainer::step on the same kind of file (+ packed ground truth)         (GPU)
+//   bounds              BoundingBox::median_size on the cases of bounding_box.rs:36-58               (no GPU needed)
+//   refine IN STEPS     STEPS x SplatTrainer::step_views (one view, one device), refine, one more step (GPU)
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -73,7 +76,21 @@ int main(int argc, char **argv) {
             try { Context c(0, 0, 64, 64); } catch (const Error &e) { caught += e.status == BG_ERR_INVALID; }
             try { check(bg_ctx_destroy(nullptr), "destroy"); } catch (const Error &e) { caught += e.status == BG_ERR_NULL; }
             std::printf("caught %d\n", caught);
-            return caught == 3 ? 0 : 1;
+            // the entry points behind step_views / refine / DpComm reject null handles before touching a device
+            int more = 0;
+            try { check(bg_train_step_views(nullptr, nullptr, nullptr, nullptr), "step_views"); } catch (const Error &e) { more += e.status == BG_ERR_NULL; }
+            try { BgRefineStats rs; check(bg_refine(nullptr, nullptr, nullptr, &rs), "refine"); } catch (const Error &e) { more += e.status == BG_ERR_NULL; }
+            try { BgDpComm *h = nullptr; uint8_t id[128] = {0}; check(bg_dp_comm_create(nullptr, id, 0, 1, &h), "dp"); } catch (const Error &e) { more += e.status == BG_ERR_NULL; }
+            std::printf("caught_more %d\n", more);
+            return caught == 3 && more == 3 ? 0 : 1;
+        }
+        if (mode == "bounds") {   // bounding_box.rs:36-58
+            BoundingBox a, b, c;
+            a.extent[0] = NAN; a.extent[1] = 2.0f; a.extent[2] = 3.0f;
+            b.extent[0] = b.extent[1] = b.extent[2] = NAN;
+            c.extent[0] = 1.0f; c.extent[1] = 2.0f; c.extent[2] = 3.0f;   // from_min_max(-1, (1, 3, 5))
+            std::printf("%.9g %.9g %.9g\n", a.median_size(), b.median_size(), c.median_size());
+            return 0;
         }
         if (mode == "render" && argc == 4) {
             std::ifstream f(argv[2], std::ios::binary);
@@ -144,6 +161,48 @@ int main(int argc, char **argv) {
                 std::printf("loss %.9g\n", loss);
             }
             return 0;
+        }
+        if (mode == "refine" && argc == 4) {   // scene file as for `train`; argv[3]: steps before the refine
+            std::ifstream f(argv[2], std::ios::binary);
+            uint32_t hdr[6];
+            f.read(reinterpret_cast<char *>(hdr), sizeof(hdr));
+            const uint32_t n = hdr[0], k = hdr[1], w = hdr[2], h = hdr[3];
+            std::string camline;
+            { uint32_t len; f.read(reinterpret_cast<char *>(&len), 4); camline.resize(len); f.read(&camline[0], len); }
+            std::istringstream ss(camline);
+            uint32_t cw, ch;
+            Camera cam = read_camera(ss, cw, ch);
+            float bg[3];
+            f.read(reinterpret_cast<char *>(bg), sizeof(bg));
+            auto tr = read_vec<float>(f, (size_t)n * 10), sh = read_vec<float>(f, (size_t)n * k * 3), op = read_vec<float>(f, n);
+            auto skip = read_vec<float>(f, (size_t)w * h * 4);
+            auto gt = read_vec<uint32_t>(f, (size_t)w * h);
+            const uint32_t cap = 2 * n;
+            Context ctx(0, cap, w, h);
+            Splats splats(tr.data(), sh.data(), op.data(), n, k);
+            DeviceBuffer<uint32_t> d_gt(gt.size());
+            d_gt.upload(gt.data(), gt.size());
+            TrainConfig cfg;
+            cfg.total_train_iters = 1000;
+            cfg.seed = 7;
+            cfg.max_splats = cap;
+            const BoundingBox bounds = bounds_from_pos(ctx, nullptr, BOUND_PERCENTILE, splats.transforms.data(), n);
+            std::printf("bounds %.9g %.9g %.9g %.9g %.9g %.9g\n", bounds.center[0], bounds.center[1], bounds.center[2], bounds.extent[0],
+                        bounds.extent[1], bounds.extent[2]);
+            SplatTrainer trainer(cfg, n, k, bounds);
+            const int steps = std::atoi(argv[3]);
+            auto one_step = [&]() {
+                const float *loss_dev = trainer.step_views(ctx, nullptr, nullptr, {cam}, {d_gt.data()}, w, h, splats);
+                float loss;
+                check_cuda(cudaMemcpy(&loss, loss_dev, 4, cudaMemcpyDeviceToHost), "loss readback");
+                std::printf("loss %.9g\n", loss);
+            };
+            for (int i = 0; i < steps; i++) one_step();
+            const RefineStats rs = trainer.refine(ctx, nullptr, (uint32_t)steps, splats);
+            std::printf("refine added %u oversized %u high_grad %u pruned %u non_finite %u total %u\n", rs.num_added, rs.num_split_oversized,
+                        rs.num_split_high_grad, rs.num_pruned, rs.num_pruned_non_finite, rs.total_splats);
+            one_step();
+            return splats.num_splats() == rs.total_splats && trainer.num_splats() == rs.total_splats ? 0 : 1;
         }
     } catch (const Error &e) {
         std::fprintf(stderr, "brush_b200::Error %d: %s\n", e.status, e.what());

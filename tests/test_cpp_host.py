@@ -93,7 +93,17 @@ def test_fov_focal_round_trip_cpp(exe):
 
 def test_errors_are_exceptions(exe):
     r = subprocess.run([exe, "errors"], capture_output=True, text=True)
-    assert r.returncode == 0 and "caught 3" in r.stdout, (r.stdout, r.stderr)
+    assert r.returncode == 0 and "caught 3" in r.stdout and "caught_more 3" in r.stdout, (r.stdout, r.stderr)
+
+
+def test_bounding_box_median_size_cpp(exe):
+    """brush-render/src/bounding_box.rs:36-58: NaN extents do not break the ordering (f32::total_cmp), normal case = 4."""
+    r = subprocess.run([exe, "bounds"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with_nan, all_nan, normal = (float(t) for t in r.stdout.split())
+    assert math.isfinite(with_nan) and with_nan == 6.0      # total order: [2, 3, NaN] -> 3 * 2
+    assert math.isnan(all_nan)
+    assert abs(normal - 4.0) < 1e-6
 
 
 @pytest.mark.gpu
@@ -177,4 +187,59 @@ def test_cpp_splat_trainer_matches_python_fused_step(exe, tmp_path):
     py_losses = [float(trainer.step_fused(batch, splats).loss.item()) for _ in range(3)]
     assert len(cpp_losses) == 3 and all(math.isfinite(x) for x in cpp_losses)
     np.testing.assert_allclose(cpp_losses, py_losses, rtol=1e-3)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: compiled and error-path checked on the CPU, "
+                                        "not yet run on hardware")
+def test_cpp_refine_and_step_views_match_python_mirror(exe, tmp_path):
+    """brush_b200::SplatTrainer::step_views / refine (C++) against SplatTrainer.step_views / refine (Python): both drive
+    bg_train_step_views and bg_refine with the same seed, so the refine counts agree (up to the blend backward's f32
+    atomics moving a value across a threshold) and the losses match."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import brush_b200.render as R
+    import brush_b200.train as T
+    from scenes import synthetic_scene
+    n, w, h, k = 15_000, 192, 128, 4
+    cam, tr, sh, op = synthetic_scene(n, w, h, k=k, seed=56)
+    op = op.copy()
+    op[:500] = np.float32(-8.0)        # opacity < 1/255: pruned and replaced (train.rs:455-520)
+    ctx = R.RenderContext(2 * n, w, h)
+    d = ctx.device
+    tgt = R.render_splats(ctx, cam, (w, h), *(torch.from_numpy(x).to(d) for x in (tr, sh, op)), rpass=0)
+    gt = (tgt.out_img | (255 << 24)).clone()
+    sh0 = (sh + np.float32(0.1)).astype(np.float32)
+    line = _cam_line(cam, w, h).encode()
+    scene = tmp_path / "refine.bin"
+    with open(scene, "wb") as f:
+        f.write(struct.pack("<6I", n, k, w, h, 0, 1))
+        f.write(struct.pack("<I", len(line)) + line)
+        f.write(np.zeros(3, np.float32).tobytes() + tr.tobytes() + sh0.tobytes() + op.tobytes())
+        f.write(np.zeros((h, w, 4), np.float32).tobytes())
+        f.write(gt.cpu().numpy().astype(np.int32).tobytes())
+    steps = 4
+    r = subprocess.run([exe, "refine", str(scene), str(steps)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    lines = r.stdout.strip().splitlines()
+    cpp_losses = [float(ln.split()[1]) for ln in lines if ln.startswith("loss")]
+    cpp_bounds = [float(t) for t in next(ln for ln in lines if ln.startswith("bounds")).split()[1:]]
+    tok = next(ln for ln in lines if ln.startswith("refine")).split()
+    cpp_stats = {tok[i]: int(tok[i + 1]) for i in range(1, len(tok), 2)}
+    cfg = T.TrainConfig(total_train_iters=1000, background_noise_strength=0.0, seed=7, max_splats=2 * n)
+    splats = T.Splats(*(torch.from_numpy(x.copy()).to(d) for x in (tr, sh0, op)))
+    bounds = T.bounds_from_pos_device(ctx, T.BOUND_PERCENTILE, splats.transforms)
+    np.testing.assert_allclose(cpp_bounds, [*bounds.center, *bounds.extent], rtol=1e-6)
+    trainer = T.SplatTrainer(cfg, ctx, bounds)
+    batch = T.SceneBatch(img_packed=gt, camera=cam)
+    py_losses = [float(trainer.step_views([batch], splats, distributed=False).loss.item()) for _ in range(steps)]
+    rs = trainer.refine(steps, splats)
+    py_losses.append(float(trainer.step_views([batch], splats, distributed=False).loss.item()))
+    assert len(cpp_losses) == steps + 1 and all(math.isfinite(x) for x in cpp_losses)
+    np.testing.assert_allclose(cpp_losses, py_losses, rtol=2e-3)
+    assert cpp_stats["pruned"] >= 500 and rs.num_pruned >= 500
+    for name, want in (("added", rs.num_added), ("pruned", rs.num_pruned), ("total", rs.total_splats)):
+        assert abs(cpp_stats[name] - want) <= max(3, want // 500), (name, cpp_stats, rs)
     ctx.close()
