@@ -357,8 +357,8 @@ class SplatTrainer:
         (bg_train_step_views): the loss is the mean of the per-view losses, i.e. the step equals accumulating the
         views' gradients sequentially on one GPU.  Under torch.distributed every rank passes ITS views (the same count
         on every rank, global view index = rank * local + i); the library exchanges the SH-factored gradients over its
-        own NCCL communicator (all-reduce 48 N B, all-gather (12 local + 8) N B per rank), runs the SH part of the
-        update pass under the all-reduce, and all ranks apply bit-identical updates.  At most 16 views per step in total.  All views of a
+        own NCCL communicator (all-reduce SUM 48 N B, all-reduce MAX 8 N B, all-gather 12 local N B per rank), runs the SH
+        part of the update pass under the all-reduces, and all ranks apply bit-identical updates.  At most 16 views per step in total.  All views of a
         step share the image size and the loss configuration.  distributed=False runs the step on this device alone even
         inside an initialised process group."""
         import torch.distributed as dist
