@@ -1,12 +1,18 @@
 """View-sharded data parallelism (no counterpart in the single-device reference).
 
-Every rank holds the full parameter set, renders its own view(s) of the step's batch and the dense
-per-Gaussian gradients are summed with ONE all-reduce over a flat buffer ((10+3K+1) N floats), then
-scaled by 1/views because the loss is a per-view mean (train.rs:254-260).  The three refine statistics
-use MAX / SUM / MAX (stats.rs:40-50).  Parity definition: equal to the single-GPU step that
-accumulates the views' gradients sequentially, up to f32 summation order.
+Every rank holds the full parameter set and renders its own view(s) of the step's batch; one exchange per step makes
+the gradient of the mean-over-views loss (train.rs:254-260) and the refine statistics (stats.rs:40-50: MAX / SUM / MAX)
+available on every rank.  Parity definition: equal to the single-GPU step that accumulates the views'
+gradients sequentially, up to f32 summation order.
 
-Backend-agnostic: NCCL over NVLink on the GPUs, gloo in the CPU tests.
+Two layers live here:
+  * DpComm -- the product path: one NCCL rank of the LIBRARY's communicator (csrc/dp.cu).  bg_train_step_views and
+    bg_dp_exchange run the SH-factored exchange (all-reduce SUM 48 N B + all-reduce MAX 8 N B + all-gather 12 local N B
+    per rank) on the library's own stream; torch.distributed only carries the 128-byte NCCL id.
+  * FlatGradients / FactoredGradients / ShFactoredReducer / ViewShardedReducer -- the same exchanges written over
+    torch.distributed collectives for hosts that drive the operators themselves (SplatTrainer.grad_hook) and for the
+    world_size-2 gloo tests that pin the host-side logic without a GPU (tests/test_dp_gloo.py).  ViewShardedReducer is the
+    plain form SURVEY 8e describes: ONE all-reduce over a flat (10+3K+1) N float buffer.
 """
 from __future__ import annotations
 
