@@ -6,8 +6,11 @@
                        opacity / f_dc / f_rest / rgb properties, subsampling, up-axis and render-mode comments)
   SplatData.subsample / into_splats <- import.rs:40-103 (defaults for missing fields)
 
-Storage format, not part of the per-step hot path: numpy on the host, one pass.  The SuperSplat compressed variant
-(import.rs:405-600, quant.rs) is not handled.
+  _load_compressed_ply <- import.rs:408-600, ply_gaussian.rs:23-34,102-122, quant.rs:1-71: the SuperSplat compressed
+                       variant (per-256-splat quantisation ranges in a leading `chunk` element, 11/10/11-bit positions and
+                       scales, smallest-three quaternions, 8-bit colour + opacity, optional 8-bit higher SH bands)
+
+Storage format, not part of the per-step hot path: numpy on the host, one pass.
 """
 from __future__ import annotations
 
@@ -184,8 +187,8 @@ def load_splat_from_ply(data: bytes, subsample_points: Optional[int] = None):
     fmt, comments, elements, off = _parse_header(data)
     if not elements or not any(e[0] == "vertex" for e in elements):
         raise ValueError("Unknown format")
-    if elements[0][0] == "chunk":
-        raise NotImplementedError("SuperSplat compressed PLY is not handled")
+    if elements[0][0] == "chunk":                       # PlyFormat::SuperSplatCompressed (import.rs:243-250)
+        return _load_compressed_ply(data, fmt, comments, elements, off, max(int(subsample_points or 1), 1))
     cols = None
     for name, count, props in elements:
         if fmt == "ascii":
@@ -254,3 +257,118 @@ def _skip_ascii(data: bytes, off: int, lines: int) -> int:
     for _ in range(lines):
         off = data.index(b"\n", off) + 1
     return off
+
+
+# ---------------------------------------------------------------------------------------------- SuperSplat compressed PLY
+_QUANT_META_FIELDS = ("min_x", "max_x", "min_y", "max_y", "min_z", "max_z", "min_scale_x", "max_scale_x", "min_scale_y",
+                      "max_scale_y", "min_scale_z", "max_scale_z", "min_r", "max_r", "min_g", "max_g", "min_b", "max_b")
+
+
+def _read_element(data: bytes, fmt: str, off: int, count: int, props):
+    """One PLY element as {property: column}; returns (columns, offset behind the element)."""
+    if fmt == "ascii":
+        end = _skip_ascii(data, off, count)
+        rows = [ln.split() for ln in data[off:end].decode("ascii").split("\n")[:count]]
+        cols = {p[0]: np.array([r[i] for r in rows], dtype=np.float64).astype(_PLY_DTYPES[p[1]]) for i, p in enumerate(props)}
+        return cols, end
+    e = "<" if fmt == "binary_little_endian" else ">"
+    dt = np.dtype([(p[0], e + _PLY_DTYPES[p[1]]) for p in props])
+    if off + dt.itemsize * count > len(data):
+        raise ValueError("unexpected end of PLY data")
+    arr = np.frombuffer(data, dtype=dt, count=count, offset=off)
+    return {p[0]: arr[p[0]] for p in props}, off + dt.itemsize * count
+
+
+def _unpack_unorm(packed: np.ndarray, bits: int) -> np.ndarray:
+    """quant.rs:4-7."""
+    return packed.astype(np.float32) / np.float32((1 << bits) - 1)
+
+
+def decode_vec_11_10_11(value: np.ndarray) -> np.ndarray:
+    """quant.rs:9-18 -> [n,3] in [0,1]."""
+    v = np.asarray(value, np.uint32)
+    return np.stack([_unpack_unorm((v >> 21) & 0x7FF, 11), _unpack_unorm((v >> 11) & 0x3FF, 10), _unpack_unorm(v & 0x7FF, 11)], -1)
+
+
+def decode_vec_8_8_8_8(value: np.ndarray) -> np.ndarray:
+    """quant.rs:20-35 -> [n,4] in [0,1], most significant byte first."""
+    v = np.asarray(value, np.uint32)
+    return np.stack([_unpack_unorm((v >> s) & 0xFF, 8) for s in (24, 16, 8, 0)], -1)
+
+
+def decode_quat(value: np.ndarray) -> np.ndarray:
+    """quant.rs:37-71, smallest-three: two bits name the dropped (largest) component of (w, x, y, z), three 10-bit
+    values hold the others in order.  Returns [n,4] in the (w, x, y, z) order the splat arrays use."""
+    v = np.atleast_1d(np.asarray(value, np.uint32))
+    largest = ((v >> 30) & 0x3).astype(np.int64)
+    norm = np.float32(0.5) * np.float32(math.sqrt(2.0))
+    abc = np.stack([(_unpack_unorm((v >> sft) & 0x3FF, 10) - np.float32(0.5)) / norm for sft in (20, 10, 0)], -1)
+    big = np.sqrt(np.float32(1.0) - (abc * abc).sum(-1, dtype=np.float32))
+    quat = np.empty((v.shape[0], 4), np.float32)
+    rows = np.arange(v.shape[0])
+    for comp in range(4):                                # component `comp` of (w, x, y, z)
+        idx = comp - (comp > largest)                    # position among the three stored values (skipping the largest)
+        quat[:, comp] = np.where(comp == largest, big, abc[rows, np.clip(idx, 0, 2)])
+    return quat
+
+
+def _load_compressed_ply(data: bytes, fmt: str, comments, elements, off: int, sub: int):
+    """parse_compressed_ply (import.rs:408-600).  Row i (0-based) uses the quantisation ranges of chunk i // 256 and is
+    kept when (i + 1) % subsample == 0; opacity and colour come post-activation and are converted back (inverse sigmoid,
+    rgb -> SH DC); the optional third element holds the higher SH bands as u8, channel-major."""
+    idx = 0
+    metas = {k: [] for k in _QUANT_META_FIELDS}
+    while idx < len(elements) and elements[idx][0] == "chunk":
+        name, count, props = elements[idx]
+        cols, off = _read_element(data, fmt, off, count, props)
+        for k in _QUANT_META_FIELDS:
+            if k not in cols:
+                raise ValueError(f"missing field `{k}`")
+            metas[k].append(np.asarray(cols[k], np.float32))
+        idx += 1
+    meta = {k: np.concatenate(v) for k, v in metas.items()}
+    if idx >= len(elements) or elements[idx][0] != "vertex":
+        raise ValueError("Unknown format")
+    name, total, props = elements[idx]
+    cols, off = _read_element(data, fmt, off, total, props)
+    for k in ("packed_position", "packed_scale", "packed_rotation", "packed_color"):   # not optional here (import.rs:484)
+        if k not in cols:
+            raise ValueError(f"missing field `{k}`")
+    keep = np.arange(sub - 1, total, sub)
+    chunk = keep // 256
+    if total and (len(meta["min_x"]) == 0 or chunk.size and chunk.max() >= len(meta["min_x"])):
+        raise ValueError("compressed PLY: fewer chunk rows than the vertex count needs")
+
+    def dequant(raw, names):                             # QuantMeta::{mean, scale, color}: raw * (max - min) + min
+        lo = np.stack([meta["min_" + nm][chunk] for nm in names], -1)
+        hi = np.stack([meta["max_" + nm][chunk] for nm in names], -1)
+        return raw * (hi - lo) + lo
+
+    means = dequant(decode_vec_11_10_11(cols["packed_position"][keep]), ("x", "y", "z")).astype(np.float32)
+    log_scales = dequant(decode_vec_11_10_11(cols["packed_scale"][keep]), ("scale_x", "scale_y", "scale_z")).astype(np.float32)
+    rotations = decode_quat(cols["packed_rotation"][keep]).reshape(-1, 4)
+    rgba = decode_vec_8_8_8_8(cols["packed_color"][keep])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        opacity = np.log(rgba[:, 3] / (np.float32(1.0) - rgba[:, 3])).astype(np.float32)      # inverse_sigmoid
+    dc = ((dequant(rgba[:, :3], ("r", "g", "b")) - np.float32(0.5)) / np.float32(SH_C0)).astype(np.float32)   # rgb_to_sh
+    n = keep.size
+    sh = dc.reshape(n, 1, 3)
+    idx += 1
+    if idx < len(elements) and len(elements) > 2:        # header.elem_defs.get(2): the higher bands, if present
+        name, count, props = elements[idx]
+        if name == "sh" and props:
+            scols, off = _read_element(data, fmt, off, count, props)
+            rest_names = sorted((nm for nm in scols if nm.startswith("f_rest_")), key=lambda t: int(t[7:]))
+            sh_count = len(rest_names)
+            skeep = np.arange(sub - 1, count, sub)[:n]
+            if skeep.size != n:
+                raise ValueError("compressed PLY: the sh element is shorter than the vertex element")
+            rest = np.stack([(np.asarray(scols[nm][skeep], np.float32) / np.float32(254.0) - np.float32(0.5)) * np.float32(8.0)
+                             for nm in rest_names], 1) if sh_count else np.zeros((n, 0), np.float32)     # de_quant_sh
+            per = sh_count // 3
+            sh = np.empty((n, 1 + per, 3), np.float32)
+            sh[:, 0, :] = dc
+            if per:
+                sh[:, 1:, :] = rest[:, :3 * per].reshape(n, 3, per).transpose(0, 2, 1)                  # interleave_coeffs
+    d = SplatData(means=means, rotations=rotations, log_scales=log_scales, sh_coeffs=sh, raw_opacities=opacity)
+    return d, ParseMetadata(up_axis=_up_axis(comments), render_mip=_render_mode(comments), total_splats=n)

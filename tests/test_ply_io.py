@@ -82,3 +82,140 @@ def test_errors():
         ply.load_splat_from_ply(b"not a ply")
     with pytest.raises(ValueError):
         ply.splat_to_ply(np.zeros((1, 10), np.float32), np.zeros((1, 5, 3), np.float32), np.zeros(1, np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- SuperSplat compressed PLY
+def test_quant_decoders_known_answers():
+    """brush-serde/src/quant.rs:73-112 restated."""
+    u = lambda *v: np.array(v, np.uint32)
+    assert np.array_equal(ply.decode_vec_11_10_11(u(0)), np.zeros((1, 3), np.float32))
+    np.testing.assert_allclose(ply.decode_vec_11_10_11(u((0x7FF << 21) | (0x3FF << 11) | 0x7FF)), np.ones((1, 3)), atol=1e-6)
+    assert np.array_equal(ply.decode_vec_8_8_8_8(u(0)), np.zeros((1, 4), np.float32))
+    np.testing.assert_allclose(ply.decode_vec_8_8_8_8(u(0xFFFFFFFF)), np.ones((1, 4)), atol=1e-6)
+    vals = u(*[(i * 42949673) & 0xFFFFFFFF for i in range(100)])
+    for dec in (ply.decode_vec_11_10_11, ply.decode_vec_8_8_8_8):
+        out = dec(vals)
+        assert out.min() >= 0.0 and out.max() <= 1.0
+    q = ply.decode_quat(u((512 << 20) | (512 << 10) | 512))
+    assert abs(np.linalg.norm(q) - 1.0) < 1e-5 and np.isfinite(q).all()
+    # field order: bits 24..31 -> x, 16..23 -> y, 8..15 -> z, 0..7 -> w; 11 | 10 | 11 from the top
+    np.testing.assert_allclose(ply.decode_vec_8_8_8_8(u(0xFF000000))[0], [1, 0, 0, 0])
+    np.testing.assert_allclose(ply.decode_vec_8_8_8_8(u(0x000000FF))[0], [0, 0, 0, 1])
+    np.testing.assert_allclose(ply.decode_vec_11_10_11(u(0x7FF << 21))[0], [1, 0, 0])
+    np.testing.assert_allclose(ply.decode_vec_11_10_11(u(0x7FF))[0], [0, 0, 1])
+
+
+def test_decode_quat_places_the_dropped_component():
+    """quant.rs:37-71: `largest` indexes (w, x, y, z); the three stored values fill the other slots in order."""
+    norm = 0.5 * np.sqrt(2.0)
+    enc = lambda f: int(round((f * norm + 0.5) * 1023))
+    a, b, c = 0.3, -0.2, 0.1
+    for largest in range(4):
+        word = np.array([(largest << 30) | (enc(a) << 20) | (enc(b) << 10) | enc(c)], np.uint32)
+        q = ply.decode_quat(word)[0]
+        others = [q[i] for i in range(4) if i != largest]
+        np.testing.assert_allclose(others, [a, b, c], atol=2e-3)
+        assert q[largest] > 0.9 and abs(np.linalg.norm(q) - 1.0) < 1e-3
+
+
+def _encode_compressed(means, log_scales, quats_wxyz, rgb, opacity, sh_rest=None, endian="<"):
+    """Test-side encoder of the SuperSplat layout (the reference only decodes): returns the PLY bytes."""
+    n = means.shape[0]
+    n_chunks = (n + 255) // 256
+    meta = np.zeros((n_chunks, 18), np.float32)
+    pos_w, scl_w, col_w = (np.zeros(n, np.uint32) for _ in range(3))
+    rot_w = np.zeros(n, np.uint32)
+
+    def pack_111011(u01):
+        a = np.round(u01[:, 0] * 2047).astype(np.uint32)
+        b = np.round(u01[:, 1] * 1023).astype(np.uint32)
+        c = np.round(u01[:, 2] * 2047).astype(np.uint32)
+        return (a << 21) | (b << 11) | c
+
+    for ci in range(n_chunks):
+        sl = slice(ci * 256, min(n, ci * 256 + 256))
+        rows = []
+        for arr, base in ((means, 0), (log_scales, 6), (rgb, 12)):
+            lo, hi = arr[sl].min(0), arr[sl].max(0)
+            hi = np.where(hi > lo, hi, lo + 1.0)
+            for ax in range(3):
+                meta[ci, base + 2 * ax], meta[ci, base + 2 * ax + 1] = lo[ax], hi[ax]
+            rows.append((arr[sl] - lo) / (hi - lo))
+        pos_w[sl], scl_w[sl] = pack_111011(rows[0]), pack_111011(rows[1])
+        c8 = np.round(rows[2] * 255).astype(np.uint32)
+        a8 = np.round(opacity[sl] * 255).astype(np.uint32)
+        col_w[sl] = (c8[:, 0] << 24) | (c8[:, 1] << 16) | (c8[:, 2] << 8) | a8
+    q = quats_wxyz / np.linalg.norm(quats_wxyz, axis=1, keepdims=True)
+    largest = np.abs(q).argmax(1)
+    q = q * np.sign(q[np.arange(n), largest])[:, None]
+    norm = 0.5 * np.sqrt(2.0)
+    for i in range(n):
+        three = [q[i, j] for j in range(4) if j != largest[i]]
+        w = [int(round((v * norm + 0.5) * 1023)) for v in three]
+        rot_w[i] = (int(largest[i]) << 30) | (w[0] << 20) | (w[1] << 10) | w[2]
+    fmt = "binary_little_endian" if endian == "<" else "binary_big_endian"
+    head = ["ply", f"format {fmt} 1.0", "comment Vertical axis: y", f"element chunk {n_chunks}"]
+    head += [f"property float {nm}" for nm in ply._QUANT_META_FIELDS]
+    head += [f"element vertex {n}"] + [f"property uint packed_{nm}" for nm in ("position", "rotation", "scale", "color")]
+    body = meta.astype(endian + "f4").tobytes()
+    body += np.stack([pos_w, rot_w, scl_w, col_w], 1).astype(endian + "u4").tobytes()
+    if sh_rest is not None:
+        head += [f"element sh {n}"] + [f"property uchar f_rest_{i}" for i in range(sh_rest.shape[1])]
+        body += np.clip(np.round((sh_rest / 8.0 + 0.5) * 254.0), 0, 255).astype(np.uint8).tobytes()
+    head.append("end_header")
+    return ("\n".join(head) + "\n").encode() + body, q
+
+
+@pytest.mark.parametrize("n,per,endian", [(1, 0, "<"), (700, 0, "<"), (513, 3, "<"), (300, 15, ">")])
+def test_compressed_ply_import(n, per, endian):
+    """import.rs:408-600 through an encoder written for the test: every field comes back within its quantisation step,
+    rows use the ranges of chunk i // 256, higher SH bands are de-interleaved from channel-major."""
+    rng = np.random.default_rng(n)
+    means = rng.normal(size=(n, 3)).astype(np.float32) * 3
+    log_scales = rng.uniform(-6, -1, size=(n, 3)).astype(np.float32)
+    quats = rng.normal(size=(n, 4))
+    rgb = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
+    opac = rng.uniform(0.05, 0.95, size=n).astype(np.float32)
+    rest = rng.uniform(-1.5, 1.5, size=(n, 3 * per)).astype(np.float32) if per else None
+    data, qn = _encode_compressed(means, log_scales, quats, rgb, opac, rest, endian)
+    d, meta = ply.load_splat_from_ply(data)
+    assert d.num_splats() == n and meta.total_splats == n and meta.up_axis == (0.0, -1.0, 0.0)
+    span = lambda a: np.maximum(a.max(0) - a.min(0), 1e-6)
+    assert np.abs(d.means - means).max() <= span(means).max() / 1023 + 1e-5
+    assert np.abs(d.log_scales - log_scales).max() <= span(log_scales).max() / 1023 + 1e-5
+    np.testing.assert_allclose(d.rotations, qn, atol=2.5e-3)           # (w, x, y, z), unit length up to 10-bit steps
+    sig = 1.0 / (1.0 + np.exp(-d.raw_opacities.astype(np.float64)))
+    assert np.abs(sig - opac).max() <= 0.5 / 255 + 1e-6                # inverse sigmoid of the 8-bit alpha
+    got_rgb = d.sh_coeffs[:, 0, :] * ply.SH_C0 + 0.5                   # rgb_to_sh inverted
+    assert np.abs(got_rgb - rgb).max() <= 0.5 / 255 + 1e-5
+    assert d.sh_coeffs.shape == (n, 1 + per, 3)
+    if per:
+        want = rest.reshape(n, 3, per).transpose(0, 2, 1)              # channel-major on disk -> [n, k, 3]
+        assert np.abs(d.sh_coeffs[:, 1:, :] - want).max() <= 4.0 / 254 + 1e-5
+    t, sh, op = d.into_arrays()
+    assert t.shape == (n, 10) and sh.shape[0] == n and op.shape == (n,)
+
+
+def test_compressed_ply_subsample_and_errors():
+    rng = np.random.default_rng(5)
+    n = 600
+    args = (rng.normal(size=(n, 3)).astype(np.float32), rng.uniform(-5, -1, size=(n, 3)).astype(np.float32), rng.normal(size=(n, 4)),
+            rng.uniform(0, 1, size=(n, 3)).astype(np.float32), rng.uniform(0.1, 0.9, size=n).astype(np.float32))
+    rest = rng.uniform(-1, 1, size=(n, 9)).astype(np.float32)
+    data, _ = _encode_compressed(*args, rest)
+    full, _ = ply.load_splat_from_ply(data)
+    sub, meta = ply.load_splat_from_ply(data, subsample_points=4)
+    assert sub.num_splats() == n // 4 == meta.total_splats
+    np.testing.assert_array_equal(sub.means, full.means[3::4])         # rows 4, 8, ... (1-based), each with ITS chunk's ranges
+    np.testing.assert_array_equal(sub.sh_coeffs, full.sh_coeffs[3::4])
+    # truncated body
+    with pytest.raises(ValueError):
+        ply.load_splat_from_ply(data[:-100])
+    # a chunk element without one of the range fields
+    broken = data.replace(b"property float max_b\n", b"property float max_q\n")
+    with pytest.raises(ValueError, match="max_b"):
+        ply.load_splat_from_ply(broken)
+    # chunk element but no vertex element
+    head = b"ply\nformat binary_little_endian 1.0\nelement chunk 0\nproperty float min_x\nend_header\n"
+    with pytest.raises(ValueError, match="Unknown format"):
+        ply.load_splat_from_ply(head)
