@@ -230,16 +230,63 @@ def split_eval_every(views: Sequence, eval_split_every: Optional[int]):
     return train, ev
 
 
+def find_mask_path(files: Sequence[str], path: str) -> Optional[str]:
+    """formats/mod.rs:150-189.  `files`: every file of the dataset (relative or absolute, one convention); `path`: the
+    image.  A mask lives under a directory called `masks` (any case), is named img.png.*, img.* or img.mask.* (any case,
+    any extension), and the directories below `masks/` must be the tail of the image's own directory:
+    masks/foo/bar/img.png matches images/foo/bar/img.jpeg.  First match in `files` order."""
+    norm = lambda q: [c for c in q.replace("\\", "/").split("/") if c not in ("", ".")]
+    comps = norm(path)
+    name = comps[-1].lower()
+    stem = name.rsplit(".", 1)[0] if "." in name[1:] else name
+    wanted = {name, stem, stem + ".mask"}
+    parent = [c for c in comps[:-1]]
+    for cand in files:
+        cc = norm(cand)
+        if not cc:
+            continue
+        cname = cc[-1].lower()
+        cstem = cname.rsplit(".", 1)[0] if "." in cname[1:] else cname
+        if cstem not in wanted:
+            continue
+        idx = next((i for i, c in enumerate(cc) if c.lower() == "masks"), None)
+        if idx is None:
+            continue
+        sub = cc[idx + 1:-1]
+        if len(sub) <= len(parent) and (not sub or parent[len(parent) - len(sub):] == sub):
+            return cand
+    return None
+
+
 @dataclass
 class SceneView:
     camera: Camera
     image_path: str
+    mask_path: Optional[str] = None      # load_image.rs:15: a separate mask image that becomes the alpha channel
+    invert_mask: bool = False            # config.rs:46-48: white means "ignore this pixel"
+
+    def default_alpha_mode(self) -> str:
+        """LoadImage::new (load_image.rs:41-47): a view with a mask file is Masked, anything else Transparent, unless the
+        load arguments override it."""
+        return ALPHA_MASKED if self.mask_path is not None else ALPHA_TRANSPARENT
 
     def load_packed(self, alpha_mode: str = ALPHA_MASKED, max_resolution: Optional[int] = None):
         from PIL import Image
         im = Image.open(self.image_path)
         if im.mode not in ("RGB", "RGBA"):
             im = im.convert("RGBA" if "A" in im.getbands() else "RGB")
+        if self.mask_path is not None:      # load_image.rs:69-113: one channel of the mask becomes the alpha channel
+            im = im.convert("RGBA")
+            mk = Image.open(self.mask_path)
+            mk = mk.convert("RGBA").getchannel("A") if "A" in mk.getbands() else mk.convert("L")
+            if mk.size != im.size:
+                mk = mk.resize(im.size, Image.BILINEAR)          # imageops::FilterType::Triangle; may squash the mask
+            alpha = np.asarray(mk, np.uint8)
+            if self.invert_mask:
+                alpha = np.uint8(255) - alpha
+            rgba = np.asarray(im, np.uint8).copy()
+            rgba[..., 3] = alpha
+            im = Image.fromarray(rgba, "RGBA")
         if max_resolution and max(im.size) > max_resolution:
             s = max_resolution / max(im.size)
             im = im.resize((max(1, round(im.size[0] * s)), max(1, round(im.size[1] * s))), Image.LANCZOS)
@@ -264,8 +311,10 @@ def _find(root: str, name: str) -> Optional[str]:
 
 
 def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
-                eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None) -> DatasetLoadResult:
-    """Text or binary COLMAP model (cameras.{txt,bin} decides; images / points3D are taken from the same directory)."""
+                eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None,
+                invert_masks: bool = False) -> DatasetLoadResult:
+    """Text or binary COLMAP model (cameras.{txt,bin} decides; images / points3D are taken from the same directory).
+    Views whose image has a counterpart under a `masks/` directory carry it as their alpha channel (colmap.rs:194-218)."""
     cam_path = _find(root, "cameras.bin") or _find(root, "cameras.txt")
     if cam_path is None:
         raise FileNotFoundError("no cameras.txt / cameras.bin under " + root)
@@ -279,6 +328,7 @@ def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: O
         infos = read_images_text(open(os.path.join(sparse, "images.txt")).read())
     infos = sorted(infos, key=lambda i: i.name)
     views, warnings = [], []
+    all_files = None                                      # the dataset's mask candidates, listed once
     picked = infos[::max(int(subsample_frames or 1), 1)]
     if max_frames is not None:
         picked = picked[:max_frames]
@@ -293,7 +343,12 @@ def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: O
         if not camera.is_valid():
             warnings.append(f"Skipped '{info.name}': camera contains nan or inf values")
             continue
-        views.append(SceneView(camera, path))
+        if all_files is None:                             # paths relative to the dataset root, like the reference's vfs
+            all_files = sorted(os.path.relpath(os.path.join(d, f), root) for d, _, fs in os.walk(root) for f in fs)
+            all_files = [f for f in all_files if any(c.lower() == "masks" for c in f.replace("\\", "/").split("/")[:-1])]
+        mask = find_mask_path(all_files, os.path.relpath(path, root)) if all_files else None
+        mask = os.path.join(root, mask) if mask is not None else None
+        views.append(SceneView(camera, path, mask, bool(invert_masks) and mask is not None))
     train, ev = split_eval_every(views, eval_split_every)
     init = None
     pts_txt, pts_bin = os.path.join(sparse, "points3D.txt"), os.path.join(sparse, "points3D.bin")

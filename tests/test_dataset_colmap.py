@@ -185,3 +185,79 @@ def test_binary_model_equals_text_model(tmp_path):
         ds.read_cameras_binary(struct.pack("<QiiQQ", 1, 1, 99, 4, 4))
     with pytest.raises(ValueError):
         ds.read_images_binary(struct.pack("<Qi7di", 1, 1, 1, 0, 0, 0, 0, 0, 0, 1) + b"unterminated")
+
+
+# ---------------------------------------------------------------------------------------------- masks
+def test_find_mask_path_rules():
+    """brush-dataset/src/formats/mod.rs:197-272 restated."""
+    f = ds.find_mask_path
+    assert f(["images/img.png", "masks/img.png"], "images/img.png") == "masks/img.png"
+    assert f(["images/img.jpeg", "masks/img.png"], "images/img.jpeg") == "masks/img.png"          # other extension
+    assert f(["images/foo.png", "masks/foo.png.mask"], "images/foo.png") == "masks/foo.png.mask"  # img.png.*
+    assert f(["images/bar.jpeg", "masks/bar.mask.png"], "images/bar.jpeg") == "masks/bar.mask.png"  # img.mask.*
+    assert f(["images/foo/bar/img.png", "masks/foo/bar/img.png"], "images/foo/bar/img.png") == "masks/foo/bar/img.png"
+    assert f(["images/baz/img.png", "masks/foo/img.png"], "images/baz/img.png") is None           # wrong sub-directory
+    assert f(["images/IMG.PNG", "masks/img.png"], "images/IMG.PNG") == "masks/img.png"            # case-insensitive
+    assert f(["images/img.png", "other/img.png"], "images/img.png") is None                       # not under masks/
+    assert f(["images/img.png", "MASKS/img.png"], "images/img.png") == "MASKS/img.png"
+
+
+def _mask_view(tmp_path, mask_img, invert):
+    from PIL import Image
+    Image.new("RGB", (4, 2), (10, 20, 30)).save(tmp_path / "img.png")
+    mask_img.save(tmp_path / "mask.png")
+    v = ds.SceneView(cm.Camera(), str(tmp_path / "img.png"), str(tmp_path / "mask.png"), invert)
+    packed, has_alpha = v.load_packed(v.default_alpha_mode())
+    assert has_alpha and packed.shape == (2, 4)
+    return packed.view(np.uint32)
+
+
+def test_mask_becomes_alpha(tmp_path):
+    """load_image.rs:256-262: the grey mask is the alpha channel, colours stay intact (Masked: no premultiplication)."""
+    from PIL import Image
+    vals = np.array([i * 30 for i in range(8)], np.uint8).reshape(2, 4)
+    px = _mask_view(tmp_path, Image.fromarray(vals, "L"), False)
+    assert np.array_equal((px >> 24).astype(np.uint8), vals)
+    assert np.array_equal(px & 0xFFFFFF, np.full((2, 4), 10 | (20 << 8) | (30 << 16), np.uint32))
+
+
+def test_inverted_mask_flips_alpha(tmp_path):
+    """load_image.rs:264-270."""
+    from PIL import Image
+    vals = np.array([i * 30 for i in range(8)], np.uint8).reshape(2, 4)
+    px = _mask_view(tmp_path, Image.fromarray(vals, "L"), True)
+    assert np.array_equal((px >> 24).astype(np.uint8), 255 - vals)
+
+
+def test_mask_with_alpha_channel_and_other_size(tmp_path):
+    """load_image.rs:85-102: a mask that has an alpha channel contributes THAT channel; a mask of another size is
+    resized to the image."""
+    from PIL import Image
+    rgba = np.zeros((2, 4, 4), np.uint8)
+    rgba[..., 0] = 255                       # the colour channels must be ignored
+    rgba[..., 3] = np.array([[0, 50, 100, 150], [200, 250, 5, 15]], np.uint8)
+    px = _mask_view(tmp_path, Image.fromarray(rgba, "RGBA"), False)
+    assert np.array_equal((px >> 24).astype(np.uint8), rgba[..., 3])
+    big = np.repeat(np.repeat(np.array([[0, 255], [255, 0]], np.uint8), 4, axis=0), 8, axis=1)    # 8 x 16 for a 2 x 4 image
+    px = _mask_view(tmp_path, Image.fromarray(big, "L"), False)
+    a = (px >> 24).astype(np.int32)
+    assert a.shape == (2, 4) and a[0, 0] < 64 and a[0, 3] > 192 and a[1, 0] > 192 and a[1, 3] < 64
+
+
+def test_colmap_loader_attaches_masks(tmp_path):
+    from PIL import Image
+    root = str(tmp_path)
+    _write_dataset(root)
+    os.makedirs(os.path.join(root, "masks"))
+    Image.fromarray(np.full((IMG_H, IMG_W), 200, np.uint8), "L").save(os.path.join(root, "masks", "img1.png"))
+    r = ds.load_colmap(root)
+    by_name = {os.path.basename(v.image_path): v for v in r.train + r.eval}
+    assert by_name["img1.png"].mask_path == os.path.join(root, "masks", "img1.png") and not by_name["img1.png"].invert_mask
+    assert by_name["img0.png"].mask_path is None and by_name["img0.png"].default_alpha_mode() == ds.ALPHA_TRANSPARENT
+    assert by_name["img1.png"].default_alpha_mode() == ds.ALPHA_MASKED
+    packed, has_alpha = by_name["img1.png"].load_packed(ds.ALPHA_MASKED)
+    assert has_alpha and np.all((packed.view(np.uint32) >> 24) == 200)
+    r2 = ds.load_colmap(root, invert_masks=True)
+    v = next(v for v in r2.train + r2.eval if v.mask_path)
+    packed, _ = v.load_packed(ds.ALPHA_MASKED)
+    assert v.invert_mask and np.all((packed.view(np.uint32) >> 24) == 55)
