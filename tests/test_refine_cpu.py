@@ -156,3 +156,18 @@ def test_bounds_from_pos_degenerate_inputs():
         one_axis = np.stack([np.arange(50), np.full(50, np.nan), np.arange(50)], 1).astype(np.float32)
         bb = fn(0.8, one_axis)
         assert np.isfinite(bb.center).all() and np.isfinite(bb.extent).all()
+
+
+def test_restatement_philox_matches_the_published_known_answers():
+    """The numpy Philox4x32-10 that tests/test_gpu_refine.py uses to re-draw the device's uniforms, against the Random123
+    known-answer vectors (kat_vectors: philox4x32 10 rounds) -- so the restatement itself is pinned."""
+    import numpy as np
+    import test_gpu_refine as tgr
+    z = np.zeros(1, np.uint64)
+    assert [int(x[0]) for x in tgr.philox4x32_10(z, z, z, z, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = np.full(1, 0xFFFFFFFF, np.uint64)
+    assert [int(x[0]) for x in tgr.philox4x32_10(f, f, f, f, 0xFFFFFFFF, 0xFFFFFFFF)] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    c = [np.array([v], np.uint64) for v in (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)]
+    assert [int(x[0]) for x in tgr.philox4x32_10(*c, 0xA4093822, 0x299F31D0)] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    u = tgr.uniform01(9, 800, np.arange(4096, dtype=np.uint32))
+    assert u.dtype == np.float32 and 0.0 < u.min() and u.max() < 1.0 and abs(float(u.mean()) - 0.5) < 0.02
