@@ -301,6 +301,24 @@ class DatasetLoadResult:
     warnings: List[str] = field(default_factory=list)
 
 
+def list_files(root: str) -> List[str]:
+    """Every file under `root`, relative, '/'-separated, sorted (the role of the reference's vfs listing)."""
+    out = []
+    for d, _, fs in os.walk(root):
+        for f in fs:
+            out.append(os.path.relpath(os.path.join(d, f), root).replace(os.sep, "/"))
+    return sorted(out)
+
+
+def find_image_by_name(files: Sequence[str], name: str) -> Optional[str]:
+    """formats/mod.rs:112-120: colmap stores a bare (or sub-directory) file name; the image is the lexicographically first
+    file whose path ends with it on a component boundary (case-insensitive, like the vfs keys), never one under a
+    `masks` directory -- an image must not resolve to its own mask."""
+    key = "/" + name.replace("\\", "/").lower().lstrip("/")
+    hits = [f for f in files if ("/" + f.lower()).endswith(key) and "masks" not in f.split("/")[:-1]]
+    return min(hits) if hits else None
+
+
 def _find(root: str, name: str) -> Optional[str]:
     low = name.lower()
     for d, _, files in os.walk(root):
@@ -328,25 +346,27 @@ def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: O
         infos = read_images_text(open(os.path.join(sparse, "images.txt")).read())
     infos = sorted(infos, key=lambda i: i.name)
     views, warnings = [], []
-    all_files = None                                      # the dataset's mask candidates, listed once
+    files = all_files = None                              # the dataset's file list / mask candidates, listed once
     picked = infos[::max(int(subsample_frames or 1), 1)]
     if max_frames is not None:
         picked = picked[:max_frames]
     for info in picked:
         if info.camera_id not in cams:
             raise ValueError(f"Image '{info.name}' references camera ID {info.camera_id} which doesn't exist in camera data")
-        path = _find(root, os.path.basename(info.name))
-        if path is None:
+        if files is None:
+            files = list_files(root)
+        rel = find_image_by_name(files, info.name)
+        if rel is None:
             warnings.append(f"Skipped '{info.name}': image file not found")
             continue
+        path = os.path.join(root, rel)
         camera = camera_from_colmap(cams[info.camera_id], info)
         if not camera.is_valid():
             warnings.append(f"Skipped '{info.name}': camera contains nan or inf values")
             continue
-        if all_files is None:                             # paths relative to the dataset root, like the reference's vfs
-            all_files = sorted(os.path.relpath(os.path.join(d, f), root) for d, _, fs in os.walk(root) for f in fs)
-            all_files = [f for f in all_files if any(c.lower() == "masks" for c in f.replace("\\", "/").split("/")[:-1])]
-        mask = find_mask_path(all_files, os.path.relpath(path, root)) if all_files else None
+        if all_files is None:                             # mask candidates: paths relative to the root, like the vfs
+            all_files = [f for f in files if any(c.lower() == "masks" for c in f.split("/")[:-1])]
+        mask = find_mask_path(all_files, rel) if all_files else None
         mask = os.path.join(root, mask) if mask is not None else None
         views.append(SceneView(camera, path, mask, bool(invert_masks) and mask is not None))
     train, ev = split_eval_every(views, eval_split_every)
@@ -364,6 +384,193 @@ def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: O
 
 
 load_colmap_text = load_colmap   # earlier name
+
+
+# ---- nerfstudio transforms.json -----------------------------------------------------------------------------
+def _quat_xyzw_from_mat(R: np.ndarray) -> Tuple[float, float, float, float]:
+    """Rotation matrix (columns = axes) -> unit quaternion in glam's (x, y, z, w) order (Quat::from_mat3's branches)."""
+    m00, m01, m02 = R[0, 0], R[0, 1], R[0, 2]
+    m10, m11, m12 = R[1, 0], R[1, 1], R[1, 2]
+    m20, m21, m22 = R[2, 0], R[2, 1], R[2, 2]
+    tr = m00 + m11 + m22
+    if tr > 0:
+        s = math.sqrt(tr + 1.0) * 2
+        q = ((m21 - m12) / s, (m02 - m20) / s, (m10 - m01) / s, 0.25 * s)
+    elif m00 > m11 and m00 > m22:
+        s = math.sqrt(1.0 + m00 - m11 - m22) * 2
+        q = (0.25 * s, (m01 + m10) / s, (m02 + m20) / s, (m21 - m12) / s)
+    elif m11 > m22:
+        s = math.sqrt(1.0 + m11 - m00 - m22) * 2
+        q = ((m01 + m10) / s, 0.25 * s, (m12 + m21) / s, (m02 - m20) / s)
+    else:
+        s = math.sqrt(1.0 + m22 - m00 - m11) * 2
+        q = ((m02 + m20) / s, (m12 + m21) / s, 0.25 * s, (m10 - m01) / s)
+    n = math.sqrt(sum(v * v for v in q))
+    return tuple(float(v / n) for v in q)
+
+
+def opengl_c2w_to_pose(c2w: np.ndarray):
+    """formats/mod.rs:122-131: an OpenGL / Blender camera-to-world matrix (+X right, +Y up, +Z back; the nerfstudio
+    `transform_matrix`) -> (position, rotation xyzw) in brush's convention (+Y down, +Z forward).  Scale is divided out
+    of the axes as glam's to_scale_rotation_translation does."""
+    m = np.array(c2w, np.float64).reshape(4, 4).copy()
+    m[:, 1] *= -1.0
+    m[:, 2] *= -1.0
+    A = m[:3, :3]
+    scale = np.linalg.norm(A, axis=0)
+    if np.linalg.det(A) < 0:
+        scale[0] = -scale[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        R = A / scale
+    pos = tuple(float(v) for v in m[:3, 3])
+    if not np.isfinite(R).all():
+        return pos, (float("nan"),) * 4
+    return pos, _quat_xyzw_from_mat(R)
+
+
+def _nerfstudio_camera_model(name, k1, k2, k3, k4, p1, p2):
+    """resolve_camera_model (nerfstudio.rs:103-140)."""
+    f = lambda o: float(np.float32(0.0 if o is None else o))
+    if name is None or name in ("PERSPECTIVE", "perspective"):
+        return cm.PINHOLE, ()
+    if name in ("OPENCV", "opencv"):
+        return cm.RADIAL_TANGENTIAL_8, (f(k1), f(k2), 0.0, 0.0, 0.0, 0.0, f(p1), f(p2))
+    if name in ("OPENCV_FISHEYE", "opencv_fisheye"):
+        return cm.KANNALA_BRANDT_4, (f(k1), f(k2), f(k3), f(k4))
+    raise ValueError(f"Error decoding camera parameters: Unsupported nerfstudio camera_model `{name}`")
+
+
+def _read_transforms_file(scene: dict, transforms_rel: str, root: str, files: Sequence[str], subsample_frames, max_frames,
+                          invert_masks: bool, warnings: List[str]) -> List[SceneView]:
+    """read_transforms_file (nerfstudio.rs:142-268).  Per-frame values override the file-level ones."""
+    lower = {f.lower(): f for f in files}
+    mask_files = [f for f in files if any(c.lower() == "masks" for c in f.split("/")[:-1])]
+    base = os.path.dirname(transforms_rel)
+    frames = scene.get("frames", [])[::max(int(subsample_frames or 1), 1)]
+    if max_frames is not None:
+        frames = frames[:max_frames]
+    views = []
+    for fr in frames:
+        flat = [float(v) for row in fr["transform_matrix"] for v in row]
+        if len(flat) != 16:
+            raise ValueError(f"Error when decoding format: frame '{fr['file_path']}' has a {len(flat)}-element transform_matrix, "
+                             "expected a 4x4 (16 elements)")
+        pos, rot = opengl_c2w_to_pose(np.array(flat, np.float32).reshape(4, 4))
+        fp = fr["file_path"]
+        if os.path.isabs(fp):        # absolute references are resolved inside the dataset directory only (brush-vfs lib.rs:313-325)
+            fp_rel = os.path.relpath(fp, os.path.abspath(root))
+            rel = fp_rel.replace(os.sep, "/") if not fp_rel.startswith("..") else "\0outside"
+        else:
+            rel = os.path.normpath(os.path.join(base, fp)).replace(os.sep, "/")
+        hit = lower.get(rel.lower())
+        if hit is None and not os.path.splitext(rel)[1]:
+            # "Assume png's by default if no extension is specified" (nerfstudio.rs:183-186; the reference tests existence
+            # before adding the extension, which would skip every such frame -- its stated intent is followed here)
+            hit = lower.get((rel + ".png").lower())
+        if hit is None:
+            warnings.append(f"Skipped '{fr['file_path']}': image file not found")
+            continue
+        get = lambda k: fr.get(k) if fr.get(k) is not None else scene.get(k)
+        w, h = get("w"), get("h")
+        if w is None or h is None:
+            from PIL import Image
+            with Image.open(os.path.join(root, hit)) as im:          # header only
+                w, h = im.size
+        w, h = int(w), int(h)
+        model, params = _nerfstudio_camera_model(get("camera_model"), *(get(k) for k in ("k1", "k2", "k3", "k4", "p1", "p2")))
+
+        def fov(angle_key, fl_key, px):
+            # frame angle, frame focal, scene angle, scene focal -- in that order (nerfstudio.rs:219-229)
+            for src in (fr, scene):
+                if src.get(angle_key) is not None:
+                    return float(src[angle_key])
+                if src.get(fl_key) is not None:
+                    return cm.focal_to_fov(float(src[fl_key]), px, model, params)
+            return None
+        fovx, fovy = fov("camera_angle_x", "fl_x", w), fov("camera_angle_y", "fl_y", h)
+        if fovx is None and fovy is None:
+            raise ValueError("Error decoding camera parameters: Must have some kind of focal length")
+        if fovx is None:
+            fovx = cm.focal_to_fov(cm.fov_to_focal(fovy, h, model, params), w, model, params)
+        if fovy is None:
+            fovy = cm.focal_to_fov(cm.fov_to_focal(fovx, w, model, params), h, model, params)
+        cx, cy = get("cx"), get("cy")
+        cuv = (float(np.float32(0.5 if cx is None else cx / w)), float(np.float32(0.5 if cy is None else cy / h)))
+        camera = Camera(position=pos, rotation=rot, fov_x=fovx, fov_y=fovy, center_uv=cuv, camera_model=model, model_params=params)
+        if not camera.is_valid():
+            warnings.append(f"Skipped '{fr['file_path']}': camera contains nan or inf values")
+            continue
+        mask = find_mask_path(mask_files, hit) if mask_files else None
+        views.append(SceneView(camera, os.path.join(root, hit), os.path.join(root, mask) if mask else None,
+                               bool(invert_masks) and mask is not None))
+    return views
+
+
+def load_nerfstudio(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
+                    eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None,
+                    invert_masks: bool = False) -> Optional[DatasetLoadResult]:
+    """nerfstudio.rs:270-388.  None when the directory holds no transforms json (the caller tries the next format).
+    The training file is the only json, else `transforms.json`, else `transforms_train.json`; `transforms_val.json` (or
+    `transforms_test.json`) provides the evaluation views, otherwise every eval_split_every-th training view does."""
+    import json
+    files = list_files(root)
+    jsons = [f for f in files if f.lower().endswith(".json")]
+    if len(jsons) == 1:
+        tpath = jsons[0]
+    else:
+        ending = lambda suffix: next((f for f in files if ("/" + f.lower()).endswith("/" + suffix)), None)
+        tpath = ending("transforms.json") or ending("transforms_train.json")
+    if tpath is None:
+        return None
+    warnings: List[str] = []
+    scene = json.load(open(os.path.join(root, tpath)))
+    train_all = _read_transforms_file(scene, tpath, root, files, subsample_frames, max_frames, invert_masks, warnings)
+    ends = lambda f, name: f.split("/")[-1] == name
+    eval_path = next((f for f in jsons if ends(f, "transforms_val.json")), None) or \
+        next((f for f in jsons if ends(f, "transforms_test.json")), None)
+    val_views = None
+    if eval_path is not None:
+        val_views = _read_transforms_file(json.load(open(os.path.join(root, eval_path))), eval_path, root, files, subsample_frames,
+                                          max_frames, invert_masks, warnings)
+    train, ev = [], []
+    for i, v in enumerate(train_all):
+        if eval_split_every and i % eval_split_every == 0 and val_views is None:   # extra eval images only without a val file
+            ev.append(v)
+        else:
+            train.append(v)
+    if val_views is not None:
+        ev.extend(val_views)
+    init = None
+    ply_rel = scene.get("ply_file_path")
+    if ply_rel:
+        p = os.path.join(root, os.path.dirname(tpath), ply_rel)
+        if os.path.exists(p):
+            from . import ply as _ply
+            init, _ = _ply.load_splat_from_ply(open(p, "rb").read(), subsample_points)
+    return DatasetLoadResult(train, ev, init, warnings)
+
+
+def load_dataset(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
+                 eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None,
+                 invert_masks: bool = False) -> DatasetLoadResult:
+    """formats/mod.rs:57-110: COLMAP first, then nerfstudio json; a dataset without a usable training view is an error; an
+    `init.ply` (else the last .ply by name) anywhere in the directory overrides the format's own initial points."""
+    args = dict(subsample_frames=subsample_frames, max_frames=max_frames, eval_split_every=eval_split_every,
+                subsample_points=subsample_points, invert_masks=invert_masks)
+    if _find(root, "cameras.bin") or _find(root, "cameras.txt"):
+        res = load_colmap(root, **args)
+    else:
+        res = load_nerfstudio(root, **args)
+        if res is None:
+            raise ValueError("Format not recognized: only colmap and nerfstudio json are supported")
+    if not res.train:
+        raise ValueError("Error when decoding format: dataset contains no usable training views (all images missing or filtered out)")
+    plys = sorted(f for f in list_files(root) if f.lower().endswith(".ply"))
+    if plys:
+        main = next((f for f in plys if f.split("/")[-1] == "init.ply"), plys[-1])
+        from . import ply as _ply
+        res.init_splat, _ = _ply.load_splat_from_ply(open(os.path.join(root, main), "rb").read(), subsample_points)
+    return res
 
 
 class SceneLoader:

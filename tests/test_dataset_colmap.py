@@ -261,3 +261,125 @@ def test_colmap_loader_attaches_masks(tmp_path):
     v = next(v for v in r2.train + r2.eval if v.mask_path)
     packed, _ = v.load_packed(ds.ALPHA_MASKED)
     assert v.invert_mask and np.all((packed.view(np.uint32) >> 24) == 55)
+
+
+# ---------------------------------------------------------------------------------------------- nerfstudio json
+def _write_nerfstudio(root, scene_extra=None, frames=None, name="transforms.json", images=("a.png", "b.png", "c.png")):
+    import json
+    from PIL import Image
+    os.makedirs(os.path.join(root, "images"), exist_ok=True)
+    for nm in images:
+        Image.new("RGB", (IMG_W, IMG_H), (10, 20, 30)).save(os.path.join(root, "images", nm))
+    ident = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    if frames is None:
+        frames = [{"file_path": f"images/{nm}", "transform_matrix": [[1, 0, 0, float(i)], [0, 1, 0, 2.0], [0, 0, 1, 3.0], [0, 0, 0, 1]]}
+                  for i, nm in enumerate(images)]
+    scene = {"camera_angle_x": 1.0, "frames": frames}
+    scene.update(scene_extra or {})
+    json.dump(scene, open(os.path.join(root, name), "w"))
+    return ident
+
+
+def test_opengl_c2w_to_pose():
+    """formats/mod.rs:122-131: the identity OpenGL pose looks down -Z with +Y up; in brush's convention (+Y down, +Z forward)
+    that is a half turn about X.  Translation passes through; a uniform scale is divided out."""
+    pos, rot = ds.opengl_c2w_to_pose(np.eye(4))
+    assert pos == (0.0, 0.0, 0.0)
+    np.testing.assert_allclose(np.abs(rot), [1, 0, 0, 0], atol=1e-12)
+    m = np.eye(4); m[:3, :3] *= 2.5; m[:3, 3] = [1, 2, 3]
+    pos, rot = ds.opengl_c2w_to_pose(m)
+    assert pos == (1.0, 2.0, 3.0)
+    np.testing.assert_allclose(np.abs(rot), [1, 0, 0, 0], atol=1e-12)
+    # a camera yawed 90 degrees about the world up axis: its forward (-Z in OpenGL) points along -X
+    c, s_ = 0.0, 1.0
+    yaw = np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], float)
+    _, rot = ds.opengl_c2w_to_pose(yaw)
+    R = cm._mat3_from_quat_xyzw(rot)                 # columns = the camera's axes in the world
+    np.testing.assert_allclose(np.asarray(R)[2], [-1, 0, 0], atol=1e-6)     # brush forward (+Z local)
+    np.testing.assert_allclose(np.asarray(R)[1], [0, -1, 0], atol=1e-6)     # brush +Y is down
+
+
+def test_loads_nerfstudio_json(tmp_path):
+    root = str(tmp_path)
+    _write_nerfstudio(root)
+    r = ds.load_dataset(root, eval_split_every=2)
+    assert [os.path.basename(v.image_path) for v in r.eval] == ["a.png", "c.png"] and len(r.train) == 1 and not r.warnings
+    v = r.train[0]
+    assert v.camera.position == (1.0, 2.0, 3.0) and v.camera.camera_model == cm.PINHOLE
+    assert abs(v.camera.fov_x - 1.0) < 1e-12
+    focal = cm.fov_to_focal(1.0, IMG_W)                                  # the missing fov follows from the same focal length
+    assert abs(v.camera.fov_y - cm.focal_to_fov(focal, IMG_H)) < 1e-12
+    assert v.camera.center_uv == (0.5, 0.5) and r.init_splat is None
+
+
+def test_nerfstudio_intrinsics_overrides_and_models(tmp_path):
+    root = str(tmp_path)
+    mat = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    frames = [{"file_path": "images/a.png", "transform_matrix": mat},
+              {"file_path": "images/b", "transform_matrix": mat, "fl_x": 90.0, "fl_y": 85.0, "cx": 16.0, "cy": 12.0, "w": 64, "h": 48,
+               "camera_model": "OPENCV_FISHEYE", "k1": 0.01, "k3": 0.003},
+              {"file_path": "images/missing.png", "transform_matrix": mat}]
+    _write_nerfstudio(root, {"camera_angle_x": None, "fl_x": 80.0, "fl_y": 70.0, "camera_model": "OPENCV", "k1": 0.1, "p2": -0.02,
+                             "cx": 30.0, "cy": 20.0}, frames)
+    r = ds.load_nerfstudio(root)
+    assert len(r.train) == 2 and r.warnings == ["Skipped 'images/missing.png': image file not found"]
+    a, b = r.train
+    assert a.camera.camera_model == cm.RADIAL_TANGENTIAL_8
+    np.testing.assert_allclose(a.camera.model_params, [0.1, 0, 0, 0, 0, 0, 0, -0.02], rtol=1e-7)
+    assert abs(a.camera.fov_x - cm.focal_to_fov(80.0, IMG_W, a.camera.camera_model, a.camera.model_params)) < 1e-12
+    assert abs(a.camera.fov_y - cm.focal_to_fov(70.0, IMG_H, a.camera.camera_model, a.camera.model_params)) < 1e-12
+    np.testing.assert_allclose(a.camera.center_uv, (30.0 / IMG_W, 20.0 / IMG_H), rtol=1e-6)
+    # frame b: its own model / focal / centre; k2, k4 fall back to the file level (absent -> 0); extension-less path -> png
+    assert b.image_path.endswith("images/b.png") and b.camera.camera_model == cm.KANNALA_BRANDT_4
+    np.testing.assert_allclose(b.camera.model_params, [0.01, 0, 0.003, 0], rtol=1e-6)
+    assert abs(b.camera.fov_x - cm.focal_to_fov(90.0, 64, b.camera.camera_model, b.camera.model_params)) < 1e-12
+    np.testing.assert_allclose(b.camera.center_uv, (0.25, 0.25), rtol=1e-6)
+
+
+def test_nerfstudio_val_file_ply_and_errors(tmp_path):
+    import json
+    root = str(tmp_path)
+    _write_nerfstudio(root, {"ply_file_path": "sparse.ply"}, name="transforms_train.json")
+    _write_nerfstudio(root, name="transforms_val.json", images=("a.png",))
+    xyz = np.array([[0, 0, 1], [1, 0, 2], [0, 1, 3], [1, 1, 4]], np.float32)
+    from brush_b200 import ply
+    open(os.path.join(root, "sparse.ply"), "wb").write(ply.splat_to_ply(
+        np.concatenate([xyz, np.tile([1, 0, 0, 0], (4, 1)), np.full((4, 3), -3.0)], 1).astype(np.float32),
+        np.zeros((4, 1, 3), np.float32), np.zeros(4, np.float32)))
+    r = ds.load_nerfstudio(root, eval_split_every=2)
+    assert len(r.train) == 3 and len(r.eval) == 1          # a val file exists: no training view is diverted to eval
+    np.testing.assert_array_equal(r.init_splat.means, xyz)
+    # load_dataset: an init.ply anywhere overrides the format's own points (formats/mod.rs:88-103)
+    os.makedirs(os.path.join(root, "extra"))
+    open(os.path.join(root, "extra", "init.ply"), "wb").write(ply.splat_to_ply(
+        np.concatenate([xyz[:2] + 10, np.tile([1, 0, 0, 0], (2, 1)), np.full((2, 3), -3.0)], 1).astype(np.float32),
+        np.zeros((2, 1, 3), np.float32), np.zeros(2, np.float32)))
+    r = ds.load_dataset(root)
+    np.testing.assert_array_equal(r.init_splat.means, xyz[:2] + 10)
+    # unsupported model, no focal at all, a 3x4 matrix, nothing recognisable, no usable view
+    bad = str(tmp_path / "bad"); os.makedirs(bad)
+    _write_nerfstudio(bad, {"camera_model": "EQUIRECTANGULAR"})
+    with pytest.raises(ValueError, match="Unsupported nerfstudio camera_model"):
+        ds.load_dataset(bad)
+    _write_nerfstudio(bad, {"camera_angle_x": None})
+    with pytest.raises(ValueError, match="Must have some kind of focal length"):
+        ds.load_dataset(bad)
+    _write_nerfstudio(bad, frames=[{"file_path": "images/a.png", "transform_matrix": [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]}])
+    with pytest.raises(ValueError, match="12-element transform_matrix"):
+        ds.load_dataset(bad)
+    _write_nerfstudio(bad, frames=[{"file_path": "images/nope.png", "transform_matrix": np.eye(4).tolist()}])
+    with pytest.raises(ValueError, match="no usable training views"):
+        ds.load_dataset(bad)
+    empty = str(tmp_path / "empty"); os.makedirs(empty)
+    with pytest.raises(ValueError, match="Format not recognized"):
+        ds.load_dataset(empty)
+
+
+def test_find_image_by_name_never_returns_a_mask():
+    """formats/mod.rs:112-120."""
+    files = ["images/sub/img.png", "masks/sub/img.png", "images_2/sub/img.png", "other/IMG.PNG"]
+    assert ds.find_image_by_name(files, "img.png") == "images/sub/img.png"            # min over the non-mask candidates
+    assert ds.find_image_by_name(files, "sub/img.png") == "images/sub/img.png"
+    assert ds.find_image_by_name(["masks/img.png"], "img.png") is None
+    assert ds.find_image_by_name(files, "mg.png") is None                             # component boundary
+    assert ds.find_image_by_name(["other/IMG.PNG"], "img.png") == "other/IMG.PNG"     # case-insensitive keys
