@@ -550,10 +550,116 @@ def load_nerfstudio(root: str, subsample_frames: Optional[int] = None, max_frame
     return DatasetLoadResult(train, ev, init, warnings)
 
 
+# ---- RealityCapture / RealityScan camera csv ---------------------------------------------------------------------
+_RC_REQUIRED = ("name", "x", "y", "alt", "heading", "pitch", "roll", "f")
+
+
+def rc_parse_header(line: str) -> Optional[dict]:
+    """realitycapture.rs:38-51: column name (lower case, leading '#' stripped) -> index; None unless the pose and focal
+    columns are all there (the format's detection signature)."""
+    cols = {name.strip().lstrip("#").lower(): i for i, name in enumerate(line.split(","))}
+    return cols if all(c in cols for c in _RC_REQUIRED) else None
+
+
+def _rc_f64(fields, header, name) -> float:
+    i = header.get(name)
+    if i is None or i >= len(fields):
+        return 0.0
+    try:
+        return float(fields[i].strip())
+    except ValueError:
+        return 0.0
+
+
+def rc_build_camera_model(k1, k2, k3, t1, t2):
+    """realitycapture.rs:205-223: brown3 + tangential -> RadialTangential8 numerator terms; all zero -> pinhole."""
+    if all(v == 0.0 for v in (k1, k2, k3, t1, t2)):
+        return cm.PINHOLE, ()
+    f = lambda v: float(np.float32(v))
+    return cm.RADIAL_TANGENTIAL_8, (f(k1), f(k2), f(k3), 0.0, 0.0, 0.0, f(t1), f(t2))
+
+
+def rc_row_to_camera(fields, header, w: int, h: int) -> Camera:
+    """realitycapture.rs:163-203.  f, px, py are in 35 mm film units (36 mm reference) and scale by the larger image
+    side; the orientation is yaw(-heading) about Z, pitch about X, roll about Y: a camera-to-world rotation in the OpenGL
+    basis."""
+    scale = float(max(w, h))
+    focal = _rc_f64(fields, header, "f") * scale / 36.0
+    cx = _rc_f64(fields, header, "px") * scale + w / 2.0
+    cy = _rc_f64(fields, header, "py") * scale + h / 2.0
+    model, params = rc_build_camera_model(*(_rc_f64(fields, header, k) for k in ("k1", "k2", "k3", "t1", "t2")))
+    fov_x, fov_y = cm.focal_to_fov(focal, w, model, params), cm.focal_to_fov(focal, h, model, params)
+    hd, pt, rl = (math.radians(float(np.float32(_rc_f64(fields, header, k)))) for k in ("heading", "pitch", "roll"))
+
+    def rot(axis, a):
+        c, s_ = math.cos(a), math.sin(a)
+        return {"x": np.array([[1, 0, 0], [0, c, -s_], [0, s_, c]]), "y": np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]]),
+                "z": np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])}[axis]
+    c2w = np.eye(4)
+    c2w[:3, :3] = rot("z", -hd) @ rot("x", pt) @ rot("y", rl)
+    c2w[:3, 3] = [float(np.float32(_rc_f64(fields, header, k))) for k in ("x", "y", "alt")]
+    pos, q = opengl_c2w_to_pose(c2w)
+    return Camera(position=pos, rotation=q, fov_x=fov_x, fov_y=fov_y,
+                  center_uv=(float(np.float32(cx / w)), float(np.float32(cy / h))), camera_model=model, model_params=params)
+
+
+def load_realitycapture(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
+                        eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None,
+                        invert_masks: bool = False) -> Optional[DatasetLoadResult]:
+    """realitycapture.rs:65-160: the first .csv whose header carries the pose and focal columns; one image per row, image
+    sizes from the file headers, no initial points.  None when no such csv exists."""
+    files = list_files(root)
+    contents = None
+    for f in files:
+        if not f.lower().endswith(".csv"):
+            continue
+        try:
+            txt = open(os.path.join(root, f), encoding="utf-8").read()
+        except (OSError, UnicodeDecodeError):
+            continue
+        first = next((ln for ln in txt.splitlines() if ln.strip()), None)
+        if first is not None and rc_parse_header(first) is not None:
+            contents = txt
+            break
+    if contents is None:
+        return None
+    lines = [ln for ln in contents.splitlines() if ln.strip()]
+    header = rc_parse_header(lines[0])
+    rows = lines[1:][::max(int(subsample_frames or 1), 1)]
+    if max_frames is not None:
+        rows = rows[:max_frames]
+    mask_files = [f for f in files if any(c.lower() == "masks" for c in f.split("/")[:-1])]
+    views, warnings, warned = [], [], False
+    from PIL import Image
+    for ln in rows:
+        fields = ln.split(",")
+        if header["name"] >= len(fields):
+            continue
+        name = fields[header["name"]].strip()
+        if not warned and _rc_f64(fields, header, "k4") != 0.0:
+            warnings.append("RealityCapture brown4 radial term (k4) isn't supported; approximating with brown3")
+            warned = True
+        rel = find_image_by_name(files, name)
+        if rel is None:
+            warnings.append(f"Skipped '{name}': image file not found")
+            continue
+        with Image.open(os.path.join(root, rel)) as im:      # header only
+            w, h = im.size
+        camera = rc_row_to_camera(fields, header, w, h)
+        if not camera.is_valid():
+            warnings.append(f"Skipped '{name}': camera contains nan or inf values")
+            continue
+        mask = find_mask_path(mask_files, rel) if mask_files else None
+        views.append(SceneView(camera, os.path.join(root, rel), os.path.join(root, mask) if mask else None,
+                               bool(invert_masks) and mask is not None))
+    train, ev = split_eval_every(views, eval_split_every)
+    return DatasetLoadResult(train, ev, None, warnings)
+
+
 def load_dataset(root: str, subsample_frames: Optional[int] = None, max_frames: Optional[int] = None,
                  eval_split_every: Optional[int] = None, subsample_points: Optional[int] = None,
                  invert_masks: bool = False) -> DatasetLoadResult:
-    """formats/mod.rs:57-110: COLMAP first, then nerfstudio json; a dataset without a usable training view is an error; an
+    """formats/mod.rs:57-110: COLMAP first, then nerfstudio json, then a RealityCapture csv; a dataset without a usable training view is an error; an
     `init.ply` (else the last .ply by name) anywhere in the directory overrides the format's own initial points."""
     args = dict(subsample_frames=subsample_frames, max_frames=max_frames, eval_split_every=eval_split_every,
                 subsample_points=subsample_points, invert_masks=invert_masks)
@@ -562,7 +668,9 @@ def load_dataset(root: str, subsample_frames: Optional[int] = None, max_frames: 
     else:
         res = load_nerfstudio(root, **args)
         if res is None:
-            raise ValueError("Format not recognized: only colmap and nerfstudio json are supported")
+            res = load_realitycapture(root, **args)
+        if res is None:
+            raise ValueError("Format not recognized: only colmap, nerfstudio json and RealityCapture csv are supported")
     if not res.train:
         raise ValueError("Error when decoding format: dataset contains no usable training views (all images missing or filtered out)")
     plys = sorted(f for f in list_files(root) if f.lower().endswith(".ply"))

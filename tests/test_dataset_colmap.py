@@ -383,3 +383,62 @@ def test_find_image_by_name_never_returns_a_mask():
     assert ds.find_image_by_name(["masks/img.png"], "img.png") is None
     assert ds.find_image_by_name(files, "mg.png") is None                             # component boundary
     assert ds.find_image_by_name(["other/IMG.PNG"], "img.png") == "other/IMG.PNG"     # case-insensitive keys
+
+
+# ---------------------------------------------------------------------------------------------- RealityCapture csv
+RC_HEADER = "#name,x,y,alt,heading,pitch,roll,f,px,py,k1,k2,k3,k4,t1,t2"
+RC_ROW = ("frame_00001.jpeg,44.5876747664166,138.823621534044,6.821916401534405,170.3483067926429,85.18637269312288,"
+          "-22.74995074830745,14.2390682243052,-9.482184385774318e-004,-2.446553068050568e-004,3.114799768048152e-003,"
+          "4.026391718074555e-003,-1.795976992379612e-003,0,0,0")
+
+
+def test_realitycapture_header_and_rows():
+    """realitycapture.rs:229-297 restated."""
+    header = ds.rc_parse_header(RC_HEADER)
+    assert header["name"] == 0 and header["alt"] == 3 and header["t2"] == 15
+    assert ds.rc_parse_header("a,b,c") is None
+    cam = ds.rc_row_to_camera(RC_ROW.split(","), header, 3840, 2880)
+    assert cam.is_valid()
+    np.testing.assert_allclose(cam.position, (44.587674, 138.82362, 6.821916), atol=1e-3)   # the basis swap does not move the camera
+    np.testing.assert_allclose(cam.center_uv, (0.5, 0.5), atol=1e-2)
+    assert cam.fov_x > cam.fov_y > 0.0 and 1.0 < cam.fov_x < 2.0                          # f = 14.24 mm (35 mm equiv.), 4:3
+    assert cam.camera_model == cm.RADIAL_TANGENTIAL_8
+    # a customised template without principal point and distortion columns: a centred pinhole
+    h2 = ds.rc_parse_header("#name,x,y,alt,heading,pitch,roll,f")
+    cam = ds.rc_row_to_camera("img.png,1,2,3,10,20,30,20.0".split(","), h2, 1920, 1080)
+    assert cam.is_valid() and cam.camera_model == cm.PINHOLE and cam.center_uv == (0.5, 0.5)
+    np.testing.assert_allclose(cam.position, (1.0, 2.0, 3.0), atol=1e-6)
+    assert ds.rc_build_camera_model(0, 0, 0, 0, 0) == (cm.PINHOLE, ())
+    assert ds.rc_build_camera_model(1.0, 2.0, 3.0, 4.0, 5.0) == (cm.RADIAL_TANGENTIAL_8, (1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 4.0, 5.0))
+
+
+def test_realitycapture_orientation():
+    """heading = pitch = roll = 0 is a camera looking straight down (-Z of the OpenGL basis is world -Z); pitch 90 levels
+    it to look along +Y; heading then turns it clockwise seen from above (yaw(-heading) about Z)."""
+    h = ds.rc_parse_header("#name,x,y,alt,heading,pitch,roll,f")
+    fwd = lambda head, pitch: np.asarray(cm._mat3_from_quat_xyzw(
+        ds.rc_row_to_camera(f"i.png,0,0,0,{head},{pitch},0,20".split(","), h, 100, 100).rotation))[2]
+    np.testing.assert_allclose(fwd(0, 0), [0, 0, -1], atol=1e-6)
+    np.testing.assert_allclose(fwd(0, 90), [0, 1, 0], atol=1e-6)
+    np.testing.assert_allclose(fwd(90, 90), [1, 0, 0], atol=1e-6)
+
+
+def test_loads_realitycapture_csv(tmp_path):
+    from PIL import Image
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "imgs"))
+    for nm in ("a.png", "b.png", "c.png"):
+        Image.new("RGB", (80, 60), (1, 2, 3)).save(os.path.join(root, "imgs", nm))
+    open(os.path.join(root, "notes.csv"), "w").write("a,b,c\n1,2,3\n")
+    open(os.path.join(root, "cams.csv"), "w").write(
+        RC_HEADER + "\n\n" + "a.png,1,2,3,10,80,0,20,0,0,0,0,0,0,0,0\n" + "b.png,4,5,6,20,85,1,20,0.01,0,0.01,0,0,0.5,0,0\n"
+        + "missing.png,0,0,0,0,0,0,20,0,0,0,0,0,0,0,0\n" + "c.png,7,8,9,30,90,2,20,0,0,0,0,0,0,0,0\n")
+    r = ds.load_dataset(root, eval_split_every=3)
+    assert [os.path.basename(v.image_path) for v in r.eval] == ["a.png"] and [os.path.basename(v.image_path) for v in r.train] == ["b.png", "c.png"]
+    assert r.init_splat is None
+    assert r.warnings == ["RealityCapture brown4 radial term (k4) isn't supported; approximating with brown3",
+                          "Skipped 'missing.png': image file not found"]
+    b = r.train[0].camera
+    assert b.camera_model == cm.RADIAL_TANGENTIAL_8 and b.position == (4.0, 5.0, 6.0)
+    np.testing.assert_allclose(b.center_uv, ((0.01 * 80 + 40) / 80, 0.5), rtol=1e-6)
+    assert abs(r.eval[0].camera.fov_x - cm.focal_to_fov(20.0 * 80 / 36.0, 80)) < 1e-12
