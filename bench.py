@@ -21,6 +21,9 @@ The other configs ride in the same JSON line under "configs":
   "4": 2M Gaussians, ONE optimizer step over 8 views sharded over the N ranks (SplatTrainer.step_views)
   "2": a short end-to-end training run on a synthetic COLMAP-format 200-view set (loader -> step -> refine -> eval),
        N=1 (scripts/train_colmap.py holds the full-length version)
+  "matrix": the sizes of the reference's own bench definitions (crates/brush-bench-test/src/benches.rs:222-287: SH degree 0,
+       {0.5, 1, 2.5} M splats at 1080p and 2 M at four resolutions), forward (packed output) and forward+backward, N=1, on
+       the SURVEY 8d scene generator (the reference's bench scene passes degrees where radians are expected)
 """
 from __future__ import annotations
 
@@ -45,6 +48,14 @@ CONFIGS = {   # BASELINE.json configs by index; seeds follow tests/scenes.py (0x
     3: dict(n=4_000_000, w=3840, h=2160, seed=0xB2000003, shift=-math.log(2.0)),   # focal doubles at 4K: scales halve
     4: dict(n=2_000_000, w=1920, h=1080, seed=0xB2000004, shift=0.0),
 }
+# benches.rs:222-287 (SPLAT_COUNTS x 1080p, 2M x RESOLUTIONS; with_sh_degree(0) :99).  Keys 100+ keep them apart from the
+# BASELINE configs; the intersection arena is sized for the larger images (the same scene covers more tiles there).
+MATRIX = [("0.5M@1080p", 500_000, 1920, 1080), ("1M@1080p", 1_000_000, 1920, 1080), ("2.5M@1080p", 2_500_000, 1920, 1080),
+          ("2M@1024x1024", 2_000_000, 1024, 1024), ("2M@1080p", 2_000_000, 1920, 1080), ("2M@1440p", 2_000_000, 2560, 1440),
+          ("2M@3200x1800", 2_000_000, 3200, 1800)]
+for _i, (_name, _n, _w, _h) in enumerate(MATRIX):
+    CONFIGS[100 + _i] = dict(n=_n, w=_w, h=_h, seed=0xB2000100 + _i, shift=0.0, k=1, forward_only=True,
+                             isect_cap=_n * (32 if _w > 1920 else 16))
 N_SPLATS, IMG_W, IMG_H = CONFIGS[1]["n"], CONFIGS[1]["w"], CONFIGS[1]["h"]
 WORKLOAD = "configs[1]: 1M synthetic Gaussians (K=16), 1920x1080, render fwd + rasterize bwd + project bwd, 1 view/GPU"
 METRIC, UNIT = "fwd+bwd Mpix/s @1M Gaussians 1080p", "Mpix/s"
@@ -110,7 +121,7 @@ class ClockSampler(threading.Thread):
 def scene_np(cfg_idx=1):
     from scenes import random_v_output, synthetic_scene
     c = CONFIGS[cfg_idx]
-    cam, tr, sh, op = synthetic_scene(c["n"], c["w"], c["h"], k=SH_K, seed=c["seed"], scale_shift=c["shift"])
+    cam, tr, sh, op = synthetic_scene(c["n"], c["w"], c["h"], k=c.get("k", SH_K), seed=c["seed"], scale_shift=c["shift"])
     return cam, tr, sh, op, random_v_output(c["h"], c["w"])
 
 
@@ -280,9 +291,10 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
     world, rank, dev = B.world, B.rank, B.dev
     cam0, tr, sh, op, v_out_np = scene_np(cfg_idx)
     cam = rank_camera(cam0, rank)
-    ctx = R.RenderContext(n, w, h, 0, device=B.local_rank)
+    ctx = R.RenderContext(n, w, h, int(c.get("isect_cap", 0)), device=B.local_rank)
     ttr, tsh, top = (torch.from_numpy(x).to(dev) for x in (tr, sh, op))
     v_out = torch.from_numpy(v_out_np).to(dev)
+    sh_k = int(c.get("k", SH_K))
     P = w * h
     dp = world > 1
     comm = None
@@ -296,7 +308,7 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
         outs = (torch.empty((n, 10), device=dev), torch.empty((n, 3), device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))
         dense = None
     else:
-        dense = (torch.empty((n, 10), device=dev), torch.empty((n, SH_K, 3), device=dev), torch.empty(n, device=dev),
+        dense = (torch.empty((n, 10), device=dev), torch.empty((n, sh_k, 3), device=dev), torch.empty(n, device=dev),
                  torch.empty(n, device=dev))
     last = [None]
     staged = [v_out]     # upstream-gradient input of the backward (static buffer)
@@ -361,6 +373,12 @@ def fwd_bwd_leg(B: Bench, cfg_idx: int, steps: int, warmup: int, headline: bool)
     ms_step = B.timed(run_step, steps) / steps
     res = {"n": n, "w": w, "h": h, "V": V, "I": I, "T": T, "P": P, "ms_step": ms_step, "launch": launch, "overflow": overflow,
            "per_tile_mean": float(per_tile.mean()), "per_tile_max": int(per_tile.max()), "stats": stats}
+    if c.get("forward_only"):   # RasterPass::Forward (packed rgba8 output), as the reference's forward_rendering group renders
+        f_only = lambda: R.render_splats(ctx, cam, (w, h), ttr, tsh, top, rpass=R.PASS_FORWARD)
+        for _ in range(3):
+            f_only()
+        torch.cuda.synchronize(dev)
+        res["ms_forward_packed"] = B.timed(lambda i: f_only(), steps) / steps
     if dp:   # phases: this rank's kernels alone (the same graphs), the exchange alone
         res["ms_compute"] = B.timed(lambda i: run_compute(), steps) / steps
         res["ms_exchange"] = B.timed(lambda i: exchange(), steps) / steps
@@ -515,6 +533,25 @@ def train_run_leg(B: Bench, iters: int):
                             max_splats=2_000_000, quiet=True)
 
 
+def matrix_leg(B: Bench, steps: int):
+    """The reference's bench matrix (benches.rs:222-287) on this path: per point forward-only and forward+backward."""
+    out = {}
+    for i, (name, n, w, h) in enumerate(MATRIX):
+        try:
+            r = fwd_bwd_leg(B, 100 + i, steps, 3, headline=False)
+            P = r["P"]
+            out[name] = {"n_gaussians": n, "width": w, "height": h, "sh_k": 1,
+                         "fwd_bwd_ms": r["ms_step"], "fwd_bwd_mpix_per_s": P / (r["ms_step"] * 1e-3) / 1e6,
+                         "forward_ms": r.get("ms_forward_packed"),
+                         "forward_mpix_per_s": (P / (r["ms_forward_packed"] * 1e-3) / 1e6) if r.get("ms_forward_packed") else None,
+                         "num_visible": r["V"], "num_intersections": r["I"], "overflow": r["overflow"],
+                         "pairs_live": r["stats"]["pairs_live"], "launch": r["launch"]}
+        except Exception as e:   # one point must not take the line down
+            out[name] = {"error": repr(e)}
+        B.torch.cuda.empty_cache()
+    return out
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -522,7 +559,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--configs", default="1,3,4,2", help="BASELINE configs to run (1 is always run)")
+    ap.add_argument("--configs", default="1,3,4,2,matrix",
+                    help="BASELINE configs to run (1 is always run); `matrix` = the reference's bench sizes (benches.rs:222-287)")
     ap.add_argument("--train-iters", type=int, default=600, help="length of the config [2] run inside the bench line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
@@ -530,7 +568,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
-    want = {int(x) for x in args.configs.split(",") if x.strip()} | {1}
+    toks = [x.strip() for x in args.configs.split(",") if x.strip()]
+    want = {int(x) for x in toks if x.isdigit()} | {1}
+    want_matrix = any(x in ("matrix", "m") for x in toks)
 
     from brush_b200.camera import build_uniforms
     B = Bench(args)
@@ -619,6 +659,12 @@ def main():
             extra["2"] = train_run_leg(B, args.train_iters)
         except Exception as e:   # the headline must survive a failure of this leg
             extra["2"] = {"error": repr(e)}
+    if want_matrix and world == 1:   # last GPU leg: nothing measured above depends on it
+        log("matrix: the reference's bench sizes (SH degree 0)")
+        try:
+            extra["matrix"] = matrix_leg(B, max(10, args.steps // 5))
+        except Exception as e:
+            extra["matrix"] = {"error": repr(e)}
     line["configs"] = extra
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         orc = _oracle_on_physical_cores()
