@@ -33,3 +33,20 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_matrix_configs_follow_the_reference_bench_sizes():
+    """crates/brush-bench-test/src/benches.rs:222-287: {0.5, 1, 2.5} M splats at 1080p, 2 M at four resolutions, SH degree 0."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sizes = {(n, w, h) for _, n, w, h in bench.MATRIX}
+    assert {(500_000, 1920, 1080), (1_000_000, 1920, 1080), (2_500_000, 1920, 1080)} <= sizes
+    assert {(2_000_000, 1024, 1024), (2_000_000, 1920, 1080), (2_000_000, 2560, 1440), (2_000_000, 3200, 1800)} <= sizes
+    for i, (_, n, w, h) in enumerate(bench.MATRIX):
+        c = bench.CONFIGS[100 + i]
+        assert (c["n"], c["w"], c["h"], c["k"]) == (n, w, h, 1) and c["forward_only"] and c["isect_cap"] >= 16 * n
+    # the BASELINE configs are untouched by the matrix entries
+    assert bench.CONFIGS[1] == dict(n=1_000_000, w=1920, h=1080, seed=0xB2000001, shift=0.0)
+    assert bench.base_config()["sh_k"] == 16
