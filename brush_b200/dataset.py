@@ -270,7 +270,16 @@ class SceneView:
         load arguments override it."""
         return ALPHA_MASKED if self.mask_path is not None else ALPHA_TRANSPARENT
 
+    def img_name(self) -> str:
+        """load_image.rs:174-180: the file name, extension included."""
+        return os.path.basename(self.image_path)
+
     def load_packed(self, alpha_mode: str = ALPHA_MASKED, max_resolution: Optional[int] = None):
+        return view_to_packed_data(self.load_image(max_resolution), alpha_mode)
+
+    def load_image(self, max_resolution: Optional[int] = None) -> np.ndarray:
+        """LoadImage::load (load_image.rs:59-123): decode, put the mask (if any) into the alpha channel, cap the long edge.
+        Returns uint8 [H,W,3] or [H,W,4]."""
         from PIL import Image
         im = Image.open(self.image_path)
         if im.mode not in ("RGB", "RGBA"):
@@ -290,7 +299,7 @@ class SceneView:
         if max_resolution and max(im.size) > max_resolution:
             s = max_resolution / max(im.size)
             im = im.resize((max(1, round(im.size[0] * s)), max(1, round(im.size[1] * s))), Image.LANCZOS)
-        return view_to_packed_data(np.asarray(im, np.uint8), alpha_mode)
+        return np.asarray(im, np.uint8)
 
 
 @dataclass

@@ -21,6 +21,15 @@ class EvalSample:
     ssim: torch.Tensor         # scalar
     render_aux: RenderOutput
 
+    def save_to_disk(self, path: str) -> None:
+        """eval.rs:66-81: the rendered image (already on the 8-bit grid) as an 8-bit RGB file; parent directories are
+        created."""
+        import os
+        from PIL import Image
+        img = (self.rendered.detach().clamp(0.0, 1.0) * 255.0).round().to(torch.uint8).cpu().numpy()
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        Image.fromarray(img, "RGB").save(path)
+
 
 def eval_stats(ctx: RenderContext, splats, camera, gt_image: np.ndarray, alpha_mode: str = ALPHA_MASKED,
                render_mip: bool = False) -> EvalSample:

@@ -16,6 +16,7 @@ import numpy as np
 @dataclass
 class ProcessConfig:                     # brush-process/src/config.rs (the fields the loop reads)
     eval_every: int = 1000
+    eval_save_to_disk: bool = False     # the rendered eval images go to <export_path>/eval_<iter>/<image name>.png
     export_every: int = 5000
     export_path: str = "."
     export_name: str = "export_{iter}.ply"
@@ -92,10 +93,11 @@ def train_loop(ctx, splats, train_views: Sequence, eval_views: Sequence, config,
             check_overflow()
             psnr, ssim = [], []
             for v in eval_views:
-                with Image.open(v.image_path) as im:
-                    gt = np.asarray(im.convert("RGBA" if "A" in im.getbands() else "RGB"), np.uint8)
+                gt = v.load_image()                        # view.image.load(): a mask file, if any, is the alpha channel
                 s = eval_stats(ctx, splats, v.camera, gt, alpha_mode, render_mip=config.render_mip)
                 psnr.append(float(s.psnr)); ssim.append(float(s.ssim))
+                if process.eval_save_to_disk:              # train_stream.rs:543-550
+                    s.save_to_disk(os.path.join(process.export_path, f"eval_{done}", f"{v.img_name()}.png"))
             evals.append({"iter": done, "psnr": float(np.mean(psnr)), "ssim": float(np.mean(ssim)), "splats": splats.num_splats()})
         if should_export(done, process.export_every, total):
             t_fold, o_fold = splats.folded(ctx)            # export.rs:183: the floor is folded into a COPY, never stored
