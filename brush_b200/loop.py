@@ -16,12 +16,12 @@ import numpy as np
 @dataclass
 class ProcessConfig:                     # brush-process/src/config.rs (the fields the loop reads)
     eval_every: int = 1000
-    eval_save_to_disk: bool = False     # the rendered eval images go to <export_path>/eval_<iter>/<image name>.png
     export_every: int = 5000
     export_path: str = "."
     export_name: str = "export_{iter}.ply"
     start_iter: int = 0
     seed: int = 42
+    eval_save_to_disk: bool = False     # the rendered eval images go to <export_path>/eval_<iter>/<image name>.png
 
 
 def should_refine(it: int, refine_every: int, total_iters: int) -> bool:
