@@ -135,7 +135,12 @@ class BoundingBox:
     extent: np.ndarray
 
     def median_size(self) -> float:
-        e = sorted(float(x) for x in self.extent)
+        """bounding_box.rs:23-29: twice the middle extent, ordered by f32::total_cmp (a NaN extent sorts last instead of
+        breaking the comparison)."""
+        def key(x):
+            b = int(np.float32(x).view(np.int32))
+            return b ^ (((b >> 31) & 0xFFFFFFFF) >> 1)
+        e = sorted((float(x) for x in self.extent), key=key)
         return e[1] * 2.0
 
 

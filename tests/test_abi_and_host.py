@@ -170,3 +170,15 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         for f, off in zip(fields[tok[0]], tok[2:]):
             name = "pass_" if f == "pass" else f
             assert getattr(cls, name).offset == int(off), (tok[0], f)
+
+
+def test_median_size_orders_like_total_cmp():
+    """brush-render/src/bounding_box.rs:36-58: a NaN extent must not break the ordering; normal case = 4."""
+    from brush_b200.train import BoundingBox
+    nan = float("nan")
+    z = np.zeros(3, np.float32)
+    assert BoundingBox(z, np.array([nan, 2.0, 3.0], np.float32)).median_size() == 6.0      # [2, 3, NaN] -> 3 * 2
+    assert math.isnan(BoundingBox(z, np.array([nan, nan, nan], np.float32)).median_size())
+    assert abs(BoundingBox(z, np.array([1.0, 2.0, 3.0], np.float32)).median_size() - 4.0) < 1e-6   # from_min_max(-1, (1, 3, 5))
+    assert BoundingBox(z, np.array([3.0, 1.0, 2.0], np.float32)).median_size() == 4.0
+    assert BoundingBox(z, np.array([-1.0, 5.0, 0.5], np.float32)).median_size() == 1.0
