@@ -355,7 +355,7 @@ def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: O
         infos = read_images_text(open(os.path.join(sparse, "images.txt")).read())
     infos = sorted(infos, key=lambda i: i.name)
     views, warnings = [], []
-    files = all_files = None                              # the dataset's file list / mask candidates, listed once
+    files = mask_files = None                              # the dataset's file list / mask candidates, listed once
     picked = infos[::max(int(subsample_frames or 1), 1)]
     if max_frames is not None:
         picked = picked[:max_frames]
@@ -373,9 +373,9 @@ def load_colmap(root: str, subsample_frames: Optional[int] = None, max_frames: O
         if not camera.is_valid():
             warnings.append(f"Skipped '{info.name}': camera contains nan or inf values")
             continue
-        if all_files is None:                             # mask candidates: paths relative to the root, like the vfs
-            all_files = [f for f in files if any(c.lower() == "masks" for c in f.split("/")[:-1])]
-        mask = find_mask_path(all_files, rel) if all_files else None
+        if mask_files is None:                             # mask candidates: paths relative to the root, like the vfs
+            mask_files = [f for f in files if any(c.lower() == "masks" for c in f.split("/")[:-1])]
+        mask = find_mask_path(mask_files, rel) if mask_files else None
         mask = os.path.join(root, mask) if mask is not None else None
         views.append(SceneView(camera, path, mask, bool(invert_masks) and mask is not None))
     train, ev = split_eval_every(views, eval_split_every)
