@@ -1,16 +1,22 @@
-"""SceneBatch producer and COLMAP model reader, host side.
+"""SceneBatch producer and dataset readers, host side.
 
   view_to_packed_data / pack_rgba <- brush-dataset/src/scene.rs:97-136 (u8 RGBA packed little endian into one int32
                                       per pixel, byte-space premultiplication for AlphaMode::Transparent)
-  load_colmap (text or binary)    <- brush-dataset/src/formats/colmap.rs:102-303 (views sorted by image name,
-                                      subsample / max frames, w2c -> c2w, fov from focal per camera model,
-                                      missing images skipped with a warning, initial points from points3D.txt)
+  load_dataset                    <- formats/mod.rs:57-110 (COLMAP, then nerfstudio json, then RealityCapture csv; an
+                                      init.ply overrides the format's own initial points)
+  load_colmap (text or binary)    <- formats/colmap.rs:102-303 (views sorted by image name, subsample / max frames,
+                                      w2c -> c2w, fov from focal per camera model, missing images skipped with a warning,
+                                      initial points from points3D)
   build_camera_model              <- formats/colmap.rs:305-390 (COLMAP sensor models -> pinhole / RT8 / KB4 / TPF)
-  split_eval_every                <- formats/mod.rs:135-148
+  load_nerfstudio                 <- formats/nerfstudio.rs (transforms*.json: per-frame / per-file intrinsics, OPENCV and
+                                      OPENCV_FISHEYE models, OpenGL camera-to-world -> brush pose, val / test file)
+  load_realitycapture             <- formats/realitycapture.rs (camera csv: 35 mm-film intrinsics, heading / pitch / roll)
+  find_image_by_name, find_mask_path, split_eval_every, opengl_c2w_to_pose <- formats/mod.rs:112-189
+  SceneView.load_image            <- load_image.rs:59-123 (decode, mask file -> alpha channel, resolution cap)
   COLMAP text / binary grammar    <- colmap-reader/src/lib.rs (cameras / images / points3D, .txt and .bin)
+  SceneLoader                     <- scene_loader.rs:13-170 (loader threads, bounded prefetch queue, packed-batch cache)
 
-The step's only host->device input is the packed [H,W] int32 image; `SceneLoader` keeps two pinned staging buffers
-so the upload of view i+1 overlaps the step on view i.
+The step's only host->device input is the packed [H,W] int32 image of a view.
 """
 from __future__ import annotations
 
